@@ -1,0 +1,77 @@
+// common.cuh -- shared helpers for the cnmfe_b200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cmath>
+
+#define CNMFE_BLOCK 256
+
+namespace cnmfe {
+
+// Launch counter: every kernel of this library launched through LAUNCH() bumps it (bench.py reports it).
+extern unsigned long long g_launch_count;
+
+#define CNMFE_CUDA_OK(expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            cnmfe::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return -1;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+void set_error(const char* fmt, ...);
+
+#define LAUNCH(kernel, grid, block, smem, stream, ...)            \
+    do {                                                          \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
+        ++cnmfe::g_launch_count;                                  \
+    } while (0)
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum; result valid in all threads. `red` = shared double[32].
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    double r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+    if (wid == 0) {
+        r = warp_sum(r);
+        if (lane == 0) red[0] = r;
+    }
+    __syncthreads();
+    r = red[0];
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ double block_max(double v, double* red) {
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    double r = (threadIdx.x < nw) ? red[threadIdx.x] : -INFINITY;
+    if (wid == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+        if (lane == 0) red[0] = r;
+    }
+    __syncthreads();
+    r = red[0];
+    __syncthreads();
+    return r;
+}
+
+}  // namespace cnmfe

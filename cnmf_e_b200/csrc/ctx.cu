@@ -1,0 +1,964 @@
+// ctx.cu -- resident-video context: Sources2D.update_{background,spatial,temporal}_parallel behind the C ABI.
+// Host code here only plans (index lists, neuron selections -- the role of the reference's host gather at
+// update_*_parallel.m:69-100) and launches; all arithmetic on the video runs in the kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "internal.h"
+#include "kernels_video.cuh"
+#include "kernels_ring.cuh"
+#include "kernels_update.cuh"
+
+namespace cnmfe {
+int ring_s2_tensor(const uint8_t* hi, const uint8_t* lo, int nrb, int ncb, int T, int Tpad, int rr, double* S2,
+                   cudaStream_t st);   // ring_tc.cu (tcgen05 INT8); returns 1 if unsupported for this shape
+}
+
+using namespace cnmfe;
+
+namespace {
+
+struct HostCsc {
+    int K = 0;
+    std::vector<int64_t> jc, ir;
+    std::vector<double> pr;
+    void set(int K_, const int64_t* jc_, const int64_t* ir_, const double* pr_) {
+        K = K_;
+        jc.assign(jc_, jc_ + K_ + 1);
+        ir.assign(ir_, ir_ + jc_[K_]);
+        if (pr_) pr.assign(pr_, pr_ + jc_[K_]); else pr.assign((size_t)jc_[K_], 1.0);
+    }
+    double lookup(int k, int64_t row) const {
+        auto b = ir.begin() + jc[k], e = ir.begin() + jc[k + 1];
+        auto it = std::lower_bound(b, e, row);
+        return (it != e && *it == row) ? pr[it - ir.begin()] : 0.0;
+    }
+};
+
+struct Rect { int r0, r1, c0, c1; };   // 0-based inclusive, FOV coordinates
+
+struct Patch {
+    Rect patch, block;
+    int nr, nc, nrb, ncb, dp, db;
+    bool owned = false, uploaded = false, w_uniform = true;
+    uint16_t* Yt = nullptr; uint8_t* hi = nullptr; uint8_t* lo = nullptr;
+    double* Ysum = nullptr; double* Ymean = nullptr;
+    double* W = nullptr; double* b0 = nullptr;
+    // spatial result bookkeeping
+    std::vector<int64_t> ind_entry;   // for each pattern entry (patch CSR order): index into the user's IND csc
+    RingGeom geom;
+};
+
+// Local (per patch) sparse view of a d x K matrix.
+struct LocalSparse {
+    std::vector<int> ids;                       // local -> global neuron
+    std::vector<int> ptr, col; std::vector<double> val;      // rows by pixel (block or patch pixel index)
+    std::vector<int> cptr, crow; std::vector<double> cval;   // columns by local neuron (rows sorted)
+    std::vector<int> bbox;                      // [K][4] r0,r1,c0,c1 in block coords (tight)
+    std::vector<int64_t> entry_src;             // csc entry index of each row-entry (for IND bookkeeping)
+    int K() const { return (int)ids.size(); }
+};
+
+struct Scratch {
+    char* base = nullptr; size_t cap = 0, off = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (base) cudaFree(base);
+        base = nullptr; cap = 0;
+        CNMFE_CUDA_OK(cudaMalloc((void**)&base, bytes));
+        cap = bytes;
+        return 0;
+    }
+    void reset() { off = 0; }
+    template <class T> T* take(size_t n) {
+        size_t b = (n * sizeof(T) + 255) / 256 * 256;
+        if (off + b > cap) return nullptr;
+        T* p = (T*)(base + off);
+        off += b;
+        return p;
+    }
+};
+
+}  // namespace
+
+struct cnmfe_ctx {
+    int device = 0, d1 = 0, d2 = 0, T = 0, Tpad = 0, npatch = 0;
+    int ring_radius = 0, rr = 0, nnb = 0;
+    std::vector<int> off_r, off_c;
+    int* d_off_r = nullptr; int* d_off_c = nullptr;
+    int* d_groups = nullptr; int ngroups = 0;
+    std::vector<Patch> patches;
+    cnmfe_options opt;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr;
+    float phase_ms[7] = {0, 0, 0, 0, 0, 0, 0};
+    bool first_bg = true;          // flag_first of update_background_parallel.m:142-146 (W{1} still uniform)
+    // neurons
+    HostCsc A, Aprev, IND;
+    int K = 0, Kprev = 0;
+    double* C = nullptr; double* Cprev = nullptr;        // [K][T]
+    double* Craw = nullptr; double* S = nullptr; double* num = nullptr; double* den = nullptr;
+    double* kpars = nullptr; double* nsn = nullptr; double* outs = nullptr;
+    size_t Kcap = 0, Kprev_cap = 0;
+    std::vector<double> sn;        // d1*d2
+    std::vector<double> A_on_IND;  // result of the spatial update on the IND pattern
+    bool have_spatial = false;
+    Scratch scr;
+    TraceArena arena;
+    unsigned int* d_ticket = nullptr; int* d_done = nullptr; int* d_order = nullptr; int* d_err = nullptr;
+    int* d_pmax = nullptr;
+};
+
+namespace {
+
+void phase_begin(cnmfe_ctx* c) { cudaEventRecord(c->pe0, c->st); }
+void phase_end(cnmfe_ctx* c, int which) {
+    cudaEventRecord(c->pe1, c->st);
+    cudaEventSynchronize(c->pe1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->pe0, c->pe1);
+    c->phase_ms[which] += ms;
+}
+
+int ensure_K(cnmfe_ctx* c, int K) {
+    if ((size_t)K <= c->Kcap) return 0;
+    size_t n = (size_t)K * c->T;
+    for (double** p : {&c->C, &c->Craw, &c->S, &c->num}) { if (*p) cudaFree(*p); *p = nullptr; }
+    for (double** p : {&c->den, &c->kpars, &c->nsn, &c->outs}) { if (*p) cudaFree(*p); *p = nullptr; }
+    if (c->d_done) cudaFree(c->d_done);
+    if (c->d_order) cudaFree(c->d_order);
+    CNMFE_CUDA_OK(cudaMalloc((void**)&c->C, n * 8));
+    CNMFE_CUDA_OK(cudaMalloc((void**)&c->Craw, n * 8));
+    CNMFE_CUDA_OK(cudaMalloc((void**)&c->S, n * 8));
+    CNMFE_CUDA_OK(cudaMalloc((void**)&c->num, n * 8));
+    CNMFE_CUDA_OK(cudaMalloc((void**)&c->den, (size_t)K * 8));
+    CNMFE_CUDA_OK(cudaMalloc((void**)&c->kpars, (size_t)K * 16));
+    CNMFE_CUDA_OK(cudaMalloc((void**)&c->nsn, (size_t)K * 8));
+    CNMFE_CUDA_OK(cudaMalloc((void**)&c->outs, (size_t)K * 48));
+    CNMFE_CUDA_OK(cudaMalloc((void**)&c->d_done, (size_t)K * 4));
+    CNMFE_CUDA_OK(cudaMalloc((void**)&c->d_order, (size_t)(K + 1) * 4));
+    CNMFE_CUDA_OK(cudaMemset(c->Craw, 0, n * 8));
+    CNMFE_CUDA_OK(cudaMemset(c->S, 0, n * 8));
+    CNMFE_CUDA_OK(cudaMemset(c->kpars, 0, (size_t)K * 16));
+    CNMFE_CUDA_OK(cudaMemset(c->nsn, 0, (size_t)K * 8));
+    c->Kcap = K;
+    return 0;
+}
+
+// MATLAB K x T column-major host -> device [K][T]
+int upload_KT(cnmfe_ctx* c, const double* hostC, int K, double* dst) {
+    if (K == 0) return 0;
+    size_t n = (size_t)K * c->T;
+    if (c->scr.reserve(std::max(c->scr.cap, n * 8 + 4096))) return -1;
+    c->scr.reset();
+    double* tmp = c->scr.take<double>(n);
+    CNMFE_CUDA_OK(cudaMemcpyAsync(tmp, hostC, n * 8, cudaMemcpyHostToDevice, c->st));
+    dim3 g((c->T + 255) / 256, K);
+    LAUNCH(colmajor_to_kt_kernel, g, 256, 0, c->st, tmp, K, c->T, dst);
+    CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+int download_KT(cnmfe_ctx* c, const double* src, int K, double* hostC) {
+    if (K == 0 || !hostC) return 0;
+    size_t n = (size_t)K * c->T;
+    if (c->scr.reserve(std::max(c->scr.cap, n * 8 + 4096))) return -1;
+    c->scr.reset();
+    double* tmp = c->scr.take<double>(n);
+    dim3 g((c->T + 255) / 256, K);
+    LAUNCH(kt_to_colmajor_kernel, g, 256, 0, c->st, src, K, c->T, tmp);
+    CNMFE_CUDA_OK(cudaMemcpyAsync(hostC, tmp, n * 8, cudaMemcpyDeviceToHost, c->st));
+    CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// get_nhood (endoscope/get_nhood.m:7-24)
+void get_nhood(int radius, int k, std::vector<int>& rs, std::vector<int>& cs) {
+    rs.clear(); cs.clear();
+    for (int c = -radius; c <= radius; ++c)
+        for (int r = -radius; r <= radius; ++r) {
+            double R = std::sqrt((double)(c * c + r * r));
+            if (R >= radius && R < radius + 1) { rs.push_back(r); cs.push_back(c); }
+        }
+    int n = (int)rs.size();
+    if (k <= 0 || k > n) return;
+    std::vector<int> ids(n);
+    for (int i = 0; i < n; ++i) ids[i] = i;
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) {
+        return std::atan2((double)rs[a], (double)cs[a]) < std::atan2((double)rs[b], (double)cs[b]);
+    });
+    std::vector<int> r2, c2;
+    for (int j = 0; j < k; ++j) {
+        double v = (k == 1) ? (double)n : 1.0 + (double)j * (double)(n - 1) / (double)(k - 1);
+        int idx = (int)std::floor(v + 0.5) - 1;
+        idx = std::min(std::max(idx, 0), n - 1);
+        r2.push_back(rs[ids[idx]]); c2.push_back(cs[ids[idx]]);
+    }
+    rs = r2; cs = c2;
+}
+
+enum SelMode { SEL_SUM_BLOCK, SEL_SUM_HALO, SEL_ANY_PATCH };
+enum RowSpace { ROWS_BLOCK, ROWS_BLOCK_PATCHONLY, ROWS_PATCH };
+
+// Build the local view of M (values from `vals`, pattern + selection from M).  rows: which pixel index space the
+// row lists use.  vals == nullptr -> M's own values.
+void build_local(const cnmfe_ctx* c, const Patch& P, const HostCsc& M, SelMode sel, RowSpace rows,
+                 const HostCsc* vals, LocalSparse* L) {
+    const int d1 = c->d1;
+    L->ids.clear();
+    const int nrows = (rows == ROWS_PATCH) ? P.dp : P.db;
+    std::vector<std::vector<std::pair<int, double>>> tmp;   // per local neuron: (pixel, value)
+    std::vector<std::vector<int64_t>> tmp_src;
+    auto in_rect = [](const Rect& R, int r, int cc) { return r >= R.r0 && r <= R.r1 && cc >= R.c0 && cc <= R.c1; };
+    for (int k = 0; k < M.K; ++k) {
+        double sum = 0.0;
+        bool any = false;
+        for (int64_t e = M.jc[k]; e < M.jc[k + 1]; ++e) {
+            int r = (int)(M.ir[e] % d1), cc = (int)(M.ir[e] / d1);
+            bool inb = in_rect(P.block, r, cc), inp = in_rect(P.patch, r, cc);
+            if (sel == SEL_SUM_BLOCK && inb) sum += M.pr[e];
+            if (sel == SEL_SUM_HALO && inb && !inp) sum += M.pr[e];
+            if (sel == SEL_ANY_PATCH && inp) any = true;
+        }
+        bool take = (sel == SEL_ANY_PATCH) ? any : (sum > 0.0);
+        if (!take) continue;
+        std::vector<std::pair<int, double>> ent;
+        std::vector<int64_t> src;
+        for (int64_t e = M.jc[k]; e < M.jc[k + 1]; ++e) {
+            int r = (int)(M.ir[e] % d1), cc = (int)(M.ir[e] / d1);
+            bool inb = in_rect(P.block, r, cc), inp = in_rect(P.patch, r, cc);
+            int idx;
+            if (rows == ROWS_PATCH) { if (!inp) continue; idx = (cc - P.patch.c0) * P.nr + (r - P.patch.r0); }
+            else if (rows == ROWS_BLOCK_PATCHONLY) { if (!inp) continue; idx = (cc - P.block.c0) * P.nrb + (r - P.block.r0); }
+            else { if (!inb) continue; idx = (cc - P.block.c0) * P.nrb + (r - P.block.r0); }
+            double v = vals ? vals->lookup(k, M.ir[e]) : M.pr[e];
+            ent.emplace_back(idx, v);
+            src.push_back(e);
+        }
+        L->ids.push_back(k);
+        tmp.push_back(std::move(ent));
+        tmp_src.push_back(std::move(src));
+    }
+    const int K = L->K();
+    // columns (entries are already sorted by pixel because ir is sorted and the index map is monotone in (c, r))
+    L->cptr.assign(K + 1, 0); L->crow.clear(); L->cval.clear(); L->bbox.assign((size_t)K * 4, 0);
+    const int nrw = (rows == ROWS_PATCH) ? P.nr : P.nrb;
+    for (int k = 0; k < K; ++k) {
+        int r0 = 1 << 30, r1 = -1, c0 = 1 << 30, c1 = -1;
+        for (auto& pv : tmp[k]) {
+            L->crow.push_back(pv.first); L->cval.push_back(pv.second);
+            int r = pv.first % nrw, cc = pv.first / nrw;
+            if (rows == ROWS_PATCH) { r += P.patch.r0 - P.block.r0; cc += P.patch.c0 - P.block.c0; }
+            r0 = std::min(r0, r); r1 = std::max(r1, r); c0 = std::min(c0, cc); c1 = std::max(c1, cc);
+        }
+        L->cptr[k + 1] = (int)L->crow.size();
+        if (r1 < 0) { r0 = 0; r1 = -1; c0 = 0; c1 = -1; }
+        L->bbox[4 * k] = r0; L->bbox[4 * k + 1] = r1; L->bbox[4 * k + 2] = c0; L->bbox[4 * k + 3] = c1;
+    }
+    // rows by pixel (ascending local neuron id inside each row)
+    L->ptr.assign(nrows + 1, 0);
+    for (int k = 0; k < K; ++k) for (auto& pv : tmp[k]) L->ptr[pv.first + 1]++;
+    for (int i = 0; i < nrows; ++i) L->ptr[i + 1] += L->ptr[i];
+    L->col.assign(L->ptr[nrows], 0); L->val.assign(L->ptr[nrows], 0.0); L->entry_src.assign(L->ptr[nrows], 0);
+    std::vector<int> fill(L->ptr.begin(), L->ptr.end() - 1);
+    for (int k = 0; k < K; ++k)
+        for (size_t x = 0; x < tmp[k].size(); ++x) {
+            int pos = fill[tmp[k][x].first]++;
+            L->col[pos] = k; L->val[pos] = tmp[k][x].second; L->entry_src[pos] = tmp_src[k][x];
+        }
+}
+
+std::vector<int> expand_bbox(const LocalSparse& L, int margin, int nrb, int ncb) {
+    std::vector<int> b(L.bbox);
+    for (int k = 0; k < L.K(); ++k) {
+        if (b[4 * k + 1] < b[4 * k]) continue;
+        b[4 * k] = std::max(0, b[4 * k] - margin); b[4 * k + 1] = std::min(nrb - 1, b[4 * k + 1] + margin);
+        b[4 * k + 2] = std::max(0, b[4 * k + 2] - margin); b[4 * k + 3] = std::min(ncb - 1, b[4 * k + 3] + margin);
+    }
+    return b;
+}
+
+template <class T> T* to_dev(cnmfe_ctx* c, const std::vector<T>& v, size_t min_n = 1) {
+    size_t n = std::max(v.size(), min_n);
+    T* p = c->scr.take<T>(n);
+    if (!p) return nullptr;
+    if (!v.empty()) cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->st);
+    return p;
+}
+
+size_t pad256(size_t b) { return (b + 255) / 256 * 256 + 256; }
+
+#define TAKE_OR_FAIL(var, expr)                                   \
+    auto var = (expr);                                            \
+    if (!var) { set_error("internal: scratch arena exhausted at %s:%d", __FILE__, __LINE__); return -1; }
+
+}  // namespace
+
+// ===================================================================================================== lifetime
+extern "C" int cnmfe_create(cnmfe_ctx** out, int d1, int d2, int T, int npatch, const int32_t* patch_pos,
+                            const int32_t* block_pos, const uint8_t* owned, int ring_radius, int num_neighbors,
+                            int device) {
+    if (!out || d1 <= 0 || d2 <= 0 || T <= 0 || npatch <= 0 || !patch_pos || !block_pos || ring_radius <= 0) {
+        set_error("cnmfe_create: bad arguments");
+        return -1;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("cnmfe_create: no CUDA device (libcnmfe_b200 has no CPU fallback)");
+        return -1;
+    }
+    if (device < 0 || device >= ndev) { set_error("cnmfe_create: device %d out of range", device); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(device));
+    cnmfe_ctx* c = new cnmfe_ctx();
+    c->device = device; c->d1 = d1; c->d2 = d2; c->T = T; c->Tpad = (T + 127) / 128 * 128; c->npatch = npatch;
+    c->ring_radius = ring_radius;
+    cnmfe_options_defaults(&c->opt);
+    get_nhood(ring_radius, num_neighbors, c->off_r, c->off_c);
+    c->nnb = (int)c->off_r.size();
+    c->rr = ring_radius;
+    c->sn.assign((size_t)d1 * d2, 1.0);
+    cudaStreamCreate(&c->st);
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1); cudaEventCreate(&c->pe0); cudaEventCreate(&c->pe1);
+    cudaMalloc((void**)&c->d_off_r, c->nnb * 4); cudaMalloc((void**)&c->d_off_c, c->nnb * 4);
+    cudaMemcpy(c->d_off_r, c->off_r.data(), c->nnb * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_off_c, c->off_c.data(), c->nnb * 4, cudaMemcpyHostToDevice);
+    cudaMalloc((void**)&c->d_ticket, 64); cudaMalloc((void**)&c->d_err, 64); cudaMalloc((void**)&c->d_pmax, 64);
+    // displacement groups for the SIMT moment kernel
+    std::vector<int> groups;
+    for (int dr = 0; dr <= 2 * c->rr; dr += 4) { groups.push_back(0); groups.push_back(dr); }
+    for (int dc = 1; dc <= 2 * c->rr; ++dc)
+        for (int dr = -2 * c->rr; dr <= 2 * c->rr; dr += 4) { groups.push_back(dc); groups.push_back(dr); }
+    c->ngroups = (int)groups.size() / 2;
+    cudaMalloc((void**)&c->d_groups, groups.size() * 4);
+    cudaMemcpy(c->d_groups, groups.data(), groups.size() * 4, cudaMemcpyHostToDevice);
+    c->patches.resize(npatch);
+    for (int i = 0; i < npatch; ++i) {
+        Patch& P = c->patches[i];
+        const int32_t* pp = patch_pos + 4 * i; const int32_t* bp = block_pos + 4 * i;
+        P.patch = {pp[0] - 1, pp[1] - 1, pp[2] - 1, pp[3] - 1};
+        P.block = {bp[0] - 1, bp[1] - 1, bp[2] - 1, bp[3] - 1};
+        P.nr = P.patch.r1 - P.patch.r0 + 1; P.nc = P.patch.c1 - P.patch.c0 + 1;
+        P.nrb = P.block.r1 - P.block.r0 + 1; P.ncb = P.block.c1 - P.block.c0 + 1;
+        P.dp = P.nr * P.nc; P.db = P.nrb * P.ncb;
+        if (P.nr <= 0 || P.nc <= 0 || P.patch.r0 < P.block.r0 || P.patch.r1 > P.block.r1 || P.patch.c0 < P.block.c0 ||
+            P.patch.c1 > P.block.c1 || P.block.r0 < 0 || P.block.r1 >= d1 || P.block.c0 < 0 || P.block.c1 >= d2) {
+            set_error("cnmfe_create: patch %d geometry invalid", i);
+            cnmfe_destroy(c);
+            return -1;
+        }
+        P.owned = owned ? owned[i] != 0 : true;
+        RingGeom& g = P.geom;
+        g.nnb = c->nnb; g.rr = c->rr; g.nrb = P.nrb; g.ncb = P.ncb; g.nr = P.nr; g.nc = P.nc;
+        g.pr_off = P.patch.r0 - P.block.r0; g.pc_off = P.patch.c0 - P.block.c0;
+        g.br0 = P.block.r0; g.bc0 = P.block.c0; g.d1 = d1; g.d2 = d2;
+        if (P.owned) {
+            if (cudaMalloc((void**)&P.W, (size_t)c->nnb * P.dp * 8) != cudaSuccess ||
+                cudaMalloc((void**)&P.b0, (size_t)P.dp * 8) != cudaSuccess) {
+                set_error("cnmfe_create: out of device memory");
+                cnmfe_destroy(c);
+                return -1;
+            }
+            LAUNCH(ring_uniform_kernel, (P.dp + 255) / 256, 256, 0, c->st, g, c->d_off_r, c->d_off_c, P.W);
+            cudaMemsetAsync(P.b0, 0, (size_t)P.dp * 8, c->st);
+        }
+    }
+    cudaStreamSynchronize(c->st);
+    *out = c;
+    return 0;
+}
+
+extern "C" void cnmfe_destroy(cnmfe_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (Patch& P : c->patches) {
+        for (void* p : {(void*)P.Yt, (void*)P.hi, (void*)P.lo, (void*)P.Ysum, (void*)P.Ymean, (void*)P.W, (void*)P.b0})
+            if (p) cudaFree(p);
+    }
+    for (void* p : {(void*)c->C, (void*)c->Cprev, (void*)c->Craw, (void*)c->S, (void*)c->num, (void*)c->den,
+                    (void*)c->kpars, (void*)c->nsn, (void*)c->outs, (void*)c->d_off_r, (void*)c->d_off_c,
+                    (void*)c->d_groups, (void*)c->d_ticket, (void*)c->d_done, (void*)c->d_order, (void*)c->d_err,
+                    (void*)c->d_pmax, (void*)c->scr.base})
+        if (p) cudaFree(p);
+    trace_arena_free(&c->arena);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->pe0) cudaEventDestroy(c->pe0);
+    if (c->pe1) cudaEventDestroy(c->pe1);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+
+extern "C" int cnmfe_set_options(cnmfe_ctx* c, const cnmfe_options* o) {
+    if (!c || !o) { set_error("cnmfe_set_options: null"); return -1; }
+    if (o->spatial_algorithm < 0 || o->spatial_algorithm > 3) { set_error("spatial_algorithm out of range"); return -1; }
+    c->opt = *o;
+    return 0;
+}
+
+static int upload_common(cnmfe_ctx* c, int ip, const void* Y, int dtype, bool on_device) {
+    if (!c || ip < 0 || ip >= c->npatch || !Y) { set_error("cnmfe_upload_block: bad arguments"); return -1; }
+    if (dtype != 0 && dtype != 1) {
+        set_error("cnmfe_upload_block: dtype %d unsupported (0 = uint8, 1 = uint16); the exact-integer path needs an integer video", dtype);
+        return -1;
+    }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    Patch& P = c->patches[ip];
+    if (!P.owned) { set_error("cnmfe_upload_block: patch %d is not owned by this context", ip); return -1; }
+    size_t n = (size_t)P.db * c->Tpad;
+    if (!P.Yt) {
+        CNMFE_CUDA_OK(cudaMalloc((void**)&P.Yt, n * 2));
+        CNMFE_CUDA_OK(cudaMalloc((void**)&P.hi, n));
+        CNMFE_CUDA_OK(cudaMalloc((void**)&P.lo, n));
+        CNMFE_CUDA_OK(cudaMalloc((void**)&P.Ysum, (size_t)P.db * 8));
+        CNMFE_CUDA_OK(cudaMalloc((void**)&P.Ymean, (size_t)P.db * 8));
+    }
+    CNMFE_CUDA_OK(cudaMemsetAsync(P.Yt, 0, n * 2, c->st));
+    CNMFE_CUDA_OK(cudaMemsetAsync(P.hi, 0, n, c->st));
+    CNMFE_CUDA_OK(cudaMemsetAsync(P.lo, 0, n, c->st));
+    const size_t esz = dtype == 0 ? 1 : 2;
+    const int chunk = 256;
+    void* stage = nullptr;
+    if (!on_device) CNMFE_CUDA_OK(cudaMalloc(&stage, (size_t)chunk * P.db * esz));
+    for (int t0 = 0; t0 < c->T; t0 += chunk) {
+        int nf = std::min(chunk, c->T - t0);
+        const char* src = (const char*)Y + (size_t)t0 * P.db * esz;
+        const void* dsrc = src;
+        if (!on_device) {
+            CNMFE_CUDA_OK(cudaMemcpyAsync(stage, src, (size_t)nf * P.db * esz, cudaMemcpyHostToDevice, c->st));
+            dsrc = stage;
+        }
+        dim3 g((P.db + 31) / 32, (nf + 31) / 32), b(32, 8);
+        if (dtype == 0) LAUNCH(transpose_chunk_kernel<uint8_t>, g, b, 0, c->st, (const uint8_t*)dsrc, P.db, nf, t0, c->Tpad, P.Yt, P.hi, P.lo);
+        else LAUNCH(transpose_chunk_kernel<uint16_t>, g, b, 0, c->st, (const uint16_t*)dsrc, P.db, nf, t0, c->Tpad, P.Yt, P.hi, P.lo);
+        if (!on_device) CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+    }
+    LAUNCH(row_sum_kernel, (P.db * 32 + 255) / 256, 256, 0, c->st, P.Yt, P.db, c->T, c->Tpad, P.Ysum);
+    CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+    if (stage) cudaFree(stage);
+    std::vector<double> ys(P.db);
+    CNMFE_CUDA_OK(cudaMemcpy(ys.data(), P.Ysum, (size_t)P.db * 8, cudaMemcpyDeviceToHost));
+    for (double& v : ys) v = v / (double)c->T;     // mean(Y,2)
+    CNMFE_CUDA_OK(cudaMemcpy(P.Ymean, ys.data(), (size_t)P.db * 8, cudaMemcpyHostToDevice));
+    P.uploaded = true;
+    return 0;
+}
+extern "C" int cnmfe_upload_block(cnmfe_ctx* c, int ip, const void* Y, int dtype) { return upload_common(c, ip, Y, dtype, false); }
+extern "C" int cnmfe_upload_block_dev(cnmfe_ctx* c, int ip, const void* Y, int dtype) { return upload_common(c, ip, Y, dtype, true); }
+
+extern "C" int cnmfe_set_neurons(cnmfe_ctx* c, int K, const int64_t* jc, const int64_t* ir, const double* pr,
+                                 const double* C) {
+    if (!c || K < 0 || (K > 0 && (!jc || !ir || !pr || !C))) { set_error("cnmfe_set_neurons: bad arguments"); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    static const int64_t zero = 0;
+    if (K == 0) { c->A.set(0, &zero, nullptr, nullptr); c->K = 0; return 0; }
+    c->A.set(K, jc, ir, pr);
+    if (K != c->K) { c->have_spatial = false; }
+    c->K = K;
+    if (ensure_K(c, K)) return -1;
+    return upload_KT(c, C, K, c->C);
+}
+
+extern "C" int cnmfe_set_prev(cnmfe_ctx* c, int K, const int64_t* jc, const int64_t* ir, const double* pr,
+                              const double* C) {
+    if (!c || K < 0 || (K > 0 && (!jc || !ir || !pr || !C))) { set_error("cnmfe_set_prev: bad arguments"); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    static const int64_t zero = 0;
+    if (K == 0) { c->Aprev.set(0, &zero, nullptr, nullptr); c->Kprev = 0; return 0; }
+    c->Aprev.set(K, jc, ir, pr);
+    c->Kprev = K;
+    if ((size_t)K > c->Kprev_cap) {
+        if (c->Cprev) cudaFree(c->Cprev);
+        CNMFE_CUDA_OK(cudaMalloc((void**)&c->Cprev, (size_t)K * c->T * 8));
+        c->Kprev_cap = K;
+    }
+    return upload_KT(c, C, K, c->Cprev);
+}
+
+extern "C" int cnmfe_set_search(cnmfe_ctx* c, int K, const int64_t* jc, const int64_t* ir) {
+    if (!c || K < 0 || (K > 0 && (!jc || !ir))) { set_error("cnmfe_set_search: bad arguments"); return -1; }
+    static const int64_t zero = 0;
+    if (K == 0) c->IND.set(0, &zero, nullptr, nullptr); else c->IND.set(K, jc, ir, nullptr);
+    return 0;
+}
+
+extern "C" int cnmfe_set_sn(cnmfe_ctx* c, const double* sn) {
+    if (!c || !sn) { set_error("cnmfe_set_sn: null"); return -1; }
+    c->sn.assign(sn, sn + (size_t)c->d1 * c->d2);
+    return 0;
+}
+
+extern "C" int cnmfe_ring_offsets(cnmfe_ctx* c, int* nnb, int32_t* r_shift, int32_t* c_shift) {
+    if (!c || !nnb) { set_error("cnmfe_ring_offsets: null"); return -1; }
+    *nnb = c->nnb;
+    if (r_shift) for (int i = 0; i < c->nnb; ++i) r_shift[i] = c->off_r[i];
+    if (c_shift) for (int i = 0; i < c->nnb; ++i) c_shift[i] = c->off_c[i];
+    return 0;
+}
+
+extern "C" int cnmfe_set_ring(cnmfe_ctx* c, int ip, const double* W, const double* b0) {
+    if (!c || ip < 0 || ip >= c->npatch) { set_error("cnmfe_set_ring: bad patch"); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    Patch& P = c->patches[ip];
+    bool uniform = true;
+    if (W) {
+        // first-run test of fit_ring_model.m:25 / update_background_parallel.m:143 on row 1 (patch pixel 0)
+        const RingGeom& g = P.geom;
+        double v0 = 0.0; bool have = false;
+        for (int i = 0; i < c->nnb; ++i) {
+            int fr = g.pr_off + c->off_r[i] + g.br0, fc = g.pc_off + c->off_c[i] + g.bc0;
+            if (fr < 0 || fr >= g.d1 || fc < 0 || fc >= g.d2) continue;
+            double v = W[(size_t)i * P.dp];
+            if (!have) { v0 = v; have = true; } else if (v != v0) uniform = false;
+        }
+    }
+    P.w_uniform = uniform;
+    if (ip == 0) c->first_bg = uniform;
+    if (!P.owned) return 0;
+    if (W) CNMFE_CUDA_OK(cudaMemcpy(P.W, W, (size_t)c->nnb * P.dp * 8, cudaMemcpyHostToDevice));
+    else {
+        LAUNCH(ring_uniform_kernel, (P.dp + 255) / 256, 256, 0, c->st, P.geom, c->d_off_r, c->d_off_c, P.W);
+        CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+    }
+    if (b0) CNMFE_CUDA_OK(cudaMemcpy(P.b0, b0, (size_t)P.dp * 8, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int cnmfe_get_ring(cnmfe_ctx* c, int ip, double* W, double* b0) {
+    if (!c || ip < 0 || ip >= c->npatch) { set_error("cnmfe_get_ring: bad patch"); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    Patch& P = c->patches[ip];
+    if (!P.owned) { set_error("cnmfe_get_ring: patch %d not owned", ip); return -1; }
+    CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+    if (W) CNMFE_CUDA_OK(cudaMemcpy(W, P.W, (size_t)c->nnb * P.dp * 8, cudaMemcpyDeviceToHost));
+    if (b0) CNMFE_CUDA_OK(cudaMemcpy(b0, P.b0, (size_t)P.dp * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int cnmfe_sync(cnmfe_ctx* c) {
+    if (!c) return -1;
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+extern "C" int cnmfe_timer_begin(cnmfe_ctx* c) {
+    if (!c) return -1;
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    CNMFE_CUDA_OK(cudaEventRecord(c->ev0, c->st));
+    return 0;
+}
+extern "C" int cnmfe_timer_end(cnmfe_ctx* c, float* ms) {
+    if (!c || !ms) return -1;
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    CNMFE_CUDA_OK(cudaEventRecord(c->ev1, c->st));
+    CNMFE_CUDA_OK(cudaEventSynchronize(c->ev1));
+    CNMFE_CUDA_OK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return 0;
+}
+extern "C" int cnmfe_last_phase_ms(cnmfe_ctx* c, float* ms7) {
+    if (!c || !ms7) return -1;
+    for (int i = 0; i < 7; ++i) ms7[i] = c->phase_ms[i];
+    return 0;
+}
+
+// ===================================================================================================== background
+static size_t bg_scratch_bytes(const cnmfe_ctx* c, const Patch& P, int Kb, size_t nnzA) {
+    size_t ND = (size_t)ring_num_disp(c->rr);
+    size_t b = 0;
+    b += pad256(ND * P.db * 8);                 // S2
+    b += pad256((size_t)P.db * std::max(Kb, 1) * 8);   // Mc / N
+    b += pad256((size_t)std::max(Kb, 1) * c->T * 8);   // Cc
+    b += pad256((size_t)P.db * 8) * 3;          // sumA, S1, spare
+    b += pad256((size_t)(P.db + 1) * 4) + pad256(nnzA * 12 + 64);
+    b += pad256((size_t)Kb * Kb * 8 + 64) + pad256((size_t)Kb * 64 + 64) * 4;
+    b += pad256((size_t)P.dp * 8);
+    b += (1 << 20);
+    return b;
+}
+
+extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
+    if (!c) { set_error("cnmfe_update_background: null ctx"); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    for (float& f : c->phase_ms) f = 0;
+    const int T = c->T;
+    const bool flag_first = c->first_bg;
+    for (int ip = 0; ip < c->npatch; ++ip) {
+        Patch& P = c->patches[ip];
+        if (!P.owned) continue;
+        if (!P.uploaded) { set_error("update_background: block %d not uploaded", ip); return -1; }
+        LocalSparse L;
+        build_local(c, P, c->A, SEL_SUM_BLOCK, ROWS_BLOCK, nullptr, &L);
+        const int Kb = L.K();
+        if (Kb == 0 && !flag_first) continue;   // update_background_parallel.m:188-199
+        if (c->scr.reserve(bg_scratch_bytes(c, P, Kb, L.col.size()))) return -1;
+        c->scr.reset();
+        const RingGeom& g = P.geom;
+        phase_begin(c);
+        TAKE_OR_FAIL(d_ptr, to_dev(c, L.ptr));
+        TAKE_OR_FAIL(d_col, to_dev(c, L.col));
+        TAKE_OR_FAIL(d_val, to_dev(c, L.val));
+        TAKE_OR_FAIL(d_ids, to_dev(c, L.ids));
+        std::vector<int> bb = expand_bbox(L, 2 * c->rr, P.nrb, P.ncb);
+        TAKE_OR_FAIL(d_bbox, to_dev(c, bb));
+        std::vector<double> sumA(P.db, 0.0);
+        for (int q = 0; q < P.db; ++q) for (int e = L.ptr[q]; e < L.ptr[q + 1]; ++e) sumA[q] += L.val[e];
+        TAKE_OR_FAIL(d_sumA, to_dev(c, sumA));
+        TAKE_OR_FAIL(d_Cc, c->scr.take<double>((size_t)std::max(Kb, 1) * T));
+        TAKE_OR_FAIL(d_Cmean, c->scr.take<double>(std::max(Kb, 1)));
+        TAKE_OR_FAIL(d_Csum, c->scr.take<double>(std::max(Kb, 1)));
+        TAKE_OR_FAIL(d_Vsel, c->scr.take<double>((size_t)std::max(Kb, 1) * std::max(Kb, 1)));
+        TAKE_OR_FAIL(d_active, c->scr.take<unsigned char>(P.dp));
+        if (Kb > 0)
+            LAUNCH(gather_center_rows_kernel, Kb, 256, 0, c->st, c->C, d_ids, Kb, T, d_Cc, d_Cmean);
+        // frames used for the weights (fit_ring_model.m:59-90)
+        const bool first_run = P.w_uniform;
+        CNMFE_CUDA_OK(cudaMemsetAsync(c->d_pmax, 0, 4, c->st));
+        LAUNCH(ring_pmax_kernel, (P.dp + 255) / 256, 256, 0, c->st, g, c->d_off_r, c->d_off_c, P.W, c->d_pmax);
+        int pmax = 0;
+        CNMFE_CUDA_OK(cudaMemcpyAsync(&pmax, c->d_pmax, 4, cudaMemcpyDeviceToHost, c->st));
+        CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+        int kf = 1;
+        if (c->opt.bg_acceleration) {
+            long long nmax = 100LL * pmax;
+            long long nk = std::min<long long>(T, nmax);
+            if (nk < 1) nk = 1;
+            kf = (int)(T / nk);
+            if (kf < 1) kf = 1;
+        }
+        const double nsel = (double)((T - 1) / kf + 1);
+        double* d_S1 = P.Ysum;
+        if (kf != 1) {
+            d_S1 = c->scr.take<double>(P.db);
+            if (!d_S1) { set_error("scratch exhausted"); return -1; }
+            LAUNCH(row_sum_strided_kernel, (P.db * 32 + 255) / 256, 256, 0, c->st, P.Yt, P.db, T, c->Tpad, kf, d_S1);
+        }
+        if (Kb > 0) {
+            dim3 gg(Kb, Kb);
+            LAUNCH(small_gram_kernel, gg, 128, 0, c->st, d_Cc, Kb, d_Cc, Kb, T, kf, d_Vsel, d_Csum);
+        }
+        LAUNCH(ring_active_b0_kernel, (P.dp + 255) / 256, 256, 0, c->st, g, c->d_off_r, c->d_off_c, P.W, d_sumA,
+               P.Ymean, d_ptr, d_col, d_val, d_Cmean, first_run ? 1 : 0, d_active, P.b0);
+        std::vector<unsigned char> act(P.dp);
+        CNMFE_CUDA_OK(cudaMemcpyAsync(act.data(), d_active, P.dp, cudaMemcpyDeviceToHost, c->st));
+        CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+        std::vector<int> alist;
+        for (int p = 0; p < P.dp; ++p) if (act[p]) alist.push_back(p);
+        phase_end(c, 6);
+        if (alist.empty()) continue;
+        TAKE_OR_FAIL(d_alist, to_dev(c, alist));
+        // projections needed by the neuron corrections
+        phase_begin(c);
+        double* d_N = c->scr.take<double>((size_t)P.db * std::max(Kb, 1));
+        if (!d_N) { set_error("scratch exhausted"); return -1; }
+        if (Kb > 0) {
+            CNMFE_CUDA_OK(cudaMemsetAsync(d_N, 0, (size_t)P.db * Kb * 8, c->st));
+            long long nw = (long long)((P.nrb + PROJ_PQ - 1) / PROJ_PQ) * P.ncb;
+            LAUNCH(proj_mc_kernel, (unsigned)((nw + 7) / 8), 256, 0, c->st, P.Yt, P.Ymean, P.nrb, P.ncb, T, c->Tpad,
+                   kf, d_Cc, Kb, d_bbox, d_N);
+            LAUNCH(ring_make_N_kernel, P.db, 64, 0, c->st, d_N, Kb, d_ptr, d_col, d_val, d_Vsel, (size_t)P.db);
+        }
+        phase_end(c, 2);
+        // second moments
+        phase_begin(c);
+        const size_t ND = (size_t)ring_num_disp(c->rr);
+        double* d_S2 = c->scr.take<double>(ND * P.db);
+        if (!d_S2) { set_error("scratch exhausted"); return -1; }
+        int tc_rc = 1;
+        if (c->opt.use_tensor_gram && kf == 1)
+            tc_rc = ring_s2_tensor(P.hi, P.lo, P.nrb, P.ncb, T, c->Tpad, c->rr, d_S2, c->st);
+        if (tc_rc < 0) return -1;
+        if (tc_rc != 0) {
+            long long nw = (long long)((P.nrb + 3) / 4) * P.ncb;
+            dim3 gg((unsigned)((nw + 7) / 8), c->ngroups);
+            LAUNCH(ring_s2_simt_kernel, gg, 256, 0, c->st, P.Yt, P.nrb, P.ncb, T, c->Tpad, kf, c->rr, c->d_groups,
+                   c->ngroups, d_S2, (size_t)P.db);
+        }
+        phase_end(c, 0);
+        // assemble + solve
+        phase_begin(c);
+        RingSolveArgs a;
+        a.g = g; a.off_r = c->d_off_r; a.off_c = c->d_off_c; a.S2 = d_S2; a.S1 = d_S1; a.Ymean = P.Ymean;
+        a.nsel = nsel; a.a_ptr = d_ptr; a.a_col = d_col; a.a_val = d_val; a.N = d_N; a.K = Kb; a.Csum = d_Csum;
+        a.active = d_active; a.active_list = d_alist; a.n_active = (int)alist.size(); a.W = P.W; a.db = (size_t)P.db;
+        const int NMAX = c->nnb + 1;
+        size_t smem = ((size_t)NMAX * (NMAX + 1) / 2 + 3 * (size_t)NMAX) * 8 + 4 * (size_t)NMAX * 4 + 64;
+        CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(ring_solve_kernel, (unsigned)alist.size(), RING_SOLVE_THREADS, smem, c->st, a);
+        CNMFE_CUDA_OK(cudaGetLastError());
+        phase_end(c, 1);
+        P.w_uniform = false;
+    }
+    c->first_bg = false;
+    // obj.A_prev = obj.A; obj.C_prev = obj.C  (update_background_parallel.m:316-317)
+    c->Aprev = c->A;
+    c->Kprev = c->K;
+    if (c->K > 0) {
+        if ((size_t)c->K > c->Kprev_cap) {
+            if (c->Cprev) cudaFree(c->Cprev);
+            CNMFE_CUDA_OK(cudaMalloc((void**)&c->Cprev, (size_t)c->K * T * 8));
+            c->Kprev_cap = c->K;
+        }
+        CNMFE_CUDA_OK(cudaMemcpyAsync(c->Cprev, c->C, (size_t)c->K * T * 8, cudaMemcpyDeviceToDevice, c->st));
+    }
+    CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+    CNMFE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ===================================================================================================== spatial
+extern "C" int cnmfe_update_spatial(cnmfe_ctx* c) {
+    if (!c) { set_error("cnmfe_update_spatial: null ctx"); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    for (float& f : c->phase_ms) f = 0;
+    if (c->IND.K != c->K) { set_error("update_spatial: search mask has %d columns, A has %d", c->IND.K, c->K); return -1; }
+    if (c->opt.spatial_algorithm == 3) {
+        set_error("update_spatial: 'lars' (utilities/lars_spatial.m) is not built yet; use hals, hals_thresh or nnls");
+        return -1;
+    }
+    const int T = c->T;
+    c->A_on_IND.assign(c->IND.ir.size(), 0.0);
+    for (int ip = 0; ip < c->npatch; ++ip) {
+        Patch& P = c->patches[ip];
+        if (!P.owned) continue;
+        if (!P.uploaded) { set_error("update_spatial: block %d not uploaded", ip); return -1; }
+        LocalSparse LS, LP;
+        build_local(c, P, c->IND, SEL_ANY_PATCH, ROWS_PATCH, &c->A, &LS);
+        const int Ks = LS.K();
+        if (Ks == 0) continue;   // update_spatial_parallel.m:121-124 (update_sn = false)
+        build_local(c, P, c->Aprev, c->opt.replicate_spatial_aprev_quirk ? SEL_SUM_HALO : SEL_SUM_BLOCK, ROWS_BLOCK,
+                    nullptr, &LP);
+        const int Kp = LP.K();
+        const size_t nent = LS.col.size();
+        size_t need = pad256((size_t)P.db * Ks * 8) + pad256((size_t)Ks * T * 8) + pad256((size_t)std::max(Kp, 1) * T * 8) +
+                      pad256((size_t)Ks * Ks * 8) + pad256((size_t)std::max(Kp, 1) * Ks * 8) + pad256(nent * 32) +
+                      pad256((size_t)(P.dp + 1) * 4) + pad256((size_t)(P.db + 1) * 4) + pad256(LP.col.size() * 12 + 64) +
+                      pad256((size_t)P.dp * 8) + pad256((size_t)(Ks + Kp) * 64 + 64) + (1 << 20);
+        if (c->scr.reserve(need)) return -1;
+        c->scr.reset();
+        const RingGeom& g = P.geom;
+        phase_begin(c);
+        TAKE_OR_FAIL(d_iptr, to_dev(c, LS.ptr));
+        TAKE_OR_FAIL(d_icol, to_dev(c, LS.col));
+        TAKE_OR_FAIL(d_a, to_dev(c, LS.val));
+        TAKE_OR_FAIL(d_ids, to_dev(c, LS.ids));
+        TAKE_OR_FAIL(d_pptr, to_dev(c, LP.ptr));
+        TAKE_OR_FAIL(d_pcol, to_dev(c, LP.col));
+        TAKE_OR_FAIL(d_pval, to_dev(c, LP.val));
+        TAKE_OR_FAIL(d_pids, to_dev(c, LP.ids));
+        std::vector<int> bb = expand_bbox(LS, c->rr, P.nrb, P.ncb);
+        TAKE_OR_FAIL(d_bbox, to_dev(c, bb));
+        std::vector<double> snp(P.dp);
+        for (int p = 0; p < P.dp; ++p) {
+            int r = p % P.nr + P.patch.r0, cc = p / P.nr + P.patch.c0;
+            snp[p] = c->sn[(size_t)cc * c->d1 + r];
+        }
+        TAKE_OR_FAIL(d_sn, to_dev(c, snp));
+        TAKE_OR_FAIL(d_Cc, c->scr.take<double>((size_t)Ks * T));
+        TAKE_OR_FAIL(d_Ccp, c->scr.take<double>((size_t)std::max(Kp, 1) * T));
+        TAKE_OR_FAIL(d_V, c->scr.take<double>((size_t)Ks * Ks));
+        TAKE_OR_FAIL(d_P2, c->scr.take<double>((size_t)std::max(Kp, 1) * Ks));
+        TAKE_OR_FAIL(d_U, c->scr.take<double>(std::max<size_t>(nent, 1)));
+        TAKE_OR_FAIL(d_D, c->scr.take<double>((size_t)P.db * Ks));
+        LAUNCH(gather_center_rows_kernel, Ks, 256, 0, c->st, c->C, d_ids, Ks, T, d_Cc, (double*)nullptr);
+        { dim3 gg(Ks, Ks); LAUNCH(small_gram_kernel, gg, 128, 0, c->st, d_Cc, Ks, d_Cc, Ks, T, 1, d_V, (double*)nullptr); }
+        if (Kp > 0) {
+            LAUNCH(gather_center_rows_kernel, Kp, 256, 0, c->st, c->Cprev, d_pids, Kp, T, d_Ccp, (double*)nullptr);
+            dim3 gg(Kp, Ks);
+            LAUNCH(small_gram_kernel, gg, 128, 0, c->st, d_Ccp, Kp, d_Cc, Ks, T, 1, d_P2, (double*)nullptr);
+        }
+        phase_end(c, 6);
+        phase_begin(c);
+        CNMFE_CUDA_OK(cudaMemsetAsync(d_D, 0, (size_t)P.db * Ks * 8, c->st));
+        {
+            long long nw = (long long)((P.nrb + PROJ_PQ - 1) / PROJ_PQ) * P.ncb;
+            LAUNCH(proj_mc_kernel, (unsigned)((nw + 7) / 8), 256, 0, c->st, P.Yt, P.Ymean, P.nrb, P.ncb, T, c->Tpad, 1,
+                   d_Cc, Ks, d_bbox, d_D);
+        }
+        if (Kp > 0) LAUNCH(spatial_make_D_kernel, P.db, 64, 0, c->st, d_D, Ks, d_pptr, d_pcol, d_pval, d_P2);
+        LAUNCH(spatial_U_kernel, (unsigned)(((size_t)P.dp * 32 + 255) / 256), 256, 0, c->st, g, c->d_off_r, c->d_off_c,
+               P.W, d_D, Ks, d_iptr, d_icol, d_pptr, d_pcol, d_pval, d_P2, d_U);
+        phase_end(c, 2);
+        phase_begin(c);
+        CNMFE_CUDA_OK(cudaMemsetAsync(c->d_err, 0, 4, c->st));
+        LAUNCH(spatial_solve_kernel, (P.dp + 127) / 128, 128, 0, c->st, P.dp, d_iptr, d_icol, d_U, d_V, Ks, d_sn,
+               c->opt.spatial_algorithm, 3, d_a, c->d_err);
+        std::vector<double> anew(nent);
+        int err = 0;
+        CNMFE_CUDA_OK(cudaMemcpyAsync(anew.data(), d_a, nent * 8, cudaMemcpyDeviceToHost, c->st));
+        CNMFE_CUDA_OK(cudaMemcpyAsync(&err, c->d_err, 4, cudaMemcpyDeviceToHost, c->st));
+        phase_end(c, 3);
+        CNMFE_CUDA_OK(cudaGetLastError());
+        if (err) { set_error("update_spatial: more than %d search masks overlap one pixel", SPATIAL_MAXROW); return -1; }
+        for (size_t e = 0; e < nent; ++e) c->A_on_IND[LS.entry_src[e]] = anew[e];
+    }
+    c->have_spatial = true;
+    // obj.A = A_new on the pattern (zeros dropped), update_spatial_parallel.m:321-335
+    HostCsc An;
+    An.K = c->K;
+    An.jc.assign(c->K + 1, 0);
+    for (int k = 0; k < c->K; ++k) {
+        for (int64_t e = c->IND.jc[k]; e < c->IND.jc[k + 1]; ++e)
+            if (c->A_on_IND[e] != 0.0) { An.ir.push_back(c->IND.ir[e]); An.pr.push_back(c->A_on_IND[e]); }
+        An.jc[k + 1] = (int64_t)An.ir.size();
+    }
+    c->A = An;
+    return 0;
+}
+
+extern "C" int cnmfe_get_spatial(cnmfe_ctx* c, double* A_on_IND) {
+    if (!c || !A_on_IND) { set_error("cnmfe_get_spatial: null"); return -1; }
+    if (!c->have_spatial) { set_error("cnmfe_get_spatial: no spatial update has run"); return -1; }
+    std::copy(c->A_on_IND.begin(), c->A_on_IND.end(), A_on_IND);
+    return 0;
+}
+
+// ===================================================================================================== temporal
+extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
+    if (!c) { set_error("cnmfe_update_temporal: null ctx"); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    for (float& f : c->phase_ms) f = 0;
+    const int T = c->T, K = c->K;
+    if (K == 0) return 0;
+    CNMFE_CUDA_OK(cudaMemsetAsync(c->num, 0, (size_t)K * T * 8, c->st));
+    CNMFE_CUDA_OK(cudaMemsetAsync(c->den, 0, (size_t)K * 8, c->st));
+    for (int ip = 0; ip < c->npatch; ++ip) {
+        Patch& P = c->patches[ip];
+        if (!P.owned) continue;
+        if (!P.uploaded) { set_error("update_temporal: block %d not uploaded", ip); return -1; }
+        LocalSparse LA, LP;
+        build_local(c, P, c->A, SEL_SUM_BLOCK, ROWS_BLOCK_PATCHONLY, nullptr, &LA);
+        const int Kt = LA.K();
+        if (Kt == 0) continue;   // update_temporal_parallel.m:123-126
+        build_local(c, P, c->Aprev, SEL_SUM_BLOCK, ROWS_BLOCK, nullptr, &LP);
+        const int Kp = LP.K();
+        size_t need = pad256((size_t)P.db * Kt * 8) + 4 * pad256((size_t)Kt * T * 8) + pad256((size_t)std::max(Kp, 1) * T * 8) +
+                      2 * pad256((size_t)Kt * Kt * 12 + 64) + pad256((size_t)Kt * std::max(Kp, 1) * 8) +
+                      2 * pad256((size_t)(P.db + 1) * 4) + pad256(LA.col.size() * 24 + 64) + pad256(LP.col.size() * 24 + 64) +
+                      pad256((size_t)(Kt + Kp) * 128 + 64) + (1 << 20);
+        if (c->scr.reserve(need)) return -1;
+        c->scr.reset();
+        const RingGeom& g = P.geom;
+        phase_begin(c);
+        TAKE_OR_FAIL(d_aptr, to_dev(c, LA.ptr));
+        TAKE_OR_FAIL(d_acol, to_dev(c, LA.col));
+        TAKE_OR_FAIL(d_aval, to_dev(c, LA.val));
+        TAKE_OR_FAIL(d_cptr, to_dev(c, LA.cptr));
+        TAKE_OR_FAIL(d_crow, to_dev(c, LA.crow));
+        TAKE_OR_FAIL(d_cval, to_dev(c, LA.cval));
+        TAKE_OR_FAIL(d_ids, to_dev(c, LA.ids));
+        TAKE_OR_FAIL(d_pcptr, to_dev(c, LP.cptr));
+        TAKE_OR_FAIL(d_pcrow, to_dev(c, LP.crow));
+        TAKE_OR_FAIL(d_pcval, to_dev(c, LP.cval));
+        TAKE_OR_FAIL(d_pids, to_dev(c, LP.ids));
+        std::vector<int> bb = expand_bbox(LA, c->rr, P.nrb, P.ncb);
+        TAKE_OR_FAIL(d_bbox, to_dev(c, bb));
+        TAKE_OR_FAIL(d_B, c->scr.take<double>((size_t)P.db * Kt));
+        TAKE_OR_FAIL(d_U, c->scr.take<double>((size_t)Kt * T));
+        TAKE_OR_FAIL(d_Cl, c->scr.take<double>((size_t)Kt * T));
+        TAKE_OR_FAIL(d_Crawl, c->scr.take<double>((size_t)Kt * T));
+        TAKE_OR_FAIL(d_Sl, c->scr.take<double>((size_t)Kt * T));
+        TAKE_OR_FAIL(d_Ccp, c->scr.take<double>((size_t)std::max(Kp, 1) * T));
+        TAKE_OR_FAIL(d_AWA, c->scr.take<double>((size_t)Kt * std::max(Kp, 1)));
+        TAKE_OR_FAIL(d_cst, c->scr.take<double>(Kt));
+        TAKE_OR_FAIL(d_V, c->scr.take<double>((size_t)Kt * Kt));
+        TAKE_OR_FAIL(d_snl, c->scr.take<double>(Kt));
+        TAKE_OR_FAIL(d_parsl, c->scr.take<double>((size_t)Kt * 2));
+        CNMFE_CUDA_OK(cudaMemsetAsync(d_B, 0, (size_t)P.db * Kt * 8, c->st));
+        LAUNCH(temporal_build_negWtA_kernel, (P.db + 127) / 128, 128, 0, c->st, g, c->d_off_r, c->d_off_c, P.W, d_aptr,
+               d_acol, d_aval, Kt, d_B);
+        if (Kp > 0) {
+            dim3 gg(Kt, (Kp + 63) / 64);
+            LAUNCH(temporal_AWA_kernel, gg, 64, 0, c->st, d_B, Kt, d_pcptr, d_pcrow, d_pcval, Kp, d_AWA);
+            LAUNCH(gather_center_rows_kernel, Kp, 256, 0, c->st, c->Cprev, d_pids, Kp, T, d_Ccp, (double*)nullptr);
+        }
+        LAUNCH(temporal_add_A_kernel, (Kt + 63) / 64, 64, 0, c->st, g, d_cptr, d_crow, d_cval, Kt, P.Ymean, P.b0, d_B,
+               d_cst);
+        { dim3 gg(Kt, (Kt + 127) / 128); LAUNCH(temporal_V_kernel, gg, 128, 0, c->st, d_cptr, d_crow, d_cval, Kt, d_V); }
+        phase_end(c, 6);
+        phase_begin(c);
+        { dim3 gg(Kt, (T + 511) / 512); LAUNCH(proj_bt_kernel, gg, 256, 0, c->st, P.Yt, P.Ymean, P.nrb, T, c->Tpad, d_B, Kt, d_bbox, d_U); }
+        { dim3 gg((T + 255) / 256, Kt); LAUNCH(add_small_matmul_kernel, gg, 256, 0, c->st, d_U, Kt, T, d_cst, d_AWA, Kp, d_Ccp); }
+        phase_end(c, 2);
+        // V -> CSR (host), sweeps
+        phase_begin(c);
+        std::vector<double> V((size_t)Kt * Kt);
+        CNMFE_CUDA_OK(cudaMemcpyAsync(V.data(), d_V, V.size() * 8, cudaMemcpyDeviceToHost, c->st));
+        CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+        std::vector<int> vptr(Kt + 1, 0), vidx;
+        std::vector<double> vval, aa(Kt);
+        for (int k = 0; k < Kt; ++k) {
+            for (int j = 0; j < Kt; ++j) {
+                double v = V[(size_t)k * Kt + j];
+                if (v != 0.0 || j == k) { vidx.push_back(j); vval.push_back(v); }
+            }
+            vptr[k + 1] = (int)vidx.size();
+            aa[k] = V[(size_t)k * Kt + k];
+        }
+        TAKE_OR_FAIL(d_vptr, to_dev(c, vptr));
+        TAKE_OR_FAIL(d_vidx, to_dev(c, vidx));
+        TAKE_OR_FAIL(d_vval, to_dev(c, vval));
+        TAKE_OR_FAIL(d_aa, to_dev(c, aa));
+        { dim3 gg((T + 255) / 256, Kt); LAUNCH(gather_rows_kernel, gg, 256, 0, c->st, c->C, d_ids, Kt, T, d_Cl); }
+        CNMFE_CUDA_OK(cudaMemsetAsync(d_Crawl, 0, (size_t)Kt * T * 8, c->st));
+        CNMFE_CUDA_OK(cudaMemsetAsync(d_Sl, 0, (size_t)Kt * T * 8, c->st));
+        CNMFE_CUDA_OK(cudaMemsetAsync(d_parsl, 0, (size_t)Kt * 16, c->st));
+        if (hals_temporal_dev(d_U, d_vptr, d_vidx, d_vval, d_aa, Kt, T, c->opt.maxIter_temporal, c->opt.deconv_flag,
+                              c->opt.deconv, d_Cl, d_Crawl, d_Sl, d_snl, d_parsl, c->d_done, c->d_ticket, c->d_order,
+                              &c->arena, c->st)) return -1;
+        { dim3 gg((T + 255) / 256, Kt); LAUNCH(temporal_merge_kernel, gg, 256, 0, c->st, d_Crawl, d_V, Kt, T, d_ids, c->num, c->den); }
+        phase_end(c, 4);
+        CNMFE_CUDA_OK(cudaGetLastError());
+    }
+    CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int cnmfe_temporal_merge_buffers(cnmfe_ctx* c, double** num_dev, double** den_dev) {
+    if (!c || !num_dev || !den_dev) { set_error("cnmfe_temporal_merge_buffers: null"); return -1; }
+    *num_dev = c->num; *den_dev = c->den;
+    return 0;
+}
+
+extern "C" int cnmfe_update_temporal_finish(cnmfe_ctx* c) {
+    if (!c) { set_error("cnmfe_update_temporal_finish: null ctx"); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    const int T = c->T, K = c->K;
+    if (K == 0) return 0;
+    phase_begin(c);
+    { dim3 gg((T + 255) / 256, K); LAUNCH(temporal_divide_kernel, gg, 256, 0, c->st, c->num, c->den, K, T); }
+    if (c->opt.deconv_flag) {
+        // obj.C = obj.deconvTemporal()  (update_temporal_parallel.m:283)
+        if (deconv_batch_dev(c->num, T, K, c->opt.deconv, nullptr, nullptr, 1, c->C, c->S, c->Craw, c->outs, &c->arena,
+                             c->st)) return -1;
+    } else {
+        LAUNCH(rows_sub_min_kernel, K, 256, 0, c->st, c->num, T);
+        CNMFE_CUDA_OK(cudaMemcpyAsync(c->Craw, c->num, (size_t)K * T * 8, cudaMemcpyDeviceToDevice, c->st));
+        CNMFE_CUDA_OK(cudaMemcpyAsync(c->C, c->num, (size_t)K * T * 8, cudaMemcpyDeviceToDevice, c->st));
+        CNMFE_CUDA_OK(cudaMemsetAsync(c->outs, 0, (size_t)K * 48, c->st));
+    }
+    phase_end(c, 5);
+    CNMFE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cnmfe_update_temporal(cnmfe_ctx* c) {
+    if (cnmfe_update_temporal_patches(c)) return -1;
+    return cnmfe_update_temporal_finish(c);
+}
+
+extern "C" int cnmfe_get_temporal(cnmfe_ctx* c, double* C, double* C_raw, double* S, double* kernel_pars,
+                                  double* neuron_sn) {
+    if (!c) { set_error("cnmfe_get_temporal: null ctx"); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    const int K = c->K;
+    if (K == 0) return 0;
+    if (download_KT(c, c->C, K, C) || download_KT(c, c->Craw, K, C_raw) || download_KT(c, c->S, K, S)) return -1;
+    if (kernel_pars || neuron_sn) {
+        std::vector<double> outs((size_t)K * 6);
+        CNMFE_CUDA_OK(cudaMemcpy(outs.data(), c->outs, (size_t)K * 48, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < K; ++k) {
+            if (kernel_pars) { kernel_pars[2 * k] = outs[6 * k + 1]; kernel_pars[2 * k + 1] = outs[6 * k + 2]; }
+            if (neuron_sn) neuron_sn[k] = outs[6 * k + 5];
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,287 @@
+// kernels_update.cuh -- per-pixel spatial solvers and the sparse algebra around the temporal projection.
+// Reference: utilities/HALS_spatial.m:33-44, utilities/HALS_spatial_thresh.m:38-53, endoscope/nnls_spatial.m:33-109,
+//            @Sources2D/update_spatial_parallel.m:157-166 (BG subtraction), update_temporal_parallel.m:144-181.
+#pragma once
+#include "common.cuh"
+#include "kernels_ring.cuh"
+
+namespace cnmfe {
+
+#define SPATIAL_MAXROW 32   // max neurons whose search mask covers one pixel
+#define NNLS_MAXP 20        // nnls_spatial maxN (update_spatial_parallel.m:211 passes 20)
+
+// D[q][k] = Mc[q][k] - sum_k' Aprev[q,k'] * P2[k'][k]   (projection of the background residual on Cc), in place.
+__global__ void spatial_make_D_kernel(double* __restrict__ Mc, int Ks, const int* __restrict__ ap_ptr,
+                                      const int* __restrict__ ap_col, const double* __restrict__ ap_val,
+                                      const double* __restrict__ P2) {
+    size_t q = blockIdx.x;
+    int e0 = ap_ptr[q], e1 = ap_ptr[q + 1];
+    if (e0 == e1) return;
+    for (int k = threadIdx.x; k < Ks; k += blockDim.x) {
+        double s = 0.0;
+        for (int e = e0; e < e1; ++e) s += ap_val[e] * P2[(size_t)ap_col[e] * Ks + k];
+        Mc[q * Ks + k] -= s;
+    }
+}
+
+// U(p,k) = Ysig(p,:) * Cc(k,:)' on the search pattern, from D:
+//   U = [D(p,k) + R(p,k)] - sum_i W(p,i) * D(q_i,k),   R(p,k) = sum_k' Aprev(p,k') P2(k',k)
+// One warp per patch pixel (rows of the pattern by patch pixel: ind_ptr / ind_col), lanes over ring slots.
+__global__ void __launch_bounds__(256)
+spatial_U_kernel(RingGeom g, const int* __restrict__ off_r, const int* __restrict__ off_c,
+                 const double* __restrict__ W, const double* __restrict__ D, int Ks,
+                 const int* __restrict__ ind_ptr, const int* __restrict__ ind_col, const int* __restrict__ ap_ptr,
+                 const int* __restrict__ ap_col, const double* __restrict__ ap_val, const double* __restrict__ P2,
+                 double* __restrict__ U) {
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int dp = g.nr * g.nc;
+    if (p >= dp) return;
+    const int e0 = ind_ptr[p], e1 = ind_ptr[p + 1];
+    if (e0 == e1) return;
+    const int r = p % g.nr + g.pr_off, c = p / g.nr + g.pc_off;
+    const size_t qp = (size_t)c * g.nrb + r;
+    for (int e = e0; e < e1; ++e) {
+        const int k = ind_col[e];
+        double acc = 0.0;
+        for (int i = lane; i < g.nnb; i += 32) {
+            int r2 = r + off_r[i], c2 = c + off_c[i];
+            int fr = r2 + g.br0, fc = c2 + g.bc0;
+            if (fr < 0 || fr >= g.d1 || fc < 0 || fc >= g.d2) continue;
+            acc = fma(W[(size_t)i * dp + p], D[((size_t)c2 * g.nrb + r2) * Ks + k], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            double rr_ = 0.0;
+            for (int x = ap_ptr[qp]; x < ap_ptr[qp + 1]; ++x) rr_ += ap_val[x] * P2[(size_t)ap_col[x] * Ks + k];
+            U[e] = (D[qp * Ks + k] + rr_) - acc;
+        }
+    }
+}
+
+__device__ inline bool chol_solve_small(double* M /*n*n row-major, overwritten*/, double* b, int n) {
+    for (int k = 0; k < n; ++k) {
+        double d = M[k * n + k];
+        for (int j = 0; j < k; ++j) d -= M[k * n + j] * M[k * n + j];
+        if (!(d > 0.0)) return false;
+        d = sqrt(d);
+        M[k * n + k] = d;
+        for (int i = k + 1; i < n; ++i) {
+            double s = M[i * n + k];
+            for (int j = 0; j < k; ++j) s -= M[i * n + j] * M[k * n + j];
+            M[i * n + k] = s / d;
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        double s = b[i];
+        for (int j = 0; j < i; ++j) s -= M[i * n + j] * b[j];
+        b[i] = s / M[i * n + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        double s = b[i];
+        for (int j = i + 1; j < n; ++j) s -= M[j * n + i] * b[j];
+        b[i] = s / M[i * n + i];
+    }
+    return true;
+}
+
+// method: 0 hals (3 sweeps, max(0,.)), 1 hals_thresh (3 sweeps, threshold 3*sn/sqrt(cc)), 2 nnls (maxN = 20).
+// One thread per patch pixel.  a_io: initial A on the pattern (in), new A (out).  V = Cc*Cc' [Ks][Ks].
+__global__ void __launch_bounds__(128)
+spatial_solve_kernel(int dp, const int* __restrict__ ind_ptr, const int* __restrict__ ind_col,
+                     const double* __restrict__ U, const double* __restrict__ V, int Ks,
+                     const double* __restrict__ sn, int method, int maxIter, double* __restrict__ a_io,
+                     int* __restrict__ err) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= dp) return;
+    const int e0 = ind_ptr[p], n = ind_ptr[p + 1] - e0;
+    if (n == 0) return;
+    if (n > SPATIAL_MAXROW) { atomicExch(err, 1); return; }
+    int col[SPATIAL_MAXROW];
+    double a[SPATIAL_MAXROW], u[SPATIAL_MAXROW];
+    for (int i = 0; i < n; ++i) { col[i] = ind_col[e0 + i]; a[i] = a_io[e0 + i]; u[i] = U[e0 + i]; }
+    if (method == 0 || method == 1) {
+        const double snp = (method == 1) ? sn[p] : 0.0;
+        for (int it = 0; it < maxIter; ++it) {
+            for (int i = 0; i < n; ++i) {
+                const int k = col[i];
+                const double cc = V[(size_t)k * Ks + k];
+                if (cc == 0.0) continue;
+                double s = 0.0;
+                for (int j = 0; j < n; ++j) s += a[j] * V[(size_t)col[j] * Ks + k];
+                double ak = a[i] + (u[i] - s) / cc;
+                if (method == 0) ak = fmax(0.0, ak);
+                else if (ak < snp * (3.0 / sqrt(cc))) ak = 0.0;
+                a[i] = ak;
+            }
+        }
+    } else {
+        // nnls(CC(ind,ind), YC(ind,px), [], 1e-4, maxN)   (nnls_spatial.m:41-109)
+        const double tol = 1e-4;
+        const int maxN = NNLS_MAXP;
+        double s[SPATIAL_MAXROW], mu[NNLS_MAXP], M[NNLS_MAXP * NNLS_MAXP];
+        int pidx[NNLS_MAXP];
+        unsigned Pset = 0u;
+        for (int i = 0; i < n; ++i) s[i] = 0.0;
+        for (int miter = 0; miter < maxN; ++miter) {
+            double lmax = -INFINITY;
+            int imax = 0;
+            for (int i = 0; i < n; ++i) {
+                double l = u[i];
+                for (int j = 0; j < n; ++j) l -= V[(size_t)col[i] * Ks + col[j]] * s[j];
+                if (l > lmax) { lmax = l; imax = i; }
+            }
+            Pset = 0u;
+            for (int i = 0; i < n; ++i) if (s[i] > 0.0) Pset |= (1u << i);
+            if (lmax < tol) break;
+            Pset |= (1u << imax);
+            if (__popc(Pset) > maxN) break;
+            int np = 0;
+            bool have_mu = false;
+            while (Pset) {
+                np = 0;
+                for (int i = 0; i < n; ++i) if (Pset & (1u << i)) pidx[np++] = i;
+                for (int x = 0; x < np; ++x) {
+                    mu[x] = u[pidx[x]];
+                    for (int y = 0; y < np; ++y) M[x * np + y] = V[(size_t)col[pidx[x]] * Ks + col[pidx[y]]];
+                }
+                if (!chol_solve_small(M, mu, np)) {
+                    // singular: regularised retry (nnls_spatial.m:92-94)
+                    for (int x = 0; x < np; ++x) {
+                        mu[x] = u[pidx[x]];
+                        for (int y = 0; y < np; ++y)
+                            M[x * np + y] = V[(size_t)col[pidx[x]] * Ks + col[pidx[y]]] + (x == y ? tol : 0.0);
+                    }
+                    chol_solve_small(M, mu, np);
+                }
+                have_mu = true;
+                bool allpos = true;
+                for (int x = 0; x < np; ++x) if (!(mu[x] > tol)) allpos = false;
+                if (allpos) break;
+                double amin = INFINITY;
+                for (int x = 0; x < np; ++x)
+                    if (!(mu[x] > tol)) amin = fmin(amin, s[pidx[x]] / (s[pidx[x]] - mu[x]));
+                for (int x = 0; x < np; ++x) s[pidx[x]] = s[pidx[x]] + amin * (mu[x] - s[pidx[x]]);
+                for (int i = 0; i < n; ++i) if (s[i] < tol) Pset &= ~(1u << i);
+                have_mu = false;
+            }
+            if (have_mu) for (int x = 0; x < np; ++x) s[pidx[x]] = mu[x];
+        }
+        for (int i = 0; i < n; ++i) a[i] = s[i];
+    }
+    for (int i = 0; i < n; ++i) a_io[e0 + i] = a[i];
+}
+
+// ---- temporal side ---------------------------------------------------------------------------------------------
+// B[q][k] = - sum_{patch pixels p with q = p + off_i} W(p,i) * A(p,k)     (the -W'A part; A(p,:) from rows by block
+// pixel, non-empty only for patch pixels).  One thread per block pixel q (gather: deterministic order).
+__global__ void temporal_build_negWtA_kernel(RingGeom g, const int* __restrict__ off_r, const int* __restrict__ off_c,
+                                             const double* __restrict__ W, const int* __restrict__ a_ptr,
+                                             const int* __restrict__ a_col, const double* __restrict__ a_val,
+                                             int Kt, double* __restrict__ B) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    int db = g.nrb * g.ncb;
+    if (q >= db) return;
+    int r = q % g.nrb, c = q / g.nrb;
+    int dp = g.nr * g.nc;
+    for (int i = 0; i < g.nnb; ++i) {
+        int r2 = r - off_r[i], c2 = c - off_c[i];        // candidate centre pixel (block coords)
+        int pr = r2 - g.pr_off, pc = c2 - g.pc_off;      // patch coords
+        if (pr < 0 || pr >= g.nr || pc < 0 || pc >= g.nc) continue;
+        size_t qc = (size_t)c2 * g.nrb + r2;
+        int e0 = a_ptr[qc], e1 = a_ptr[qc + 1];
+        if (e0 == e1) continue;
+        double w = W[(size_t)i * dp + ((size_t)pc * g.nr + pr)];
+        for (int e = e0; e < e1; ++e) B[(size_t)q * Kt + a_col[e]] -= w * a_val[e];
+    }
+}
+
+// AWA[k][k'] = sum_q (-B[q][k]) * Aprev[q,k']  with Aprev by column (CSC over local prev neurons, rows = block pixels)
+__global__ void temporal_AWA_kernel(const double* __restrict__ B, int Kt, const int* __restrict__ pc_ptr,
+                                    const int* __restrict__ pc_row, const double* __restrict__ pc_val, int Kp,
+                                    double* __restrict__ AWA) {
+    int k = blockIdx.x, kp = blockIdx.y * blockDim.x + threadIdx.x;
+    if (kp >= Kp) return;
+    double s = 0.0;
+    for (int e = pc_ptr[kp]; e < pc_ptr[kp + 1]; ++e) s -= B[(size_t)pc_row[e] * Kt + k] * pc_val[e];
+    AWA[(size_t)k * Kp + kp] = s;
+}
+
+// B[q][k] += A(q,k) on patch rows;  cst[k] = sum_p A(p,k) (Ymean_p - b0_p);  aa via V later.
+__global__ void temporal_add_A_kernel(RingGeom g, const int* __restrict__ c_ptr, const int* __restrict__ c_row,
+                                      const double* __restrict__ c_val, int Kt, const double* __restrict__ Ymean,
+                                      const double* __restrict__ b0, double* __restrict__ B,
+                                      double* __restrict__ cst) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Kt) return;
+    double s = 0.0;
+    for (int e = c_ptr[k]; e < c_ptr[k + 1]; ++e) {
+        int q = c_row[e];
+        int r = q % g.nrb - g.pr_off, c = q / g.nrb - g.pc_off;
+        B[(size_t)q * Kt + k] += c_val[e];
+        s += c_val[e] * (Ymean[q] - b0[(size_t)c * g.nr + r]);
+    }
+    cst[k] = s;
+}
+
+// V = A'A from sorted CSC columns (deterministic sparse dot).  grid (Kt, ceil(Kt/128))
+__global__ void temporal_V_kernel(const int* __restrict__ c_ptr, const int* __restrict__ c_row,
+                                  const double* __restrict__ c_val, int Kt, double* __restrict__ V) {
+    int k = blockIdx.x, j = blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= Kt) return;
+    int a = c_ptr[k], a1 = c_ptr[k + 1], b = c_ptr[j], b1 = c_ptr[j + 1];
+    double s = 0.0;
+    if (a < a1 && b < b1 && c_row[a1 - 1] >= c_row[b] && c_row[b1 - 1] >= c_row[a]) {
+        while (a < a1 && b < b1) {
+            int ra = c_row[a], rb = c_row[b];
+            if (ra == rb) { s += c_val[a] * c_val[b]; ++a; ++b; }
+            else if (ra < rb) ++a;
+            else ++b;
+        }
+    }
+    V[(size_t)k * Kt + j] = s;
+}
+
+// num[ids[k]][t] += aa[k] * Craw[k][t]; den[ids[k]] += aa[k]   (update_temporal_parallel.m:269-280)
+__global__ void temporal_merge_kernel(const double* __restrict__ Craw, const double* __restrict__ V, int Kt, int T,
+                                      const int* __restrict__ ids, double* __restrict__ num,
+                                      double* __restrict__ den) {
+    int k = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    double aa = V[(size_t)k * Kt + k];
+    if (t < T) num[(size_t)ids[k] * T + t] += Craw[(size_t)k * T + t] * aa;
+    if (t == 0) den[ids[k]] += aa;
+}
+
+__global__ void temporal_divide_kernel(double* __restrict__ num, const double* __restrict__ den, int K, int T) {
+    int k = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double d = den[k];
+    if (d == 0.0) d = 1.0;
+    num[(size_t)k * T + t] = num[(size_t)k * T + t] * (1.0 / d);   // bsxfun(@times, C_new, 1./aa)
+}
+
+__global__ void rows_sub_min_kernel(double* __restrict__ X, int T) {
+    __shared__ double red[32];
+    double* x = X + (size_t)blockIdx.x * T;
+    double mn = INFINITY;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) mn = fmin(mn, x[t]);
+    mn = -block_max(-mn, red);
+    for (int t = threadIdx.x; t < T; t += blockDim.x) x[t] -= mn;
+}
+
+__global__ void gather_rows_kernel(const double* __restrict__ src, const int* __restrict__ ids, int n, int T,
+                                   double* __restrict__ dst) {
+    int i = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) dst[(size_t)i * T + t] = src[(size_t)ids[i] * T + t];
+}
+
+// [K][T] <-> MATLAB column-major K x T
+__global__ void kt_to_colmajor_kernel(const double* __restrict__ src, int K, int T, double* __restrict__ dst) {
+    int k = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) dst[(size_t)t * K + k] = src[(size_t)k * T + t];
+}
+__global__ void colmajor_to_kt_kernel(const double* __restrict__ src, int K, int T, double* __restrict__ dst) {
+    int k = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) dst[(size_t)k * T + t] = src[(size_t)t * K + k];
+}
+
+}  // namespace cnmfe

@@ -1,0 +1,684 @@
+// oasis.cuh -- block-cooperative device routines for the per-trace part of the CNMF-E temporal update:
+// Welch-PSD noise (GetSn), Yule-Walker time constant, order statistics, AR(1)/AR(2) pool-adjacent-violators
+// (OASIS) and the FOOPSI hyper-parameter loop.  One CTA (CNMFE_BLOCK threads) owns one trace; all arithmetic
+// is IEEE double, in the operation order of the reference wherever that order is observable.
+//
+// Reference behaviour being reproduced (file:line under /root/reference/OASIS_matlab):
+//   GetSn                  functions/GetSn.m:33-41  (+ documented pwelch defaults)
+//   estimate_time_constant functions/estimate_time_constant.m:36-67 (randn jitter -> 0; p>2 fallback -> "fail")
+//   oasisAR1               packages/oasis/oasisAR1.m:57-109
+//   oasisAR2               packages/oasis/oasisAR2.m:49-156
+//   foopsi_oasisAR1        packages/oasis/foopsi_oasisAR1.m:78-179 (incl. the shared-`h` quirk of update_g)
+//   constrained_oasisAR1   packages/oasis/constrained_oasisAR1.m:84-199
+//   thresholded_oasisAR1   packages/oasis/thresholded_oasisAR1.m:104-213
+//   fminbnd                MathWorks fminbnd = FMM golden section + parabolic interpolation, TolX 1e-4
+#pragma once
+#include "common.cuh"
+
+namespace cnmfe {
+
+// Per-CTA workspace in global memory (all arrays sized for T, see trace_ws_doubles()).
+struct TraceWS {
+    double* yb;    // T    working trace (y - b)
+    double* c;     // T
+    double* s;     // T
+    double* pv;    // T    pools: v
+    double* pw;    // T    pools: w
+    int* pt;       // T    pools: start (0-based)
+    int* pl;       // T    pools: length
+    double* h;     // T+1  kernel table of update_g / AR2 g11
+    double* hh;    // T+1  cumsum(h.^2)          / AR2 g12
+    double* gp;    // 2T+2 powers g^l            / AR2 g11g11, g11g12 (T each)
+    double* scr;   // scratch: max(3*nfft + nfft/4 + 8, 2T) doubles
+    double* sv;    // T+1  saved pools v (constrained/thresholded trial copies)
+    double* sw;    // T+1
+    int* st;       // T
+    int* sl;       // T
+};
+
+struct BlockShared {
+    double red[32];
+    int hist[256];
+    int ibc[4];
+    double dbc[4];
+};
+
+__host__ __device__ inline int nextpow2_int(int L) {
+    int n = 1;
+    while (n < L) n <<= 1;
+    return n;
+}
+
+__host__ __device__ inline int welch_nfft(int T) {
+    int L = (int)floor((double)T / 4.5);
+    int n = nextpow2_int(L);
+    return n < 256 ? 256 : n;
+}
+
+__host__ __device__ inline size_t trace_scratch_doubles(int T) {
+    size_t nfft = (size_t)welch_nfft(T);
+    size_t a = 3 * nfft + nfft / 4 + 8;
+    size_t b = 2 * (size_t)T + 8;
+    return a > b ? a : b;
+}
+
+// ------------------------------------------------------------------------------------------------ order stats
+__device__ __forceinline__ unsigned long long dkey(double x) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+    unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
+// k-th smallest (0-based) of x[0..n) by 8-pass MSB radix select.  All threads call; result in all threads.
+__device__ double select_kth(const double* __restrict__ x, int n, int k, BlockShared* sh) {
+    unsigned long long prefix = 0, mask = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) sh->ibc[0] = k;
+    for (int pass = 7; pass >= 0; --pass) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) sh->hist[i] = 0;
+        __syncthreads();
+        int shift = pass * 8;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            unsigned long long key = dkey(x[i]);
+            if ((key & mask) == prefix) atomicAdd(&sh->hist[(int)((key >> shift) & 255ull)], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int kk = sh->ibc[0], cum = 0, b = 0;
+            for (b = 0; b < 256; ++b) {
+                int h = sh->hist[b];
+                if (cum + h > kk) break;
+                cum += h;
+            }
+            sh->ibc[0] = kk - cum;
+            sh->ibc[1] = b;
+        }
+        __syncthreads();
+        unsigned long long b = (unsigned long long)sh->ibc[1];
+        prefix |= (b << shift);
+        mask |= (255ull << shift);
+        __syncthreads();
+    }
+    return dkey_inv(prefix);
+}
+
+__device__ double block_median(const double* x, int n, BlockShared* sh) {
+    if (n & 1) return select_kth(x, n, n / 2, sh);
+    double a = select_kth(x, n, n / 2 - 1, sh);
+    double b = select_kth(x, n, n / 2, sh);
+    return (a + b) / 2.0;
+}
+
+// MATLAB quantile(x,p): linear interpolation at plotting positions (i-0.5)/n.
+__device__ double block_quantile(const double* x, int n, double p, BlockShared* sh) {
+    double pos = p * (double)n + 0.5;   // 1-based fractional rank
+    if (pos < 1.0) return select_kth(x, n, 0, sh);
+    if (pos >= (double)n) return select_kth(x, n, n - 1, sh);
+    int lo = (int)floor(pos);
+    double fr = pos - (double)lo;
+    double a = select_kth(x, n, lo - 1, sh);
+    double b = select_kth(x, n, lo, sh);
+    return a + fr * (b - a);
+}
+
+// HALS_temporal.m:78  b = mean(ck_raw(ck_raw<median(ck_raw)))
+__device__ double block_mean_below(const double* x, int n, double thr, BlockShared* sh) {
+    double s = 0.0, cnt = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double v = x[i];
+        if (v < thr) { s += v; cnt += 1.0; }
+    }
+    s = block_sum(s, sh->red);
+    cnt = block_sum(cnt, sh->red);
+    return s / cnt;   // NaN when empty, as in MATLAB
+}
+
+// ------------------------------------------------------------------------------------------------ GetSn
+// In-place radix-2 DIT FFT of z[0..n) (interleaved re,im), twiddles tw[j] = (cos, -sin)(2 pi j / n), j < n/2.
+__device__ void block_fft(double2* z, const double2* tw, int n, int logn) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int j = (int)(__brev((unsigned)i) >> (32 - logn));
+        if (j > i) { double2 a = z[i]; z[i] = z[j]; z[j] = a; }
+    }
+    __syncthreads();
+    for (int s = 1; s <= logn; ++s) {
+        int m = 1 << s, half = m >> 1, tstride = n >> s;
+        for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
+            int grp = b / half, j = b - grp * half;
+            int i0 = grp * m + j, i1 = i0 + half;
+            double2 w = tw[j * tstride];
+            double2 u = z[i0], v = z[i1];
+            double tr = v.x * w.x - v.y * w.y, ti = v.x * w.y + v.y * w.x;
+            z[i0] = make_double2(u.x + tr, u.y + ti);
+            z[i1] = make_double2(u.x - tr, u.y - ti);
+        }
+        __syncthreads();
+    }
+}
+
+// sn = sqrt(exp(mean(log(Pxx(f)/2)))), 0.25 <= f <= 0.5, Pxx = pwelch(x,[],[],[],1).
+// scr needs 3*nfft + nfft/4 + 8 doubles.
+__device__ double block_getsn(const double* __restrict__ x, int N, double* scr, BlockShared* sh) {
+    const int L = (int)floor((double)N / 4.5);
+    const int nov = L / 2;
+    const int nseg = (N - nov) / (L - nov);
+    const int nfft = welch_nfft(N);
+    int logn = 0;
+    while ((1 << logn) < nfft) ++logn;
+    double2* z = reinterpret_cast<double2*>(scr);
+    double2* tw = reinterpret_cast<double2*>(scr + 2 * (size_t)nfft);
+    double* acc = scr + 3 * (size_t)nfft;
+    const int f0 = nfft / 4, nf = nfft / 4 + 1;
+    __syncthreads();
+    for (int j = threadIdx.x; j < nfft / 2; j += blockDim.x) {
+        double sn_, cs_;
+        sincospi(2.0 * (double)j / (double)nfft, &sn_, &cs_);
+        tw[j] = make_double2(cs_, -sn_);
+    }
+    for (int j = threadIdx.x; j < nf; j += blockDim.x) acc[j] = 0.0;
+    double usum = 0.0;
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+        double w = 0.54 - 0.46 * cospi(2.0 * (double)j / (double)(L - 1));
+        usum += w * w;
+    }
+    usum = block_sum(usum, sh->red);
+    const int step = L - nov;
+    for (int sg = 0; sg < nseg; sg += 2) {
+        const bool two = (sg + 1 < nseg);
+        const double* xa = x + (size_t)sg * step;
+        const double* xb = x + (size_t)(sg + 1) * step;
+        for (int j = threadIdx.x; j < nfft; j += blockDim.x) {
+            double re = 0.0, im = 0.0;
+            if (j < L) {
+                double w = 0.54 - 0.46 * cospi(2.0 * (double)j / (double)(L - 1));
+                re = w * xa[j];
+                if (two) im = w * xb[j];
+            }
+            z[j] = make_double2(re, im);
+        }
+        __syncthreads();
+        block_fft(z, tw, nfft, logn);
+        for (int j = threadIdx.x; j < nf; j += blockDim.x) {
+            int f = f0 + j;
+            double2 a = z[f], b = z[(nfft - f) & (nfft - 1)];
+            double xr = 0.5 * (a.x + b.x), xi = 0.5 * (a.y - b.y);
+            double p = xr * xr + xi * xi;
+            if (two) {
+                double yr = 0.5 * (a.y + b.y), yi = 0.5 * (b.x - a.x);
+                p += yr * yr + yi * yi;
+            }
+            acc[j] += p;
+        }
+        __syncthreads();
+    }
+    double ls = 0.0;
+    for (int j = threadIdx.x; j < nf; j += blockDim.x) {
+        double p = acc[j] / ((double)nseg * usum);
+        if (f0 + j != nfft / 2) p *= 2.0;
+        ls += log(p / 2.0);
+    }
+    ls = block_sum(ls, sh->red);
+    return sqrt(exp(ls / (double)nf));
+}
+
+// ------------------------------------------------------------------------------------------------ time constant
+// estimate_time_constant(y, p, sn) for p in {1,2}.  Returns number of coefficients written (p) or 0 on "no stable
+// AR(p) model" (the reference then escalates p and deconvolveCa.m:84-101 returns zeros for the trace).
+__device__ int block_time_constant(const double* __restrict__ y, int T, int p, double sn, double* g,
+                                   BlockShared* sh) {
+    const int lags = 5 + p;
+    double m = 0.0;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) m += y[i];
+    m = block_sum(m, sh->red) / (double)T;
+    double xc[8];
+    for (int k = 0; k <= lags; ++k) {
+        double a = 0.0;
+        for (int i = threadIdx.x; i + k < T; i += blockDim.x) a += (y[i + k] - m) * (y[i] - m);
+        xc[k] = block_sum(a, sh->red) / (double)T;
+    }
+    const double s2 = sn * sn;
+    if (p == 1) {
+        double num = 0.0, den = 0.0;
+        for (int i = 0; i < lags; ++i) {
+            double a = xc[i] - (i == 0 ? s2 : 0.0);
+            num += a * xc[i + 1];
+            den += a * a;
+        }
+        double g1 = num / den;
+        if (!(fabs(g1) <= 1.0)) return 0;
+        if (g1 < 0.0) g1 = 0.15;
+        g[0] = g1;
+        return 1;
+    }
+    // p == 2: A(i,1) = xc(i) - s2*[i==0], A(i,2) = xc(|i-1|) - s2*[i==1]
+    double a11 = 0, a12 = 0, a22 = 0, b1 = 0, b2 = 0;
+    for (int i = 0; i < lags; ++i) {
+        double c1 = xc[i] - (i == 0 ? s2 : 0.0);
+        double c2 = xc[i == 0 ? 1 : i - 1] - (i == 1 ? s2 : 0.0);
+        a11 += c1 * c1; a12 += c1 * c2; a22 += c2 * c2;
+        b1 += c1 * xc[i + 1]; b2 += c2 * xc[i + 1];
+    }
+    double det = a11 * a22 - a12 * a12;
+    double g1 = (a22 * b1 - a12 * b2) / det, g2 = (a11 * b2 - a12 * b1) / det;
+    double disc = g1 * g1 + 4.0 * g2, r1, r2;
+    if (disc < 0.0) {
+        if (-g2 > 1.0) return 0;
+        r1 = r2 = 0.5 * g1;
+    } else {
+        double sq = sqrt(disc);
+        r1 = 0.5 * (g1 + sq); r2 = 0.5 * (g1 - sq);
+        if (fmax(fabs(r1), fabs(r2)) > 1.0) return 0;
+    }
+    if (r1 > 1.0) r1 = 0.95;
+    if (r2 > 1.0) r2 = 0.95;
+    if (r1 < 0.0) r1 = 0.15;
+    if (r2 < 0.0) r2 = 0.15;
+    g[0] = r1 + r2;
+    g[1] = -r1 * r2;
+    return 2;
+}
+
+// ------------------------------------------------------------------------------------------------ AR(1) PAV
+// gp[m] = g^m for m in [0, 2T+1]; pow() in the loop is replaced by this table (same values: gp[m] = pow(g,m)).
+__device__ void block_pow_table(double g, int T, double* gp) {
+    for (int m = threadIdx.x; m <= 2 * T + 1; m += blockDim.x) gp[m] = pow(g, (double)m);
+    __syncthreads();
+}
+
+__device__ void block_init_pools_ar1(const double* __restrict__ y, int T, double g, double lam, TraceWS& ws) {
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        ws.pv[i] = (i == T - 1) ? (y[i] - lam) : (y[i] - lam * (1.0 - g));
+        ws.pw[i] = 1.0;
+        ws.pt[i] = i;
+        ws.pl[i] = 1;
+    }
+    __syncthreads();
+}
+
+// oasisAR1.m:57-98 on n pools held in ws (in place, stack form).  Thread 0 runs the scan; returns pool count.
+__device__ int block_oasis_ar1_run(TraceWS& ws, int n, double smin, BlockShared* sh) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double* v = ws.pv; double* w = ws.pw; int* t = ws.pt; int* l = ws.pl;
+        const double* gp = ws.gp;
+        int top = 0;
+        double vt = v[0], wt = w[0];
+        int lt = l[0];
+        for (int i = 1; i < n; ++i) {
+            double vi = v[i], wi = w[i];
+            int li = l[i];
+            if (vi / wi >= vt / wt * gp[lt] + smin) {
+                v[top] = vt; w[top] = wt; l[top] = lt;
+                ++top;
+                t[top] = t[i];
+                vt = vi; wt = wi; lt = li;
+                continue;
+            }
+            vt = vt + vi * gp[lt];
+            wt = wt + wi * gp[2 * lt];
+            lt = lt + li;
+            while (top > 0) {
+                double vp = v[top - 1], wp = w[top - 1];
+                int lp = l[top - 1];
+                if (vt / wt < fmax(0.0, vp / wp * gp[lp]) + smin) {
+                    vt = vp + vt * gp[lp];
+                    wt = wp + wt * gp[2 * lp];
+                    lt = lp + lt;
+                    --top;
+                } else break;
+            }
+        }
+        v[top] = vt; w[top] = wt; l[top] = lt;
+        sh->ibc[2] = (n > 0) ? top + 1 : 0;
+    }
+    __syncthreads();
+    int r = sh->ibc[2];
+    __syncthreads();
+    return r;
+}
+
+// oasisAR1.m:101-109
+__device__ void block_oasis_ar1_solution(const TraceWS& ws, int n, double g, int T, double* c, double* s) {
+    for (int i = threadIdx.x; i < T; i += blockDim.x) s[i] = 0.0;
+    __syncthreads();
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int p = warp; p < n; p += nw) {
+        double a = fmax(0.0, ws.pv[p] / ws.pw[p]);
+        int t0 = ws.pt[p], l = ws.pl[p];
+        for (int j = lane; j < l; j += 32) c[t0 + j] = a * ws.gp[j];
+    }
+    __syncthreads();
+    for (int p = 1 + threadIdx.x; p < n; p += blockDim.x) {
+        int t0 = ws.pt[p];
+        s[t0] = c[t0] - g * c[t0 - 1];
+    }
+    __syncthreads();
+}
+
+// Cold oasisAR1(y, g, lam, smin): pools + solution into ws.c / ws.s.  Returns pool count.
+__device__ int block_oasis_ar1(const double* y, int T, double g, double lam, double smin, TraceWS& ws,
+                               BlockShared* sh) {
+    block_pow_table(g, T, ws.gp);
+    block_init_pools_ar1(y, T, g, lam, ws);
+    int n = block_oasis_ar1_run(ws, T, smin, sh);
+    block_oasis_ar1_solution(ws, n, g, T, ws.c, ws.s);
+    return n;
+}
+
+// exclusive->inclusive cumsum of squares of h[0..m] into hh (block scan, chunked).
+__device__ void block_cumsum_sq(const double* h, double* hh, int m1, BlockShared* sh, double* part /*blockDim*/) {
+    int per = (m1 + blockDim.x - 1) / blockDim.x;
+    int b = threadIdx.x * per, e = min(m1, b + per);
+    double a = 0.0;
+    for (int j = b; j < e; ++j) a += h[j] * h[j];
+    part[threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double run = 0.0;
+        for (int i = 0; i < (int)blockDim.x; ++i) { double x = part[i]; part[i] = run; run += x; }
+    }
+    __syncthreads();
+    a = part[threadIdx.x];
+    for (int j = b; j < e; ++j) { a += h[j] * h[j]; hh[j] = a; }
+    __syncthreads();
+}
+
+// rss_g of update_g (foopsi_oasisAR1.m:165-178).  Leaves ws.h / ws.hh holding this g's tables.
+__device__ double block_rss_g(const double* __restrict__ y, int n, double g, double lam, int maxl, TraceWS& ws,
+                              BlockShared* sh) {
+    const double lg = log(g), pen = lam * (1.0 - g);
+    __syncthreads();
+    for (int j = threadIdx.x; j <= maxl; j += blockDim.x) ws.h[j] = exp(lg * (double)j);
+    __syncthreads();
+    block_cumsum_sq(ws.h, ws.hh, maxl + 1, sh, ws.scr);
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    double rss = 0.0;
+    for (int p = warp; p < n; p += nw) {
+        int t0 = ws.pt[p], l = ws.pl[p];
+        double dot = 0.0;
+        for (int j = lane; j < l; j += 32) dot += (y[t0 + j] - pen) * ws.h[j];
+        dot = warp_sum(dot);
+        double tv = fmax(dot / ws.hh[l - 1], 0.0);
+        for (int j = lane; j < l; j += 32) {
+            double r = y[t0 + j] - tv * ws.h[j];
+            rss += r * r;
+        }
+    }
+    return block_sum(rss, sh->red);
+}
+
+// MATLAB fminbnd on rss_g over [ax,bx]; returns xf (all threads run the scalar logic redundantly).
+__device__ double block_fminbnd_rss(const double* y, int n, double lam, int maxl, double ax, double bx,
+                                    TraceWS& ws, BlockShared* sh) {
+    const double tol = 1e-4, seps = 1.4901161193847656e-08, cgold = 0.3819660112501051;
+    double a = ax, b = bx;
+    double v = a + cgold * (b - a), w = v, xf = v, d = 0.0, e = 0.0, x = xf;
+    double fx = block_rss_g(y, n, x, lam, maxl, ws, sh);
+    int funccount = 1, iter = 0;
+    double fv = fx, fw = fx;
+    double xm = 0.5 * (a + b);
+    double tol1 = seps * fabs(xf) + tol / 3.0, tol2 = 2.0 * tol1;
+    while (fabs(xf - xm) > (tol2 - 0.5 * (b - a))) {
+        bool gs = true;
+        if (fabs(e) > tol1) {
+            gs = false;
+            double r = (xf - w) * (fx - fv);
+            double q = (xf - v) * (fx - fw);
+            double p = (xf - v) * q - (xf - w) * r;
+            q = 2.0 * (q - r);
+            if (q > 0.0) p = -p;
+            q = fabs(q);
+            r = e;
+            e = d;
+            if ((fabs(p) < fabs(0.5 * q * r)) && (p > q * (a - xf)) && (p < q * (b - xf))) {
+                d = p / q;
+                x = xf + d;
+                if (((x - a) < tol2) || ((b - x) < tol2)) {
+                    double df = xm - xf;
+                    double si = (df > 0.0 ? 1.0 : (df < 0.0 ? -1.0 : 0.0)) + (df == 0.0 ? 1.0 : 0.0);
+                    d = tol1 * si;
+                }
+            } else {
+                gs = true;
+            }
+        }
+        if (gs) {
+            e = (xf >= xm) ? (a - xf) : (b - xf);
+            d = cgold * e;
+        }
+        double si = (d > 0.0 ? 1.0 : (d < 0.0 ? -1.0 : 0.0)) + (d == 0.0 ? 1.0 : 0.0);
+        x = xf + si * fmax(fabs(d), tol1);
+        double fu = block_rss_g(y, n, x, lam, maxl, ws, sh);
+        ++funccount; ++iter;
+        if (fu <= fx) {
+            if (x >= xf) a = xf; else b = xf;
+            v = w; fv = fw;
+            w = xf; fw = fx;
+            xf = x; fx = fu;
+        } else {
+            if (x < xf) a = x; else b = x;
+            if ((fu <= fw) || (w == xf)) {
+                v = w; fv = fw;
+                w = x; fw = fu;
+            } else if ((fu <= fv) || (v == xf) || (v == w)) {
+                v = x; fv = fu;
+            }
+        }
+        xm = 0.5 * (a + b);
+        tol1 = seps * fabs(xf) + tol / 3.0;
+        tol2 = 2.0 * tol1;
+        if (funccount >= 500 || iter >= 500) break;
+    }
+    return xf;
+}
+
+// update_g (foopsi_oasisAR1.m:124-163): returns new g; pools/solution updated (warm oasisAR1).
+__device__ double block_update_g(const double* y, int T, int* n_io, double lam, double smin, double g_lo,
+                                 double g_hi, TraceWS& ws, BlockShared* sh) {
+    int n = *n_io;
+    double ml = 0.0;
+    for (int p = threadIdx.x; p < n; p += blockDim.x) ml = fmax(ml, (double)ws.pl[p]);
+    int maxl = (int)block_max(ml, sh->red);
+    double g = block_fminbnd_rss(y, n, lam, maxl, g_lo, g_hi, ws, sh);
+    // rebuild pools: v from the returned g, w from the LAST evaluated kernel (ws.hh), foopsi_oasisAR1.m:153-162
+    const double lg = log(g), pen = lam * (1.0 - g);
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int p = warp; p < n; p += nw) {
+        int t0 = ws.pt[p], l = ws.pl[p];
+        double dot = 0.0;
+        for (int j = lane; j < l; j += 32) dot += (y[t0 + j] - pen) * exp(lg * (double)j);
+        dot = warp_sum(dot);
+        if (lane == 0) { ws.pv[p] = dot; ws.pw[p] = ws.hh[l - 1]; }
+    }
+    __syncthreads();
+    block_pow_table(g, T, ws.gp);
+    n = block_oasis_ar1_run(ws, n, smin, sh);
+    block_oasis_ar1_solution(ws, n, g, T, ws.c, ws.s);
+    *n_io = n;
+    return g;
+}
+
+struct DeconvOut {
+    double b, g1, g2, smin, lam, sn;
+    int npars;   // 1 or 2; 0 => failed (outputs are zeros)
+};
+
+// foopsi_oasisAR1(y, g, lam, smin, optimize_b, optimize_g, [], maxIter, tau_range, gmax)  (foopsi_oasisAR1.m:78-122)
+// y: input trace (read-only).  Outputs in ws.c / ws.s.
+__device__ void block_foopsi_ar1(const double* __restrict__ y, int T, double g, double lam, double smin,
+                                 bool optimize_b, bool optimize_g, int maxIter, double g_lo, double g_hi,
+                                 bool has_tau_range, double gmax, TraceWS& ws, BlockShared* sh, DeconvOut* out) {
+    if (has_tau_range) g = fmin(fmax(g, g_lo), g_hi);
+    double b = 0.0;
+    int n;
+    if (!optimize_b) {
+        n = block_oasis_ar1(y, T, g, lam, smin, ws, sh);
+        if (optimize_g && n > 0) g = block_update_g(y, T, &n, lam, smin, g_lo, g_hi, ws, sh);
+    } else {
+        b = block_quantile(y, T, 0.15, sh);
+        for (int i = threadIdx.x; i < T; i += blockDim.x) ws.yb[i] = y[i] - b;
+        __syncthreads();
+        n = block_oasis_ar1(ws.yb, T, g, lam, smin, ws, sh);
+        for (int m = 0; m < maxIter; ++m) {
+            double a = 0.0;
+            for (int i = threadIdx.x; i < T; i += blockDim.x) a += y[i] - ws.c[i];
+            b = block_sum(a, sh->red) / (double)T;
+            if (!optimize_g) break;
+            if (n == 0) break;
+            double g0 = g;
+            for (int i = threadIdx.x; i < T; i += blockDim.x) ws.yb[i] = y[i] - b;
+            __syncthreads();
+            if (g > gmax) {
+                // spike counts too small (foopsi_oasisAR1.m:104-108): g = estimate_time_constant(y,1) (sn from GetSn(y))
+                double sn = block_getsn(y, T, ws.scr, sh);
+                double gg[2];
+                int np = block_time_constant(y, T, 1, sn, gg, sh);
+                if (np != 1) {   // oasisAR1 with length(g)>1 returns zeros (oasisAR1.m:40-45)
+                    for (int i = threadIdx.x; i < T; i += blockDim.x) { ws.c[i] = 0.0; ws.s[i] = 0.0; }
+                    __syncthreads();
+                    out->npars = 2;   // reference would carry a vector g; flagged to the caller
+                    g = 0.0;
+                } else {
+                    g = gg[0];
+                    n = block_oasis_ar1(ws.yb, T, g, lam, smin, ws, sh);
+                }
+                break;
+            }
+            g = block_update_g(ws.yb, T, &n, lam, smin, g_lo, g_hi, ws, sh);
+            if (fabs(g - g0) / g0 < 1e-3) optimize_g = false;
+        }
+    }
+    out->b = b;
+    out->g1 = g;
+    out->g2 = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------ AR(2) PAV
+// oasisAR2.m:49-156 (cold start).  Tables: h=g11, hh=g12, gp[0..T)=g11g11, gp[T..2T)=g11g12.  yp in ws.yb.
+// Warp 0 runs the scan (lanes share the merge dot product); outputs ws.c / ws.s; returns pool count.
+__device__ int block_oasis_ar2(const double* __restrict__ y, int T, double g1, double g2, double lam, double smin,
+                               TraceWS& ws, BlockShared* sh) {
+    const double disc = g1 * g1 + 4.0 * g2;
+    const double sq = sqrt(fmax(disc, 0.0));
+    const double dd = 0.5 * (g1 + sq), rr = 0.5 * (g1 - sq);
+    const double ld = log(dd), lr = log(rr);
+    double* g11 = ws.h; double* g12 = ws.hh; double* g11g11 = ws.gp; double* g11g12 = ws.gp + T;
+    double* yp = ws.yb;
+    __syncthreads();
+    for (int k = threadIdx.x; k < T; k += blockDim.x) {
+        g11[k] = (exp(ld * (double)(k + 1)) - exp(lr * (double)(k + 1))) / (dd - rr);
+        double v = y[k] - lam * (1.0 - g1 - g2);
+        if (k == T - 2) v = y[k] - lam * (1.0 - g1);
+        if (k == T - 1) v = y[k] - lam;
+        yp[k] = v;
+        ws.pv[k] = v; ws.pw[k] = v; ws.pt[k] = k; ws.pl[k] = 1;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < T; k += blockDim.x) g12[k] = (k == 0) ? 0.0 : g2 * g11[k - 1];
+    __syncthreads();
+    if (threadIdx.x == 0) {   // sequential cumsums (reference order, oasisAR2.m:75-76)
+        double a1 = 0.0, a2 = 0.0;
+        for (int k = 0; k < T; ++k) {
+            a1 += g11[k] * g11[k]; g11g11[k] = a1;
+            a2 += g11[k] * g12[k]; g11g12[k] = a2;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        double* v = ws.pv; double* w = ws.pw; int* t = ws.pt; int* l = ws.pl;
+        int top = 0;   // stack [0..top]; pool 0 is never merged (scan starts at the 2nd pool)
+        if (T >= 3) {
+            top = 1;
+            for (int i = 2; i < T; ++i) {
+                double vi = v[i];
+                int li = l[i];
+                // forward test against stack top (oasisAR2.m:83-84)
+                if (g11[l[top]] * v[top] + g12[l[top]] * w[top - 1] + smin <= vi) {
+                    ++top;
+                    if (lane == 0) { v[top] = vi; w[top] = w[i]; t[top] = t[i]; l[top] = li; }
+                    __syncwarp();
+                    continue;
+                }
+                // merge incoming pool i into top (oasisAR2.m:93-104)
+                int lnew = l[top] + li, ti = t[top];
+                double dot = 0.0;
+                for (int j = lane; j < lnew; j += 32) dot += g11[j] * yp[ti + j];
+                dot = warp_sum(dot);
+                double vn = (dot - g11g12[lnew - 1] * w[top - 1]) / g11g11[lnew - 1];
+                double wn = g11[lnew - 1] * vn + g12[lnew - 1] * w[top - 1];
+                __syncwarp();
+                if (lane == 0) { l[top] = lnew; v[top] = vn; w[top] = wn; }
+                __syncwarp();
+                // backtrack (oasisAR2.m:109-128): needs prev-prev
+                while (top >= 2 &&
+                       (g11[l[top - 1]] * v[top - 1] + g12[l[top - 1]] * w[top - 2] + smin > v[top])) {
+                    int lm = l[top - 1] + l[top], tm = t[top - 1];
+                    double d2 = 0.0;
+                    for (int j = lane; j < lm; j += 32) d2 += g11[j] * yp[tm + j];
+                    d2 = warp_sum(d2);
+                    double v2 = (d2 - g11g12[lm - 1] * w[top - 2]) / g11g11[lm - 1];
+                    double w2 = g11[lm - 1] * v2 + g12[lm - 1] * w[top - 2];
+                    __syncwarp();
+                    if (lane == 0) { l[top - 1] = lm; v[top - 1] = v2; w[top - 1] = w2; }
+                    --top;
+                    __syncwarp();
+                }
+            }
+        } else {
+            top = T - 1;
+        }
+        if (lane == 0) sh->ibc[2] = top + 1;
+    }
+    __syncthreads();
+    const int n = sh->ibc[2];
+    // construct solution (oasisAR2.m:140-156): AR(2) recursion inside each pool needs the two previous samples,
+    // which belong to the previous pool -> sequential over time; thread 0.
+    if (threadIdx.x == 0) {
+        double c1 = 0.0, c2 = 0.0;   // c(t-1), c(t-2) before clamping
+        for (int p = 0; p < n; ++p) {
+            int ti = ws.pt[p], li = ws.pl[p];
+            double cur = ws.pv[p];
+            ws.c[ti] = cur;
+            c2 = c1; c1 = cur;
+            for (int j = 1; j < li; ++j) {
+                cur = g1 * c1 + g2 * c2;
+                ws.c[ti + j] = cur;
+                c2 = c1; c1 = cur;
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < T; k += blockDim.x) if (ws.c[k] < 0.0) ws.c[k] = 0.0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < T; k += blockDim.x) {
+        double sv = 0.0;
+        if (k >= 3) {
+            sv = ws.c[k] - g1 * ws.c[k - 1] - g2 * ws.c[k - 2];
+            if (sv < smin) sv = 0.0;
+        }
+        ws.s[k] = sv;
+    }
+    __syncthreads();
+    return n;
+}
+
+// max_ht(pars) for AR(2)  (functions/max_ht.m:11-29)
+__device__ double ar2_max_ht(double g1, double g2) {
+    double sq = sqrt(fmax(g1 * g1 + 4.0 * g2, 0.0));
+    double d = 0.5 * (g1 + sq), r = 0.5 * (g1 - sq);
+    double tau_d = -1.0 / log(d), tau_r = -1.0 / log(r);
+    int n = (int)ceil(tau_d * 2.0);
+    double dd = exp(-1.0 / tau_d), rr = exp(-1.0 / tau_r);
+    double ld = log(dd), lr = log(rr), vmax = -INFINITY;
+    for (int t = 1; t <= n; ++t) {
+        double ht = (exp(ld * (double)t) - exp(lr * (double)t)) / (dd - rr);
+        vmax = fmax(vmax, ht);
+    }
+    return vmax;
+}
+
+}  // namespace cnmfe

@@ -1,0 +1,371 @@
+"""Host-side mirror of the reference's `Sources2D` handle class for the alternating-update hot path.
+
+Same method names, argument meaning and side effects as
+  ca_source_extraction/@Sources2D/update_background_parallel.m:1   (obj.W, obj.b0, obj.b0_new, obj.A_prev, obj.C_prev)
+  ca_source_extraction/@Sources2D/update_spatial_parallel.m:1      (obj.A, obj.b0_new)
+  ca_source_extraction/@Sources2D/update_temporal_parallel.m:1     (obj.C_raw, obj.C, obj.S, obj.P.kernel_pars, obj.P.neuron_sn)
+plus the short aliases BASELINE.json names (update_background / update_spatial / update_temporal).
+The video is uploaded once (the analogue of getReady + map_data_to_memory, Sources2D.m:185-194,214-265) and stays
+resident on the GPU in its native integer dtype; every update runs in libcnmfe_b200.so (no CPU fallback).
+
+Out of scope hooks, supplied by the caller exactly where the reference calls them:
+  IND = determine_search_location(...)   -> `update_spatial_parallel(..., IND=...)` (or `self.search_fn`)
+  post_process_spatial(...)              -> `self.post_process_fn` (default identity)
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib as L
+from .oasis import make_deconv_opts
+
+_SPATIAL = {"hals": 0, "hals_thresh": 1, "nnls": 2, "lars": 3}
+
+
+def patch_geometry(d1, d2, patch_dims, w_overlap):
+    """patch_pos / block_pos of endoscope/distribute_data.m:39,55-77,163-173 (1-based inclusive [r0 r1 c0 c1])."""
+    min_w = 2 * w_overlap + 3
+
+    def idx(dn, pd, force_last):
+        x = dn / pd
+        npatch = int(np.floor(x + 0.5))            # MATLAB round (positive arguments)
+        if npatch <= 1:
+            return np.array([1, dn])
+        pi = np.ceil(np.linspace(1, dn, npatch + 1)).astype(int)
+        if force_last:
+            pi[-1] = dn
+        if pi[1] - pi[0] < min_w:
+            pi = np.arange(1, dn + 1, min_w)
+            pi[-1] = dn
+        return pi
+
+    pr = idx(d1, patch_dims[0], True)
+    pc = idx(d2, patch_dims[1], False)
+    nr_p, nc_p = len(pr) - 1, len(pc) - 1
+    patch_pos = np.zeros((nr_p, nc_p, 4), dtype=np.int32)
+    block_pos = np.zeros((nr_p, nc_p, 4), dtype=np.int32)
+    for m in range(nr_p):
+        for n in range(nc_p):
+            patch_pos[m, n] = [pr[m], pr[m + 1] - (m != nr_p - 1), pc[n], pc[n + 1] - (n != nc_p - 1)]
+            block_pos[m, n] = [max(1, pr[m] - w_overlap - 1), min(d1, pr[m + 1] + w_overlap),
+                               max(1, pc[n] - w_overlap - 1), min(d2, pc[n + 1] + w_overlap)]
+    return patch_pos, block_pos
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Sources2D:
+    def __init__(self, d1, d2, T, patch_dims=None, ring_radius=18, num_neighbors=None, device=0, rank=0,
+                 world_size=1, options=None):
+        self.d1, self.d2, self.T = int(d1), int(d2), int(T)
+        self.device, self.rank, self.world_size = device, rank, world_size
+        if patch_dims is None:
+            patch_dims = (d1, d2)
+        # CNMFSetParms.m:286-308 defaults + demo_large_data_1p.m:11-55 overrides relevant to this path
+        self.options = dict(ring_radius=ring_radius, bg_ssub=1, background_model="ring", bg_acceleration=True,
+                            num_neighbors=num_neighbors, thresh_outlier=np.nan, spatial_algorithm="hals", maxIter=5,
+                            deconv_flag=True, deconv_options=dict(type="ar1", method="foopsi", smin=-5,
+                                                                  optimize_pars=True, optimize_b=True, max_tau=100),
+                            replicate_spatial_aprev_quirk=True, use_tensor_gram=True)
+        if options:
+            self.options.update(options)
+        self.patch_pos, self.block_pos = patch_geometry(self.d1, self.d2, patch_dims, ring_radius)
+        self.nr_patch, self.nc_patch = self.patch_pos.shape[:2]
+        self.patches = [(m, n) for n in range(self.nc_patch) for m in range(self.nr_patch)]   # MATLAB linear order
+        self.npatch = len(self.patches)
+        # patch -> rank (blocked assignment)
+        self.owner = np.array([(i * world_size) // self.npatch for i in range(self.npatch)], dtype=np.int64)
+        owned = (self.owner == rank).astype(np.uint8)
+        pp = np.ascontiguousarray(np.stack([self.patch_pos[mp] for mp in self.patches]).astype(np.int32))
+        bp = np.ascontiguousarray(np.stack([self.block_pos[mp] for mp in self.patches]).astype(np.int32))
+        self._lib = L.lib()
+        h = ctypes.c_void_p()
+        L.check(self._lib.cnmfe_create(ctypes.byref(h), self.d1, self.d2, self.T, self.npatch, _ptr(pp), _ptr(bp),
+                                       _ptr(owned), int(ring_radius), int(num_neighbors or 0), int(device)))
+        self._h = h
+        self._owned = owned.astype(bool)
+        nnb = ctypes.c_int()
+        L.check(self._lib.cnmfe_ring_offsets(self._h, ctypes.byref(nnb), None, None))
+        self.nnb = nnb.value
+        rs = np.zeros(self.nnb, dtype=np.int32)
+        cs = np.zeros(self.nnb, dtype=np.int32)
+        L.check(self._lib.cnmfe_ring_offsets(self._h, ctypes.byref(nnb), _ptr(rs), _ptr(cs)))
+        self.r_shift, self.c_shift = rs, cs
+        d = self.d1 * self.d2
+        self.A = sp.csc_matrix((d, 0))
+        self.C = np.zeros((0, self.T))
+        self.C_raw = np.zeros((0, self.T))
+        self.S = np.zeros((0, self.T))
+        self.A_prev = sp.csc_matrix((d, 0))
+        self.C_prev = np.zeros((0, self.T))
+        self.W = {}
+        self.b0 = {}
+        self.b0_new = np.zeros((self.d1, self.d2))
+        self.P = dict(sn=np.ones((self.d1, self.d2)), kernel_pars=None, neuron_sn=None, Ymean=None)
+        self.search_fn = None
+        self.post_process_fn = None
+        self.frame_range = (1, self.T)
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cnmfe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ data
+    def owned_patches(self):
+        return [i for i in range(self.npatch) if self._owned[i]]
+
+    def block_of(self, i):
+        return self.block_pos[self.patches[i]]
+
+    def patch_of(self, i):
+        return self.patch_pos[self.patches[i]]
+
+    def load_video(self, Y):
+        """Y: (d1,d2,T) uint8/uint16 array (numpy).  Uploads the blocks of the owned patches (get_patch_data.m with
+        with_overlap=true) and keeps them resident."""
+        Y = np.asarray(Y)
+        if Y.dtype not in (np.uint8, np.uint16):
+            raise L.CnmfeError("video dtype %s unsupported: the exact-integer path takes uint8/uint16" % Y.dtype)
+        dt = 0 if Y.dtype == np.uint8 else 1
+        for i in self.owned_patches():
+            b = self.block_of(i)
+            blk = Y[b[0] - 1:b[1], b[2] - 1:b[3], :]
+            # frame-major, pixel index r + c*nrb fastest  == MATLAB memory order of the (nrb, ncb, T) array
+            buf = np.ascontiguousarray(np.transpose(blk, (2, 1, 0)))
+            L.check(self._lib.cnmfe_upload_block(self._h, i, _ptr(buf), dt))
+        self.P["Ymean"] = Y.mean(axis=2, dtype=np.float64) if self.world_size == 1 else None
+
+    def load_block_dev(self, i, dev_ptr, dtype):
+        """Block of patch i already on the device (frame-major); dtype 0 = uint8, 1 = uint16."""
+        L.check(self._lib.cnmfe_upload_block_dev(self._h, i, ctypes.c_void_p(dev_ptr), dtype))
+
+    # ------------------------------------------------------------------ option / state marshalling
+    def _push_options(self):
+        o = L.Options()
+        self._lib.cnmfe_options_defaults(ctypes.byref(o))
+        opt = self.options
+        if str(opt["background_model"]).lower() != "ring" or opt["bg_ssub"] != 1:
+            raise L.CnmfeError("only background_model='ring' with bg_ssub=1 is built in this round")
+        if not (opt["thresh_outlier"] is None or np.isnan(opt["thresh_outlier"])):
+            raise L.CnmfeError("thresh_outlier (fit_ring_model.m:50-70 outlier clamp) is not built; leave it NaN")
+        o.spatial_algorithm = _SPATIAL[str(opt["spatial_algorithm"]).lower()] if \
+            str(opt["spatial_algorithm"]).lower() in _SPATIAL else 2
+        o.maxIter_temporal = int(opt["maxIter"])
+        o.deconv_flag = int(bool(opt["deconv_flag"]))
+        o.bg_acceleration = int(bool(opt["bg_acceleration"]))
+        o.replicate_spatial_aprev_quirk = int(bool(opt["replicate_spatial_aprev_quirk"]))
+        o.use_tensor_gram = int(bool(opt["use_tensor_gram"]))
+        if opt["deconv_flag"]:
+            d, _, _ = make_deconv_opts(opt["deconv_options"] or {})
+            o.deconv = d
+        L.check(self._lib.cnmfe_set_options(self._h, ctypes.byref(o)))
+
+    @staticmethod
+    def _csc(A):
+        A = sp.csc_matrix(A)
+        A.sort_indices()
+        return (np.ascontiguousarray(A.indptr, dtype=np.int64), np.ascontiguousarray(A.indices, dtype=np.int64),
+                np.ascontiguousarray(A.data, dtype=np.float64))
+
+    def push_neurons(self):
+        jc, ir, pr = self._csc(self.A)
+        C = np.asfortranarray(self.C, dtype=np.float64)
+        K = self.A.shape[1]
+        assert C.shape == (K, self.T), "C must be K x T"
+        L.check(self._lib.cnmfe_set_neurons(self._h, K, _ptr(jc), _ptr(ir), _ptr(pr), _ptr(C)))
+
+    def push_prev(self):
+        jc, ir, pr = self._csc(self.A_prev)
+        C = np.asfortranarray(self.C_prev, dtype=np.float64)
+        K = self.A_prev.shape[1]
+        L.check(self._lib.cnmfe_set_prev(self._h, K, _ptr(jc), _ptr(ir), _ptr(pr), _ptr(C)))
+
+    def push_ring(self):
+        for i in range(self.npatch):
+            W = self.W.get(i)
+            b0 = self.b0.get(i)
+            if W is None and b0 is None:
+                continue
+            Wf = None if W is None else np.asfortranarray(W, dtype=np.float64)
+            b0f = None if b0 is None else np.ascontiguousarray(b0, dtype=np.float64)
+            L.check(self._lib.cnmfe_set_ring(self._h, i, _ptr(Wf), _ptr(b0f)))
+
+    def pull_ring(self):
+        for i in self.owned_patches():
+            p = self.patch_of(i)
+            dp = (p[1] - p[0] + 1) * (p[3] - p[2] + 1)
+            W = np.zeros((dp, self.nnb), order="F")
+            b0 = np.zeros(dp)
+            L.check(self._lib.cnmfe_get_ring(self._h, i, _ptr(W), _ptr(b0)))
+            self.W[i], self.b0[i] = W, b0
+
+    def ring_as_sparse(self, i):
+        """obj.W{i} as the reference stores it: sparse (d_patch x d_block), initComponents_parallel.m:221-236."""
+        W = self.W[i]
+        p, b = self.patch_of(i), self.block_of(i)
+        nr, nc = p[1] - p[0] + 1, p[3] - p[2] + 1
+        nrb, ncb = b[1] - b[0] + 1, b[3] - b[2] + 1
+        rr = np.tile(np.arange(p[0], p[1] + 1), nc)
+        cc = np.repeat(np.arange(p[2], p[3] + 1), nr)
+        rows, cols, vals = [], [], []
+        for s in range(self.nnb):
+            r2, c2 = rr + self.r_shift[s], cc + self.c_shift[s]
+            ok = (r2 >= 1) & (r2 <= self.d1) & (c2 >= 1) & (c2 <= self.d2)
+            jj = (c2 - b[2]) * nrb + (r2 - b[0])
+            rows.append(np.nonzero(ok)[0])
+            cols.append(jj[ok])
+            vals.append(W[ok, s])
+        return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                             shape=(nr * nc, nrb * ncb))
+
+    def reconstruct_b0(self):
+        out = np.zeros((self.d1, self.d2))
+        for i in self.owned_patches():
+            p = self.patch_of(i)
+            out[p[0] - 1:p[1], p[2] - 1:p[3]] = self.b0[i].reshape(p[1] - p[0] + 1, p[3] - p[2] + 1, order="F")
+        return out
+
+    # ------------------------------------------------------------------ the three updates
+    def update_background_parallel(self, use_parallel=True, sync_host=True):
+        """update_background_parallel(obj, use_parallel).  `use_parallel` is accepted for signature compatibility; the
+        library does its own intra-call concurrency (SURVEY.md §8b threading)."""
+        self._push_options()
+        if sync_host:
+            self.push_neurons()
+            self.push_ring()
+        L.check(self._lib.cnmfe_update_background(self._h))
+        if sync_host:
+            self.pull_ring()
+            self.b0_new = self.reconstruct_b0()
+            self.A_prev = self.A.copy()
+            self.C_prev = np.array(self.C, copy=True)
+
+    def update_spatial_parallel(self, use_parallel=True, update_sn=False, IND=None, sync_host=True):
+        """update_spatial_parallel(obj, use_parallel, update_sn).  IND: (d,K) boolean search mask
+        (determine_search_location output, update_spatial_parallel.m:66); defaults to self.search_fn(self)."""
+        if update_sn:
+            raise L.CnmfeError("update_sn=true (per-pixel GetSn of the BG-subtracted video) is not built in this round")
+        self._push_options()
+        if IND is None:
+            if self.search_fn is None:
+                raise L.CnmfeError("no search mask: pass IND or set search_fn (determine_search_location stays in MATLAB)")
+            IND = self.search_fn(self)
+        INDc = sp.csc_matrix(IND).astype(bool)
+        INDc.sort_indices()
+        if sync_host:
+            self.push_neurons()
+            self.push_prev()
+            self.push_ring()
+            L.check(self._lib.cnmfe_set_sn(self._h, _ptr(np.asfortranarray(self.P["sn"], dtype=np.float64))))
+        jc = np.ascontiguousarray(INDc.indptr, dtype=np.int64)
+        ir = np.ascontiguousarray(INDc.indices, dtype=np.int64)
+        L.check(self._lib.cnmfe_set_search(self._h, INDc.shape[1], _ptr(jc), _ptr(ir)))
+        L.check(self._lib.cnmfe_update_spatial(self._h))
+        if sync_host:
+            vals = np.zeros(ir.size)
+            L.check(self._lib.cnmfe_get_spatial(self._h, _ptr(vals)))
+            vals = self._allreduce_sum(vals)
+            A_new = sp.csc_matrix((vals, ir.copy(), jc.copy()), shape=INDc.shape)
+            A_new.eliminate_zeros()
+            if self.post_process_fn is not None:
+                A_new = sp.csc_matrix(self.post_process_fn(A_new))
+            self.A = A_new
+            if self.P.get("Ymean") is not None:
+                self.b0_new = self.P["Ymean"] - (self.A @ self.C.mean(axis=1)).reshape(self.d1, self.d2, order="F")
+            if self.world_size > 1 or self.post_process_fn is not None:
+                self.push_neurons()
+
+    def update_temporal_parallel(self, use_parallel=True, use_c_hat=True, sync_host=True):
+        """update_temporal_parallel(obj, use_parallel, use_c_hat)."""
+        if not use_c_hat:
+            raise L.CnmfeError("use_c_hat=false (fast_temporal, update_temporal_parallel.m:314-337) is not built")
+        self._push_options()
+        if sync_host:
+            self.push_neurons()
+            self.push_prev()
+            self.push_ring()
+        L.check(self._lib.cnmfe_update_temporal_patches(self._h))
+        if self.world_size > 1:
+            self._allreduce_merge_buffers()
+        L.check(self._lib.cnmfe_update_temporal_finish(self._h))
+        if sync_host:
+            self.pull_temporal()
+
+    def pull_temporal(self):
+        K = self.A.shape[1]
+        C = np.zeros((K, self.T), order="F")
+        Cr = np.zeros((K, self.T), order="F")
+        S = np.zeros((K, self.T), order="F")
+        kp = np.zeros((K, 2))
+        nsn = np.zeros(K)
+        L.check(self._lib.cnmfe_get_temporal(self._h, _ptr(C), _ptr(Cr), _ptr(S), _ptr(kp), _ptr(nsn)))
+        self.C, self.C_raw, self.S = np.ascontiguousarray(C), np.ascontiguousarray(Cr), np.ascontiguousarray(S)
+        self.P["kernel_pars"], self.P["neuron_sn"] = kp, nsn
+        if self.P.get("Ymean") is not None:
+            self.b0_new = self.P["Ymean"] - (self.A @ self.C.mean(axis=1)).reshape(self.d1, self.d2, order="F")
+
+    # aliases named by BASELINE.json north_star
+    update_background = update_background_parallel
+    update_spatial = update_spatial_parallel
+    update_temporal = update_temporal_parallel
+
+    # ------------------------------------------------------------------ multi-GPU exchange (torch.distributed)
+    def _allreduce_sum(self, vec):
+        if self.world_size == 1:
+            return vec
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(vec).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def _allreduce_merge_buffers(self):
+        """C_raw = sum_p aa_p C_raw,p / sum_p aa_p across ranks (update_temporal_parallel.m:269-280): all-reduce of the
+        K x T numerator and K denominator, in place on the device buffers (NCCL over NVLink) -- or staged through the
+        host for the gloo backend used by the CPU-side tests of the host logic."""
+        import torch
+        import torch.distributed as dist
+        K = self.A.shape[1]
+        num = ctypes.c_void_p()
+        den = ctypes.c_void_p()
+        L.check(self._lib.cnmfe_temporal_merge_buffers(self._h, ctypes.byref(num), ctypes.byref(den)))
+        L.check(self._lib.cnmfe_sync(self._h))
+
+        class _Dev:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = dict(shape=(n,), typestr="<f8", data=(ptr, False), version=3)
+
+        tn = torch.as_tensor(_Dev(num.value, K * self.T), device=torch.device("cuda", self.device))
+        td = torch.as_tensor(_Dev(den.value, K), device=torch.device("cuda", self.device))
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(tn, op=dist.ReduceOp.SUM)
+            dist.all_reduce(td, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize(self.device)
+        else:
+            a, b = tn.cpu(), td.cpu()
+            dist.all_reduce(a, op=dist.ReduceOp.SUM)
+            dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            tn.copy_(a)
+            td.copy_(b)
+            torch.cuda.synchronize(self.device)
+
+    # ------------------------------------------------------------------ timing helpers (bench.py)
+    def phase_ms(self):
+        ms = (ctypes.c_float * 7)()
+        L.check(self._lib.cnmfe_last_phase_ms(self._h, ms))
+        return list(ms)
+
+    def sync(self):
+        L.check(self._lib.cnmfe_sync(self._h))

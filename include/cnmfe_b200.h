@@ -1,0 +1,148 @@
+/*
+ * cnmfe_b200.h -- C ABI of libcnmfe_b200.so: the B200-native (sm_100a) implementation of CNMF-E's
+ * alternating-update hot path (ring background regression -> spatial update -> temporal update + OASIS).
+ *
+ * The reference (zhoupc/CNMF_E) is MATLAB and has no FFI for this path; its seam is the Sources2D method
+ * surface.  Each entry point below names the reference interface it replaces (file:line under
+ * /root/reference).  A MEX gateway (matlab/cnmfe_b200_mex.cpp) binds these 1:1; INTEGRATION.md shows the
+ * MATLAB-side stubs.  Conventions:
+ *   - plain pointers and sizes only; all HOST arrays unless the name ends in _dev;
+ *   - dense matrices are MATLAB column-major doubles; sparse matrices are MATLAB CSC (jc, ir, pr) with
+ *     0-based indices (exactly mxGetJc / mxGetIr / mxGetPr);
+ *   - pixel linear index = r + c*d1 (0-based, MATLAB order); positions [r0 r1 c0 c1] are 1-based inclusive,
+ *     exactly as stored in mat_data.patch_pos / block_pos (endoscope/distribute_data.m:163-173);
+ *   - every function returns 0 on success, nonzero on error; cnmfe_last_error() gives the message
+ *     (the MEX gateway forwards it through mexErrMsgIdAndTxt, cf. utilities/graph_conn_comp_mex.cpp:44-53);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef CNMFE_B200_H
+#define CNMFE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cnmfe_ctx cnmfe_ctx;
+
+/* deconvolveCa options (OASIS_matlab/deconvolveCa.m:208-230 defaults in cnmfe_deconv_defaults). */
+typedef struct cnmfe_deconv_opts {
+    int type;            /* 1 = 'ar1', 2 = 'ar2' */
+    int method;          /* 0 = 'foopsi', 1 = 'constrained', 2 = 'thresholded' */
+    int optimize_b;
+    int optimize_pars;
+    int maxIter;         /* default 10 */
+    int has_tau_range;
+    double smin;         /* <0: multiple of the noise level (deconvolveCa.m:116-118,125-127) */
+    double lambda;
+    double b;            /* initial baseline */
+    double max_tau;      /* default 100 */
+    double tau_range[2];
+    double thresh_factor;/* default 1.0 */
+    double p_noise;      /* default 0.9999 */
+} cnmfe_deconv_opts;
+
+/* Options of the three updates (ca_source_extraction/CNMFSetParms.m:286-308 + demo overrides). */
+typedef struct cnmfe_options {
+    int spatial_algorithm;   /* 0 'hals', 1 'hals_thresh', 2 'nnls', 3 'lars' (update_spatial_parallel.m:202-212) */
+    int maxIter_temporal;    /* options.maxIter, default 5 (update_temporal_parallel.m:60) */
+    int deconv_flag;         /* options.deconv_flag */
+    int bg_acceleration;     /* options.bg_acceleration -> fit_ring_model(..., with_projection) */
+    int replicate_spatial_aprev_quirk; /* 1 = select A_prev neurons by HALO only in the spatial update, as
+                                          update_spatial_parallel.m:82-98 does (mask==1 after the patch is set to 2) */
+    int use_tensor_gram;     /* 1 = tcgen05 INT8 kernel for the ring second moments, 0 = SIMT reference kernel */
+    cnmfe_deconv_opts deconv;
+} cnmfe_options;
+
+const char* cnmfe_last_error(void);
+void cnmfe_deconv_defaults(cnmfe_deconv_opts* o);
+void cnmfe_options_defaults(cnmfe_options* o);
+/* number of kernels of this library launched so far in this process */
+unsigned long long cnmfe_launch_count(void);
+
+/* ---- stand-alone trace routines (host arrays; batch of N traces, each trace contiguous: Y is T x N) --------- */
+
+/* [c,s,options] = deconvolveCa(y, ...)  (OASIS_matlab/deconvolveCa.m:1; also @Sources2D/deconvTemporal.m:45-60).
+ * sn_in / pars_in may be NULL (estimate: GetSn / estimate_time_constant); pars_in is 2 x N, zeros = estimate.
+ * Outputs (any may be NULL): c,s (T x N), b,sn,smin,lam (N), pars (2 x N). */
+int cnmfe_deconvolve(const double* Y, int T, int N, const cnmfe_deconv_opts* opts, const double* sn_in,
+                     const double* pars_in, double* c, double* s, double* b, double* pars, double* sn,
+                     double* smin, double* lam, int device);
+
+/* sn = GetSn(Y)  (OASIS_matlab/functions/GetSn.m:1; logmexp over [0.25,0.5]).  Y is T x N, sn has N entries. */
+int cnmfe_get_sn(const double* Y, int T, int N, double* sn, int device);
+
+/* [C,C_raw,results_deconv] = HALS_temporal(Y,A,C,maxIter,deconv_options) (utilities/HALS_temporal.m:1) given the
+ * projections U = A'*Y (K x T col-major), V = A'*A (K x K dense col-major).  C is updated in place (K x T);
+ * outputs C_raw, S (K x T), sn (K), kernel_pars (2 x K).  deconv may be NULL (no deconvolution). */
+int cnmfe_hals_temporal_uv(const double* U, const double* V, int K, int T, double* C, int maxIter,
+                           const cnmfe_deconv_opts* deconv, double* C_raw, double* S, double* sn,
+                           double* kernel_pars, int device);
+
+/* ---- resident-video context: Sources2D.update_{background,spatial,temporal}_parallel ------------------------- */
+
+/* Geometry as produced by distribute_data.m:163-173.  patch_pos / block_pos: 4 x npatch int32 (col-major, 1-based
+ * inclusive [r0 r1 c0 c1]), patches in MATLAB linear order.  owned: npatch flags (NULL = all) -- the patches this
+ * process/GPU holds (multi-GPU sharding).  ring_radius, num_neighbors (0 = all) as in
+ * CNMFSetParms.m:289-291 (bg_ssub = 1). */
+int cnmfe_create(cnmfe_ctx** ctx, int d1, int d2, int T, int npatch, const int32_t* patch_pos,
+                 const int32_t* block_pos, const uint8_t* owned, int ring_radius, int num_neighbors, int device);
+void cnmfe_destroy(cnmfe_ctx* ctx);
+int cnmfe_set_options(cnmfe_ctx* ctx, const cnmfe_options* opts);
+
+/* get_patch_data(mat_data, patch_pos, frame_range, true) (endoscope/get_patch_data.m:1): hand the block of patch
+ * `ipatch` (nr_block x nc_block x T, column-major, native dtype) to the device once; it stays resident.
+ * dtype: 0 = uint8, 1 = uint16 (the dtypes distribute_data.m:144-147 writes for the demos). */
+int cnmfe_upload_block(cnmfe_ctx* ctx, int ipatch, const void* Y, int dtype);
+/* same, Y already in device memory (frame-major nr_block*nc_block per frame, as MATLAB lays it out) */
+int cnmfe_upload_block_dev(cnmfe_ctx* ctx, int ipatch, const void* Y_dev, int dtype);
+
+/* obj.A (d x K sparse), obj.C (K x T)   (Sources2D.m:11-13) */
+int cnmfe_set_neurons(cnmfe_ctx* ctx, int K, const int64_t* A_jc, const int64_t* A_ir, const double* A_pr,
+                      const double* C);
+/* obj.A_prev, obj.C_prev (Sources2D.m:14-15); cnmfe_update_background snapshots them itself (:316-317) */
+int cnmfe_set_prev(cnmfe_ctx* ctx, int K, const int64_t* A_jc, const int64_t* A_ir, const double* A_pr,
+                   const double* C);
+/* IND = determine_search_location(...) (update_spatial_parallel.m:66): d x K logical sparse */
+int cnmfe_set_search(cnmfe_ctx* ctx, int K, const int64_t* IND_jc, const int64_t* IND_ir);
+/* obj.P.sn (d1 x d2) */
+int cnmfe_set_sn(cnmfe_ctx* ctx, const double* sn);
+/* obj.W{ipatch}, obj.b0{ipatch}: ring weights in slot form, W[p + i*d_patch] = weight of patch pixel p for ring
+ * offset i (cnmfe_ring_offsets); entries whose neighbour falls outside the FOV are ignored.  NULL W = uniform
+ * initialisation (initComponents_parallel.m:213-236). */
+int cnmfe_ring_offsets(cnmfe_ctx* ctx, int* nnb, int32_t* r_shift, int32_t* c_shift);
+int cnmfe_set_ring(cnmfe_ctx* ctx, int ipatch, const double* W_slots, const double* b0);
+int cnmfe_get_ring(cnmfe_ctx* ctx, int ipatch, double* W_slots, double* b0);
+
+/* update_background_parallel(obj, use_parallel) (@Sources2D/update_background_parallel.m:1), ring model, bg_ssub=1.
+ * Result stays on the device (W, b0, A_prev<-A, C_prev<-C); fetch with cnmfe_get_ring. */
+int cnmfe_update_background(cnmfe_ctx* ctx);
+/* update_spatial_parallel(obj, use_parallel, update_sn=false) (@Sources2D/update_spatial_parallel.m:1) up to
+ * (not including) post_process_spatial (:341, host/MATLAB).  New A lives on the search pattern. */
+int cnmfe_update_spatial(cnmfe_ctx* ctx);
+/* A on the search pattern: values aligned with (IND_jc, IND_ir) given to cnmfe_set_search */
+int cnmfe_get_spatial(cnmfe_ctx* ctx, double* A_on_IND);
+/* update_temporal_parallel(obj, use_parallel, use_c_hat=true) (@Sources2D/update_temporal_parallel.m:1).
+ * phase 1: per-patch HALS_temporal -> energy-weighted sums; phase 2 (after an optional cross-GPU all-reduce of the
+ * buffers exposed by cnmfe_temporal_merge_buffers): C_raw = num/den, deconvTemporal (deconvTemporal.m:1). */
+int cnmfe_update_temporal_patches(cnmfe_ctx* ctx);
+int cnmfe_temporal_merge_buffers(cnmfe_ctx* ctx, double** num_dev /* K*T, [k][t] */, double** den_dev /* K */);
+int cnmfe_update_temporal_finish(cnmfe_ctx* ctx);
+int cnmfe_update_temporal(cnmfe_ctx* ctx);   /* = patches + finish (single process) */
+/* obj.C, obj.C_raw, obj.S (K x T col-major), obj.P.kernel_pars (2 x K), obj.P.neuron_sn (K); any may be NULL */
+int cnmfe_get_temporal(cnmfe_ctx* ctx, double* C, double* C_raw, double* S, double* kernel_pars,
+                       double* neuron_sn);
+/* block the host until all queued device work of ctx is done */
+int cnmfe_sync(cnmfe_ctx* ctx);
+/* CUDA-event timing of the kernels on the ctx stream: begin/end bracket a region, returns milliseconds */
+int cnmfe_timer_begin(cnmfe_ctx* ctx);
+int cnmfe_timer_end(cnmfe_ctx* ctx, float* ms);
+/* per-phase device time of the last update call (ms): [0] gram (second moments), [1] ring assemble+solve,
+ * [2] projections, [3] spatial solve, [4] temporal sweeps, [5] deconvTemporal, [6] other */
+int cnmfe_last_phase_ms(cnmfe_ctx* ctx, float* ms7);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNMFE_B200_H */
