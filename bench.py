@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- one "step" = one CNMF-E update iteration (update_background_parallel + update_spatial_parallel +
+update_temporal_parallel, the triple at demos/demo_large_data_1p.m:199-201) over a resident synthetic 1p video.
+
+Workload at N=1: BASELINE.json configs[1]: 512x512x10000 uint16, 300 neurons, ring background (radius 18, 120
+neighbours, bg_ssub=1), single patch, nnls spatial, foopsi/ar1 deconvolution with the demo's options.
+N>1 (weak scaling): the FOV grows to 512 x 512N, one 512x512 patch (+19 px halo) and 300 neurons per GPU;
+one all-reduce of the K x T merge buffers per step (update_temporal_parallel.m:269-280) + the A-row exchange.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the float64 CPU restatement of the reference algorithm
+(oracle/, NumPy/SciPy, all host cores) on a bounded sample -- MATLAB is not installed on these boxes.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20260925 + 2
+D1 = 512
+D2_PER_GPU = 512
+T_FULL = 10000
+K_PER_GPU = 300
+RING = 18
+
+
+# ----------------------------------------------------------------------------------------------- synthetic data
+def _place_centres(rng, d1, d2, K, min_dist=8.0, margin=8):
+    pts = np.zeros((0, 2))
+    while len(pts) < K:
+        cand = np.stack([rng.uniform(margin, d1 - 1 - margin, 4 * K), rng.uniform(margin, d2 - 1 - margin, 4 * K)], 1)
+        for p in cand:
+            if len(pts) >= K:
+                break
+            if len(pts) == 0 or np.min(np.sum((pts - p) ** 2, axis=1)) >= min_dist ** 2:
+                pts = np.vstack([pts, p])
+    return pts
+
+
+def _footprints(d1, d2, centres, amp, gSig=3.0, radius=6.5):
+    import scipy.sparse as sp
+    rows, cols, vals = [], [], []
+    R = int(np.ceil(radius))
+    dr, dc = np.meshgrid(np.arange(-R, R + 1), np.arange(-R, R + 1), indexing="ij")
+    for k, (r0, c0) in enumerate(centres):
+        r = int(round(r0)) + dr.ravel()
+        c = int(round(c0)) + dc.ravel()
+        d2_ = (r - r0) ** 2 + (c - c0) ** 2
+        ok = (r >= 0) & (r < d1) & (c >= 0) & (c < d2) & (d2_ <= radius ** 2)
+        rows.append(r[ok] + c[ok] * d1)
+        cols.append(np.full(ok.sum(), k))
+        vals.append(amp[k] * np.exp(-d2_[ok] / (2 * gSig ** 2)))
+    return sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(d1 * d2, len(centres)))
+
+
+def _disk_mask(d1, d2, centres, radius):
+    import scipy.sparse as sp
+    rows, cols = [], []
+    R = int(np.ceil(radius))
+    dr, dc = np.meshgrid(np.arange(-R, R + 1), np.arange(-R, R + 1), indexing="ij")
+    for k, (r0, c0) in enumerate(centres):
+        r = int(round(r0)) + dr.ravel()
+        c = int(round(c0)) + dc.ravel()
+        ok = (r >= 0) & (r < d1) & (c >= 0) & (c < d2) & ((r - r0) ** 2 + (c - c0) ** 2 <= radius ** 2)
+        rows.append(r[ok] + c[ok] * d1)
+        cols.append(np.full(ok.sum(), k))
+    return sp.csc_matrix((np.ones(sum(len(x) for x in rows), dtype=bool), (np.concatenate(rows), np.concatenate(cols))),
+                         shape=(d1 * d2, len(centres)))
+
+
+def make_problem(d1, d2, T, K, seed):
+    """Global (all-rank) description: neurons, traces, background parameters.  SURVEY.md §8d recipe."""
+    from scipy.ndimage import gaussian_filter
+    rng = np.random.default_rng(seed)
+    centres = _place_centres(rng, d1, d2, K)
+    amp = rng.uniform(0.5, 1.5, K) * 20.0
+    A = _footprints(d1, d2, centres, amp)
+    S = (rng.random((K, T)) < 0.5 / 30).astype(np.float64)
+    C = S.copy()
+    for t in range(1, T):
+        C[:, t] += 0.95 * C[:, t - 1]
+    b0 = 2000.0 + gaussian_filter(rng.normal(0, 300.0, (d1, d2)), 40.0) * 10.0
+    nblob = 8 * max(1, d2 // 512)
+    bc = np.stack([rng.uniform(0, d1, nblob), rng.uniform(0, d2, nblob)], 1)
+    width = 150.0
+    f = gaussian_filter(rng.standard_normal((nblob, T + 6 * int(width))), sigma=(0, width), mode="wrap")
+    f = f[:, 3 * int(width):3 * int(width) + T]
+    f -= f.mean(axis=1, keepdims=True)
+    f /= f.std(axis=1, keepdims=True)
+    f *= 100.0
+    A0 = A.copy()
+    A0.data = np.maximum(A0.data * (1 + 0.2 * rng.standard_normal(A0.data.size)), 0.0)
+    C0 = C + rng.normal(0, 0.2, C.shape)
+    IND = _disk_mask(d1, d2, centres, 8.5)
+    return dict(A=A, C=C, S=S, b0=b0, blob_centres=bc, f=f, A0=A0, C0=C0, IND=IND, centres=centres)
+
+
+def build_block_on_gpu(prob, block, d1, T, seed, device, sn=10.0, chunk=500):
+    """uint16 frame-major block [T][nrb*ncb] on the GPU (torch), deterministic per (seed, FOV column)."""
+    import torch
+    r0, r1, c0, c1 = [int(x) for x in block]       # 1-based inclusive
+    nrb, ncb = r1 - r0 + 1, c1 - c0 + 1
+    dev = torch.device("cuda", device)
+    rows = torch.arange(r0 - 1, r1, device=dev, dtype=torch.float32)
+    out = torch.empty((T, ncb, nrb), dtype=torch.int16, device=dev)   # uint16 bit patterns
+    A = prob["A"].tocsr()
+    pix = (np.arange(c0 - 1, c1)[:, None] * d1 + np.arange(r0 - 1, r1)[None, :]).ravel()   # block order: c major, r fastest
+    Ab = A[pix, :]
+    keep = np.nonzero(np.asarray(Ab.sum(axis=0)).ravel() > 0)[0]
+    Abk = Ab[:, keep].tocoo()
+    A_t = torch.sparse_coo_tensor(np.vstack([Abk.row, Abk.col]), Abk.data.astype(np.float32),
+                                  size=(nrb * ncb, len(keep)), device=dev).coalesce()
+    C_t = torch.from_numpy(prob["C"][keep].astype(np.float32)).to(dev)
+    f_t = torch.from_numpy(prob["f"].astype(np.float32)).to(dev)
+    b0_t = torch.from_numpy(prob["b0"][r0 - 1:r1, c0 - 1:c1].T.astype(np.float32).copy()).to(dev)   # (ncb, nrb)
+    cols = torch.arange(c0 - 1, c1, device=dev, dtype=torch.float32)
+    blobs = []
+    for (br, bcc) in prob["blob_centres"]:
+        g = torch.exp(-((rows[None, :] - br) ** 2 + (cols[:, None] - bcc) ** 2) / (2 * 60.0 ** 2))
+        blobs.append(g.reshape(-1))
+    blobs = torch.stack(blobs, 1)          # (ncb*nrb, nblob)
+    gen = torch.Generator(device=dev)
+    for t0 in range(0, T, chunk):
+        t1 = min(T, t0 + chunk)
+        X = torch.sparse.mm(A_t, C_t[:, t0:t1]) + blobs @ f_t[:, t0:t1] + b0_t.reshape(-1, 1)
+        X = X.reshape(ncb, nrb, t1 - t0)
+        for j in range(ncb):
+            gen.manual_seed(seed * 1000003 + (c0 - 1 + j) * 4099 + t0)
+            X[j] += torch.randn((nrb, t1 - t0), generator=gen, device=dev) * sn
+        X = torch.clamp(torch.round(X), 0, 65535)
+        out[t0:t1] = X.permute(2, 0, 1).to(torch.int32).to(torch.int16)   # wraps: same bits as uint16
+    return out.reshape(T, ncb * nrb)
+
+
+# ----------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            p = [x.strip() for x in s.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+SAMPLE = dict(d1=64, d2=64, T=1000, K=6, ring=RING)
+
+
+def cpu_reference_step(state=None):
+    """One update iteration of the float64 oracle on the bounded sample.  Returns (seconds, pixel*frames)."""
+    from oracle import gen, cnmfe as OC
+    if state is None:
+        D = gen.make_synthetic(SAMPLE["d1"], SAMPLE["d2"], SAMPLE["T"], SAMPLE["K"], seed=SEED, nblob=4)
+        o = OC.OracleSources2D(D["Y"], (SAMPLE["d1"], SAMPLE["d2"]), ring_radius=SAMPLE["ring"],
+                               options=dict(spatial_algorithm="nnls"))
+        o.A, o.C = D["A0"].copy(), D["C0"].copy()
+        o.P["sn"] = np.full((SAMPLE["d1"], SAMPLE["d2"]), 10.0)
+        state = dict(o=o, IND=D["IND"])
+    o = state["o"]
+    t = time.perf_counter()
+    o.update_background_parallel()
+    o.update_spatial_parallel(IND=state["IND"])
+    o.update_temporal_parallel()
+    dt = time.perf_counter() - t
+    return dt, SAMPLE["d1"] * SAMPLE["d2"] * SAMPLE["T"], state
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    state = None
+    for _ in range(args.warmup):
+        _, _, state = cpu_reference_step(state)
+    t0 = time.perf_counter()
+    units = 0
+    for _ in range(args.steps):
+        dt, u, state = cpu_reference_step(state)
+        units += u
+    el = time.perf_counter() - t0
+    val = units / el
+    sample = "%dx%dx%d uint16, K=%d, ring r=%d (120 nbrs), single patch, nnls + foopsi/ar1; per-pixel-frame cost is size-independent" % (
+        SAMPLE["d1"], SAMPLE["d2"], SAMPLE["T"], SAMPLE["K"], SAMPLE["ring"])
+    line = dict(impl="reference", metric="pixels*frames/sec per spatial+temporal+BG update iter", value=val,
+                unit="pixel*frames/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * el / max(args.steps, 1), higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic",
+                config=dict(workload="CNMF-E update iteration (BG ring fit + nnls spatial + HALS temporal/OASIS), bounded sample of configs[1]",
+                            sample=sample),
+                cpu_baseline=dict(value=val, unit="pixel*frames/s", cores=cores, kind="port", sample=sample,
+                                  note="float64 NumPy/SciPy restatement of the reference algorithm (oracle/); MATLAB is not installed"),
+                e2e=dict(value=val, unit="pixel*frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cnmf_e_b200 import _lib
+    from cnmf_e_b200.sources2d import Sources2D
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    lib = _lib.lib()
+    d1, d2, T, K = D1, D2_PER_GPU * world, args.frames, K_PER_GPU * world
+    prob = make_problem(d1, d2, T, K, SEED)
+    opts = dict(spatial_algorithm="nnls", use_tensor_gram=bool(args.tensor))
+    obj = Sources2D(d1, d2, T, (D1, D2_PER_GPU), ring_radius=RING, device=local, rank=rank, world_size=world,
+                    options=opts)
+    for i in obj.owned_patches():
+        blk = build_block_on_gpu(prob, obj.block_of(i), d1, T, SEED, local)
+        torch.cuda.synchronize()
+        obj.load_block_dev(i, blk.data_ptr(), 1)
+        del blk
+        torch.cuda.empty_cache()
+    obj.A, obj.C = prob["A0"].copy(), prob["C0"].copy()
+    obj.P["sn"] = np.full((d1, d2), 10.0)
+    IND = prob["IND"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        obj.update_background_parallel(sync_host=False)
+        obj.update_spatial_parallel(IND=IND, sync_host=False)
+        if world > 1:
+            obj.exchange_spatial()
+        obj.update_temporal_parallel(sync_host=False)
+
+    def step_e2e():
+        obj.update_background_parallel()
+        obj.update_spatial_parallel(IND=IND)
+        obj.update_temporal_parallel()
+
+    # state to the device once; resident steps follow
+    obj._push_options(); obj.push_neurons(); obj.push_prev(); obj.push_ring()
+    import ctypes
+    lib.cnmfe_set_sn(obj._h, np.asfortranarray(obj.P["sn"]).ctypes.data_as(ctypes.c_void_p))
+    phases = np.zeros(7)
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.cnmfe_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lib.cnmfe_timer_begin(obj._h)
+    t0 = time.perf_counter()
+    gram_ms = 0.0
+    for _ in range(args.steps):
+        obj.update_background_parallel(sync_host=False)
+        p = np.array(obj.phase_ms()); phases += p; gram_ms += p[0]
+        obj.update_spatial_parallel(IND=IND, sync_host=False)
+        phases += np.array(obj.phase_ms())
+        if world > 1:
+            obj.exchange_spatial()
+        obj.update_temporal_parallel(sync_host=False)
+        phases += np.array(obj.phase_ms())
+    ms = ctypes.c_float()
+    lib.cnmfe_timer_end(obj._h, ctypes.byref(ms))
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = lib.cnmfe_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = max(ms.value / 1e3, 1e-9)
+    t_use = max(t_dev, wall)   # host planning between launches is part of the step
+    tt = torch.tensor([t_use], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_max = float(tt.item())
+    units = float(d1) * d2 * T * args.steps
+    value = units / t_max
+    # ---- e2e through the public API with host buffers (H2D of A, C, W, ...; D2H of W, A, C, C_raw, S)
+    obj.pull_ring(); obj.pull_spatial(); obj.pull_temporal()
+    nE = max(1, min(args.steps, 2))
+    barrier()
+    te = time.perf_counter()
+    for _ in range(nE):
+        step_e2e()
+    barrier()
+    e2e_t = (time.perf_counter() - te) / nE
+    te_t = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+    e2e_val = float(d1) * d2 * T / float(te_t.item())
+    Kg = obj.A.shape[1]
+    w_bytes = sum(obj.W[i].nbytes + obj.b0[i].nbytes for i in obj.owned_patches())
+    h2d = 3 * (Kg * T * 8 + obj.A.nnz * 20) + 2 * (obj.C_prev.size * 8 + obj.A_prev.nnz * 20) + 3 * w_bytes + d1 * d2 * 8 + IND.nnz * 8
+    d2h = w_bytes + IND.nnz * 8 + 3 * Kg * T * 8 + Kg * 24
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (ring second moments), live CUDA-event time on the launching stream
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "2x measured bf16 sustained (MEASURED_PEAKS.json)" if peaks else "2x fallback 1.4 PF bf16 sustained"
+    rr = RING
+    ND = 2 * rr * (4 * rr + 1) + (2 * rr + 1)
+    nblk = [obj.block_of(i) for i in obj.owned_patches()]
+    db = float(sum(int(b[1] - b[0] + 1) * int(b[3] - b[2] + 1) for b in nblk))
+    int8_ops = 2.0 * 4.0 * ND * db * T           # u16 x u16 = 4 u8 x u8 products, 2 ops per MAC
+    gram_s = max(gram_ms / 1e3 / args.steps, 1e-9)
+    achieved = int8_ops / gram_s / 1e12
+    roofline = dict(bound="tensor", kernel="ring second moments S2 (%s)" % ("tcgen05 INT8" if lib.cnmfe_last_gram_was_tensor(obj._h) else "SIMT u64"),
+                    achieved=achieved, peak=2.0 * bf16, unit="TOP/s (int8 dense)", frac=achieved / (2.0 * bf16),
+                    traffic=None, peak_source=peak_src, ms_per_launch=1e3 * gram_s,
+                    algorithmic_ops_per_launch=int8_ops,
+                    hbm_iteration=dict(algorithmic_bytes=3.0 * d1 * d2 * T * 2 / world, gbs=3.0 * d1 * d2 * T * 2 / world / (t_max / args.steps) / 1e9,
+                                       peak_gbs=peaks.get("hbm_gbs", 6650.0)))
+    # ---- CPU baseline, bounded sample, rank 0
+    cores = os.cpu_count()
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        dt, u, st = cpu_reference_step(None)
+        dt2, u2, st = cpu_reference_step(st)
+        cpu = dict(value=u2 / dt2, unit="pixel*frames/s", cores=cores, kind="port",
+                   sample="%dx%dx%d, K=%d, ring r=%d, 1 steady-state iteration (%.1f s)" % (SAMPLE["d1"], SAMPLE["d2"], SAMPLE["T"], SAMPLE["K"], SAMPLE["ring"], dt2))
+    line = dict(metric="pixels*frames/sec per spatial+temporal+BG update iter", value=value, unit="pixel*frames/s",
+                n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * t_max / args.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64 (exact int64 second moments from the u16 video)",
+                data="synthetic",
+                config=dict(workload="configs[1]: synthetic 1p %dx%dx%d uint16, %d neurons, ring-BG r=18 (120 nbrs, bg_ssub=1), one %dx%d patch per GPU, nnls spatial, foopsi/ar1 OASIS (smin=-5, optimize_pars, optimize_b)" % (d1, d2, T, K, D1, D2_PER_GPU),
+                            l2="inputs (%.1f GB resident video per GPU) larger than L2; no flush needed" % (float(db) * T * 2 / 1e9),
+                            seed=SEED, device_ms_per_step=1e3 * t_dev / args.steps, wall_ms_per_step=1e3 * wall / args.steps,
+                            phase_ms_per_step=dict(zip(["gram", "ring_solve", "projections", "spatial_solve", "temporal_sweeps", "deconvTemporal", "other"],
+                                                       [float(x) / args.steps for x in phases]))),
+                clocks=clocks, gpu_launches=int(launches),
+                e2e=dict(value=e2e_val, unit="pixel*frames/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                         note="Sources2D.update_* with host numpy state pushed/pulled every call; video resident"),
+                roofline=roofline, cpu_baseline=cpu)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=T_FULL)
+    ap.add_argument("--tensor", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

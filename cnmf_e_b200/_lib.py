@@ -62,6 +62,7 @@ SYMBOLS = {
     "cnmfe_update_background": (I, [V]),
     "cnmfe_update_spatial": (I, [V]),
     "cnmfe_get_spatial": (I, [V, V]),
+    "cnmfe_set_spatial": (I, [V, V]),
     "cnmfe_update_temporal_patches": (I, [V]),
     "cnmfe_temporal_merge_buffers": (I, [V, ctypes.POINTER(V), ctypes.POINTER(V)]),
     "cnmfe_update_temporal_finish": (I, [V]),
@@ -71,6 +72,8 @@ SYMBOLS = {
     "cnmfe_timer_begin": (I, [V]),
     "cnmfe_timer_end": (I, [V, c_float_p]),
     "cnmfe_last_phase_ms": (I, [V, c_float_p]),
+    "cnmfe_debug_second_moments": (I, [V, I, I, V]),
+    "cnmfe_last_gram_was_tensor": (I, [V]),
 }
 
 

@@ -93,6 +93,7 @@ struct cnmfe_ctx {
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr;
     float phase_ms[7] = {0, 0, 0, 0, 0, 0, 0};
+    int last_gram_tensor = 0;
     bool first_bg = true;          // flag_first of update_background_parallel.m:142-146 (W{1} still uniform)
     // neurons
     HostCsc A, Aprev, IND;
@@ -666,11 +667,12 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         if (c->opt.use_tensor_gram && kf == 1)
             tc_rc = ring_s2_tensor(P.hi, P.lo, P.nrb, P.ncb, T, c->Tpad, c->rr, d_S2, c->st);
         if (tc_rc < 0) return -1;
+        c->last_gram_tensor = (tc_rc == 0);
         if (tc_rc != 0) {
             long long nw = (long long)((P.nrb + 3) / 4) * P.ncb;
             dim3 gg((unsigned)((nw + 7) / 8), c->ngroups);
             LAUNCH(ring_s2_simt_kernel, gg, 256, 0, c->st, P.Yt, P.nrb, P.ncb, T, c->Tpad, kf, c->rr, c->d_groups,
-                   c->ngroups, d_S2, (size_t)P.db);
+                   c->ngroups, d_S2, ND);
         }
         phase_end(c, 0);
         // assemble + solve
@@ -678,7 +680,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         RingSolveArgs a;
         a.g = g; a.off_r = c->d_off_r; a.off_c = c->d_off_c; a.S2 = d_S2; a.S1 = d_S1; a.Ymean = P.Ymean;
         a.nsel = nsel; a.a_ptr = d_ptr; a.a_col = d_col; a.a_val = d_val; a.N = d_N; a.K = Kb; a.Csum = d_Csum;
-        a.active = d_active; a.active_list = d_alist; a.n_active = (int)alist.size(); a.W = P.W; a.db = (size_t)P.db;
+        a.active = d_active; a.active_list = d_alist; a.n_active = (int)alist.size(); a.W = P.W; a.db = (size_t)P.db; a.ND = ND;
         const int NMAX = c->nnb + 1;
         size_t smem = ((size_t)NMAX * (NMAX + 1) / 2 + 3 * (size_t)NMAX) * 8 + 4 * (size_t)NMAX * 4 + 64;
         CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -791,7 +793,14 @@ extern "C" int cnmfe_update_spatial(cnmfe_ctx* c) {
         for (size_t e = 0; e < nent; ++e) c->A_on_IND[LS.entry_src[e]] = anew[e];
     }
     c->have_spatial = true;
-    // obj.A = A_new on the pattern (zeros dropped), update_spatial_parallel.m:321-335
+    return cnmfe_set_spatial(c, c->A_on_IND.data());
+}
+
+// obj.A = A_new on the pattern (zeros dropped), update_spatial_parallel.m:321-335
+extern "C" int cnmfe_set_spatial(cnmfe_ctx* c, const double* vals) {
+    if (!c || !vals) { set_error("cnmfe_set_spatial: null"); return -1; }
+    if (c->IND.K != c->K) { set_error("cnmfe_set_spatial: search mask has %d columns, A has %d", c->IND.K, c->K); return -1; }
+    if (vals != c->A_on_IND.data()) c->A_on_IND.assign(vals, vals + c->IND.ir.size());
     HostCsc An;
     An.K = c->K;
     An.jc.assign(c->K + 1, 0);
@@ -801,6 +810,7 @@ extern "C" int cnmfe_update_spatial(cnmfe_ctx* c) {
         An.jc[k + 1] = (int64_t)An.ir.size();
     }
     c->A = An;
+    c->have_spatial = true;
     return 0;
 }
 
@@ -962,3 +972,32 @@ extern "C" int cnmfe_get_temporal(cnmfe_ctx* c, double* C, double* C_raw, double
     }
     return 0;
 }
+
+// ===================================================================================================== test hooks
+// Second moments S2[q][id] of block `ip` (all frames) by the tensor (use_tensor=1) or SIMT (0) kernel -> host.
+extern "C" int cnmfe_debug_second_moments(cnmfe_ctx* c, int ip, int use_tensor, double* out) {
+    if (!c || ip < 0 || ip >= c->npatch || !out) { set_error("cnmfe_debug_second_moments: bad arguments"); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    Patch& P = c->patches[ip];
+    if (!P.owned || !P.uploaded) { set_error("cnmfe_debug_second_moments: block not resident"); return -1; }
+    const size_t ND = (size_t)ring_num_disp(c->rr);
+    if (c->scr.reserve(ND * P.db * 8 + (1 << 20))) return -1;
+    c->scr.reset();
+    double* d_S2 = c->scr.take<double>(ND * P.db);
+    CNMFE_CUDA_OK(cudaMemsetAsync(d_S2, 0, ND * P.db * 8, c->st));
+    if (use_tensor) {
+        int rc = ring_s2_tensor(P.hi, P.lo, P.nrb, P.ncb, c->T, c->Tpad, c->rr, d_S2, c->st);
+        if (rc < 0) return -1;
+        if (rc > 0) { set_error("tensor kernel does not support this shape"); return -1; }
+    } else {
+        long long nw = (long long)((P.nrb + 3) / 4) * P.ncb;
+        dim3 gg((unsigned)((nw + 7) / 8), c->ngroups);
+        LAUNCH(ring_s2_simt_kernel, gg, 256, 0, c->st, P.Yt, P.nrb, P.ncb, c->T, c->Tpad, 1, c->rr, c->d_groups,
+               c->ngroups, d_S2, ND);
+    }
+    CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+    CNMFE_CUDA_OK(cudaGetLastError());
+    CNMFE_CUDA_OK(cudaMemcpy(out, d_S2, ND * P.db * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int cnmfe_last_gram_was_tensor(cnmfe_ctx* c) { return c ? c->last_gram_tensor : 0; }

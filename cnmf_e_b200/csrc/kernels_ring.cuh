@@ -1,7 +1,7 @@
 // kernels_ring.cuh -- ring-model background regression (endoscope/fit_ring_model.m:92-108) from exact integer
 // second moments of the resident video.
 //
-//   S2[id(D)][q] = sum_{t in sel} Y[q,t] * Y[q+D,t]      (exact, < 2^53)   D in the canonical half plane
+//   S2[q][id(D)] = sum_{t in sel} Y[q,t] * Y[q+D,t]      (exact, < 2^53)   D in the canonical half plane
 //   Cov_Bf(p,q)  = S2c(p,q) - N[p,:].A[q,:] - A[p,:].N[q,:]              
 // so the (nnb+1)^2 Gram of every pixel is ASSEMBLED from the banded moment table instead of being recomputed
 // (the reference gathers a 121 x T matrix per pixel and forms X*X').
@@ -31,7 +31,7 @@ __host__ __device__ inline int ring_disp_id(int dr, int dc, int rr) {
 // groups: [ngroups][2] = (dc, dr_start).
 __global__ void __launch_bounds__(256)
 ring_s2_simt_kernel(const uint16_t* __restrict__ Yt, int nrb, int ncb, int T, int Tpad, int kf, int rr,
-                    const int* __restrict__ groups, int ngroups, double* __restrict__ S2, size_t db) {
+                    const int* __restrict__ groups, int ngroups, double* __restrict__ S2, size_t ND) {
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gpc = (nrb + 3) / 4;
     const long long wid = (long long)blockIdx.x * 8 + wib;
@@ -98,7 +98,7 @@ ring_s2_simt_kernel(const uint16_t* __restrict__ Yt, int nrb, int ncb, int T, in
             int dr = dr0 + dd;
             if (lane == 0 && yv[p] && zv[p + dd] && dr <= 2 * rr && dr >= -2 * rr && (dc > 0 || dr >= 0)) {
                 size_t q = (size_t)c * nrb + r0 + p;
-                S2[(size_t)ring_disp_id(dr, dc, rr) * db + q] = (double)v;
+                S2[q * ND + ring_disp_id(dr, dc, rr)] = (double)v;
             }
         }
 }
@@ -173,7 +173,7 @@ struct RingSolveArgs {
     const unsigned char* active;
     const int* active_list; int n_active;
     double* W;   // [nnb][dp]
-    size_t db;
+    size_t db, ND;
 };
 
 #define RING_SOLVE_THREADS 128
@@ -230,16 +230,16 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS) ring_solve_kernel(RingSolv
         int j = e - i * (i + 1) / 2;   // j <= i
         int ddr = sdr[i] - sdr[j], ddc = sdc[i] - sdc[j];   // displacement from p_j to p_i
         double s2;
-        if (ddc > 0 || (ddc == 0 && ddr >= 0)) s2 = a.S2[(size_t)ring_disp_id(ddr, ddc, g.rr) * a.db + qi[j]];
-        else s2 = a.S2[(size_t)ring_disp_id(-ddr, -ddc, g.rr) * a.db + qi[i]];
+        if (ddc > 0 || (ddc == 0 && ddr >= 0)) s2 = a.S2[(size_t)qi[j] * a.ND + ring_disp_id(ddr, ddc, g.rr)];
+        else s2 = a.S2[(size_t)qi[i] * a.ND + ring_disp_id(-ddr, -ddc, g.rr)];
         G[e] = s2 - a.nsel * ym[i] * ym[j] - ym[j] * s1c[i] - ym[i] * s1c[j];
     }
     for (int i = tid; i < n; i += blockDim.x) {
         // rhs_i = Cov(p_i, m): displacement from m to p_i is (sdr, sdc)
         int ddr = sdr[i], ddc = sdc[i];
         double s2;
-        if (ddc > 0 || (ddc == 0 && ddr >= 0)) s2 = a.S2[(size_t)ring_disp_id(ddr, ddc, g.rr) * a.db + qm];
-        else s2 = a.S2[(size_t)ring_disp_id(-ddr, -ddc, g.rr) * a.db + qi[i]];
+        if (ddc > 0 || (ddc == 0 && ddr >= 0)) s2 = a.S2[qm * a.ND + ring_disp_id(ddr, ddc, g.rr)];
+        else s2 = a.S2[(size_t)qi[i] * a.ND + ring_disp_id(-ddr, -ddc, g.rr)];
         rhs[i] = s2 - a.nsel * ym[i] * ymm - ymm * s1c[i] - ym[i] * s1cm;
         G[(size_t)n * (n + 1) / 2 + i] = s1c[i];   // ones row: sum_sel Bf(p_i)
     }

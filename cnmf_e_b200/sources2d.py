@@ -270,6 +270,7 @@ class Sources2D:
             L.check(self._lib.cnmfe_set_sn(self._h, _ptr(np.asfortranarray(self.P["sn"], dtype=np.float64))))
         jc = np.ascontiguousarray(INDc.indptr, dtype=np.int64)
         ir = np.ascontiguousarray(INDc.indices, dtype=np.int64)
+        self._ind_jc, self._ind_ir = jc, ir
         L.check(self._lib.cnmfe_set_search(self._h, INDc.shape[1], _ptr(jc), _ptr(ir)))
         L.check(self._lib.cnmfe_update_spatial(self._h))
         if sync_host:
@@ -301,6 +302,23 @@ class Sources2D:
         L.check(self._lib.cnmfe_update_temporal_finish(self._h))
         if sync_host:
             self.pull_temporal()
+
+    def pull_spatial(self):
+        """obj.A from the device (values on the search pattern last given to update_spatial_parallel)."""
+        jc, ir = self._ind_jc, self._ind_ir
+        vals = np.zeros(ir.size)
+        L.check(self._lib.cnmfe_get_spatial(self._h, _ptr(vals)))
+        A_new = sp.csc_matrix((vals, ir.copy(), jc.copy()), shape=(self.d1 * self.d2, jc.size - 1))
+        A_new.eliminate_zeros()
+        self.A = A_new
+
+    def exchange_spatial(self):
+        """Multi-GPU: every rank solved the rows of its own patches; one all-reduce (disjoint supports => a gather) of
+        the values on the search pattern gives every rank the full new A."""
+        vals = np.zeros(self._ind_ir.size)
+        L.check(self._lib.cnmfe_get_spatial(self._h, _ptr(vals)))
+        vals = self._allreduce_sum(vals)
+        L.check(self._lib.cnmfe_set_spatial(self._h, _ptr(vals)))
 
     def pull_temporal(self):
         K = self.A.shape[1]

@@ -123,6 +123,9 @@ int cnmfe_update_background(cnmfe_ctx* ctx);
 int cnmfe_update_spatial(cnmfe_ctx* ctx);
 /* A on the search pattern: values aligned with (IND_jc, IND_ir) given to cnmfe_set_search */
 int cnmfe_get_spatial(cnmfe_ctx* ctx, double* A_on_IND);
+/* replace obj.A by values on the search pattern (e.g. after the cross-GPU exchange of the patches' rows, or after
+ * post_process_spatial on the host); obj.C on the device is untouched */
+int cnmfe_set_spatial(cnmfe_ctx* ctx, const double* A_on_IND);
 /* update_temporal_parallel(obj, use_parallel, use_c_hat=true) (@Sources2D/update_temporal_parallel.m:1).
  * phase 1: per-patch HALS_temporal -> energy-weighted sums; phase 2 (after an optional cross-GPU all-reduce of the
  * buffers exposed by cnmfe_temporal_merge_buffers): C_raw = num/den, deconvTemporal (deconvTemporal.m:1). */
@@ -141,6 +144,13 @@ int cnmfe_timer_end(cnmfe_ctx* ctx, float* ms);
 /* per-phase device time of the last update call (ms): [0] gram (second moments), [1] ring assemble+solve,
  * [2] projections, [3] spatial solve, [4] temporal sweeps, [5] deconvTemporal, [6] other */
 int cnmfe_last_phase_ms(cnmfe_ctx* ctx, float* ms7);
+
+/* ---- diagnostics (used by tests/ and bench.py) ---------------------------------------------------------------- */
+/* banded second moments S2[q][id] (nr_block*nc_block x ND doubles, ND = 2rr(4rr+1)+2rr+1) of block ipatch computed by
+ * the tcgen05 kernel (use_tensor=1) or the exact SIMT kernel (0); entries whose neighbour is outside the block are 0 */
+int cnmfe_debug_second_moments(cnmfe_ctx* ctx, int ipatch, int use_tensor, double* out);
+/* 1 if the last cnmfe_update_background used the tensor-core kernel for the second moments */
+int cnmfe_last_gram_was_tensor(cnmfe_ctx* ctx);
 
 #ifdef __cplusplus
 }
