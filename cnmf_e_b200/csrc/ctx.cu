@@ -642,7 +642,14 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         CNMFE_CUDA_OK(cudaMemcpyAsync(act.data(), d_active, P.dp, cudaMemcpyDeviceToHost, c->st));
         CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
         std::vector<int> alist;
-        for (int p = 0; p < P.dp; ++p) if (act[p]) alist.push_back(p);
+        // 16 x 16 pixel tiles: concurrently solved pixels share their ring rows of the moment table in L2
+        for (int tc0 = 0; tc0 < P.nc; tc0 += 16)
+            for (int tr0 = 0; tr0 < P.nr; tr0 += 16)
+                for (int cc = tc0; cc < std::min(P.nc, tc0 + 16); ++cc)
+                    for (int rr_ = tr0; rr_ < std::min(P.nr, tr0 + 16); ++rr_) {
+                        int p = cc * P.nr + rr_;
+                        if (act[p]) alist.push_back(p);
+                    }
         phase_end(c, 6);
         if (alist.empty()) continue;
         TAKE_OR_FAIL(d_alist, to_dev(c, alist));
@@ -682,7 +689,8 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         a.nsel = nsel; a.a_ptr = d_ptr; a.a_col = d_col; a.a_val = d_val; a.N = d_N; a.K = Kb; a.Csum = d_Csum;
         a.active = d_active; a.active_list = d_alist; a.n_active = (int)alist.size(); a.W = P.W; a.db = (size_t)P.db; a.ND = ND;
         const int NMAX = c->nnb + 1;
-        size_t smem = ((size_t)NMAX * (NMAX + 1) / 2 + 3 * (size_t)NMAX) * 8 + 4 * (size_t)NMAX * 4 + 64;
+        size_t smem = ((size_t)(NMAX + 1) * (NMAX + 2) / 2 + 128 + 2 * (size_t)(NMAX + 1) +
+                       2 * (size_t)(NMAX + 1) * RING_KSET + RING_KSET) * 8 + (6 * (size_t)(NMAX + 1) + RING_KALL) * 4 + 64;
         CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LAUNCH(ring_solve_kernel, (unsigned)alist.size(), RING_SOLVE_THREADS, smem, c->st, a);
         CNMFE_CUDA_OK(cudaGetLastError());

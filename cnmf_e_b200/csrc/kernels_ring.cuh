@@ -176,29 +176,83 @@ struct RingSolveArgs {
     size_t db, ND;
 };
 
-#define RING_SOLVE_THREADS 128
+#define RING_SOLVE_THREADS 256
+#define RING_KSET 16
+#define RING_KALL 128
 // One CTA per active patch pixel: assemble the (n+1)x(n+1) normal equations, ridge, Cholesky, write weights.
 // fit_ring_model.m:92-108:  X=[Bf(ring,:);1]; w=(X*X'+1e-5*trace(X*X')*I)\(X*y'); W(m,ring)=w(1:end-1)+1e-100
-__global__ void __launch_bounds__(RING_SOLVE_THREADS) ring_solve_kernel(RingSolveArgs a) {
+//
+// The lower triangle of the AUGMENTED matrix [G; rhs'] (row n1 = right-hand side, so the forward substitution falls
+// out of the factorisation) lives in REGISTERS: 256 threads form a 16 x 16 grid, thread (ti,tj) owns the elements
+// (i, j) = (ti + 16a, tj + 16b), b <= a < 8.  Each elimination step broadcasts column k through shared memory and
+// every thread updates its own 36 registers; the step is templated on k/16 so finished register blocks are skipped.
+struct RingRegs { double g[8][8]; };
+
+template <int KA>
+__device__ __forceinline__ void ring_chol_block(RingRegs& R, int n1, int ti, int tj, double* colk, double* s_d) {
+    const int kend = min(16 * KA + 15, n1 - 1);
+    for (int k = 16 * KA; k <= kend; ++k) {
+        const int kr = k & 15;
+        if (ti == kr && tj == kr) {   // LAPACK dpotf2: ajj = sqrt(ajj); scale the column by 1/ajj
+            const double d = sqrt(R.g[KA][KA]);
+            s_d[0] = d;
+            s_d[1] = 1.0 / d;
+        }
+        __syncthreads();
+        if (tj == kr) {
+            const double rinv = s_d[1];
+#pragma unroll
+            for (int a = KA; a < 8; ++a) {
+                const int i = ti + 16 * a;
+                if (i > k && i <= n1) {
+                    double v = R.g[a][KA] * rinv;
+                    R.g[a][KA] = v;
+                    colk[i] = v;
+                }
+            }
+            if (ti == kr) R.g[KA][KA] = s_d[0];
+        }
+        __syncthreads();
+        double ci[8], cj[8];
+#pragma unroll
+        for (int a = KA; a < 8; ++a) {
+            const int i = ti + 16 * a, j = tj + 16 * a;
+            ci[a] = (i > k && i <= n1) ? colk[i] : 0.0;
+            cj[a] = (j > k && j < n1) ? colk[j] : 0.0;
+        }
+#pragma unroll
+        for (int a = KA; a < 8; ++a)
+#pragma unroll
+            for (int b = KA; b <= a; ++b) R.g[a][b] = fma(-ci[a], cj[b], R.g[a][b]);
+    }
+}
+
+__global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingSolveArgs a) {
     extern __shared__ double smem[];
     const RingGeom& g = a.g;
     const int dp = g.nr * g.nc;
     const int p = a.active_list[blockIdx.x];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
     const int pr = p % g.nr + g.pr_off, pc = p / g.nr + g.pc_off;
     const size_t qm = (size_t)pc * g.nrb + pr;
-    // shared layout
     const int NMAX = g.nnb + 1;
-    double* G = smem;                                   // packed lower, NMAX*(NMAX+1)/2
-    double* rhs = G + (size_t)NMAX * (NMAX + 1) / 2;    // NMAX
-    double* ym = rhs + NMAX;                            // NMAX  (Ymean of ring pixels)
-    double* s1c = ym + NMAX;                            // NMAX  (centred S1)
-    int* qi = reinterpret_cast<int*>(s1c + NMAX);       // NMAX  block pixel index
-    int* slot = qi + NMAX;                              // NMAX  ring slot
-    int* sdr = slot + NMAX;                             // NMAX
-    int* sdc = sdr + NMAX;                              // NMAX
-    __shared__ int s_n;
-    __shared__ double s_tr;
+    // shared layout
+    double* L = smem;                                         // packed lower (after the factorisation), (NMAX+1)(NMAX+2)/2
+    double* colk = L + (size_t)(NMAX + 1) * (NMAX + 2) / 2;   // 128
+    double* ym = colk + 128;                                  // NMAX+1   (index n = the centre pixel m)
+    double* s1c = ym + NMAX + 1;                              // NMAX+1
+    double* Ar = s1c + NMAX + 1;                              // (NMAX+1) * RING_KSET
+    double* Nr = Ar + (size_t)(NMAX + 1) * RING_KSET;         // (NMAX+1) * RING_KSET
+    double* cs = Nr + (size_t)(NMAX + 1) * RING_KSET;         // RING_KSET
+    int* qi = reinterpret_cast<int*>(cs + RING_KSET);         // NMAX+1  block pixel index (index n = m)
+    int* slot = qi + NMAX + 1;
+    int* sdr = slot + NMAX + 1;                               // index n: 0
+    int* sdc = sdr + NMAX + 1;
+    int* kall = sdc + NMAX + 1;                               // RING_KALL
+    int* ap0 = kall + RING_KALL;                              // NMAX+1  A-row extents of the ring pixels / centre
+    int* ap1 = ap0 + NMAX + 1;
+    __shared__ int s_n, s_nk;
+    __shared__ double s_tr, s_d[2];
     if (tid == 0) {
         int n = 0;
         for (int i = 0; i < g.nnb; ++i) {
@@ -208,120 +262,167 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS) ring_solve_kernel(RingSolv
             qi[n] = c2 * g.nrb + r2; slot[n] = i; sdr[n] = a.off_r[i]; sdc[n] = a.off_c[i];
             ++n;
         }
+        qi[n] = (int)qm; sdr[n] = 0; sdc[n] = 0;
         s_n = n;
     }
     __syncthreads();
     const int n = s_n, n1 = n + 1;
-    const double ymm = a.Ymean[qm];
-    const double s1cm = a.S1[qm] - a.nsel * ymm;
-    for (int i = tid; i < n; i += blockDim.x) {
+    for (int i = tid; i <= n; i += blockDim.x) {
         double y = a.Ymean[qi[i]];
         ym[i] = y;
         s1c[i] = a.S1[qi[i]] - a.nsel * y;
+        ap0[i] = a.a_ptr[qi[i]];
+        ap1[i] = a.a_ptr[qi[i] + 1];
     }
     __syncthreads();
-    // --- moments of the centred video: S2c(p,q) = S2 - Ybar_q S1_p - Ybar_p S1_q + nsel Ybar_p Ybar_q
-    //     = S2 - nsel*Ybar_p*Ybar_q - Ybar_q*S1c_p - Ybar_p*S1c_q   with S1c = S1 - nsel*Ybar
-    const int npair = n * (n + 1) / 2;
-    for (int e = tid; e < npair; e += blockDim.x) {
-        int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-        while ((i + 1) * (i + 2) / 2 <= e) ++i;
-        while (i * (i + 1) / 2 > e) --i;
-        int j = e - i * (i + 1) / 2;   // j <= i
-        int ddr = sdr[i] - sdr[j], ddc = sdc[i] - sdc[j];   // displacement from p_j to p_i
-        double s2;
-        if (ddc > 0 || (ddc == 0 && ddr >= 0)) s2 = a.S2[(size_t)qi[j] * a.ND + ring_disp_id(ddr, ddc, g.rr)];
-        else s2 = a.S2[(size_t)qi[i] * a.ND + ring_disp_id(-ddr, -ddc, g.rr)];
-        G[e] = s2 - a.nsel * ym[i] * ym[j] - ym[j] * s1c[i] - ym[i] * s1c[j];
-    }
-    for (int i = tid; i < n; i += blockDim.x) {
-        // rhs_i = Cov(p_i, m): displacement from m to p_i is (sdr, sdc)
-        int ddr = sdr[i], ddc = sdc[i];
-        double s2;
-        if (ddc > 0 || (ddc == 0 && ddr >= 0)) s2 = a.S2[qm * a.ND + ring_disp_id(ddr, ddc, g.rr)];
-        else s2 = a.S2[(size_t)qi[i] * a.ND + ring_disp_id(-ddr, -ddc, g.rr)];
-        rhs[i] = s2 - a.nsel * ym[i] * ymm - ymm * s1c[i] - ym[i] * s1cm;
-        G[(size_t)n * (n + 1) / 2 + i] = s1c[i];   // ones row: sum_sel Bf(p_i)
-    }
-    if (tid == 0) {
-        G[(size_t)n * (n + 1) / 2 + n] = a.nsel;
-        rhs[n] = s1cm;
-    }
-    __syncthreads();
-    // --- neuron corrections (sequential over sparse entries; threads over the other index)
-    const int K = a.K;
-    for (int x = 0; x < n; ++x) {
-        int e0 = a.a_ptr[qi[x]], e1 = a.a_ptr[qi[x] + 1];
-        for (int e = e0; e < e1; ++e) {
-            int k = a.a_col[e];
-            double av = a.a_val[e];
-            for (int y = tid; y < n; y += blockDim.x) {
-                double nv = a.N[(size_t)qi[y] * K + k];
-                int hi = x > y ? x : y, lo = x > y ? y : x;
-                double f = (x == y) ? 2.0 : 1.0;
-                G[(size_t)hi * (hi + 1) / 2 + lo] -= f * av * nv;
+    // --- assemble into registers.  Rows 0..n-1: ring pixels; row n: ones; row n1: right-hand side (pixel m = index n
+    //     of the qi/ym/s1c arrays).  Cov(x, y) of the centred video for "pixel indices" x, y in [0, n]:
+    //     S2c = S2 - nsel*Yb_x*Yb_y - Yb_y*S1c_x - Yb_x*S1c_y,  S1c = S1 - nsel*Yb
+    RingRegs R;
+    // address of the raw second moment of "pixel indices" (x, y) (canonical orientation chosen branch-free)
+    auto s2ptr = [&](int x, int y) -> const double* {
+        int ddr = sdr[x] - sdr[y], ddc = sdc[x] - sdc[y];   // displacement from pixel y to pixel x
+        bool canon = (ddc > 0) || (ddc == 0 && ddr >= 0);
+        int base = canon ? qi[y] : qi[x];
+        int id = canon ? ring_disp_id(ddr, ddc, g.rr) : ring_disp_id(-ddr, -ddc, g.rr);
+        return a.S2 + (size_t)base * a.ND + id;
+    };
+#pragma unroll
+    for (int aa = 0; aa < 8; ++aa) {
+        const int i = ti + 16 * aa;
+        const double* ptr[8];
+        double raw[8];
+#pragma unroll
+        for (int bb = 0; bb <= aa; ++bb) {
+            const int j = tj + 16 * bb;
+            const bool pair = (j <= i) && (j < n) && (i < n || i == n1);
+            ptr[bb] = pair ? s2ptr(i < n ? i : n, j) : a.S2;
+        }
+#pragma unroll
+        for (int bb = 0; bb <= aa; ++bb) raw[bb] = __ldg(ptr[bb]);
+#pragma unroll
+        for (int bb = 0; bb <= aa; ++bb) {
+            const int j = tj + 16 * bb;
+            double v = 0.0;
+            if (j <= i && i <= n1 && j <= n) {
+                const int x = (i < n) ? i : n;   // row n1 (rhs) pairs the centre pixel (index n) with p_j
+                if ((i < n || i == n1) && j < n) v = raw[bb] - a.nsel * ym[x] * ym[j] - ym[j] * s1c[x] - ym[x] * s1c[j];
+                else if (i == n) v = (j < n) ? s1c[j] : a.nsel;   // ones row
+                else v = s1c[n];                                    // i == n1, j == n: sum Bf(m)
             }
-            if (tid == 0) {
-                rhs[x] -= av * a.N[qm * K + k];                       // - A[p_x,:].N[m,:]
-                G[(size_t)n * (n + 1) / 2 + x] -= av * a.Csum[k];     // ones row
-            }
-            __syncthreads();
+            R.g[aa][bb] = v;
         }
     }
+    // --- neuron corrections: Cov_Bf = Cov_Y - N_x.A_y - A_x.N_y ; sum_sel Bf(x) = S1c_x - A_x.Csum
+    // distinct neurons touching the ring pixels / the centre (deterministic scan order), handled RING_KSET at a time
+    if (tid == 0) {
+        int nall = 0;
+        for (int y = 0; y <= n; ++y)
+            for (int e = ap0[y]; e < ap1[y]; ++e) {
+                int k = a.a_col[e];
+                bool dup = false;
+                for (int z = 0; z < nall; ++z) if (kall[z] == k) dup = true;
+                if (!dup && nall < RING_KALL) kall[nall++] = k;
+            }
+        s_nk = nall;
+    }
+    __syncthreads();
+    const int nall = s_nk;
+    for (int kbase = 0; kbase < nall; kbase += RING_KSET) {
+        const int* kset = kall + kbase;
+        __syncthreads();
+        const int nk = min(RING_KSET, nall - kbase);
+        for (int x = tid; x < (n + 1) * RING_KSET; x += blockDim.x) { Ar[x] = 0.0; }
+        for (int x = tid; x < (n + 1) * nk; x += blockDim.x) {
+            int y = x / nk, z = x - y * nk;
+            Nr[y * RING_KSET + z] = a.N[(size_t)qi[y] * a.K + kset[z]];
+        }
+        if (tid < nk) cs[tid] = a.Csum[kset[tid]];
+        __syncthreads();
+        for (int y = tid; y <= n; y += blockDim.x)
+            for (int e = ap0[y]; e < ap1[y]; ++e) {
+                int k = a.a_col[e];
+                for (int z = 0; z < nk; ++z) if (kset[z] == k) Ar[y * RING_KSET + z] = a.a_val[e];
+            }
+        __syncthreads();
+#pragma unroll
+        for (int aa = 0; aa < 8; ++aa)
+#pragma unroll
+            for (int bb = 0; bb <= aa; ++bb) {
+                const int i = ti + 16 * aa, j = tj + 16 * bb;
+                if (j <= i && i <= n1 && j <= n) {
+                    double c = 0.0;
+                    if (i < n) {
+                        for (int z = 0; z < nk; ++z)
+                            c += Ar[j * RING_KSET + z] * Nr[i * RING_KSET + z] + Ar[i * RING_KSET + z] * Nr[j * RING_KSET + z];
+                    } else if (i == n) {
+                        if (j < n) for (int z = 0; z < nk; ++z) c += Ar[j * RING_KSET + z] * cs[z];
+                    } else {
+                        if (j < n) {
+                            for (int z = 0; z < nk; ++z)
+                                c += Ar[n * RING_KSET + z] * Nr[j * RING_KSET + z] + Ar[j * RING_KSET + z] * Nr[n * RING_KSET + z];
+                        } else {
+                            for (int z = 0; z < nk; ++z) c += Ar[n * RING_KSET + z] * cs[z];
+                        }
+                    }
+                    R.g[aa][bb] -= c;
+                }
+            }
+    }
+    // --- ridge: trace over the n1 x n1 system (diagonal owners are the threads with ti == tj)
     {
-        int e0 = a.a_ptr[qm], e1 = a.a_ptr[qm + 1];
-        for (int e = e0; e < e1; ++e) {
-            int k = a.a_col[e];
-            double av = a.a_val[e];
-            for (int y = tid; y < n; y += blockDim.x) rhs[y] -= av * a.N[(size_t)qi[y] * K + k];   // - N[p_y,:].A[m,:]
-            if (tid == 0) rhs[n] -= av * a.Csum[k];
-            __syncthreads();
-        }
-    }
-    // --- ridge
-    if (tid == 0) {
         double tr = 0.0;
-        for (int i = 0; i < n1; ++i) tr += G[(size_t)i * (i + 1) / 2 + i];
-        s_tr = tr * 1e-5;
-    }
-    __syncthreads();
-    for (int i = tid; i < n1; i += blockDim.x) G[(size_t)i * (i + 1) / 2 + i] += s_tr;
-    __syncthreads();
-    // --- Cholesky (packed lower, right-looking)
-    for (int k = 0; k < n1; ++k) {
-        double dkk = sqrt(G[(size_t)k * (k + 1) / 2 + k]);
-        __syncthreads();
-        if (tid == 0) G[(size_t)k * (k + 1) / 2 + k] = dkk;
-        for (int i = k + 1 + tid; i < n1; i += blockDim.x) G[(size_t)i * (i + 1) / 2 + k] /= dkk;
-        __syncthreads();
-        const int m = n1 - k - 1;
-        const int ne = m * (m + 1) / 2;
-        for (int e = tid; e < ne; e += blockDim.x) {
-            int ia = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-            while ((ia + 1) * (ia + 2) / 2 <= e) ++ia;
-            while (ia * (ia + 1) / 2 > e) --ia;
-            int jb = e - ia * (ia + 1) / 2;
-            int i = k + 1 + ia, j = k + 1 + jb;
-            G[(size_t)i * (i + 1) / 2 + j] -= G[(size_t)i * (i + 1) / 2 + k] * G[(size_t)j * (j + 1) / 2 + k];
+        if (ti == tj) {
+#pragma unroll
+            for (int aa = 0; aa < 8; ++aa) if (ti + 16 * aa < n1) tr += R.g[aa][aa];
         }
         __syncthreads();
+        if (tid == 0) s_tr = 0.0;
+        __syncthreads();
+        if (ti == tj) atomicAdd(&s_tr, tr);
+        __syncthreads();
+        const double lam = s_tr * 1e-5;
+        if (ti == tj) {
+#pragma unroll
+            for (int aa = 0; aa < 8; ++aa) if (ti + 16 * aa < n1) R.g[aa][aa] += lam;
+        }
     }
-    // --- forward / backward substitution
-    for (int k = 0; k < n1; ++k) {
-        if (tid == 0) rhs[k] /= G[(size_t)k * (k + 1) / 2 + k];
-        __syncthreads();
-        double zk = rhs[k];
-        for (int i = k + 1 + tid; i < n1; i += blockDim.x) rhs[i] -= G[(size_t)i * (i + 1) / 2 + k] * zk;
-        __syncthreads();
+    // --- Cholesky of the augmented matrix
+    ring_chol_block<0>(R, n1, ti, tj, colk, s_d);
+    if (n1 > 16) ring_chol_block<1>(R, n1, ti, tj, colk, s_d);
+    if (n1 > 32) ring_chol_block<2>(R, n1, ti, tj, colk, s_d);
+    if (n1 > 48) ring_chol_block<3>(R, n1, ti, tj, colk, s_d);
+    if (n1 > 64) ring_chol_block<4>(R, n1, ti, tj, colk, s_d);
+    if (n1 > 80) ring_chol_block<5>(R, n1, ti, tj, colk, s_d);
+    if (n1 > 96) ring_chol_block<6>(R, n1, ti, tj, colk, s_d);
+    if (n1 > 112) ring_chol_block<7>(R, n1, ti, tj, colk, s_d);
+    __syncthreads();
+    // --- dump L, back substitution L' w = z (z = row n1) by one warp
+#pragma unroll
+    for (int aa = 0; aa < 8; ++aa)
+#pragma unroll
+        for (int bb = 0; bb <= aa; ++bb) {
+            const int i = ti + 16 * aa, j = tj + 16 * bb;
+            if (j <= i && i <= n1 && j < n1) L[(size_t)i * (i + 1) / 2 + j] = R.g[aa][bb];
+        }
+    __syncthreads();
+    double* rdiag = ym;   // ym is dead after the assembly: reciprocal pivots
+    for (int i = tid; i < n1; i += blockDim.x) rdiag[i] = 1.0 / L[(size_t)i * (i + 1) / 2 + i];
+    __syncthreads();
+    if (tid < 32) {
+        for (int i = tid; i < n1; i += 32) colk[i] = L[(size_t)n1 * (n1 + 1) / 2 + i];
+        __syncwarp();
+        for (int k = n1 - 1; k >= 0; --k) {
+            const double* row = L + (size_t)k * (k + 1) / 2;
+            double wk = colk[k] * rdiag[k];
+            __syncwarp();
+            if (tid == 0) colk[k] = wk;
+            for (int i = tid; i < k; i += 32) colk[i] -= row[i] * wk;
+            __syncwarp();
+        }
     }
-    for (int k = n1 - 1; k >= 0; --k) {
-        if (tid == 0) rhs[k] /= G[(size_t)k * (k + 1) / 2 + k];
-        __syncthreads();
-        double wk = rhs[k];
-        for (int i = tid; i < k; i += blockDim.x) rhs[i] -= G[(size_t)k * (k + 1) / 2 + i] * wk;
-        __syncthreads();
-    }
-    for (int i = tid; i < n; i += blockDim.x) a.W[(size_t)slot[i] * dp + p] = rhs[i] + 1e-100;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) a.W[(size_t)slot[i] * dp + p] = colk[i] + 1e-100;
 }
 
 // uniform ring initialisation (initComponents_parallel.m:213-236): W[i][p] = 1/#valid neighbours

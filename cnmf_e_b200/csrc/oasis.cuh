@@ -358,12 +358,100 @@ __device__ void block_oasis_ar1_solution(const TraceWS& ws, int n, double g, int
     __syncthreads();
 }
 
+// Cold-start scan (every incoming pool is a singleton, oasisAR1.m:46-50) by ONE WARP with exact speculation:
+// the next 32 elements are tentatively absorbed into the top pool -- the running (v, w) are accumulated in the
+// reference's sequential order -- then all 32 forward / back-track tests are evaluated in parallel and everything up
+// to the first event (a new pool is accepted, or a back-track merge is needed) is committed.  Decisions and values are
+// identical to the element-by-element loop; only the divisions/table look-ups are parallelised.
+__device__ int warp_oasis_ar1_cold(const double* __restrict__ y, int T, double g, double lam, double smin,
+                                   TraceWS& ws) {
+    const int lane = threadIdx.x & 31;
+    const double pen = lam * (1.0 - g);
+    const double* gp = ws.gp;
+    double* pv = ws.pv; double* pw = ws.pw; int* pt = ws.pt; int* pl = ws.pl;
+    auto val = [&](int idx) { return (idx == T - 1) ? (y[idx] - lam) : (y[idx] - pen); };
+    int top = 0, i = 1, lt = 1;
+    double vt = val(0), wt = 1.0;
+    if (lane == 0) pt[0] = 0;
+    double rp = 0.0;   // back-track threshold of the pool below the top (valid when top > 0)
+    while (i < T) {
+        const int m = min(32, T - i);
+        const int idx = i + lane;
+        const bool in = lane < m;
+        const double yj = in ? val(idx) : 0.0;
+        const double e1 = in ? gp[lt + lane] : 0.0;
+        const double e2 = in ? gp[2 * (lt + lane)] : 0.0;
+        const double aj = yj * e1;
+        double v = vt, w = wt, vj = 0.0, wj = 1.0, vj1 = 0.0, wj1 = 1.0;
+        for (int mm = 0; mm < m; ++mm) {
+            const double am = __shfl_sync(0xffffffffu, aj, mm);
+            const double bm = __shfl_sync(0xffffffffu, e2, mm);
+            if (lane == mm) { vj = v; wj = w; }
+            v = v + am;
+            w = w + bm;
+            if (lane == mm) { vj1 = v; wj1 = w; }
+        }
+        const bool fwd = in && (yj >= vj / wj * e1 + smin);
+        const bool back = in && !fwd && (top > 0) && (vj1 / wj1 < rp);
+        const unsigned mf = __ballot_sync(0xffffffffu, fwd), mb = __ballot_sync(0xffffffffu, back);
+        const unsigned ev = mf | mb;
+        if (ev == 0u) {
+            vt = v; wt = w; lt += m; i += m;
+            continue;
+        }
+        const int e = __ffs(ev) - 1;
+        if (mf & (1u << e)) {
+            // elements 0..e-1 absorbed, element e starts a new pool
+            vt = __shfl_sync(0xffffffffu, vj, e);
+            wt = __shfl_sync(0xffffffffu, wj, e);
+            lt += e;
+            if (lane == 0) { pv[top] = vt; pw[top] = wt; pl[top] = lt; pt[top + 1] = i + e; }
+            rp = fmax(0.0, vt / wt * gp[lt]) + smin;
+            ++top;
+            vt = __shfl_sync(0xffffffffu, yj, e);
+            wt = 1.0; lt = 1;
+            i += e + 1;
+        } else {
+            // elements 0..e absorbed, then back-track (oasisAR1.m:82-95)
+            vt = __shfl_sync(0xffffffffu, vj1, e);
+            wt = __shfl_sync(0xffffffffu, wj1, e);
+            lt += e + 1;
+            i += e + 1;
+            __syncwarp();
+            while (top > 0) {
+                const double vp = pv[top - 1], wp = pw[top - 1];
+                const int lp = pl[top - 1];
+                if (vt / wt < fmax(0.0, vp / wp * gp[lp]) + smin) {
+                    vt = vp + vt * gp[lp];
+                    wt = wp + wt * gp[2 * lp];
+                    lt = lp + lt;
+                    --top;
+                } else break;
+            }
+            if (top > 0) {
+                const double vp = pv[top - 1], wp = pw[top - 1];
+                rp = fmax(0.0, vp / wp * gp[pl[top - 1]]) + smin;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { pv[top] = vt; pw[top] = wt; pl[top] = lt; }
+    __syncwarp();
+    return top + 1;
+}
+
 // Cold oasisAR1(y, g, lam, smin): pools + solution into ws.c / ws.s.  Returns pool count.
 __device__ int block_oasis_ar1(const double* y, int T, double g, double lam, double smin, TraceWS& ws,
                                BlockShared* sh) {
     block_pow_table(g, T, ws.gp);
-    block_init_pools_ar1(y, T, g, lam, ws);
-    int n = block_oasis_ar1_run(ws, T, smin, sh);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int n = warp_oasis_ar1_cold(y, T, g, lam, smin, ws);
+        if (threadIdx.x == 0) sh->ibc[2] = n;
+    }
+    __syncthreads();
+    const int n = sh->ibc[2];
+    __syncthreads();
     block_oasis_ar1_solution(ws, n, g, T, ws.c, ws.s);
     return n;
 }
