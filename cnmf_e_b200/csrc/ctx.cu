@@ -508,7 +508,7 @@ extern "C" int cnmfe_set_ring(cnmfe_ctx* c, int ip, const double* W, const doubl
         for (int i = 0; i < c->nnb; ++i) {
             int fr = g.pr_off + c->off_r[i] + g.br0, fc = g.pc_off + c->off_c[i] + g.bc0;
             if (fr < 0 || fr >= g.d1 || fc < 0 || fc >= g.d2) continue;
-            double v = W[(size_t)i * P.dp];
+            double v = W[i];
             if (!have) { v0 = v; have = true; } else if (v != v0) uniform = false;
         }
     }

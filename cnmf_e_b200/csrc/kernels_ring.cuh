@@ -122,7 +122,7 @@ __global__ void ring_active_b0_kernel(RingGeom g, const int* __restrict__ off_r,
             int r2 = r + off_r[i], c2 = c + off_c[i];
             int fr = r2 + g.br0, fc = c2 + g.bc0;
             if (fr < 0 || fr >= g.d1 || fc < 0 || fc >= g.d2) continue;
-            acc += fabs(W[(size_t)i * dp + p]) * sumA[(size_t)c2 * g.nrb + r2];
+            acc += fabs(W[(size_t)p * g.nnb + i]) * sumA[(size_t)c2 * g.nrb + r2];
         }
     }
     active[p] = (first_run || acc > 0.0) ? 1 : 0;
@@ -142,7 +142,7 @@ __global__ void ring_pmax_kernel(RingGeom g, const int* __restrict__ off_r, cons
         for (int i = 0; i < g.nnb; ++i) {
             int fr = r + off_r[i] + g.br0, fc = c + off_c[i] + g.bc0;
             if (fr < 0 || fr >= g.d1 || fc < 0 || fc >= g.d2) continue;
-            if (W[(size_t)i * dp + p] > 0.0) ++cnt;
+            if (W[(size_t)p * g.nnb + i] > 0.0) ++cnt;
         }
     }
     for (int o = 16; o > 0; o >>= 1) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o));
@@ -172,7 +172,7 @@ struct RingSolveArgs {
     const double* N; int K; const double* Csum;
     const unsigned char* active;
     const int* active_list; int n_active;
-    double* W;   // [nnb][dp]
+    double* W;   // [dp][nnb]
     size_t db, ND;
 };
 
@@ -345,12 +345,23 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
                 for (int z = 0; z < nk; ++z) if (kset[z] == k) Ar[y * RING_KSET + z] = a.a_val[e];
             }
         __syncthreads();
+        // rows/columns of this thread that carry neuron entries (index n = centre pixel, needed by row n1)
+        unsigned rmask = 0u, cmask = 0u;
+#pragma unroll
+        for (int aa = 0; aa < 8; ++aa) {
+            int i = ti + 16 * aa, j = tj + 16 * aa;
+            if (i == n1) i = n;
+            if (i <= n && ap1[i] > ap0[i]) rmask |= 1u << aa;
+            if (j <= n && ap1[j] > ap0[j]) cmask |= 1u << aa;
+        }
+        const bool centre_has = ap1[n] > ap0[n];
 #pragma unroll
         for (int aa = 0; aa < 8; ++aa)
 #pragma unroll
             for (int bb = 0; bb <= aa; ++bb) {
                 const int i = ti + 16 * aa, j = tj + 16 * bb;
-                if (j <= i && i <= n1 && j <= n) {
+                const bool touch = ((rmask >> aa) & 1u) || ((cmask >> bb) & 1u) || (i == n1 && centre_has);
+                if (touch && j <= i && i <= n1 && j <= n) {
                     double c = 0.0;
                     if (i < n) {
                         for (int z = 0; z < nk; ++z)
@@ -422,7 +433,7 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
         }
     }
     __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) a.W[(size_t)slot[i] * dp + p] = colk[i] + 1e-100;
+    for (int i = tid; i < n; i += blockDim.x) a.W[(size_t)p * g.nnb + slot[i]] = colk[i] + 1e-100;
 }
 
 // uniform ring initialisation (initComponents_parallel.m:213-236): W[i][p] = 1/#valid neighbours
@@ -441,7 +452,7 @@ __global__ void ring_uniform_kernel(RingGeom g, const int* __restrict__ off_r, c
     for (int i = 0; i < g.nnb; ++i) {
         int fr = r + off_r[i] + g.br0, fc = c + off_c[i] + g.bc0;
         bool ok = !(fr < 0 || fr >= g.d1 || fc < 0 || fc >= g.d2);
-        W[(size_t)i * dp + p] = ok ? v : 0.0;
+        W[(size_t)p * g.nnb + i] = ok ? v : 0.0;
     }
 }
 

@@ -47,7 +47,7 @@ spatial_U_kernel(RingGeom g, const int* __restrict__ off_r, const int* __restric
             int r2 = r + off_r[i], c2 = c + off_c[i];
             int fr = r2 + g.br0, fc = c2 + g.bc0;
             if (fr < 0 || fr >= g.d1 || fc < 0 || fc >= g.d2) continue;
-            acc = fma(W[(size_t)i * dp + p], D[((size_t)c2 * g.nrb + r2) * Ks + k], acc);
+            acc = fma(W[(size_t)p * g.nnb + i], D[((size_t)c2 * g.nrb + r2) * Ks + k], acc);
         }
         acc = warp_sum(acc);
         if (lane == 0) {
@@ -190,7 +190,7 @@ __global__ void temporal_build_negWtA_kernel(RingGeom g, const int* __restrict__
         size_t qc = (size_t)c2 * g.nrb + r2;
         int e0 = a_ptr[qc], e1 = a_ptr[qc + 1];
         if (e0 == e1) continue;
-        double w = W[(size_t)i * dp + ((size_t)pc * g.nr + pr)];
+        double w = W[((size_t)pc * g.nr + pr) * g.nnb + i];
         for (int e = e0; e < e1; ++e) B[(size_t)q * Kt + a_col[e]] -= w * a_val[e];
     }
 }

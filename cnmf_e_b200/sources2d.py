@@ -53,6 +53,17 @@ def patch_geometry(d1, d2, patch_dims, w_overlap):
     return patch_pos, block_pos
 
 
+def patch_owners(npatch, world_size):
+    """Blocked patch -> rank assignment (patches in MATLAB linear order): rank r owns a contiguous run."""
+    return np.array([(i * world_size) // npatch for i in range(npatch)], dtype=np.int64)
+
+
+def merge_temporal(num, den):
+    """C_raw = sum_p aa_p C_raw,p / sum_p aa_p with 0 -> 1 denominators (update_temporal_parallel.m:269-280)."""
+    den = np.where(den == 0, 1.0, den)
+    return num * (1.0 / den)[:, None]
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
@@ -77,7 +88,7 @@ class Sources2D:
         self.patches = [(m, n) for n in range(self.nc_patch) for m in range(self.nr_patch)]   # MATLAB linear order
         self.npatch = len(self.patches)
         # patch -> rank (blocked assignment)
-        self.owner = np.array([(i * world_size) // self.npatch for i in range(self.npatch)], dtype=np.int64)
+        self.owner = patch_owners(self.npatch, world_size)
         owned = (self.owner == rank).astype(np.uint8)
         pp = np.ascontiguousarray(np.stack([self.patch_pos[mp] for mp in self.patches]).astype(np.int32))
         bp = np.ascontiguousarray(np.stack([self.block_pos[mp] for mp in self.patches]).astype(np.int32))
@@ -197,7 +208,7 @@ class Sources2D:
             b0 = self.b0.get(i)
             if W is None and b0 is None:
                 continue
-            Wf = None if W is None else np.asfortranarray(W, dtype=np.float64)
+            Wf = None if W is None else np.ascontiguousarray(W, dtype=np.float64)   # (d_patch, nnb) C-order == nnb x d_patch col-major
             b0f = None if b0 is None else np.ascontiguousarray(b0, dtype=np.float64)
             L.check(self._lib.cnmfe_set_ring(self._h, i, _ptr(Wf), _ptr(b0f)))
 
@@ -205,7 +216,7 @@ class Sources2D:
         for i in self.owned_patches():
             p = self.patch_of(i)
             dp = (p[1] - p[0] + 1) * (p[3] - p[2] + 1)
-            W = np.zeros((dp, self.nnb), order="F")
+            W = np.zeros((dp, self.nnb))
             b0 = np.zeros(dp)
             L.check(self._lib.cnmfe_get_ring(self._h, i, _ptr(W), _ptr(b0)))
             self.W[i], self.b0[i] = W, b0

@@ -108,8 +108,9 @@ int cnmfe_set_prev(cnmfe_ctx* ctx, int K, const int64_t* A_jc, const int64_t* A_
 int cnmfe_set_search(cnmfe_ctx* ctx, int K, const int64_t* IND_jc, const int64_t* IND_ir);
 /* obj.P.sn (d1 x d2) */
 int cnmfe_set_sn(cnmfe_ctx* ctx, const double* sn);
-/* obj.W{ipatch}, obj.b0{ipatch}: ring weights in slot form, W[p + i*d_patch] = weight of patch pixel p for ring
- * offset i (cnmfe_ring_offsets); entries whose neighbour falls outside the FOV are ignored.  NULL W = uniform
+/* obj.W{ipatch}, obj.b0{ipatch}: ring weights in slot form, W[i + p*nnb] = weight of patch pixel p for ring
+ * offset i (cnmfe_ring_offsets), i.e. an nnb x d_patch column-major matrix; entries whose neighbour falls outside
+ * the FOV are ignored.  NULL W = uniform
  * initialisation (initComponents_parallel.m:213-236). */
 int cnmfe_ring_offsets(cnmfe_ctx* ctx, int* nnb, int32_t* r_shift, int32_t* c_shift);
 int cnmfe_set_ring(cnmfe_ctx* ctx, int ipatch, const double* W_slots, const double* b0);

@@ -1,0 +1,152 @@
+// cnmfe_b200_mex.cpp -- MEX gateway binding libcnmfe_b200.so (include/cnmfe_b200.h) into MATLAB.
+//
+// Build on a machine with MATLAB + the built library (cannot be compiled in the development image: no mex.h):
+//   mex -O -largeArrayDims cnmfe_b200_mex.cpp -I../include -L../cnmf_e_b200 -lcnmfe_b200
+// Conventions follow the only native file of the reference, utilities/graph_conn_comp_mex.cpp: outputs allocated with
+// mxCreate* and owned by MATLAB (:58-65), inputs const (:38-56), errors through mexErrMsgIdAndTxt (:44-53).
+//
+// Usage:  varargout = cnmfe_b200_mex(command, args...)   -- see matlab/@Sources2D/*.m for the call sites.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "mex.h"
+#include "cnmfe_b200.h"
+
+static void check(int rc, const char* where) {
+    if (rc) mexErrMsgIdAndTxt("cnmfe:b200", "%s: %s", where, cnmfe_last_error());
+}
+static cnmfe_ctx* ctx_of(const mxArray* h) {
+    if (!mxIsUint64(h) || mxGetNumberOfElements(h) != 1) mexErrMsgIdAndTxt("cnmfe:handle", "bad context handle");
+    return reinterpret_cast<cnmfe_ctx*>(*static_cast<uint64_t*>(mxGetData(h)));
+}
+// MATLAB sparse -> 0-based int64 CSC (mwIndex is already 0-based)
+static void csc_of(const mxArray* A, std::vector<int64_t>& jc, std::vector<int64_t>& ir) {
+    if (!mxIsSparse(A)) mexErrMsgIdAndTxt("cnmfe:sparse", "sparse matrix expected");
+    size_t K = mxGetN(A);
+    const mwIndex* j = mxGetJc(A);
+    const mwIndex* i = mxGetIr(A);
+    jc.assign(j, j + K + 1);
+    ir.assign(i, i + j[K]);
+}
+static double getfield_d(const mxArray* s, const char* f, double dflt) {
+    const mxArray* v = mxGetField(s, 0, f);
+    return (v && !mxIsEmpty(v)) ? mxGetScalar(v) : dflt;
+}
+static void deconv_opts_of(const mxArray* s, cnmfe_deconv_opts* o) {
+    // struct produced by deconvolveCa's own parser fields (OASIS_matlab/deconvolveCa.m:212-230)
+    cnmfe_deconv_defaults(o);
+    if (!s || mxIsEmpty(s)) return;
+    char buf[32];
+    const mxArray* v;
+    if ((v = mxGetField(s, 0, "type")) && !mxGetString(v, buf, sizeof buf)) o->type = strcmp(buf, "ar2") ? 1 : 2;
+    if ((v = mxGetField(s, 0, "method")) && !mxGetString(v, buf, sizeof buf))
+        o->method = !strcmp(buf, "foopsi") ? 0 : (!strcmp(buf, "thresholded") ? 2 : 1);
+    o->optimize_b = (int)getfield_d(s, "optimize_b", 0);
+    o->optimize_pars = (int)getfield_d(s, "optimize_pars", 0);
+    o->maxIter = (int)getfield_d(s, "maxIter", 10);
+    o->smin = getfield_d(s, "smin", 0);
+    o->lambda = getfield_d(s, "lambda", 0);
+    o->b = getfield_d(s, "b", 0);
+    o->max_tau = getfield_d(s, "max_tau", 100);
+    o->thresh_factor = getfield_d(s, "thresh_factor", 1.0);
+    o->p_noise = getfield_d(s, "p_noise", 0.9999);
+    if ((v = mxGetField(s, 0, "tau_range")) && mxGetNumberOfElements(v) == 2) {
+        o->has_tau_range = 1; o->tau_range[0] = mxGetPr(v)[0]; o->tau_range[1] = mxGetPr(v)[1];
+    }
+}
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (nrhs < 1 || !mxIsChar(prhs[0])) mexErrMsgIdAndTxt("cnmfe:usage", "cnmfe_b200_mex(command, ...)");
+    char cmd[64];
+    mxGetString(prhs[0], cmd, sizeof cmd);
+    const std::string c(cmd);
+    if (c == "create") {   // h = create(d1,d2,T,patch_pos(4 x np int32),block_pos,ring_radius,num_neighbors,device)
+        cnmfe_ctx* h = nullptr;
+        int np = (int)mxGetN(prhs[4]);
+        check(cnmfe_create(&h, (int)mxGetScalar(prhs[1]), (int)mxGetScalar(prhs[2]), (int)mxGetScalar(prhs[3]), np,
+                           (const int32_t*)mxGetData(prhs[4]), (const int32_t*)mxGetData(prhs[5]), nullptr,
+                           (int)mxGetScalar(prhs[6]), (int)mxGetScalar(prhs[7]), (int)mxGetScalar(prhs[8])), "create");
+        plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+        *static_cast<uint64_t*>(mxGetData(plhs[0])) = reinterpret_cast<uint64_t>(h);
+        mexLock();
+    } else if (c == "destroy") {
+        cnmfe_destroy(ctx_of(prhs[1]));
+        mexUnlock();
+    } else if (c == "upload_block") {   // upload_block(h, ipatch0, Yblock)  Yblock: nr_b x nc_b x T uint8/uint16
+        int dt = mxIsUint8(prhs[3]) ? 0 : (mxIsUint16(prhs[3]) ? 1 : -1);
+        if (dt < 0) mexErrMsgIdAndTxt("cnmfe:dtype", "video must be uint8 or uint16");
+        check(cnmfe_upload_block(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), mxGetData(prhs[3]), dt), "upload_block");
+    } else if (c == "set_neurons" || c == "set_prev") {   // (h, A sparse d x K, C K x T)
+        std::vector<int64_t> jc, ir;
+        csc_of(prhs[2], jc, ir);
+        int K = (int)mxGetN(prhs[2]);
+        int rc = (c == "set_neurons")
+                     ? cnmfe_set_neurons(ctx_of(prhs[1]), K, jc.data(), ir.data(), mxGetPr(prhs[2]), mxGetPr(prhs[3]))
+                     : cnmfe_set_prev(ctx_of(prhs[1]), K, jc.data(), ir.data(), mxGetPr(prhs[2]), mxGetPr(prhs[3]));
+        check(rc, cmd);
+    } else if (c == "set_search") {   // (h, IND sparse logical d x K)
+        std::vector<int64_t> jc, ir;
+        csc_of(prhs[2], jc, ir);
+        check(cnmfe_set_search(ctx_of(prhs[1]), (int)mxGetN(prhs[2]), jc.data(), ir.data()), cmd);
+    } else if (c == "set_sn") {
+        check(cnmfe_set_sn(ctx_of(prhs[1]), mxGetPr(prhs[2])), cmd);
+    } else if (c == "set_options") {   // (h, spatial_alg, maxIter, deconv_flag, bg_acceleration, deconv_options struct)
+        cnmfe_options o;
+        cnmfe_options_defaults(&o);
+        o.spatial_algorithm = (int)mxGetScalar(prhs[2]);
+        o.maxIter_temporal = (int)mxGetScalar(prhs[3]);
+        o.deconv_flag = (int)mxGetScalar(prhs[4]);
+        o.bg_acceleration = (int)mxGetScalar(prhs[5]);
+        deconv_opts_of(nrhs > 6 ? prhs[6] : nullptr, &o.deconv);
+        check(cnmfe_set_options(ctx_of(prhs[1]), &o), cmd);
+    } else if (c == "ring_offsets") {   // [r_shift, c_shift] = ring_offsets(h)
+        int nnb = 0;
+        check(cnmfe_ring_offsets(ctx_of(prhs[1]), &nnb, nullptr, nullptr), cmd);
+        plhs[0] = mxCreateNumericMatrix(1, nnb, mxINT32_CLASS, mxREAL);
+        plhs[1] = mxCreateNumericMatrix(1, nnb, mxINT32_CLASS, mxREAL);
+        check(cnmfe_ring_offsets(ctx_of(prhs[1]), &nnb, (int32_t*)mxGetData(plhs[0]), (int32_t*)mxGetData(plhs[1])), cmd);
+    } else if (c == "set_ring") {   // (h, ipatch0, Wslots (nnb x d_patch) or [], b0)
+        const double* W = mxIsEmpty(prhs[3]) ? nullptr : mxGetPr(prhs[3]);
+        const double* b0 = mxIsEmpty(prhs[4]) ? nullptr : mxGetPr(prhs[4]);
+        check(cnmfe_set_ring(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), W, b0), cmd);
+    } else if (c == "get_ring") {   // [Wslots, b0] = get_ring(h, ipatch0, nnb, d_patch)
+        mwSize nnb = (mwSize)mxGetScalar(prhs[3]), dp = (mwSize)mxGetScalar(prhs[4]);
+        plhs[0] = mxCreateDoubleMatrix(nnb, dp, mxREAL);
+        plhs[1] = mxCreateDoubleMatrix(dp, 1, mxREAL);
+        check(cnmfe_get_ring(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), mxGetPr(plhs[0]), mxGetPr(plhs[1])), cmd);
+    } else if (c == "update_background") {
+        check(cnmfe_update_background(ctx_of(prhs[1])), cmd);
+    } else if (c == "update_spatial") {   // vals = update_spatial(h, nnz(IND))  -> values on find(IND) order
+        check(cnmfe_update_spatial(ctx_of(prhs[1])), cmd);
+        plhs[0] = mxCreateDoubleMatrix((mwSize)mxGetScalar(prhs[2]), 1, mxREAL);
+        check(cnmfe_get_spatial(ctx_of(prhs[1]), mxGetPr(plhs[0])), "get_spatial");
+    } else if (c == "set_spatial") {
+        check(cnmfe_set_spatial(ctx_of(prhs[1]), mxGetPr(prhs[2])), cmd);
+    } else if (c == "update_temporal") {   // [C, C_raw, S, kernel_pars, neuron_sn] = update_temporal(h, K, T)
+        check(cnmfe_update_temporal(ctx_of(prhs[1])), cmd);
+        mwSize K = (mwSize)mxGetScalar(prhs[2]), T = (mwSize)mxGetScalar(prhs[3]);
+        plhs[0] = mxCreateDoubleMatrix(K, T, mxREAL); plhs[1] = mxCreateDoubleMatrix(K, T, mxREAL);
+        plhs[2] = mxCreateDoubleMatrix(K, T, mxREAL); plhs[3] = mxCreateDoubleMatrix(2, K, mxREAL);
+        plhs[4] = mxCreateDoubleMatrix(K, 1, mxREAL);
+        check(cnmfe_get_temporal(ctx_of(prhs[1]), mxGetPr(plhs[0]), mxGetPr(plhs[1]), mxGetPr(plhs[2]),
+                                 mxGetPr(plhs[3]), mxGetPr(plhs[4])), "get_temporal");
+    } else if (c == "deconvolve") {   // [c,s,b,pars,sn,smin,lam] = deconvolve(Y (T x N), opts struct, sn or [], pars (2 x N) or [])
+        cnmfe_deconv_opts o;
+        deconv_opts_of(prhs[2], &o);
+        mwSize T = mxGetM(prhs[1]), N = mxGetN(prhs[1]);
+        const double* sn = (nrhs > 3 && !mxIsEmpty(prhs[3])) ? mxGetPr(prhs[3]) : nullptr;
+        const double* pars = (nrhs > 4 && !mxIsEmpty(prhs[4])) ? mxGetPr(prhs[4]) : nullptr;
+        plhs[0] = mxCreateDoubleMatrix(T, N, mxREAL); plhs[1] = mxCreateDoubleMatrix(T, N, mxREAL);
+        plhs[2] = mxCreateDoubleMatrix(N, 1, mxREAL); plhs[3] = mxCreateDoubleMatrix(2, N, mxREAL);
+        plhs[4] = mxCreateDoubleMatrix(N, 1, mxREAL); plhs[5] = mxCreateDoubleMatrix(N, 1, mxREAL);
+        plhs[6] = mxCreateDoubleMatrix(N, 1, mxREAL);
+        check(cnmfe_deconvolve(mxGetPr(prhs[1]), (int)T, (int)N, &o, sn, pars, mxGetPr(plhs[0]), mxGetPr(plhs[1]),
+                               mxGetPr(plhs[2]), mxGetPr(plhs[3]), mxGetPr(plhs[4]), mxGetPr(plhs[5]), mxGetPr(plhs[6]), 0), cmd);
+    } else if (c == "get_sn") {   // sn = get_sn(Y (T x N))
+        plhs[0] = mxCreateDoubleMatrix(mxGetN(prhs[1]), 1, mxREAL);
+        check(cnmfe_get_sn(mxGetPr(prhs[1]), (int)mxGetM(prhs[1]), (int)mxGetN(prhs[1]), mxGetPr(plhs[0]), 0), cmd);
+    } else {
+        mexErrMsgIdAndTxt("cnmfe:usage", "unknown command %s", cmd);
+    }
+}
