@@ -317,6 +317,11 @@ extern "C" int cnmfe_create(cnmfe_ctx** out, int d1, int d2, int T, int npatch, 
     get_nhood(ring_radius, num_neighbors, c->off_r, c->off_c);
     c->nnb = (int)c->off_r.size();
     c->rr = ring_radius;
+    if (c->nnb + 2 > 128) {
+        set_error("cnmfe_create: ring radius %d has %d neighbours; the register-resident solver handles <= 126 (pass num_neighbors)", ring_radius, c->nnb);
+        delete c;
+        return -1;
+    }
     c->sn.assign((size_t)d1 * d2, 1.0);
     cudaStreamCreate(&c->st);
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1); cudaEventCreate(&c->pe0); cudaEventCreate(&c->pe1);
@@ -590,6 +595,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         build_local(c, P, c->A, SEL_SUM_BLOCK, ROWS_BLOCK, nullptr, &L);
         const int Kb = L.K();
         if (Kb == 0 && !flag_first) continue;   // update_background_parallel.m:188-199
+        if (Kb > 4096) { set_error("update_background: %d neurons touch block %d; the solver's neuron bitmap handles <= 4096 per block", Kb, ip); return -1; }
         if (c->scr.reserve(bg_scratch_bytes(c, P, Kb, L.col.size()))) return -1;
         c->scr.reset();
         const RingGeom& g = P.geom;
@@ -689,8 +695,8 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         a.nsel = nsel; a.a_ptr = d_ptr; a.a_col = d_col; a.a_val = d_val; a.N = d_N; a.K = Kb; a.Csum = d_Csum;
         a.active = d_active; a.active_list = d_alist; a.n_active = (int)alist.size(); a.W = P.W; a.db = (size_t)P.db; a.ND = ND;
         const int NMAX = c->nnb + 1;
-        size_t smem = ((size_t)(NMAX + 1) * (NMAX + 2) / 2 + 128 + 2 * (size_t)(NMAX + 1) +
-                       2 * (size_t)(NMAX + 1) * RING_KSET + RING_KSET) * 8 + (6 * (size_t)(NMAX + 1) + RING_KALL) * 4 + 64;
+        size_t smem = ((size_t)(NMAX + 1) * (NMAX + 2) / 2 + 384 + 2 * (size_t)(NMAX + 1) +
+                       2 * (size_t)(NMAX + 1) * RING_KSET + RING_KSET) * 8 + (7 * (size_t)(NMAX + 1) + RING_KALL) * 4 + 64;
         CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LAUNCH(ring_solve_kernel, (unsigned)alist.size(), RING_SOLVE_THREADS, smem, c->st, a);
         CNMFE_CUDA_OK(cudaGetLastError());

@@ -52,9 +52,14 @@ __device__ inline void carve_ws(char* base, size_t slot_bytes, int slot, int T, 
 }
 
 int default_trace_slots(int device) {
-    cudaDeviceProp pr;
-    if (cudaGetDeviceProperties(&pr, device) != cudaSuccess) return 148 * 4;
-    return pr.multiProcessorCount * 4;
+    static int cached_dev = -1, cached = 148 * 4;
+    if (device != cached_dev) {
+        int sms = 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) sms = 148;
+        cached = sms * 4;
+        cached_dev = device;
+    }
+    return cached;
 }
 
 int trace_arena_reserve(TraceArena* a, int T, int nslots) {

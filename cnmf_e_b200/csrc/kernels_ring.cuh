@@ -188,42 +188,40 @@ struct RingSolveArgs {
 // every thread updates its own 36 registers; the step is templated on k/16 so finished register blocks are skipped.
 struct RingRegs { double g[8][8]; };
 
+// Right-looking elimination with ONE barrier per column: the owners of column k publish its UNSCALED entries x_i and the
+// pivot g_kk (double-buffered), then every thread applies G(i,j) -= (x_i / g_kk) * x_j to its registers.  The column of
+// the Cholesky factor is L(i,k) = x_i * (1/sqrt(g_kk)) (LAPACK dpotf2 scales by the reciprocal pivot); the registers keep
+// x_i and the pivots are stored in piv[] so that the scaling is applied once, when L is written out.
 template <int KA>
-__device__ __forceinline__ void ring_chol_block(RingRegs& R, int n1, int ti, int tj, double* colk, double* s_d) {
+__device__ __forceinline__ void ring_chol_block(RingRegs& R, int n1, int ti, int tj, double* xbuf, double* piv) {
     const int kend = min(16 * KA + 15, n1 - 1);
     for (int k = 16 * KA; k <= kend; ++k) {
         const int kr = k & 15;
-        if (ti == kr && tj == kr) {   // LAPACK dpotf2: ajj = sqrt(ajj); scale the column by 1/ajj
-            const double d = sqrt(R.g[KA][KA]);
-            s_d[0] = d;
-            s_d[1] = 1.0 / d;
-        }
-        __syncthreads();
+        double* xb = xbuf + (k & 1) * 128;
         if (tj == kr) {
-            const double rinv = s_d[1];
 #pragma unroll
             for (int a = KA; a < 8; ++a) {
                 const int i = ti + 16 * a;
-                if (i > k && i <= n1) {
-                    double v = R.g[a][KA] * rinv;
-                    R.g[a][KA] = v;
-                    colk[i] = v;
-                }
+                if (i > k && i <= n1) xb[i] = R.g[a][KA];
             }
-            if (ti == kr) R.g[KA][KA] = s_d[0];
+            if (ti == kr) { piv[k] = R.g[KA][KA]; xb[127] = 1.0 / R.g[KA][KA]; }
         }
         __syncthreads();
+        const double rinv = xb[127];
         double ci[8], cj[8];
 #pragma unroll
         for (int a = KA; a < 8; ++a) {
             const int i = ti + 16 * a, j = tj + 16 * a;
-            ci[a] = (i > k && i <= n1) ? colk[i] : 0.0;
-            cj[a] = (j > k && j < n1) ? colk[j] : 0.0;
+            ci[a] = (i > k && i <= n1) ? xb[i] * rinv : 0.0;
+            cj[a] = (j > k && j < n1) ? xb[j] : 0.0;
         }
 #pragma unroll
         for (int a = KA; a < 8; ++a)
 #pragma unroll
-            for (int b = KA; b <= a; ++b) R.g[a][b] = fma(-ci[a], cj[b], R.g[a][b]);
+            for (int b = KA; b <= a; ++b) {
+                // column k itself (b == KA && tj == kr) is final: keep x_i there
+                R.g[a][b] = fma(-ci[a], cj[b], R.g[a][b]);
+            }
     }
 }
 
@@ -238,8 +236,9 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
     const int NMAX = g.nnb + 1;
     // shared layout
     double* L = smem;                                         // packed lower (after the factorisation), (NMAX+1)(NMAX+2)/2
-    double* colk = L + (size_t)(NMAX + 1) * (NMAX + 2) / 2;   // 128
-    double* ym = colk + 128;                                  // NMAX+1   (index n = the centre pixel m)
+    double* colk = L + (size_t)(NMAX + 1) * (NMAX + 2) / 2;   // 256: double-buffered column, later the solution
+    double* piv = colk + 256;                                 // 128: pivots g_kk, later 1/sqrt(g_kk)
+    double* ym = piv + 128;                                  // NMAX+1   (index n = the centre pixel m)
     double* s1c = ym + NMAX + 1;                              // NMAX+1
     double* Ar = s1c + NMAX + 1;                              // (NMAX+1) * RING_KSET
     double* Nr = Ar + (size_t)(NMAX + 1) * RING_KSET;         // (NMAX+1) * RING_KSET
@@ -251,19 +250,35 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
     int* kall = sdc + NMAX + 1;                               // RING_KALL
     int* ap0 = kall + RING_KALL;                              // NMAX+1  A-row extents of the ring pixels / centre
     int* ap1 = ap0 + NMAX + 1;
+    int* rows_with = ap1 + NMAX + 1;                          // NMAX+1  ring pixels that carry neuron entries
     __shared__ int s_n, s_nk;
-    __shared__ double s_tr, s_d[2];
-    if (tid == 0) {
-        int n = 0;
-        for (int i = 0; i < g.nnb; ++i) {
-            int r2 = pr + a.off_r[i], c2 = pc + a.off_c[i];
-            int fr = r2 + g.br0, fc = c2 + g.bc0;
-            if (fr < 0 || fr >= g.d1 || fc < 0 || fc >= g.d2) continue;
-            qi[n] = c2 * g.nrb + r2; slot[n] = i; sdr[n] = a.off_r[i]; sdc[n] = a.off_c[i];
-            ++n;
+    __shared__ double s_tr;
+    // valid ring neighbours (inside the FOV), compacted in slot order: parallel ballot scan over <= 8 warps
+    {
+        const int lane = tid & 31, wid = tid >> 5;
+        __shared__ int s_wcnt[8];
+        int dr = 0, dc = 0;
+        bool ok = false;
+        if (tid < g.nnb) {
+            dr = a.off_r[tid]; dc = a.off_c[tid];
+            int fr = pr + dr + g.br0, fc = pc + dc + g.bc0;
+            ok = !(fr < 0 || fr >= g.d1 || fc < 0 || fc >= g.d2);
         }
-        qi[n] = (int)qm; sdr[n] = 0; sdc[n] = 0;
-        s_n = n;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_wcnt[wid] = __popc(m);
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < wid; ++w) base += s_wcnt[w];
+        if (ok) {
+            const int pos = base + __popc(m & ((1u << lane) - 1));
+            qi[pos] = (pc + dc) * g.nrb + (pr + dr); slot[pos] = tid; sdr[pos] = dr; sdc[pos] = dc;
+        }
+        if (tid == 0) {
+            int n = 0;
+            for (int w = 0; w < 8; ++w) n += s_wcnt[w];
+            qi[n] = (int)qm; sdr[n] = 0; sdc[n] = 0;
+            s_n = n;
+        }
     }
     __syncthreads();
     const int n = s_n, n1 = n + 1;
@@ -315,16 +330,27 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
     }
     // --- neuron corrections: Cov_Bf = Cov_Y - N_x.A_y - A_x.N_y ; sum_sel Bf(x) = S1c_x - A_x.Csum
     // distinct neurons touching the ring pixels / the centre (deterministic scan order), handled RING_KSET at a time
-    if (tid == 0) {
-        int nall = 0;
-        for (int y = 0; y <= n; ++y)
-            for (int e = ap0[y]; e < ap1[y]; ++e) {
-                int k = a.a_col[e];
-                bool dup = false;
-                for (int z = 0; z < nall; ++z) if (kall[z] == k) dup = true;
-                if (!dup && nall < RING_KALL) kall[nall++] = k;
-            }
-        s_nk = nall;
+    // distinct neurons: bitmap over local neuron ids (K <= 4096), compacted in ascending id order (deterministic)
+    __shared__ unsigned s_bits[128];
+    if (tid < 128) s_bits[tid] = 0u;
+    __syncthreads();
+    for (int y = tid; y <= n; y += blockDim.x)
+        for (int e = ap0[y]; e < ap1[y]; ++e) { int k = a.a_col[e]; atomicOr(&s_bits[(k >> 5) & 127], 1u << (k & 31)); }
+    __syncthreads();
+    if (tid < 32) {
+        int base = 0;
+        for (int w0 = 0; w0 < 128; w0 += 32) {
+            const unsigned bits = s_bits[w0 + tid];
+            const int cnt = __popc(bits);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += t; }
+            int pos = base + incl - cnt;
+            unsigned b = bits;
+            while (b) { int bit = __ffs(b) - 1; b &= b - 1; if (pos < RING_KALL) kall[pos] = ((w0 + tid) << 5) + bit; ++pos; }
+            base += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (tid == 0) s_nk = min(base, RING_KALL);
     }
     __syncthreads();
     const int nall = s_nk;
@@ -399,37 +425,41 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
         }
     }
     // --- Cholesky of the augmented matrix
-    ring_chol_block<0>(R, n1, ti, tj, colk, s_d);
-    if (n1 > 16) ring_chol_block<1>(R, n1, ti, tj, colk, s_d);
-    if (n1 > 32) ring_chol_block<2>(R, n1, ti, tj, colk, s_d);
-    if (n1 > 48) ring_chol_block<3>(R, n1, ti, tj, colk, s_d);
-    if (n1 > 64) ring_chol_block<4>(R, n1, ti, tj, colk, s_d);
-    if (n1 > 80) ring_chol_block<5>(R, n1, ti, tj, colk, s_d);
-    if (n1 > 96) ring_chol_block<6>(R, n1, ti, tj, colk, s_d);
-    if (n1 > 112) ring_chol_block<7>(R, n1, ti, tj, colk, s_d);
+    ring_chol_block<0>(R, n1, ti, tj, colk, piv);
+    if (n1 > 16) ring_chol_block<1>(R, n1, ti, tj, colk, piv);
+    if (n1 > 32) ring_chol_block<2>(R, n1, ti, tj, colk, piv);
+    if (n1 > 48) ring_chol_block<3>(R, n1, ti, tj, colk, piv);
+    if (n1 > 64) ring_chol_block<4>(R, n1, ti, tj, colk, piv);
+    if (n1 > 80) ring_chol_block<5>(R, n1, ti, tj, colk, piv);
+    if (n1 > 96) ring_chol_block<6>(R, n1, ti, tj, colk, piv);
+    if (n1 > 112) ring_chol_block<7>(R, n1, ti, tj, colk, piv);
     __syncthreads();
-    // --- dump L, back substitution L' w = z (z = row n1) by one warp
+    // --- write out L (scaling column k by 1/sqrt(g_kk)), back substitution L' w = z (z = row n1) by one warp
+    for (int k = tid; k < n1; k += blockDim.x) piv[k] = 1.0 / sqrt(piv[k]);
+    __syncthreads();
 #pragma unroll
     for (int aa = 0; aa < 8; ++aa)
 #pragma unroll
         for (int bb = 0; bb <= aa; ++bb) {
             const int i = ti + 16 * aa, j = tj + 16 * bb;
-            if (j <= i && i <= n1 && j < n1) L[(size_t)i * (i + 1) / 2 + j] = R.g[aa][bb];
+            // diagonal: L(j,j) = sqrt(g_jj) = g_jj * (1/sqrt(g_jj));  below: x_i * (1/sqrt(g_jj))
+            if (j <= i && i <= n1 && j < n1) L[(size_t)i * (i + 1) / 2 + j] = R.g[aa][bb] * piv[j];
         }
     __syncthreads();
-    double* rdiag = ym;   // ym is dead after the assembly: reciprocal pivots
-    for (int i = tid; i < n1; i += blockDim.x) rdiag[i] = 1.0 / L[(size_t)i * (i + 1) / 2 + i];
-    __syncthreads();
+    double* rdiag = piv;   // 1/L(k,k) = 1/sqrt(g_kk)
     if (tid < 32) {
-        for (int i = tid; i < n1; i += 32) colk[i] = L[(size_t)n1 * (n1 + 1) / 2 + i];
-        __syncwarp();
+        // lane l keeps z_i for i = l + 32 m (m < 4) in registers; step k broadcasts w_k by shuffle
+        double z[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { int i = tid + 32 * m; z[m] = (i < n1) ? L[(size_t)n1 * (n1 + 1) / 2 + i] : 0.0; }
         for (int k = n1 - 1; k >= 0; --k) {
             const double* row = L + (size_t)k * (k + 1) / 2;
-            double wk = colk[k] * rdiag[k];
-            __syncwarp();
-            if (tid == 0) colk[k] = wk;
-            for (int i = tid; i < k; i += 32) colk[i] -= row[i] * wk;
-            __syncwarp();
+            const int km = k >> 5;
+            double zk = km == 0 ? z[0] : (km == 1 ? z[1] : (km == 2 ? z[2] : z[3]));
+            const double wk = __shfl_sync(0xffffffffu, zk, k & 31) * rdiag[k];
+            if (tid == (k & 31)) colk[k] = wk;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { int i = tid + 32 * m; if (i < k) z[m] -= row[i] * wk; }
         }
     }
     __syncthreads();
