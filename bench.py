@@ -354,7 +354,9 @@ def run_ours(args):
     achieved = int8_ops / gram_s / 1e12
     roofline = dict(bound="tensor", kernel="ring second moments S2 (%s)" % ("tcgen05 INT8" if lib.cnmfe_last_gram_was_tensor(obj._h) else "SIMT u64"),
                     achieved=achieved, peak=2.0 * bf16, unit="TOP/s (int8 dense)", frac=achieved / (2.0 * bf16),
-                    traffic=None, peak_source=peak_src, ms_per_launch=1e3 * gram_s,
+                    traffic=(88.4e9 * (T / 10000.0) if lib.cnmfe_last_gram_was_tensor(obj._h) else None),
+                    traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/r1_ncu_full_gram.csv), scaled by T/10000",
+                    peak_source=peak_src, ms_per_launch=1e3 * gram_s,
                     algorithmic_ops_per_launch=int8_ops,
                     hbm_iteration=dict(algorithmic_bytes=3.0 * d1 * d2 * T * 2 / world, gbs=3.0 * d1 * d2 * T * 2 / world / (t_max / args.steps) / 1e9,
                                        peak_gbs=peaks.get("hbm_gbs", 6650.0)))

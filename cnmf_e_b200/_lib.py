@@ -61,6 +61,8 @@ SYMBOLS = {
     "cnmfe_get_ring": (I, [V, I, V, V]),
     "cnmfe_update_background": (I, [V]),
     "cnmfe_update_spatial": (I, [V]),
+    "cnmfe_update_spatial_ex": (I, [V, I]),
+    "cnmfe_get_sn_map": (I, [V, V]),
     "cnmfe_get_spatial": (I, [V, V]),
     "cnmfe_set_spatial": (I, [V, V]),
     "cnmfe_update_temporal_patches": (I, [V]),

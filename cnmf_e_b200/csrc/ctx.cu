@@ -721,15 +721,20 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
 }
 
 // ===================================================================================================== spatial
-extern "C" int cnmfe_update_spatial(cnmfe_ctx* c) {
+extern "C" int cnmfe_update_spatial(cnmfe_ctx* c) { return cnmfe_update_spatial_ex(c, 0); }
+
+extern "C" int cnmfe_get_sn_map(cnmfe_ctx* c, double* sn) {
+    if (!c || !sn) { set_error("cnmfe_get_sn_map: null"); return -1; }
+    std::copy(c->sn.begin(), c->sn.end(), sn);
+    return 0;
+}
+
+extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
     if (!c) { set_error("cnmfe_update_spatial: null ctx"); return -1; }
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
     for (float& f : c->phase_ms) f = 0;
     if (c->IND.K != c->K) { set_error("update_spatial: search mask has %d columns, A has %d", c->IND.K, c->K); return -1; }
-    if (c->opt.spatial_algorithm == 3) {
-        set_error("update_spatial: 'lars' (utilities/lars_spatial.m) is not built yet; use hals, hals_thresh or nnls");
-        return -1;
-    }
+    const bool lars = (c->opt.spatial_algorithm == 3);
     const int T = c->T;
     c->A_on_IND.assign(c->IND.ir.size(), 0.0);
     for (int ip = 0; ip < c->npatch; ++ip) {
@@ -739,7 +744,7 @@ extern "C" int cnmfe_update_spatial(cnmfe_ctx* c) {
         LocalSparse LS, LP;
         build_local(c, P, c->IND, SEL_ANY_PATCH, ROWS_PATCH, &c->A, &LS);
         const int Ks = LS.K();
-        if (Ks == 0) continue;   // update_spatial_parallel.m:121-124 (update_sn = false)
+        if (Ks == 0 && !update_sn) continue;   // update_spatial_parallel.m:121-124
         build_local(c, P, c->Aprev, c->opt.replicate_spatial_aprev_quirk ? SEL_SUM_HALO : SEL_SUM_BLOCK, ROWS_BLOCK,
                     nullptr, &LP);
         const int Kp = LP.K();
@@ -748,9 +753,12 @@ extern "C" int cnmfe_update_spatial(cnmfe_ctx* c) {
                       pad256((size_t)Ks * Ks * 8) + pad256((size_t)std::max(Kp, 1) * Ks * 8) + pad256(nent * 32) +
                       pad256((size_t)(P.dp + 1) * 4) + pad256((size_t)(P.db + 1) * 4) + pad256(LP.col.size() * 12 + 64) +
                       pad256((size_t)P.dp * 8) + pad256((size_t)(Ks + Kp) * 64 + 64) + (1 << 20);
+        const int CH = 2048;   // rows of explicit Ysig per chunk (update_sn / lars only)
+        if (update_sn || lars) need += pad256((size_t)CH * T * 8) + 3 * pad256((size_t)CH * 8) + pad256((size_t)P.dp * 8);
         if (c->scr.reserve(need)) return -1;
         c->scr.reset();
         const RingGeom& g = P.geom;
+        if ((update_sn || lars) && Kp > YSIG_MAXK) { set_error("update_spatial: %d previous neurons touch block %d (explicit rows handle <= %d)", Kp, ip, YSIG_MAXK); return -1; }
         phase_begin(c);
         TAKE_OR_FAIL(d_iptr, to_dev(c, LS.ptr));
         TAKE_OR_FAIL(d_icol, to_dev(c, LS.col));
@@ -768,20 +776,73 @@ extern "C" int cnmfe_update_spatial(cnmfe_ctx* c) {
             snp[p] = c->sn[(size_t)cc * c->d1 + r];
         }
         TAKE_OR_FAIL(d_sn, to_dev(c, snp));
-        TAKE_OR_FAIL(d_Cc, c->scr.take<double>((size_t)Ks * T));
+        TAKE_OR_FAIL(d_Cc, c->scr.take<double>((size_t)std::max(Ks, 1) * T));
         TAKE_OR_FAIL(d_Ccp, c->scr.take<double>((size_t)std::max(Kp, 1) * T));
-        TAKE_OR_FAIL(d_V, c->scr.take<double>((size_t)Ks * Ks));
-        TAKE_OR_FAIL(d_P2, c->scr.take<double>((size_t)std::max(Kp, 1) * Ks));
+        TAKE_OR_FAIL(d_V, c->scr.take<double>((size_t)std::max(Ks, 1) * std::max(Ks, 1)));
+        TAKE_OR_FAIL(d_P2, c->scr.take<double>((size_t)std::max(Kp, 1) * std::max(Ks, 1)));
         TAKE_OR_FAIL(d_U, c->scr.take<double>(std::max<size_t>(nent, 1)));
-        TAKE_OR_FAIL(d_D, c->scr.take<double>((size_t)P.db * Ks));
-        LAUNCH(gather_center_rows_kernel, Ks, 256, 0, c->st, c->C, d_ids, Ks, T, d_Cc, (double*)nullptr);
-        { dim3 gg(Ks, Ks); LAUNCH(small_gram_kernel, gg, 128, 0, c->st, d_Cc, Ks, d_Cc, Ks, T, 1, d_V, (double*)nullptr); }
+        TAKE_OR_FAIL(d_D, c->scr.take<double>((size_t)P.db * std::max(Ks, 1)));
+        TAKE_OR_FAIL(d_thr, c->scr.take<double>(P.dp));
+        if (Ks > 0) {
+            LAUNCH(gather_center_rows_kernel, Ks, 256, 0, c->st, c->C, d_ids, Ks, T, d_Cc, (double*)nullptr);
+            dim3 gg(Ks, Ks);
+            LAUNCH(small_gram_kernel, gg, 128, 0, c->st, d_Cc, Ks, d_Cc, Ks, T, 1, d_V, (double*)nullptr);
+        }
         if (Kp > 0) {
             LAUNCH(gather_center_rows_kernel, Kp, 256, 0, c->st, c->Cprev, d_pids, Kp, T, d_Ccp, (double*)nullptr);
-            dim3 gg(Kp, Ks);
-            LAUNCH(small_gram_kernel, gg, 128, 0, c->st, d_Ccp, Kp, d_Cc, Ks, T, 1, d_P2, (double*)nullptr);
+            if (Ks > 0) {
+                dim3 gg(Kp, Ks);
+                LAUNCH(small_gram_kernel, gg, 128, 0, c->st, d_Ccp, Kp, d_Cc, Ks, T, 1, d_P2, (double*)nullptr);
+            }
         }
         phase_end(c, 6);
+        // ---- optional explicit rows of the BG-subtracted video (update_sn: GetSn per pixel, :191-194; lars: energy)
+        if (update_sn || lars) {
+            phase_begin(c);
+            double* d_rowsY = c->scr.take<double>((size_t)CH * T);
+            int* d_rows = c->scr.take<int>(CH);
+            double* d_tmp = c->scr.take<double>(CH);
+            if (!d_rowsY || !d_rows || !d_tmp) { set_error("scratch exhausted"); return -1; }
+            auto run_rows = [&](int nrows_total, bool want_sn, std::vector<double>& outv) -> int {
+                outv.assign(nrows_total, 0.0);
+                std::vector<int> rows(CH);
+                for (int b = 0; b < nrows_total; b += CH) {
+                    const int nr = std::min(CH, nrows_total - b);
+                    for (int i = 0; i < nr; ++i) rows[i] = b + i;
+                    CNMFE_CUDA_OK(cudaMemcpyAsync(d_rows, rows.data(), (size_t)nr * 4, cudaMemcpyHostToDevice, c->st));
+                    dim3 gg(nr, (T + YSIG_TCHUNK - 1) / YSIG_TCHUNK);
+                    LAUNCH(ysig_rows_kernel, gg, 256, 0, c->st, g, c->d_off_r, c->d_off_c, P.W, P.b0, P.Yt, P.Ymean, T,
+                           c->Tpad, d_pptr, d_pcol, d_pval, Kp, d_Ccp, d_rows, d_rowsY);
+                    if (want_sn) { if (getsn_batch_dev(d_rowsY, T, nr, d_tmp, &c->arena, c->st)) return -1; }
+                    else LAUNCH(rows_centered_energy_kernel, nr, 256, 0, c->st, d_rowsY, T, d_tmp);
+                    CNMFE_CUDA_OK(cudaMemcpyAsync(outv.data() + b, d_tmp, (size_t)nr * 8, cudaMemcpyDeviceToHost, c->st));
+                    CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+                }
+                return 0;
+            };
+            if (update_sn) {
+                std::vector<double> snew;
+                if (run_rows(P.dp, true, snew)) return -1;
+                for (int p = 0; p < P.dp; ++p) {
+                    int r = p % P.nr + P.patch.r0, cc = p / P.nr + P.patch.c0;
+                    c->sn[(size_t)cc * c->d1 + r] = snew[p];
+                    snp[p] = snew[p];
+                }
+                CNMFE_CUDA_OK(cudaMemcpyAsync(d_sn, snp.data(), (size_t)P.dp * 8, cudaMemcpyHostToDevice, c->st));
+            }
+            if (lars && Ks > 0) {
+                // thresh = sn.^2*T - sum(Y.^2,2) indexed by the LOOP COUNTER m over ind_fit (lars_spatial.m:50,55)
+                std::vector<int> fit;
+                for (int p = 0; p < P.dp; ++p) if (LS.ptr[p + 1] > LS.ptr[p]) fit.push_back(p);
+                std::vector<double> en, thr(P.dp, 0.0);
+                if (run_rows((int)fit.size(), false, en)) return -1;
+                for (size_t m = 0; m < fit.size(); ++m) thr[fit[m]] = snp[m] * snp[m] * (double)T - en[m];
+                CNMFE_CUDA_OK(cudaMemcpyAsync(d_thr, thr.data(), (size_t)P.dp * 8, cudaMemcpyHostToDevice, c->st));
+                CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+            }
+            phase_end(c, 6);
+        }
+        if (Ks == 0) continue;
         phase_begin(c);
         CNMFE_CUDA_OK(cudaMemsetAsync(d_D, 0, (size_t)P.db * Ks * 8, c->st));
         {
@@ -796,7 +857,7 @@ extern "C" int cnmfe_update_spatial(cnmfe_ctx* c) {
         phase_begin(c);
         CNMFE_CUDA_OK(cudaMemsetAsync(c->d_err, 0, 4, c->st));
         LAUNCH(spatial_solve_kernel, (P.dp + 127) / 128, 128, 0, c->st, P.dp, d_iptr, d_icol, d_U, d_V, Ks, d_sn,
-               c->opt.spatial_algorithm, 3, d_a, c->d_err);
+               c->opt.spatial_algorithm, 3, d_thr, d_a, c->d_err);
         std::vector<double> anew(nent);
         int err = 0;
         CNMFE_CUDA_OK(cudaMemcpyAsync(anew.data(), d_a, nent * 8, cudaMemcpyDeviceToHost, c->st));

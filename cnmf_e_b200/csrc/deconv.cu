@@ -266,8 +266,12 @@ int deconv_batch_dev(const double* Y, int T, int N, const cnmfe_deconv_opts& o, 
     if (N <= 0) return 0;
     if (T < 32) { set_error("deconvolve: T=%d too short (need >= 32 frames)", T); return -1; }
     if (o.type != 1 && o.type != 2) { set_error("deconvolve: type must be 1 (ar1) or 2 (ar2)"); return -1; }
-    if (o.type == 2 && o.method != 0) {
-        set_error("deconvolve: ar2 supports method 'foopsi' only in this build (constrained_foopsi/thresholded_oasisAR2 not built)");
+    if (o.type == 2 && o.method == 1) {
+        set_error("deconvolve: ar2 + 'constrained' is the legacy constrained_foopsi (CVX/LARS) path: not built");
+        return -1;
+    }
+    if (o.type == 2 && o.method == 2 && (o.optimize_b || o.optimize_pars)) {
+        set_error("deconvolve: thresholded_oasisAR2 with optimize_b / optimize_pars is not built");
         return -1;
     }
     if (o.method == 2 && o.optimize_b) {

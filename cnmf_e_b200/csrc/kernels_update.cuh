@@ -8,7 +8,7 @@
 namespace cnmfe {
 
 #define SPATIAL_MAXROW 32   // max neurons whose search mask covers one pixel
-#define NNLS_MAXP 20        // nnls_spatial maxN (update_spatial_parallel.m:211 passes 20)
+#define NNLS_MAXP 32        // passive-set capacity (nnls_spatial maxN = 20; lars_spatial: maxIter = #masks <= 32)
 
 // D[q][k] = Mc[q][k] - sum_k' Aprev[q,k'] * P2[k'][k]   (projection of the background residual on Cc), in place.
 __global__ void spatial_make_D_kernel(double* __restrict__ Mc, int Ks, const int* __restrict__ ap_ptr,
@@ -84,13 +84,15 @@ __device__ inline bool chol_solve_small(double* M /*n*n row-major, overwritten*/
     return true;
 }
 
-// method: 0 hals (3 sweeps, max(0,.)), 1 hals_thresh (3 sweeps, threshold 3*sn/sqrt(cc)), 2 nnls (maxN = 20).
+// method: 0 hals (3 sweeps, max(0,.)), 1 hals_thresh (3 sweeps, threshold 3*sn/sqrt(cc)), 2 nnls (maxN = 20),
+// 3 lars (nnls with tol 1e-9, maxIter = #masks and the noise-constrained early exit of lars_spatial.m:105-109;
+//   lars_thr[p] = the threshold the reference uses for pixel p -- INCLUDING its thresh(m) indexing quirk, :55).
 // One thread per patch pixel.  a_io: initial A on the pattern (in), new A (out).  V = Cc*Cc' [Ks][Ks].
 __global__ void __launch_bounds__(128)
 spatial_solve_kernel(int dp, const int* __restrict__ ind_ptr, const int* __restrict__ ind_col,
                      const double* __restrict__ U, const double* __restrict__ V, int Ks,
-                     const double* __restrict__ sn, int method, int maxIter, double* __restrict__ a_io,
-                     int* __restrict__ err) {
+                     const double* __restrict__ sn, int method, int maxIter, const double* __restrict__ lars_thr,
+                     double* __restrict__ a_io, int* __restrict__ err) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= dp) return;
     const int e0 = ind_ptr[p], n = ind_ptr[p + 1] - e0;
@@ -116,8 +118,10 @@ spatial_solve_kernel(int dp, const int* __restrict__ ind_ptr, const int* __restr
         }
     } else {
         // nnls(CC(ind,ind), YC(ind,px), [], 1e-4, maxN)   (nnls_spatial.m:41-109)
-        const double tol = 1e-4;
-        const int maxN = NNLS_MAXP;
+        const double tol = (method == 3) ? 1e-9 : 1e-4;
+        const int maxN = (method == 3) ? n : 20;
+        const bool has_thr = (method == 3);
+        const double thr = has_thr ? lars_thr[p] : 0.0;
         double s[SPATIAL_MAXROW], mu[NNLS_MAXP], M[NNLS_MAXP * NNLS_MAXP];
         int pidx[NNLS_MAXP];
         unsigned Pset = 0u;
@@ -133,6 +137,15 @@ spatial_solve_kernel(int dp, const int* __restrict__ ind_ptr, const int* __restr
             Pset = 0u;
             for (int i = 0; i < n; ++i) if (s[i] > 0.0) Pset |= (1u << i);
             if (lmax < tol) break;
+            if (has_thr) {   // s'*A*s - 2*s'*b <= thresh  (lars_spatial.m:105-109)
+                double q = 0.0;
+                for (int i = 0; i < n; ++i) {
+                    double as = 0.0;
+                    for (int j = 0; j < n; ++j) as += V[(size_t)col[i] * Ks + col[j]] * s[j];
+                    q += s[i] * as - 2.0 * s[i] * u[i];
+                }
+                if (q <= thr) break;
+            }
             Pset |= (1u << imax);
             if (__popc(Pset) > maxN) break;
             int np = 0;
@@ -282,6 +295,89 @@ __global__ void kt_to_colmajor_kernel(const double* __restrict__ src, int K, int
 __global__ void colmajor_to_kt_kernel(const double* __restrict__ src, int K, int T, double* __restrict__ dst) {
     int k = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < T) dst[(size_t)k * T + t] = src[(size_t)t * K + k];
+}
+
+}  // namespace cnmfe
+
+namespace cnmfe {
+
+// Explicit background-subtracted rows (update_spatial_parallel.m:157-166, bg_ssub = 1) for a list of patch pixels:
+//   Ysig(p,t) = Y(p,t) - b0(p) - sum_i W(p,i) * [ (Y(q_i,t) - Ybar(q_i)) - sum_k Aprev(q_i,k) * Cc_prev(k,t) ]
+// Only the optional paths need the rows themselves (update_sn, lars_spatial); the main path works from projections.
+// grid = (nrows, ceil(T / YSIG_TCHUNK)), block = 256.
+#define YSIG_TCHUNK 2048
+#define YSIG_MAXK 1024
+__global__ void __launch_bounds__(256)
+ysig_rows_kernel(RingGeom g, const int* __restrict__ off_r, const int* __restrict__ off_c,
+                 const double* __restrict__ W, const double* __restrict__ b0, const uint16_t* __restrict__ Yt,
+                 const double* __restrict__ Ymean, int T, int Tpad, const int* __restrict__ ap_ptr,
+                 const int* __restrict__ ap_col, const double* __restrict__ ap_val, int Kp,
+                 const double* __restrict__ Ccp, const int* __restrict__ rows, double* __restrict__ out) {
+    __shared__ double s_w[128], s_ym[128];
+    __shared__ long long s_q[128];
+    __shared__ int s_e0[128], s_e1[128];
+    __shared__ double s_wa[YSIG_MAXK];
+    __shared__ int s_list[64];
+    __shared__ int s_nl;
+    const int p = rows[blockIdx.x];
+    const int r = p % g.nr + g.pr_off, c = p / g.nr + g.pc_off;
+    const int tid = threadIdx.x;
+    const size_t qp0 = (size_t)c * g.nrb + r;
+    if (tid < 128) {
+        double w = 0.0;
+        long long q = (long long)qp0;
+        if (tid < g.nnb) {
+            int r2 = r + off_r[tid], c2 = c + off_c[tid];
+            int fr = r2 + g.br0, fc = c2 + g.bc0;
+            if (!(fr < 0 || fr >= g.d1 || fc < 0 || fc >= g.d2)) {
+                q = (long long)c2 * g.nrb + r2;
+                w = W[(size_t)p * g.nnb + tid];
+            }
+        }
+        s_w[tid] = w; s_q[tid] = q; s_ym[tid] = Ymean[q];
+        s_e0[tid] = (w != 0.0) ? ap_ptr[q] : 0;
+        s_e1[tid] = (w != 0.0) ? ap_ptr[q + 1] : 0;
+    }
+    __syncthreads();
+    // WA(p,k) = sum_i W(p,i) * Aprev(q_i,k): one thread per neuron, slots in order (deterministic)
+    for (int k = tid; k < Kp; k += blockDim.x) {
+        double wa = 0.0;
+        for (int i = 0; i < g.nnb; ++i)
+            for (int e = s_e0[i]; e < s_e1[i]; ++e)
+                if (ap_col[e] == k) wa += s_w[i] * ap_val[e];
+        s_wa[k] = wa;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nl = 0;
+        for (int k = 0; k < Kp && nl < 64; ++k) if (s_wa[k] != 0.0) s_list[nl++] = k;
+        s_nl = nl;
+    }
+    __syncthreads();
+    const int n = g.nnb, nl = s_nl;
+    const size_t qp = qp0;
+    const double b0p = b0[p];
+    const int t0 = blockIdx.y * YSIG_TCHUNK, t1 = min(T, t0 + YSIG_TCHUNK);
+    for (int t = t0 + tid; t < t1; t += blockDim.x) {
+        double acc = 0.0;
+        for (int i = 0; i < n; ++i) acc += s_w[i] * ((double)Yt[(size_t)s_q[i] * Tpad + t] - s_ym[i]);
+        double corr = 0.0;
+        for (int x = 0; x < nl; ++x) { int k = s_list[x]; corr += s_wa[k] * Ccp[(size_t)k * T + t]; }
+        out[(size_t)blockIdx.x * T + t] = ((double)Yt[qp * Tpad + t] - b0p) - acc + corr;
+    }
+}
+
+// energy[i] = sum_t (X[i][t] - mean_t X[i])^2   (lars_spatial.m:42,50: Y centred, sum(Y.^2,2))
+__global__ void rows_centered_energy_kernel(const double* __restrict__ X, int T, double* __restrict__ energy) {
+    __shared__ double red[32];
+    const double* x = X + (size_t)blockIdx.x * T;
+    double a = 0.0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) a += x[t];
+    const double m = block_sum(a, red) / (double)T;
+    double e = 0.0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) { double d = x[t] - m; e += d * d; }
+    e = block_sum(e, red);
+    if (threadIdx.x == 0) energy[blockIdx.x] = e;
 }
 
 }  // namespace cnmfe

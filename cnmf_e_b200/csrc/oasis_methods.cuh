@@ -135,6 +135,17 @@ __device__ double choose_smin_ar1(double g, double sn, double prob) {
     return sn / sqrt(nrm) * normcdfinv(prob);
 }
 
+// choose_smin for an AR(2) pair: h = filter(1,[1,-g1,-g2],impulse(1000))  (choose_smin.m:38-42)
+__device__ double choose_smin_ar2(double g1, double g2, double sn, double prob) {
+    double h1 = 0.0, h2 = 0.0, nrm = 0.0;
+    for (int k = 0; k < 1000; ++k) {
+        double h = (k == 0 ? 1.0 : 0.0) + g1 * h1 + g2 * h2;
+        nrm += h * h;
+        h2 = h1; h1 = h;
+    }
+    return sn / sqrt(nrm) * normcdfinv(prob);
+}
+
 // thresholded_oasisAR1, optimize_b = false branch (thresholded_oasisAR1.m:104-140,186-213)
 __device__ void block_thresholded_ar1(const double* __restrict__ y, int T, double g, double sn, bool optimize_g,
                                       int maxIter, double thresh_factor, double p_noise, double g_lo, double g_hi,
@@ -244,9 +255,15 @@ __device__ void block_deconvolveCa(const double* __restrict__ y, int T, const cn
     } else if (o.method == 1) {
         block_constrained_ar1(y, T, g1, sn, o.optimize_b != 0, o.optimize_pars != 0, maxIter, g_lo, g_hi,
                               o.has_tau_range != 0, ws, sh, out);
-    } else {
+    } else if (o.type == 1) {
         block_thresholded_ar1(y, T, g1, sn, o.optimize_pars != 0, maxIter, o.thresh_factor, o.p_noise, g_lo, g_hi,
                               o.has_tau_range != 0, ws, sh, out);
+    } else {
+        // thresholded_oasisAR2 with optimize_b = optimize_g = false: its loop (:96-126) exits at the first
+        // abs(RSS-RSS0)<tol test, so the result is one oasisAR2 pass with smin = choose_smin(g, sn, 0.99999999) (:72)
+        const double smin = choose_smin_ar2(g1, g2, sn, 0.99999999);
+        block_oasis_ar2(y, T, g1, g2, 0.0, smin, ws, sh);
+        out->b = 0.0; out->smin = smin;
     }
     // avoid nan output (deconvolveCa.m:206)
     for (int i = threadIdx.x; i < T; i += blockDim.x) {

@@ -265,8 +265,6 @@ class Sources2D:
     def update_spatial_parallel(self, use_parallel=True, update_sn=False, IND=None, sync_host=True):
         """update_spatial_parallel(obj, use_parallel, update_sn).  IND: (d,K) boolean search mask
         (determine_search_location output, update_spatial_parallel.m:66); defaults to self.search_fn(self)."""
-        if update_sn:
-            raise L.CnmfeError("update_sn=true (per-pixel GetSn of the BG-subtracted video) is not built in this round")
         self._push_options()
         if IND is None:
             if self.search_fn is None:
@@ -283,7 +281,11 @@ class Sources2D:
         ir = np.ascontiguousarray(INDc.indices, dtype=np.int64)
         self._ind_jc, self._ind_ir = jc, ir
         L.check(self._lib.cnmfe_set_search(self._h, INDc.shape[1], _ptr(jc), _ptr(ir)))
-        L.check(self._lib.cnmfe_update_spatial(self._h))
+        L.check(self._lib.cnmfe_update_spatial_ex(self._h, int(bool(update_sn))))
+        if update_sn:
+            snm = np.zeros((self.d1, self.d2), order="F")
+            L.check(self._lib.cnmfe_get_sn_map(self._h, _ptr(snm)))
+            self.P["sn"] = self._allreduce_owned_pixels(np.ascontiguousarray(snm)) if self.world_size > 1 else np.ascontiguousarray(snm)
         if sync_host:
             vals = np.zeros(ir.size)
             L.check(self._lib.cnmfe_get_spatial(self._h, _ptr(vals)))
@@ -350,6 +352,14 @@ class Sources2D:
     update_temporal = update_temporal_parallel
 
     # ------------------------------------------------------------------ multi-GPU exchange (torch.distributed)
+    def _allreduce_owned_pixels(self, img):
+        """Combine a per-pixel map whose entries are valid only on the pixels of the owned patches."""
+        m = np.zeros_like(img)
+        for i in self.owned_patches():
+            p = self.patch_of(i)
+            m[p[0] - 1:p[1], p[2] - 1:p[3]] = img[p[0] - 1:p[1], p[2] - 1:p[3]]
+        return self._allreduce_sum(m.ravel()).reshape(img.shape)
+
     def _allreduce_sum(self, vec):
         if self.world_size == 1:
             return vec

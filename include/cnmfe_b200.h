@@ -122,6 +122,10 @@ int cnmfe_update_background(cnmfe_ctx* ctx);
 /* update_spatial_parallel(obj, use_parallel, update_sn=false) (@Sources2D/update_spatial_parallel.m:1) up to
  * (not including) post_process_spatial (:341, host/MATLAB).  New A lives on the search pattern. */
 int cnmfe_update_spatial(cnmfe_ctx* ctx);
+/* same with update_sn = true: obj.P.sn is re-estimated per pixel from the BG-subtracted video (GetSn,
+ * update_spatial_parallel.m:191-194) before the solve; read it back with cnmfe_get_sn_map (d1 x d2) */
+int cnmfe_update_spatial_ex(cnmfe_ctx* ctx, int update_sn);
+int cnmfe_get_sn_map(cnmfe_ctx* ctx, double* sn);
 /* A on the search pattern: values aligned with (IND_jc, IND_ir) given to cnmfe_set_search */
 int cnmfe_get_spatial(cnmfe_ctx* ctx, double* A_on_IND);
 /* replace obj.A by values on the search pattern (e.g. after the cross-GPU exchange of the patches' rows, or after

@@ -633,6 +633,34 @@ def thresholded_oasisAR1(y, g=None, sn=None, optimize_b=False, optimize_g=False,
     return solution, spks, b, g, smin, aset
 
 
+def thresholded_oasisAR2(y, g, sn, smin=None, optimize_b=False, optimize_g=False, decimate=None, maxIter=10,
+                         thresh_factor=1.0):
+    """thresholded_oasisAR2.m:38-126 with optimize_b = optimize_g = false.  NB: in that configuration the loop at
+    :96-126 exits at its first `abs(RSS-RSS0)<tol` test (RSS is recomputed from the unchanged solution), so the result
+    is ONE oasisAR2 pass with smin = choose_smin(g, sn, 0.99999999) (:72); update_smin (:175-201, warm-started AR2) is
+    unreachable and not restated."""
+    if optimize_b or optimize_g:
+        raise NotImplementedError("thresholded_oasisAR2 oracle: optimize_b / optimize_g branches not restated")
+    y = np.asarray(y, dtype=np.float64).ravel()
+    T = y.size
+    smin = choose_smin(g, sn, 0.99999999)
+    thresh = thresh_factor * sn * sn * T
+    tol = 1e-4
+    b = 0.0
+    solution, spks, aset = oasisAR2(y, g, None, smin)
+    res = y - solution
+    RSS0 = float(res @ res)
+    for _ in range(int(maxIter)):
+        if len(aset) == 0:
+            break
+        res = y - solution
+        RSS = float(res @ res)
+        if abs(RSS - RSS0) < tol:
+            break
+        raise NotImplementedError("thresholded_oasisAR2 oracle: update_smin reached")   # pragma: no cover
+    return solution, spks, b, np.asarray(g, dtype=np.float64)[:2], smin, aset
+
+
 # ----------------------------------------------------------------------------- deconvolveCa
 _DEFAULTS = dict(type="ar1", pars=None, sn=None, b=0.0, lam=0.0, optimize_b=False, optimize_pars=False,
                  optimize_smin=False, method="constrained", window=200, shift=100, smin=0.0, maxIter=10,
@@ -705,8 +733,13 @@ def deconvolveCa(y, options=None, **kw):
                                                   None, o["maxIter"], o["tau_range"])
         o["b"], o["pars"], o["lam"] = b, g, lam
     elif method == "thresholded":
-        if o["type"] != "ar1":
-            raise NotImplementedError("thresholded_oasisAR2 not restated yet")
+        if o["type"] == "ar2":
+            c, s, b, g, smin, _ = thresholded_oasisAR2(y, o["pars"], o["sn"], o["smin"], o["optimize_b"],
+                                                       o["optimize_pars"], None, o["maxIter"], o["thresh_factor"])
+            o["b"], o["pars"], o["smin"] = b, g, smin
+            c = np.array(c, dtype=np.float64)
+            c[~np.isfinite(c)] = 0
+            return c, s, o
         c, s, b, g, smin, _ = thresholded_oasisAR1(y, o["pars"], o["sn"], o["optimize_b"], o["optimize_pars"],
                                                    None, o["maxIter"], o["thresh_factor"], o["p_noise"],
                                                    o["tau_range"])

@@ -68,6 +68,12 @@ def test_foopsi_ar2(built_lib):
     _compare(Y, dict(type="ar2", method="foopsi", smin=-3), built_lib, rtol=1e-6)
 
 
+def test_thresholded_ar2(built_lib):
+    from oracle import oasis as O
+    Y, _, _ = O.gen_data([1.7, -0.712], 1.0, 3000, 30, 0.5, 0, 3, 3)
+    _compare(Y, dict(type="ar2", method="thresholded", pars=[1.7, -0.712]), built_lib)
+
+
 def test_pav_invariants_large(built_lib):
     """Size-independent properties at a BASELINE-scale T: s>=smin or 0, c_t = g c_{t-1} off spikes."""
     from cnmf_e_b200 import oasis as G

@@ -130,3 +130,23 @@ def test_bg_identity_property(built_lib):
     # regression residual must be orthogonal to the regressors' mean: rows of W reproduce a constant-free model
     assert np.isfinite(W.data).all() and np.abs(W.data).max() < 10
     g.close()
+
+
+def test_update_sn_and_lars(built_lib):
+    """update_spatial_parallel(obj, use_parallel, update_sn=true) (:191-194) and spatial_algorithm='lars'
+    (utilities/lars_spatial.m incl. its thresh(m) indexing quirk) need the explicit BG-subtracted rows."""
+    D, orc, gpu = _make(64, 48, 700, 5, (64, 48), 9, seed=21)
+    orc.update_background_parallel(); gpu.update_background_parallel()
+    for o in (orc, gpu):
+        o.options["spatial_algorithm"] = "hals_thresh"
+    orc.update_spatial_parallel(True, True, IND=D["IND"])
+    gpu.update_spatial_parallel(True, True, IND=D["IND"])
+    _close(gpu.P["sn"], orc.P["sn"], 1e-9)
+    _close(gpu.A.toarray(), orc.A.toarray())
+    _sync_from_oracle(orc, gpu)
+    for o in (orc, gpu):
+        o.options["spatial_algorithm"] = "lars"
+    orc.update_spatial_parallel(IND=D["IND"])
+    gpu.update_spatial_parallel(IND=D["IND"])
+    _close(gpu.A.toarray(), orc.A.toarray(), 1e-6)
+    gpu.close()
