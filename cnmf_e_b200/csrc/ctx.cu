@@ -9,6 +9,7 @@
 #include "kernels_video.cuh"
 #include "kernels_ring.cuh"
 #include "kernels_update.cuh"
+#include "kernels_svd.cuh"
 
 namespace cnmfe {
 int ring_s2_tensor(const uint8_t* hi, const uint8_t* lo, int nrb, int ncb, int T, int Tpad, int rr, double* S2,
@@ -45,6 +46,8 @@ struct Patch {
     uint16_t* Yt = nullptr; uint8_t* hi = nullptr; uint8_t* lo = nullptr;
     double* Ysum = nullptr; double* Ymean = nullptr;
     double* W = nullptr; double* b0 = nullptr;
+    double* bsvd = nullptr; double* fsvd = nullptr;   // svd background: b [nb][dp] (col-major dp x nb), f [nb][T]
+    int nb_alloc = 0; bool b_zero = true;
     // spatial result bookkeeping
     std::vector<int64_t> ind_entry;   // for each pattern entry (patch CSR order): index into the user's IND csc
     RingGeom geom;
@@ -377,7 +380,7 @@ extern "C" void cnmfe_destroy(cnmfe_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (Patch& P : c->patches) {
-        for (void* p : {(void*)P.Yt, (void*)P.hi, (void*)P.lo, (void*)P.Ysum, (void*)P.Ymean, (void*)P.W, (void*)P.b0})
+        for (void* p : {(void*)P.Yt, (void*)P.hi, (void*)P.lo, (void*)P.Ysum, (void*)P.Ymean, (void*)P.W, (void*)P.b0, (void*)P.bsvd, (void*)P.fsvd})
             if (p) cudaFree(p);
     }
     for (void* p : {(void*)c->C, (void*)c->Cprev, (void*)c->Craw, (void*)c->S, (void*)c->num, (void*)c->den,
@@ -397,6 +400,8 @@ extern "C" void cnmfe_destroy(cnmfe_ctx* c) {
 extern "C" int cnmfe_set_options(cnmfe_ctx* c, const cnmfe_options* o) {
     if (!c || !o) { set_error("cnmfe_set_options: null"); return -1; }
     if (o->spatial_algorithm < 0 || o->spatial_algorithm > 3) { set_error("spatial_algorithm out of range"); return -1; }
+    if (o->background_model < 0 || o->background_model > 1) { set_error("background_model must be 0 (ring) or 1 (svd)"); return -1; }
+    if (o->background_model == 1 && (o->nb < 1 || o->nb > SVD_MAXNB)) { set_error("svd background: nb must be in 1..%d", SVD_MAXNB); return -1; }
     c->opt = *o;
     return 0;
 }
@@ -581,8 +586,13 @@ static size_t bg_scratch_bytes(const cnmfe_ctx* c, const Patch& P, int Kb, size_
     return b;
 }
 
+static int update_background_svd(cnmfe_ctx* c);
+static int update_spatial_svd(cnmfe_ctx* c);
+static int update_temporal_patches_svd(cnmfe_ctx* c);
+
 extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
     if (!c) { set_error("cnmfe_update_background: null ctx"); return -1; }
+    if (c->opt.background_model == 1) return update_background_svd(c);
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
     for (float& f : c->phase_ms) f = 0;
     const int T = c->T;
@@ -734,6 +744,10 @@ extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
     for (float& f : c->phase_ms) f = 0;
     if (c->IND.K != c->K) { set_error("update_spatial: search mask has %d columns, A has %d", c->IND.K, c->K); return -1; }
+    if (c->opt.background_model == 1) {
+        if (update_sn || c->opt.spatial_algorithm == 3) { set_error("update_spatial: update_sn / lars are built for the ring model only"); return -1; }
+        return update_spatial_svd(c);
+    }
     const bool lars = (c->opt.spatial_algorithm == 3);
     const int T = c->T;
     c->A_on_IND.assign(c->IND.ir.size(), 0.0);
@@ -899,6 +913,7 @@ extern "C" int cnmfe_get_spatial(cnmfe_ctx* c, double* A_on_IND) {
 // ===================================================================================================== temporal
 extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
     if (!c) { set_error("cnmfe_update_temporal: null ctx"); return -1; }
+    if (c->opt.background_model == 1) return update_temporal_patches_svd(c);
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
     for (float& f : c->phase_ms) f = 0;
     const int T = c->T, K = c->K;
@@ -1076,3 +1091,5 @@ extern "C" int cnmfe_debug_second_moments(cnmfe_ctx* c, int ip, int use_tensor, 
     return 0;
 }
 extern "C" int cnmfe_last_gram_was_tensor(cnmfe_ctx* c) { return c ? c->last_gram_tensor : 0; }
+
+#include "ctx_svd.inc"

@@ -80,7 +80,7 @@ class Sources2D:
                             num_neighbors=num_neighbors, thresh_outlier=np.nan, spatial_algorithm="hals", maxIter=5,
                             deconv_flag=True, deconv_options=dict(type="ar1", method="foopsi", smin=-5,
                                                                   optimize_pars=True, optimize_b=True, max_tau=100),
-                            replicate_spatial_aprev_quirk=True, use_tensor_gram=True)
+                            replicate_spatial_aprev_quirk=True, use_tensor_gram=True, nb=1)
         if options:
             self.options.update(options)
         self.patch_pos, self.block_pos = patch_geometry(self.d1, self.d2, patch_dims, ring_radius)
@@ -114,6 +114,8 @@ class Sources2D:
         self.C_prev = np.zeros((0, self.T))
         self.W = {}
         self.b0 = {}
+        self.b = {}
+        self.f = {}
         self.b0_new = np.zeros((self.d1, self.d2))
         self.P = dict(sn=np.ones((self.d1, self.d2)), kernel_pars=None, neuron_sn=None, Ymean=None)
         self.search_fn = None
@@ -166,8 +168,10 @@ class Sources2D:
         o = L.Options()
         self._lib.cnmfe_options_defaults(ctypes.byref(o))
         opt = self.options
-        if str(opt["background_model"]).lower() != "ring" or opt["bg_ssub"] != 1:
-            raise L.CnmfeError("only background_model='ring' with bg_ssub=1 is built in this round")
+        model = str(opt["background_model"]).lower()
+        if model not in ("ring", "svd") or (model == "ring" and opt["bg_ssub"] != 1):
+            raise L.CnmfeError("built background models: 'ring' with bg_ssub=1, and 'svd' (not 'nmf': nnmf is randomly "
+                               "initialised in the reference; not bg_ssub>1)")
         if not (opt["thresh_outlier"] is None or np.isnan(opt["thresh_outlier"])):
             raise L.CnmfeError("thresh_outlier (fit_ring_model.m:50-70 outlier clamp) is not built; leave it NaN")
         o.spatial_algorithm = _SPATIAL[str(opt["spatial_algorithm"]).lower()] if \
@@ -177,6 +181,8 @@ class Sources2D:
         o.bg_acceleration = int(bool(opt["bg_acceleration"]))
         o.replicate_spatial_aprev_quirk = int(bool(opt["replicate_spatial_aprev_quirk"]))
         o.use_tensor_gram = int(bool(opt["use_tensor_gram"]))
+        o.background_model = 1 if model == "svd" else 0
+        o.nb = int(opt.get("nb", 1))
         if opt["deconv_flag"]:
             d, _, _ = make_deconv_opts(opt["deconv_options"] or {})
             o.deconv = d
@@ -203,6 +209,16 @@ class Sources2D:
         L.check(self._lib.cnmfe_set_prev(self._h, K, _ptr(jc), _ptr(ir), _ptr(pr), _ptr(C)))
 
     def push_ring(self):
+        if str(self.options["background_model"]).lower() == "svd":
+            for i in range(self.npatch):
+                b, f, b0 = self.b.get(i), self.f.get(i), self.b0.get(i)
+                if b is None and f is None and b0 is None:
+                    continue
+                bf = None if b is None else np.asfortranarray(b, dtype=np.float64)
+                ff = None if f is None else np.asfortranarray(f, dtype=np.float64)
+                b0f = None if b0 is None else np.ascontiguousarray(b0, dtype=np.float64)
+                L.check(self._lib.cnmfe_set_bf(self._h, i, _ptr(bf), _ptr(ff), _ptr(b0f)))
+            return
         for i in range(self.npatch):
             W = self.W.get(i)
             b0 = self.b0.get(i)
@@ -213,6 +229,15 @@ class Sources2D:
             L.check(self._lib.cnmfe_set_ring(self._h, i, _ptr(Wf), _ptr(b0f)))
 
     def pull_ring(self):
+        if str(self.options["background_model"]).lower() == "svd":
+            nb = int(self.options.get("nb", 1))
+            for i in self.owned_patches():
+                p = self.patch_of(i)
+                dp = (p[1] - p[0] + 1) * (p[3] - p[2] + 1)
+                b = np.zeros((dp, nb), order="F"); f = np.zeros((nb, self.T), order="F"); b0 = np.zeros(dp)
+                L.check(self._lib.cnmfe_get_bf(self._h, i, _ptr(b), _ptr(f), _ptr(b0)))
+                self.b[i], self.f[i], self.b0[i] = np.ascontiguousarray(b), np.ascontiguousarray(f), b0
+            return
         for i in self.owned_patches():
             p = self.patch_of(i)
             dp = (p[1] - p[0] + 1) * (p[3] - p[2] + 1)

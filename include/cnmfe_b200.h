@@ -53,6 +53,8 @@ typedef struct cnmfe_options {
                                           update_spatial_parallel.m:82-98 does (mask==1 after the patch is set to 2) */
     int use_tensor_gram;     /* 1 = tcgen05 INT8 kernel for the ring second moments, 0 = SIMT reference kernel */
     cnmfe_deconv_opts deconv;
+    int background_model;    /* 0 = 'ring' (1p, bg_ssub = 1), 1 = 'svd' (2p default, endoscope/fit_svd_model.m) */
+    int nb;                  /* options.nb: number of svd background components (default 1) */
 } cnmfe_options;
 
 const char* cnmfe_last_error(void);
@@ -115,6 +117,9 @@ int cnmfe_set_sn(cnmfe_ctx* ctx, const double* sn);
 int cnmfe_ring_offsets(cnmfe_ctx* ctx, int* nnb, int32_t* r_shift, int32_t* c_shift);
 int cnmfe_set_ring(cnmfe_ctx* ctx, int ipatch, const double* W_slots, const double* b0);
 int cnmfe_get_ring(cnmfe_ctx* ctx, int ipatch, double* W_slots, double* b0);
+/* obj.b{ipatch} (d_patch x nb), obj.f{ipatch} (nb x T), obj.b0{ipatch} of the svd background model (column-major) */
+int cnmfe_set_bf(cnmfe_ctx* ctx, int ipatch, const double* b, const double* f, const double* b0);
+int cnmfe_get_bf(cnmfe_ctx* ctx, int ipatch, double* b, double* f, double* b0);
 
 /* update_background_parallel(obj, use_parallel) (@Sources2D/update_background_parallel.m:1), ring model, bg_ssub=1.
  * Result stays on the device (W, b0, A_prev<-A, C_prev<-C); fetch with cnmfe_get_ring. */

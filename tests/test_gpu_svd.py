@@ -1,0 +1,43 @@
+"""GPU parity of the svd background model (2p path, demo_large_data_2p.m:46) against oracle/svd_bg.py.
+b and f are defined up to a common sign per component (eigs), so parity is stated on the product b*f and on b0."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, tol=1e-7):
+    scale = max(1.0, float(np.abs(b).max()))
+    err = float(np.abs(np.asarray(a) - np.asarray(b)).max())
+    assert err <= tol * scale, "max abs err %g (scale %g)" % (err, scale)
+
+
+@pytest.mark.parametrize("shape", [(48, 40, 500, 5, (48, 40), 1), (64, 60, 400, 8, (32, 30), 2)])
+def test_svd_background_chain(built_lib, shape):
+    from oracle import gen, oasis as O
+    from oracle.svd_bg import OracleSources2DSVD
+    from cnmf_e_b200.sources2d import Sources2D
+    d1, d2, T, K, patch, nb = shape
+    D = gen.make_synthetic(d1, d2, T, K, seed=31, nblob=3, bg_amp=60.0)
+    sn = O.GetSn(D["Y"].reshape(-1, T, order="F").astype(np.float64)).reshape(d1, d2, order="F")
+    orc = OracleSources2DSVD(D["Y"], patch, ring_radius=6, nb=nb, options=dict(spatial_algorithm="hals"))
+    gpu = Sources2D(d1, d2, T, patch, ring_radius=6, options=dict(background_model="svd", nb=nb, spatial_algorithm="hals"))
+    gpu.load_video(D["Y"])
+    for o in (orc, gpu):
+        o.A, o.C = D["A0"].copy(), D["C0"].copy()
+        o.P["sn"] = sn
+    orc.update_background_parallel()
+    gpu.update_background_parallel()
+    for i, mp in enumerate(orc.patches()):
+        _close(gpu.b[i] @ gpu.f[i], orc.b[mp] @ orc.f[mp], 1e-7)
+        _close(gpu.b0[i], orc.b0[mp], 1e-7)
+    orc.update_spatial_parallel(IND=D["IND"])
+    gpu.update_spatial_parallel(IND=D["IND"])
+    _close(gpu.A.toarray(), orc.A.toarray(), 1e-6)
+    orc.update_temporal_parallel()
+    gpu.update_temporal_parallel()
+    _close(gpu.C_raw, orc.C_raw, 1e-6)
+    _close(gpu.C, orc.C, 1e-6)
+    assert np.array_equal(gpu.S > 0, orc.S > 0)
+    gpu.close()
