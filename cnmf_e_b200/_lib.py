@@ -71,6 +71,7 @@ SYMBOLS = {
     "cnmfe_temporal_merge_buffers": (I, [V, ctypes.POINTER(V), ctypes.POINTER(V)]),
     "cnmfe_update_temporal_finish": (I, [V]),
     "cnmfe_update_temporal": (I, [V]),
+    "cnmfe_set_use_c_hat": (I, [V, I]),
     "cnmfe_get_temporal": (I, [V, V, V, V, V, V]),
     "cnmfe_sync": (I, [V]),
     "cnmfe_timer_begin": (I, [V]),

@@ -97,6 +97,7 @@ struct cnmfe_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr;
     float phase_ms[7] = {0, 0, 0, 0, 0, 0, 0};
     int last_gram_tensor = 0;
+    int use_c_hat = 1;            // update_temporal_parallel(obj, use_parallel, use_c_hat)
     bool first_bg = true;          // flag_first of update_background_parallel.m:142-146 (W{1} still uniform)
     // neurons
     HostCsc A, Aprev, IND;
@@ -400,8 +401,8 @@ extern "C" void cnmfe_destroy(cnmfe_ctx* c) {
 extern "C" int cnmfe_set_options(cnmfe_ctx* c, const cnmfe_options* o) {
     if (!c || !o) { set_error("cnmfe_set_options: null"); return -1; }
     if (o->spatial_algorithm < 0 || o->spatial_algorithm > 3) { set_error("spatial_algorithm out of range"); return -1; }
-    if (o->background_model < 0 || o->background_model > 1) { set_error("background_model must be 0 (ring) or 1 (svd)"); return -1; }
-    if (o->background_model == 1 && (o->nb < 1 || o->nb > SVD_MAXNB)) { set_error("svd background: nb must be in 1..%d", SVD_MAXNB); return -1; }
+    if (o->background_model < 0 || o->background_model > 2) { set_error("background_model must be 0 (ring), 1 (svd) or 2 (nmf)"); return -1; }
+    if (o->background_model >= 1 && (o->nb < 1 || o->nb > SVD_MAXNB)) { set_error("svd background: nb must be in 1..%d", SVD_MAXNB); return -1; }
     c->opt = *o;
     return 0;
 }
@@ -593,6 +594,10 @@ static int update_temporal_patches_svd(cnmfe_ctx* c);
 extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
     if (!c) { set_error("cnmfe_update_background: null ctx"); return -1; }
     if (c->opt.background_model == 1) return update_background_svd(c);
+    if (c->opt.background_model == 2) {
+        set_error("update_background: the nmf model calls the Statistics-toolbox nnmf with a RANDOM initialisation (fit_nmf_model.m:19); fit it in MATLAB and hand b, f over with cnmfe_set_bf -- the nmf BG subtraction of the spatial/temporal updates is built");
+        return -1;
+    }
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
     for (float& f : c->phase_ms) f = 0;
     const int T = c->T;
@@ -744,7 +749,7 @@ extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
     for (float& f : c->phase_ms) f = 0;
     if (c->IND.K != c->K) { set_error("update_spatial: search mask has %d columns, A has %d", c->IND.K, c->K); return -1; }
-    if (c->opt.background_model == 1) {
+    if (c->opt.background_model >= 1) {
         if (update_sn || c->opt.spatial_algorithm == 3) { set_error("update_spatial: update_sn / lars are built for the ring model only"); return -1; }
         return update_spatial_svd(c);
     }
@@ -913,7 +918,7 @@ extern "C" int cnmfe_get_spatial(cnmfe_ctx* c, double* A_on_IND) {
 // ===================================================================================================== temporal
 extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
     if (!c) { set_error("cnmfe_update_temporal: null ctx"); return -1; }
-    if (c->opt.background_model == 1) return update_temporal_patches_svd(c);
+    if (c->opt.background_model >= 1) return update_temporal_patches_svd(c);
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
     for (float& f : c->phase_ms) f = 0;
     const int T = c->T, K = c->K;
@@ -928,6 +933,17 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
         build_local(c, P, c->A, SEL_SUM_BLOCK, ROWS_BLOCK_PATCHONLY, nullptr, &LA);
         const int Kt = LA.K();
         if (Kt == 0) continue;   // update_temporal_parallel.m:123-126
+        if (!c->use_c_hat) {
+            // fast_temporal (update_temporal_parallel.m:314-337): keep only the pixels with A >= 0.5*max(A) per neuron
+            std::vector<double> amax(Kt, 0.0);
+            for (int k = 0; k < Kt; ++k)
+                for (int e = LA.cptr[k]; e < LA.cptr[k + 1]; ++e) amax[k] = std::max(amax[k], LA.cval[e]);
+            for (int k = 0; k < Kt; ++k)
+                for (int e = LA.cptr[k]; e < LA.cptr[k + 1]; ++e)
+                    if (!(LA.cval[e] / amax[k] >= 0.5)) LA.cval[e] = 0.0;
+            for (size_t e = 0; e < LA.col.size(); ++e)
+                if (!(LA.val[e] / amax[LA.col[e]] >= 0.5)) LA.val[e] = 0.0;
+        }
         build_local(c, P, c->Aprev, SEL_SUM_BLOCK, ROWS_BLOCK, nullptr, &LP);
         const int Kp = LP.K();
         size_t need = pad256((size_t)P.db * Kt * 8) + 4 * pad256((size_t)Kt * T * 8) + pad256((size_t)std::max(Kp, 1) * T * 8) +
@@ -1001,7 +1017,11 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
         CNMFE_CUDA_OK(cudaMemsetAsync(d_Crawl, 0, (size_t)Kt * T * 8, c->st));
         CNMFE_CUDA_OK(cudaMemsetAsync(d_Sl, 0, (size_t)Kt * T * 8, c->st));
         CNMFE_CUDA_OK(cudaMemsetAsync(d_parsl, 0, (size_t)Kt * 16, c->st));
-        if (hals_temporal_dev(d_U, d_vptr, d_vidx, d_vval, d_aa, Kt, T, c->opt.maxIter_temporal, c->opt.deconv_flag,
+        if (!c->use_c_hat) {
+            // C_raw = (tmp_A'*Y) ./ aa  (aa = 0 -> row of zeros, weight 0)
+            dim3 gg((T + 255) / 256, Kt);
+            LAUNCH(rows_div_diag_kernel, gg, 256, 0, c->st, d_U, d_V, Kt, T, d_Crawl);
+        } else if (hals_temporal_dev(d_U, d_vptr, d_vidx, d_vval, d_aa, Kt, T, c->opt.maxIter_temporal, c->opt.deconv_flag,
                               c->opt.deconv, d_Cl, d_Crawl, d_Sl, d_snl, d_parsl, c->d_done, c->d_ticket, c->d_order,
                               &c->arena, c->st)) return -1;
         { dim3 gg((T + 255) / 256, Kt); LAUNCH(temporal_merge_kernel, gg, 256, 0, c->st, d_Crawl, d_V, Kt, T, d_ids, c->num, c->den); }
@@ -1043,6 +1063,13 @@ extern "C" int cnmfe_update_temporal_finish(cnmfe_ctx* c) {
 extern "C" int cnmfe_update_temporal(cnmfe_ctx* c) {
     if (cnmfe_update_temporal_patches(c)) return -1;
     return cnmfe_update_temporal_finish(c);
+}
+
+extern "C" int cnmfe_set_use_c_hat(cnmfe_ctx* c, int use_c_hat) {
+    if (!c) { set_error("cnmfe_set_use_c_hat: null ctx"); return -1; }
+    if (!use_c_hat && c->opt.background_model != 0) { set_error("use_c_hat=false is built for the ring model only"); return -1; }
+    c->use_c_hat = use_c_hat ? 1 : 0;
+    return 0;
 }
 
 extern "C" int cnmfe_get_temporal(cnmfe_ctx* c, double* C, double* C_raw, double* S, double* kernel_pars,

@@ -264,6 +264,15 @@ __global__ void temporal_merge_kernel(const double* __restrict__ Craw, const dou
     if (t == 0) den[ids[k]] += aa;
 }
 
+// dst[k][t] = U[k][t] / V[k][k]  (0 when V[k][k] == 0): fast_temporal, update_temporal_parallel.m:329-335
+__global__ void rows_div_diag_kernel(const double* __restrict__ U, const double* __restrict__ V, int K, int T,
+                                     double* __restrict__ dst) {
+    int k = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double aa = V[(size_t)k * K + k];
+    dst[(size_t)k * T + t] = (aa == 0.0) ? 0.0 : U[(size_t)k * T + t] / aa;
+}
+
 __global__ void temporal_divide_kernel(double* __restrict__ num, const double* __restrict__ den, int K, int T) {
     int k = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;

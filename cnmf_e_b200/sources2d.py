@@ -169,7 +169,7 @@ class Sources2D:
         self._lib.cnmfe_options_defaults(ctypes.byref(o))
         opt = self.options
         model = str(opt["background_model"]).lower()
-        if model not in ("ring", "svd") or (model == "ring" and opt["bg_ssub"] != 1):
+        if model not in ("ring", "svd", "nmf") or (model == "ring" and opt["bg_ssub"] != 1):
             raise L.CnmfeError("built background models: 'ring' with bg_ssub=1, and 'svd' (not 'nmf': nnmf is randomly "
                                "initialised in the reference; not bg_ssub>1)")
         if not (opt["thresh_outlier"] is None or np.isnan(opt["thresh_outlier"])):
@@ -181,7 +181,7 @@ class Sources2D:
         o.bg_acceleration = int(bool(opt["bg_acceleration"]))
         o.replicate_spatial_aprev_quirk = int(bool(opt["replicate_spatial_aprev_quirk"]))
         o.use_tensor_gram = int(bool(opt["use_tensor_gram"]))
-        o.background_model = 1 if model == "svd" else 0
+        o.background_model = {"ring": 0, "svd": 1, "nmf": 2}[model]
         o.nb = int(opt.get("nb", 1))
         if opt["deconv_flag"]:
             d, _, _ = make_deconv_opts(opt["deconv_options"] or {})
@@ -209,7 +209,7 @@ class Sources2D:
         L.check(self._lib.cnmfe_set_prev(self._h, K, _ptr(jc), _ptr(ir), _ptr(pr), _ptr(C)))
 
     def push_ring(self):
-        if str(self.options["background_model"]).lower() == "svd":
+        if str(self.options["background_model"]).lower() in ("svd", "nmf"):
             for i in range(self.npatch):
                 b, f, b0 = self.b.get(i), self.f.get(i), self.b0.get(i)
                 if b is None and f is None and b0 is None:
@@ -229,7 +229,7 @@ class Sources2D:
             L.check(self._lib.cnmfe_set_ring(self._h, i, _ptr(Wf), _ptr(b0f)))
 
     def pull_ring(self):
-        if str(self.options["background_model"]).lower() == "svd":
+        if str(self.options["background_model"]).lower() in ("svd", "nmf"):
             nb = int(self.options.get("nb", 1))
             for i in self.owned_patches():
                 p = self.patch_of(i)
@@ -327,9 +327,8 @@ class Sources2D:
 
     def update_temporal_parallel(self, use_parallel=True, use_c_hat=True, sync_host=True):
         """update_temporal_parallel(obj, use_parallel, use_c_hat)."""
-        if not use_c_hat:
-            raise L.CnmfeError("use_c_hat=false (fast_temporal, update_temporal_parallel.m:314-337) is not built")
         self._push_options()
+        L.check(self._lib.cnmfe_set_use_c_hat(self._h, int(bool(use_c_hat))))
         if sync_host:
             self.push_neurons()
             self.push_prev()

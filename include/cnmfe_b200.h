@@ -53,7 +53,9 @@ typedef struct cnmfe_options {
                                           update_spatial_parallel.m:82-98 does (mask==1 after the patch is set to 2) */
     int use_tensor_gram;     /* 1 = tcgen05 INT8 kernel for the ring second moments, 0 = SIMT reference kernel */
     cnmfe_deconv_opts deconv;
-    int background_model;    /* 0 = 'ring' (1p, bg_ssub = 1), 1 = 'svd' (2p default, endoscope/fit_svd_model.m) */
+    int background_model;    /* 0 = 'ring' (1p, bg_ssub = 1), 1 = 'svd' (2p default, endoscope/fit_svd_model.m),
+                                2 = 'nmf' (BG subtraction Y - b*f only, update_spatial_parallel.m:179-182; the nnmf fit
+                                itself is randomly initialised in the reference and stays in MATLAB: cnmfe_set_bf) */
     int nb;                  /* options.nb: number of svd background components (default 1) */
 } cnmfe_options;
 
@@ -143,6 +145,9 @@ int cnmfe_update_temporal_patches(cnmfe_ctx* ctx);
 int cnmfe_temporal_merge_buffers(cnmfe_ctx* ctx, double** num_dev /* K*T, [k][t] */, double** den_dev /* K */);
 int cnmfe_update_temporal_finish(cnmfe_ctx* ctx);
 int cnmfe_update_temporal(cnmfe_ctx* ctx);   /* = patches + finish (single process) */
+/* use_c_hat argument of update_temporal_parallel (default 1); 0 = fast_temporal (update_temporal_parallel.m:314-337):
+ * mean fluorescence over the pixels with A >= 0.5 max(A) instead of the HALS sweeps */
+int cnmfe_set_use_c_hat(cnmfe_ctx* ctx, int use_c_hat);
 /* obj.C, obj.C_raw, obj.S (K x T col-major), obj.P.kernel_pars (2 x K), obj.P.neuron_sn (K); any may be NULL */
 int cnmfe_get_temporal(cnmfe_ctx* ctx, double* C, double* C_raw, double* S, double* kernel_pars,
                        double* neuron_sn);

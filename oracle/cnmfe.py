@@ -540,8 +540,17 @@ class OracleSources2D:
             A_patch = np.asarray(Acsr[bm, :][:, ind].todense())[ind_patch, :]
             C_patch = self.C[ind, :]
             Ysig = self._ysig(mp, "temporal")
-            _, C_raw_p, _, _ = HALS_temporal(Ysig, A_patch, C_patch, o["maxIter"], dopt)
-            aa_p = np.sum(A_patch ** 2, axis=0)
+            if not use_c_hat:
+                # fast_temporal (update_temporal_parallel.m:314-337)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    tmpA = A_patch / A_patch.max(axis=0, keepdims=True)
+                tmp_A = A_patch * (tmpA >= 0.5)
+                aa_p = np.sum(tmp_A ** 2, axis=0)
+                den = np.where(aa_p == 0, np.inf, aa_p)
+                C_raw_p = (tmp_A.T @ Ysig) / den[:, None]
+            else:
+                _, C_raw_p, _, _ = HALS_temporal(Ysig, A_patch, C_patch, o["maxIter"], dopt)
+                aa_p = np.sum(A_patch ** 2, axis=0)
             C_new[ind, :] += C_raw_p * aa_p[:, None]
             aa[ind] += aa_p
         aa[aa == 0] = 1

@@ -41,3 +41,36 @@ def test_svd_background_chain(built_lib, shape):
     _close(gpu.C, orc.C, 1e-6)
     assert np.array_equal(gpu.S > 0, orc.S > 0)
     gpu.close()
+
+
+def test_nmf_background_subtraction(built_lib):
+    """nmf model: the fit (nnmf, random init) stays in MATLAB; given b, f the BG subtraction Y - b*f of the spatial and
+    temporal updates (update_spatial_parallel.m:179-182, update_temporal_parallel.m:165-168) must match the oracle."""
+    from oracle import gen
+    from oracle.svd_bg import OracleSources2DSVD
+    from cnmf_e_b200.sources2d import Sources2D
+    d1, d2, T, K = 40, 36, 400, 4
+    D = gen.make_synthetic(d1, d2, T, K, seed=8, nblob=2, bg_amp=50.0)
+    Yf = D["Y"].reshape(-1, T, order="F").astype(np.float64)
+    u, s, vt = np.linalg.svd(Yf, full_matrices=False)
+    b = np.abs(u[:, :1] * s[0]); f = np.abs(vt[:1])                 # a deterministic non-negative rank-1 factorisation
+
+    class NmfOracle(OracleSources2DSVD):
+        def _ysig(self, mp, phase):
+            return self._get_block(self.patch_pos[mp]).astype(np.float64) - self.b[mp] @ self.f[mp]
+
+    orc = NmfOracle(D["Y"], (d1, d2), ring_radius=6, nb=1, options=dict(spatial_algorithm="hals"))
+    gpu = Sources2D(d1, d2, T, (d1, d2), ring_radius=6, options=dict(background_model="nmf", nb=1, spatial_algorithm="hals"))
+    gpu.load_video(D["Y"])
+    for o in (orc, gpu):
+        o.A, o.C = D["A0"].copy(), D["C0"].copy()
+    orc.b[(0, 0)], orc.f[(0, 0)] = b, f
+    gpu.b[0], gpu.f[0], gpu.b0[0] = b, f, np.zeros(d1 * d2)
+    orc.update_spatial_parallel(IND=D["IND"]); gpu.update_spatial_parallel(IND=D["IND"])
+    _close(gpu.A.toarray(), orc.A.toarray(), 1e-6)
+    orc.update_temporal_parallel(); gpu.update_temporal_parallel()
+    _close(gpu.C_raw, orc.C_raw, 1e-6)
+    assert np.array_equal(gpu.S > 0, orc.S > 0)
+    with pytest.raises(Exception):
+        gpu.update_background_parallel()
+    gpu.close()

@@ -150,3 +150,15 @@ def test_update_sn_and_lars(built_lib):
     gpu.update_spatial_parallel(IND=D["IND"])
     _close(gpu.A.toarray(), orc.A.toarray(), 1e-6)
     gpu.close()
+
+
+def test_fast_temporal_use_c_hat_false(built_lib):
+    """update_temporal_parallel(obj, use_parallel, use_c_hat=false): fast_temporal (:314-337) instead of the HALS sweeps."""
+    D, orc, gpu = _make(64, 48, 600, 5, (64, 48), 9, seed=33)
+    orc.update_background_parallel(); gpu.update_background_parallel()
+    orc.update_temporal_parallel(True, False)
+    gpu.update_temporal_parallel(True, False)
+    _close(gpu.C_raw, orc.C_raw)
+    _close(gpu.C, orc.C)
+    assert np.array_equal(gpu.S > 0, orc.S > 0)
+    gpu.close()
