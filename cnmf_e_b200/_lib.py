@@ -27,7 +27,7 @@ class Options(ctypes.Structure):
     _fields_ = [("spatial_algorithm", ctypes.c_int), ("maxIter_temporal", ctypes.c_int),
                 ("deconv_flag", ctypes.c_int), ("bg_acceleration", ctypes.c_int),
                 ("replicate_spatial_aprev_quirk", ctypes.c_int), ("use_tensor_gram", ctypes.c_int),
-                ("deconv", DeconvOpts), ("background_model", ctypes.c_int), ("nb", ctypes.c_int)]
+                ("deconv", DeconvOpts), ("background_model", ctypes.c_int), ("nb", ctypes.c_int), ("bg_ssub", ctypes.c_int)]
 
 
 class CnmfeError(RuntimeError):
@@ -59,6 +59,7 @@ SYMBOLS = {
     "cnmfe_ring_offsets": (I, [V, c_int_p, V, V]),
     "cnmfe_set_ring": (I, [V, I, V, V]),
     "cnmfe_get_ring": (I, [V, I, V, V]),
+    "cnmfe_ssub_dims": (I, [V, I, c_int_p, c_int_p, c_int_p, V, V]),
     "cnmfe_set_bf": (I, [V, I, V, V, V]),
     "cnmfe_get_bf": (I, [V, I, V, V, V]),
     "cnmfe_update_background": (I, [V]),

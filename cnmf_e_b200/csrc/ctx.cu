@@ -10,6 +10,7 @@
 #include "kernels_ring.cuh"
 #include "kernels_update.cuh"
 #include "kernels_svd.cuh"
+#include "kernels_ssub.cuh"
 
 namespace cnmfe {
 int ring_s2_tensor(const uint8_t* hi, const uint8_t* lo, int nrb, int ncb, int T, int Tpad, int rr, double* S2,
@@ -98,6 +99,8 @@ struct cnmfe_ctx {
     float phase_ms[7] = {0, 0, 0, 0, 0, 0, 0};
     int last_gram_tensor = 0;
     int use_c_hat = 1;            // update_temporal_parallel(obj, use_parallel, use_c_hat)
+    void* ssub_state = nullptr;   // SsubCtx (ctx_ssub.inc): coarse-grid ring model for options.bg_ssub > 1
+    int num_neighbors = 0;
     bool first_bg = true;          // flag_first of update_background_parallel.m:142-146 (W{1} still uniform)
     // neurons
     HostCsc A, Aprev, IND;
@@ -299,6 +302,11 @@ size_t pad256(size_t b) { return (b + 255) / 256 * 256 + 256; }
 
 }  // namespace
 
+static int ssub_configure(cnmfe_ctx* c, int ssub);
+static int ssub_set_ring(cnmfe_ctx* c, int ip, const double* W, const double* b0);
+static int ssub_get_ring(cnmfe_ctx* c, int ip, double* W, double* b0);
+static void ssub_destroy(cnmfe_ctx* c);
+
 // ===================================================================================================== lifetime
 extern "C" int cnmfe_create(cnmfe_ctx** out, int d1, int d2, int T, int npatch, const int32_t* patch_pos,
                             const int32_t* block_pos, const uint8_t* owned, int ring_radius, int num_neighbors,
@@ -317,6 +325,7 @@ extern "C" int cnmfe_create(cnmfe_ctx** out, int d1, int d2, int T, int npatch, 
     cnmfe_ctx* c = new cnmfe_ctx();
     c->device = device; c->d1 = d1; c->d2 = d2; c->T = T; c->Tpad = (T + 127) / 128 * 128; c->npatch = npatch;
     c->ring_radius = ring_radius;
+    c->num_neighbors = num_neighbors;
     cnmfe_options_defaults(&c->opt);
     get_nhood(ring_radius, num_neighbors, c->off_r, c->off_c);
     c->nnb = (int)c->off_r.size();
@@ -380,6 +389,7 @@ extern "C" int cnmfe_create(cnmfe_ctx** out, int d1, int d2, int T, int npatch, 
 extern "C" void cnmfe_destroy(cnmfe_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    ssub_destroy(c);
     for (Patch& P : c->patches) {
         for (void* p : {(void*)P.Yt, (void*)P.hi, (void*)P.lo, (void*)P.Ysum, (void*)P.Ymean, (void*)P.W, (void*)P.b0, (void*)P.bsvd, (void*)P.fsvd})
             if (p) cudaFree(p);
@@ -403,6 +413,8 @@ extern "C" int cnmfe_set_options(cnmfe_ctx* c, const cnmfe_options* o) {
     if (o->spatial_algorithm < 0 || o->spatial_algorithm > 3) { set_error("spatial_algorithm out of range"); return -1; }
     if (o->background_model < 0 || o->background_model > 2) { set_error("background_model must be 0 (ring), 1 (svd) or 2 (nmf)"); return -1; }
     if (o->background_model >= 1 && (o->nb < 1 || o->nb > SVD_MAXNB)) { set_error("svd background: nb must be in 1..%d", SVD_MAXNB); return -1; }
+    if (o->bg_ssub < 1 || o->bg_ssub > 8) { set_error("bg_ssub must be in 1..8"); return -1; }
+    if (o->background_model == 0) { CNMFE_CUDA_OK(cudaSetDevice(c->device)); if (ssub_configure(c, o->bg_ssub)) return -1; }
     c->opt = *o;
     return 0;
 }
@@ -510,6 +522,7 @@ extern "C" int cnmfe_ring_offsets(cnmfe_ctx* c, int* nnb, int32_t* r_shift, int3
 extern "C" int cnmfe_set_ring(cnmfe_ctx* c, int ip, const double* W, const double* b0) {
     if (!c || ip < 0 || ip >= c->npatch) { set_error("cnmfe_set_ring: bad patch"); return -1; }
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    if (c->opt.background_model == 0 && c->opt.bg_ssub > 1) return ssub_set_ring(c, ip, W, b0);
     Patch& P = c->patches[ip];
     bool uniform = true;
     if (W) {
@@ -538,6 +551,7 @@ extern "C" int cnmfe_set_ring(cnmfe_ctx* c, int ip, const double* W, const doubl
 extern "C" int cnmfe_get_ring(cnmfe_ctx* c, int ip, double* W, double* b0) {
     if (!c || ip < 0 || ip >= c->npatch) { set_error("cnmfe_get_ring: bad patch"); return -1; }
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    if (c->opt.background_model == 0 && c->opt.bg_ssub > 1) return ssub_get_ring(c, ip, W, b0);
     Patch& P = c->patches[ip];
     if (!P.owned) { set_error("cnmfe_get_ring: patch %d not owned", ip); return -1; }
     CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
@@ -588,6 +602,14 @@ static size_t bg_scratch_bytes(const cnmfe_ctx* c, const Patch& P, int Kb, size_
 }
 
 static int update_background_svd(cnmfe_ctx* c);
+static int ssub_configure(cnmfe_ctx* c, int ssub);
+static int ssub_ensure_patch(cnmfe_ctx* c, int ip, bool need_video);
+static int update_background_ssub(cnmfe_ctx* c);
+static int ssub_forward(cnmfe_ctx* c, int ip, const double* in, int K, double* out, double* t1, double* t2);
+static int ssub_transpose(cnmfe_ctx* c, int ip, const double* in, int K, double* out, double* t1, double* t2);
+static int ssub_set_ring(cnmfe_ctx* c, int ip, const double* W, const double* b0);
+static int ssub_get_ring(cnmfe_ctx* c, int ip, double* W, double* b0);
+static void ssub_destroy(cnmfe_ctx* c);
 static int update_spatial_svd(cnmfe_ctx* c);
 static int update_temporal_patches_svd(cnmfe_ctx* c);
 
@@ -598,6 +620,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         set_error("update_background: the nmf model calls the Statistics-toolbox nnmf with a RANDOM initialisation (fit_nmf_model.m:19); fit it in MATLAB and hand b, f over with cnmfe_set_bf -- the nmf BG subtraction of the spatial/temporal updates is built");
         return -1;
     }
+    if (c->opt.bg_ssub > 1) return update_background_ssub(c);
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
     for (float& f : c->phase_ms) f = 0;
     const int T = c->T;
@@ -754,6 +777,8 @@ extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
         return update_spatial_svd(c);
     }
     const bool lars = (c->opt.spatial_algorithm == 3);
+    const bool ssub = (c->opt.bg_ssub > 1);
+    if (ssub && (lars || update_sn)) { set_error("update_spatial: update_sn / lars are built for bg_ssub = 1 only"); return -1; }
     const int T = c->T;
     c->A_on_IND.assign(c->IND.ir.size(), 0.0);
     for (int ip = 0; ip < c->npatch; ++ip) {
@@ -774,6 +799,7 @@ extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
                       pad256((size_t)P.dp * 8) + pad256((size_t)(Ks + Kp) * 64 + 64) + (1 << 20);
         const int CH = 2048;   // rows of explicit Ysig per chunk (update_sn / lars only)
         if (update_sn || lars) need += pad256((size_t)CH * T * 8) + 3 * pad256((size_t)CH * 8) + pad256((size_t)P.dp * 8);
+        if (ssub) need += 3 * pad256((size_t)P.db * Ks * 8);
         if (c->scr.reserve(need)) return -1;
         c->scr.reset();
         const RingGeom& g = P.geom;
@@ -787,7 +813,9 @@ extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
         TAKE_OR_FAIL(d_pcol, to_dev(c, LP.col));
         TAKE_OR_FAIL(d_pval, to_dev(c, LP.val));
         TAKE_OR_FAIL(d_pids, to_dev(c, LP.ids));
-        std::vector<int> bb = expand_bbox(LS, c->rr, P.nrb, P.ncb);
+        // reach of the BG reconstruction operator: the ring (bg_ssub = 1) or up(4 taps) o ring o down(8/scale taps)
+        const int reach_s = (c->opt.bg_ssub > 1) ? c->opt.bg_ssub * ((c->ring_radius + c->opt.bg_ssub - 1) / c->opt.bg_ssub + 6) + 4 : c->rr;
+        std::vector<int> bb = expand_bbox(LS, reach_s, P.nrb, P.ncb);
         TAKE_OR_FAIL(d_bbox, to_dev(c, bb));
         std::vector<double> snp(P.dp);
         for (int p = 0; p < P.dp; ++p) {
@@ -870,8 +898,20 @@ extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
                    d_Cc, Ks, d_bbox, d_D);
         }
         if (Kp > 0) LAUNCH(spatial_make_D_kernel, P.db, 64, 0, c->st, d_D, Ks, d_pptr, d_pcol, d_pval, d_P2);
-        LAUNCH(spatial_U_kernel, (unsigned)(((size_t)P.dp * 32 + 255) / 256), 256, 0, c->st, g, c->d_off_r, c->d_off_c,
-               P.W, d_D, Ks, d_iptr, d_icol, d_pptr, d_pcol, d_pval, d_P2, d_U);
+        if (!ssub) {
+            LAUNCH(spatial_U_kernel, (unsigned)(((size_t)P.dp * 32 + 255) / 256), 256, 0, c->st, g, c->d_off_r, c->d_off_c,
+                   P.W, d_D, Ks, d_iptr, d_icol, d_pptr, d_pcol, d_pval, d_P2, d_U);
+        } else {
+            // Bf = imresize(W * imresize(R - mean(R), 1/ssub), [nr_block nc_block]) projected on Cc (:167-177)
+            if (ssub_ensure_patch(c, ip, false)) return -1;
+            double* d_F = c->scr.take<double>((size_t)P.db * Ks);
+            double* d_t1 = c->scr.take<double>((size_t)P.db * Ks);
+            double* d_t2 = c->scr.take<double>((size_t)P.db * Ks);
+            if (!d_F || !d_t1 || !d_t2) { set_error("scratch exhausted"); return -1; }
+            if (ssub_forward(c, ip, d_D, Ks, d_F, d_t1, d_t2)) return -1;
+            LAUNCH(spatial_U_ssub_kernel, (P.dp + 127) / 128, 128, 0, c->st, P.dp, P.nr, P.nrb, g.pr_off, g.pc_off, d_D, d_F,
+                   Ks, d_iptr, d_icol, d_pptr, d_pcol, d_pval, d_P2, d_U);
+        }
         phase_end(c, 2);
         phase_begin(c);
         CNMFE_CUDA_OK(cudaMemsetAsync(c->d_err, 0, 4, c->st));
@@ -946,7 +986,7 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
         }
         build_local(c, P, c->Aprev, SEL_SUM_BLOCK, ROWS_BLOCK, nullptr, &LP);
         const int Kp = LP.K();
-        size_t need = pad256((size_t)P.db * Kt * 8) + 4 * pad256((size_t)Kt * T * 8) + pad256((size_t)std::max(Kp, 1) * T * 8) +
+        size_t need = (c->opt.bg_ssub > 1 ? 4 : 1) * pad256((size_t)P.db * Kt * 8) + 4 * pad256((size_t)Kt * T * 8) + pad256((size_t)std::max(Kp, 1) * T * 8) +
                       2 * pad256((size_t)Kt * Kt * 12 + 64) + pad256((size_t)Kt * std::max(Kp, 1) * 8) +
                       2 * pad256((size_t)(P.db + 1) * 4) + pad256(LA.col.size() * 24 + 64) + pad256(LP.col.size() * 24 + 64) +
                       pad256((size_t)(Kt + Kp) * 128 + 64) + (1 << 20);
@@ -965,7 +1005,8 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
         TAKE_OR_FAIL(d_pcrow, to_dev(c, LP.crow));
         TAKE_OR_FAIL(d_pcval, to_dev(c, LP.cval));
         TAKE_OR_FAIL(d_pids, to_dev(c, LP.ids));
-        std::vector<int> bb = expand_bbox(LA, c->rr, P.nrb, P.ncb);
+        const int reach_t = (c->opt.bg_ssub > 1) ? c->opt.bg_ssub * ((c->ring_radius + c->opt.bg_ssub - 1) / c->opt.bg_ssub + 6) + 4 : c->rr;
+        std::vector<int> bb = expand_bbox(LA, reach_t, P.nrb, P.ncb);
         TAKE_OR_FAIL(d_bbox, to_dev(c, bb));
         TAKE_OR_FAIL(d_B, c->scr.take<double>((size_t)P.db * Kt));
         TAKE_OR_FAIL(d_U, c->scr.take<double>((size_t)Kt * T));
@@ -979,8 +1020,21 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
         TAKE_OR_FAIL(d_snl, c->scr.take<double>(Kt));
         TAKE_OR_FAIL(d_parsl, c->scr.take<double>((size_t)Kt * 2));
         CNMFE_CUDA_OK(cudaMemsetAsync(d_B, 0, (size_t)P.db * Kt * 8, c->st));
-        LAUNCH(temporal_build_negWtA_kernel, (P.db + 127) / 128, 128, 0, c->st, g, c->d_off_r, c->d_off_c, P.W, d_aptr,
-               d_acol, d_aval, Kt, d_B);
+        if (c->opt.bg_ssub <= 1) {
+            LAUNCH(temporal_build_negWtA_kernel, (P.db + 127) / 128, 128, 0, c->st, g, c->d_off_r, c->d_off_c, P.W, d_aptr,
+                   d_acol, d_aval, Kt, d_B);
+        } else {
+            // B = -(down' * W' * up') * A_patch   (transpose of the BG reconstruction operator)
+            if (ssub_ensure_patch(c, ip, false)) return -1;
+            double* d_Ai = c->scr.take<double>((size_t)P.db * Kt);
+            double* d_t1 = c->scr.take<double>((size_t)P.db * Kt);
+            double* d_t2 = c->scr.take<double>((size_t)P.db * Kt);
+            if (!d_Ai || !d_t1 || !d_t2) { set_error("scratch exhausted"); return -1; }
+            CNMFE_CUDA_OK(cudaMemsetAsync(d_Ai, 0, (size_t)P.db * Kt * 8, c->st));
+            LAUNCH(csr_to_dense_kernel, (P.db + 127) / 128, 128, 0, c->st, d_aptr, d_acol, d_aval, P.db, Kt, d_Ai);
+            if (ssub_transpose(c, ip, d_Ai, Kt, d_B, d_t1, d_t2)) return -1;
+            LAUNCH(negate_kernel, (unsigned)(((size_t)P.db * Kt + 255) / 256), 256, 0, c->st, d_B, (size_t)P.db * Kt);
+        }
         if (Kp > 0) {
             dim3 gg(Kt, (Kp + 63) / 64);
             LAUNCH(temporal_AWA_kernel, gg, 64, 0, c->st, d_B, Kt, d_pcptr, d_pcrow, d_pcval, Kp, d_AWA);
@@ -1120,3 +1174,4 @@ extern "C" int cnmfe_debug_second_moments(cnmfe_ctx* c, int ip, int use_tensor, 
 extern "C" int cnmfe_last_gram_was_tensor(cnmfe_ctx* c) { return c ? c->last_gram_tensor : 0; }
 
 #include "ctx_svd.inc"
+#include "ctx_ssub.inc"

@@ -169,9 +169,8 @@ class Sources2D:
         self._lib.cnmfe_options_defaults(ctypes.byref(o))
         opt = self.options
         model = str(opt["background_model"]).lower()
-        if model not in ("ring", "svd", "nmf") or (model == "ring" and opt["bg_ssub"] != 1):
-            raise L.CnmfeError("built background models: 'ring' with bg_ssub=1, and 'svd' (not 'nmf': nnmf is randomly "
-                               "initialised in the reference; not bg_ssub>1)")
+        if model not in ("ring", "svd", "nmf"):
+            raise L.CnmfeError("background_model must be 'ring', 'svd' or 'nmf'")
         if not (opt["thresh_outlier"] is None or np.isnan(opt["thresh_outlier"])):
             raise L.CnmfeError("thresh_outlier (fit_ring_model.m:50-70 outlier clamp) is not built; leave it NaN")
         o.spatial_algorithm = _SPATIAL[str(opt["spatial_algorithm"]).lower()] if \
@@ -183,6 +182,7 @@ class Sources2D:
         o.use_tensor_gram = int(bool(opt["use_tensor_gram"]))
         o.background_model = {"ring": 0, "svd": 1, "nmf": 2}[model]
         o.nb = int(opt.get("nb", 1))
+        o.bg_ssub = int(opt.get("bg_ssub", 1)) if model == "ring" else 1
         if opt["deconv_flag"]:
             d, _, _ = make_deconv_opts(opt["deconv_options"] or {})
             o.deconv = d
@@ -241,10 +241,38 @@ class Sources2D:
         for i in self.owned_patches():
             p = self.patch_of(i)
             dp = (p[1] - p[0] + 1) * (p[3] - p[2] + 1)
+            if int(self.options.get("bg_ssub", 1)) > 1:
+                d1s, d2s, nnb, _, _ = self.ssub_dims(i)
+                W = np.zeros((d1s * d2s, nnb))
+                b0 = np.zeros(dp)
+                L.check(self._lib.cnmfe_get_ring(self._h, i, _ptr(W), _ptr(b0)))
+                self.W[i], self.b0[i] = W, b0
+                continue
             W = np.zeros((dp, self.nnb))
             b0 = np.zeros(dp)
             L.check(self._lib.cnmfe_get_ring(self._h, i, _ptr(W), _ptr(b0)))
             self.W[i], self.b0[i] = W, b0
+
+    def ssub_dims(self, i):
+        """(d1s, d2s, nnb, r_shift, c_shift) of the coarse ring grid of patch i (bg_ssub > 1)."""
+        d1s, d2s, nnb = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        L.check(self._lib.cnmfe_ssub_dims(self._h, i, ctypes.byref(d1s), ctypes.byref(d2s), ctypes.byref(nnb), None, None))
+        rs = np.zeros(nnb.value, dtype=np.int32); cs = np.zeros(nnb.value, dtype=np.int32)
+        L.check(self._lib.cnmfe_ssub_dims(self._h, i, ctypes.byref(d1s), ctypes.byref(d2s), ctypes.byref(nnb), _ptr(rs), _ptr(cs)))
+        return d1s.value, d2s.value, nnb.value, rs, cs
+
+    def ring_as_sparse_ssub(self, i):
+        """obj.W{i} for bg_ssub > 1: sparse (d1s*d2s x d1s*d2s) on the coarse grid (initComponents_parallel.m:237-253)."""
+        d1s, d2s, nnb, rs, cs = self.ssub_dims(i)
+        W = self.W[i]
+        rr = np.tile(np.arange(d1s), d2s)
+        cc = np.repeat(np.arange(d2s), d1s)
+        rows, cols, vals = [], [], []
+        for s in range(nnb):
+            r2, c2 = rr + rs[s], cc + cs[s]
+            ok = (r2 >= 0) & (r2 < d1s) & (c2 >= 0) & (c2 < d2s)
+            rows.append(np.nonzero(ok)[0]); cols.append((c2 * d1s + r2)[ok]); vals.append(W[ok, s])
+        return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(d1s * d2s, d1s * d2s))
 
     def ring_as_sparse(self, i):
         """obj.W{i} as the reference stores it: sparse (d_patch x d_block), initComponents_parallel.m:221-236."""

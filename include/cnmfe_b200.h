@@ -57,6 +57,8 @@ typedef struct cnmfe_options {
                                 2 = 'nmf' (BG subtraction Y - b*f only, update_spatial_parallel.m:179-182; the nnmf fit
                                 itself is randomly initialised in the reference and stays in MATLAB: cnmfe_set_bf) */
     int nb;                  /* options.nb: number of svd background components (default 1) */
+    int bg_ssub;             /* options.bg_ssub (ring model): 1, or > 1 = ring weights on the ceil(block/bg_ssub) grid
+                                (demo_large_data_1p.m:30 uses 2); changing it re-initialises W (update_background_parallel.m:70-118) */
 } cnmfe_options;
 
 const char* cnmfe_last_error(void);
@@ -119,6 +121,9 @@ int cnmfe_set_sn(cnmfe_ctx* ctx, const double* sn);
 int cnmfe_ring_offsets(cnmfe_ctx* ctx, int* nnb, int32_t* r_shift, int32_t* c_shift);
 int cnmfe_set_ring(cnmfe_ctx* ctx, int ipatch, const double* W_slots, const double* b0);
 int cnmfe_get_ring(cnmfe_ctx* ctx, int ipatch, double* W_slots, double* b0);
+/* with bg_ssub > 1 the ring weights handled by cnmfe_set_ring / cnmfe_get_ring live on the coarse grid: nnb x (d1s*d2s)
+ * slots; this returns the coarse dimensions and ring offsets of patch ipatch */
+int cnmfe_ssub_dims(cnmfe_ctx* ctx, int ipatch, int* d1s, int* d2s, int* nnb, int32_t* r_shift, int32_t* c_shift);
 /* obj.b{ipatch} (d_patch x nb), obj.f{ipatch} (nb x T), obj.b0{ipatch} of the svd background model (column-major) */
 int cnmfe_set_bf(cnmfe_ctx* ctx, int ipatch, const double* b, const double* f, const double* b0);
 int cnmfe_get_bf(cnmfe_ctx* ctx, int ipatch, double* b, double* f, double* b0);
