@@ -246,7 +246,7 @@ def run_ours(args):
     lib = _lib.lib()
     d1, d2, T, K = D1, D2_PER_GPU * world, args.frames, K_PER_GPU * world
     prob = make_problem(d1, d2, T, K, SEED)
-    opts = dict(spatial_algorithm="nnls", use_tensor_gram=bool(args.tensor))
+    opts = dict(spatial_algorithm="nnls", use_tensor_gram=bool(args.tensor), bg_ssub=args.bg_ssub)
     obj = Sources2D(d1, d2, T, (D1, D2_PER_GPU), ring_radius=RING, device=local, rank=rank, world_size=world,
                     options=opts)
     for i in obj.owned_patches():
@@ -293,14 +293,21 @@ def run_ours(args):
     lib.cnmfe_timer_begin(obj._h)
     t0 = time.perf_counter()
     gram_ms = 0.0
+    call_ms = np.zeros(3)
     for _ in range(args.steps):
+        tc = time.perf_counter()
         obj.update_background_parallel(sync_host=False)
+        call_ms[0] += 1e3 * (time.perf_counter() - tc)
         p = np.array(obj.phase_ms()); phases += p; gram_ms += p[0]
+        tc = time.perf_counter()
         obj.update_spatial_parallel(IND=IND, sync_host=False)
+        call_ms[1] += 1e3 * (time.perf_counter() - tc)
         phases += np.array(obj.phase_ms())
         if world > 1:
             obj.exchange_spatial()
+        tc = time.perf_counter()
         obj.update_temporal_parallel(sync_host=False)
+        call_ms[2] += 1e3 * (time.perf_counter() - tc)
         phases += np.array(obj.phase_ms())
     ms = ctypes.c_float()
     lib.cnmfe_timer_end(obj._h, ctypes.byref(ms))
@@ -345,16 +352,17 @@ def run_ours(args):
         pass
     bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "2x measured bf16 sustained (MEASURED_PEAKS.json)" if peaks else "2x fallback 1.4 PF bf16 sustained"
-    rr = RING
+    ss = max(1, args.bg_ssub)
+    rr = -(-RING // ss)
     ND = 2 * rr * (4 * rr + 1) + (2 * rr + 1)
     nblk = [obj.block_of(i) for i in obj.owned_patches()]
-    db = float(sum(int(b[1] - b[0] + 1) * int(b[3] - b[2] + 1) for b in nblk))
+    db = float(sum(-(-int(b[1] - b[0] + 1) // ss) * -(-int(b[3] - b[2] + 1) // ss) for b in nblk))
     int8_ops = 2.0 * 4.0 * ND * db * T           # u16 x u16 = 4 u8 x u8 products, 2 ops per MAC
     gram_s = max(gram_ms / 1e3 / args.steps, 1e-9)
     achieved = int8_ops / gram_s / 1e12
     roofline = dict(bound="tensor", kernel="ring second moments S2 (%s)" % ("tcgen05 INT8" if lib.cnmfe_last_gram_was_tensor(obj._h) else "SIMT u64"),
                     achieved=achieved, peak=2.0 * bf16, unit="TOP/s (int8 dense)", frac=achieved / (2.0 * bf16),
-                    traffic=(88.4e9 * (T / 10000.0) if lib.cnmfe_last_gram_was_tensor(obj._h) else None),
+                    traffic=(88.4e9 * (T / 10000.0) if (lib.cnmfe_last_gram_was_tensor(obj._h) and ss == 1) else None),
                     traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/r1_ncu_full_gram.csv), scaled by T/10000",
                     peak_source=peak_src, ms_per_launch=1e3 * gram_s,
                     algorithmic_ops_per_launch=int8_ops,
@@ -372,9 +380,10 @@ def run_ours(args):
                 n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * t_max / args.steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64 (exact int64 second moments from the u16 video)",
                 data="synthetic",
-                config=dict(workload="configs[1]: synthetic 1p %dx%dx%d uint16, %d neurons, ring-BG r=18 (120 nbrs, bg_ssub=1), one %dx%d patch per GPU, nnls spatial, foopsi/ar1 OASIS (smin=-5, optimize_pars, optimize_b)" % (d1, d2, T, K, D1, D2_PER_GPU),
-                            l2="inputs (%.1f GB resident video per GPU) larger than L2; no flush needed" % (float(db) * T * 2 / 1e9),
+                config=dict(workload="configs[1]: synthetic 1p %dx%dx%d uint16, %d neurons, ring-BG r=18 (120 nbrs, bg_ssub=BGSSUB), one %dx%d patch per GPU, nnls spatial, foopsi/ar1 OASIS (smin=-5, optimize_pars, optimize_b)".replace("BGSSUB", str(args.bg_ssub)) % (d1, d2, T, K, D1, D2_PER_GPU),
+                            l2="inputs (%.1f GB resident video per GPU) larger than L2; no flush needed" % (float(sum(int(b[1] - b[0] + 1) * int(b[3] - b[2] + 1) for b in nblk)) * T * 2 / 1e9),
                             seed=SEED, device_ms_per_step=1e3 * t_dev / args.steps, wall_ms_per_step=1e3 * wall / args.steps,
+                            call_wall_ms_per_step=dict(zip(["update_background", "update_spatial", "update_temporal"], [float(x) / args.steps for x in call_ms])),
                             phase_ms_per_step=dict(zip(["gram", "ring_solve", "projections", "spatial_solve", "temporal_sweeps", "deconvTemporal", "other"],
                                                        [float(x) / args.steps for x in phases]))),
                 clocks=clocks, gpu_launches=int(launches),
@@ -433,6 +442,7 @@ def main():
     ap.add_argument("--frames", type=int, default=T_FULL)
     ap.add_argument("--tensor", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--bg-ssub", type=int, default=1, help="options.bg_ssub of the ring model (configs[1] is quoted at 1)")
     ap.add_argument("--workload", default="iteration", choices=["iteration", "oasis"])
     ap.add_argument("--oasis-traces", type=int, default=5000)
     ap.add_argument("--oasis-frames", type=int, default=100000)

@@ -73,6 +73,7 @@ SYMBOLS = {
     "cnmfe_update_temporal_finish": (I, [V]),
     "cnmfe_update_temporal": (I, [V]),
     "cnmfe_set_use_c_hat": (I, [V, I]),
+    "cnmfe_set_trace_major": (I, [V, I]),
     "cnmfe_get_temporal": (I, [V, V, V, V, V, V]),
     "cnmfe_sync": (I, [V]),
     "cnmfe_timer_begin": (I, [V]),

@@ -99,6 +99,7 @@ struct cnmfe_ctx {
     float phase_ms[7] = {0, 0, 0, 0, 0, 0, 0};
     int last_gram_tensor = 0;
     int use_c_hat = 1;            // update_temporal_parallel(obj, use_parallel, use_c_hat)
+    int trace_major = 0;          // 1: K x T arrays cross the ABI trace-contiguous ([K][T]) instead of MATLAB column-major
     void* ssub_state = nullptr;   // SsubCtx (ctx_ssub.inc): coarse-grid ring model for options.bg_ssub > 1
     int num_neighbors = 0;
     bool first_bg = true;          // flag_first of update_background_parallel.m:142-146 (W{1} still uniform)
@@ -158,6 +159,11 @@ int ensure_K(cnmfe_ctx* c, int K) {
 int upload_KT(cnmfe_ctx* c, const double* hostC, int K, double* dst) {
     if (K == 0) return 0;
     size_t n = (size_t)K * c->T;
+    if (c->trace_major) {   // host array already trace-contiguous ([K][T], NumPy C order): no transposition
+        CNMFE_CUDA_OK(cudaMemcpyAsync(dst, hostC, n * 8, cudaMemcpyHostToDevice, c->st));
+        CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+        return 0;
+    }
     if (c->scr.reserve(std::max(c->scr.cap, n * 8 + 4096))) return -1;
     c->scr.reset();
     double* tmp = c->scr.take<double>(n);
@@ -170,6 +176,11 @@ int upload_KT(cnmfe_ctx* c, const double* hostC, int K, double* dst) {
 int download_KT(cnmfe_ctx* c, const double* src, int K, double* hostC) {
     if (K == 0 || !hostC) return 0;
     size_t n = (size_t)K * c->T;
+    if (c->trace_major) {
+        CNMFE_CUDA_OK(cudaMemcpyAsync(hostC, src, n * 8, cudaMemcpyDeviceToHost, c->st));
+        CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+        return 0;
+    }
     if (c->scr.reserve(std::max(c->scr.cap, n * 8 + 4096))) return -1;
     c->scr.reset();
     double* tmp = c->scr.take<double>(n);
@@ -796,7 +807,7 @@ extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
         size_t need = pad256((size_t)P.db * Ks * 8) + pad256((size_t)Ks * T * 8) + pad256((size_t)std::max(Kp, 1) * T * 8) +
                       pad256((size_t)Ks * Ks * 8) + pad256((size_t)std::max(Kp, 1) * Ks * 8) + pad256(nent * 32) +
                       pad256((size_t)(P.dp + 1) * 4) + pad256((size_t)(P.db + 1) * 4) + pad256(LP.col.size() * 12 + 64) +
-                      pad256((size_t)P.dp * 8) + pad256((size_t)(Ks + Kp) * 64 + 64) + (1 << 20);
+                      3 * pad256((size_t)P.dp * 8) + pad256((size_t)(Ks + Kp) * 64 + 64) + (16 << 20);
         const int CH = 2048;   // rows of explicit Ysig per chunk (update_sn / lars only)
         if (update_sn || lars) need += pad256((size_t)CH * T * 8) + 3 * pad256((size_t)CH * 8) + pad256((size_t)P.dp * 8);
         if (ssub) need += 3 * pad256((size_t)P.db * Ks * 8);
@@ -1117,6 +1128,12 @@ extern "C" int cnmfe_update_temporal_finish(cnmfe_ctx* c) {
 extern "C" int cnmfe_update_temporal(cnmfe_ctx* c) {
     if (cnmfe_update_temporal_patches(c)) return -1;
     return cnmfe_update_temporal_finish(c);
+}
+
+extern "C" int cnmfe_set_trace_major(cnmfe_ctx* c, int on) {
+    if (!c) { set_error("cnmfe_set_trace_major: null ctx"); return -1; }
+    c->trace_major = on ? 1 : 0;
+    return 0;
 }
 
 extern "C" int cnmfe_set_use_c_hat(cnmfe_ctx* c, int use_c_hat) {

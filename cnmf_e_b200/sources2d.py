@@ -97,6 +97,7 @@ class Sources2D:
         L.check(self._lib.cnmfe_create(ctypes.byref(h), self.d1, self.d2, self.T, self.npatch, _ptr(pp), _ptr(bp),
                                        _ptr(owned), int(ring_radius), int(num_neighbors or 0), int(device)))
         self._h = h
+        L.check(self._lib.cnmfe_set_trace_major(self._h, 1))   # NumPy (K, T) C-order arrays are trace-contiguous
         self._owned = owned.astype(bool)
         nnb = ctypes.c_int()
         L.check(self._lib.cnmfe_ring_offsets(self._h, ctypes.byref(nnb), None, None))
@@ -114,6 +115,7 @@ class Sources2D:
         self.C_prev = np.zeros((0, self.T))
         self.W = {}
         self.b0 = {}
+        self._ring_synced = {}
         self.b = {}
         self.f = {}
         self.b0_new = np.zeros((self.d1, self.d2))
@@ -197,14 +199,14 @@ class Sources2D:
 
     def push_neurons(self):
         jc, ir, pr = self._csc(self.A)
-        C = np.asfortranarray(self.C, dtype=np.float64)
+        C = np.ascontiguousarray(self.C, dtype=np.float64)
         K = self.A.shape[1]
         assert C.shape == (K, self.T), "C must be K x T"
         L.check(self._lib.cnmfe_set_neurons(self._h, K, _ptr(jc), _ptr(ir), _ptr(pr), _ptr(C)))
 
     def push_prev(self):
         jc, ir, pr = self._csc(self.A_prev)
-        C = np.asfortranarray(self.C_prev, dtype=np.float64)
+        C = np.ascontiguousarray(self.C_prev, dtype=np.float64)
         K = self.A_prev.shape[1]
         L.check(self._lib.cnmfe_set_prev(self._h, K, _ptr(jc), _ptr(ir), _ptr(pr), _ptr(C)))
 
@@ -224,9 +226,14 @@ class Sources2D:
             b0 = self.b0.get(i)
             if W is None and b0 is None:
                 continue
+            # arrays handed out by pull_ring are read-only: an unchanged identity means the device copy is current
+            # (the ring weights are ~250 MB at 512x512; re-sending them on every call would dominate the step)
+            if self._ring_synced.get(i) == (id(W), id(b0)):
+                continue
             Wf = None if W is None else np.ascontiguousarray(W, dtype=np.float64)   # (d_patch, nnb) C-order == nnb x d_patch col-major
             b0f = None if b0 is None else np.ascontiguousarray(b0, dtype=np.float64)
             L.check(self._lib.cnmfe_set_ring(self._h, i, _ptr(Wf), _ptr(b0f)))
+            self._ring_synced[i] = (id(W), id(b0))
 
     def pull_ring(self):
         if str(self.options["background_model"]).lower() in ("svd", "nmf"):
@@ -243,15 +250,19 @@ class Sources2D:
             dp = (p[1] - p[0] + 1) * (p[3] - p[2] + 1)
             if int(self.options.get("bg_ssub", 1)) > 1:
                 d1s, d2s, nnb, _, _ = self.ssub_dims(i)
-                W = np.zeros((d1s * d2s, nnb))
-                b0 = np.zeros(dp)
+                W = np.empty((d1s * d2s, nnb))
+                b0 = np.empty(dp)
                 L.check(self._lib.cnmfe_get_ring(self._h, i, _ptr(W), _ptr(b0)))
+                W.setflags(write=False); b0.setflags(write=False)
                 self.W[i], self.b0[i] = W, b0
+                self._ring_synced[i] = (id(W), id(b0))
                 continue
-            W = np.zeros((dp, self.nnb))
-            b0 = np.zeros(dp)
+            W = np.empty((dp, self.nnb))
+            b0 = np.empty(dp)
             L.check(self._lib.cnmfe_get_ring(self._h, i, _ptr(W), _ptr(b0)))
+            W.setflags(write=False); b0.setflags(write=False)
             self.W[i], self.b0[i] = W, b0
+            self._ring_synced[i] = (id(W), id(b0))
 
     def ssub_dims(self, i):
         """(d1s, d2s, nnb, r_shift, c_shift) of the coarse ring grid of patch i (bg_ssub > 1)."""
@@ -387,13 +398,13 @@ class Sources2D:
 
     def pull_temporal(self):
         K = self.A.shape[1]
-        C = np.zeros((K, self.T), order="F")
-        Cr = np.zeros((K, self.T), order="F")
-        S = np.zeros((K, self.T), order="F")
+        C = np.empty((K, self.T))
+        Cr = np.empty((K, self.T))
+        S = np.empty((K, self.T))
         kp = np.zeros((K, 2))
         nsn = np.zeros(K)
         L.check(self._lib.cnmfe_get_temporal(self._h, _ptr(C), _ptr(Cr), _ptr(S), _ptr(kp), _ptr(nsn)))
-        self.C, self.C_raw, self.S = np.ascontiguousarray(C), np.ascontiguousarray(Cr), np.ascontiguousarray(S)
+        self.C, self.C_raw, self.S = C, Cr, S
         self.P["kernel_pars"], self.P["neuron_sn"] = kp, nsn
         if self.P.get("Ymean") is not None:
             self.b0_new = self.P["Ymean"] - (self.A @ self.C.mean(axis=1)).reshape(self.d1, self.d2, order="F")

@@ -153,6 +153,9 @@ int cnmfe_update_temporal(cnmfe_ctx* ctx);   /* = patches + finish (single proce
 /* use_c_hat argument of update_temporal_parallel (default 1); 0 = fast_temporal (update_temporal_parallel.m:314-337):
  * mean fluorescence over the pixels with A >= 0.5 max(A) instead of the HALS sweeps */
 int cnmfe_set_use_c_hat(cnmfe_ctx* ctx, int use_c_hat);
+/* Layout of the K x T arrays (C, C_prev, C_raw, S) at this boundary: 0 (default) = MATLAB column-major (k fastest);
+ * 1 = trace-contiguous [K][T] (NumPy C order; what the device uses) -- saves two transpositions per array per call */
+int cnmfe_set_trace_major(cnmfe_ctx* ctx, int on);
 /* obj.C, obj.C_raw, obj.S (K x T col-major), obj.P.kernel_pars (2 x K), obj.P.neuron_sn (K); any may be NULL */
 int cnmfe_get_temporal(cnmfe_ctx* ctx, double* C, double* C_raw, double* S, double* kernel_pars,
                        double* neuron_sn);
