@@ -74,6 +74,8 @@ SYMBOLS = {
     "cnmfe_update_temporal": (I, [V]),
     "cnmfe_set_use_c_hat": (I, [V, I]),
     "cnmfe_set_trace_major": (I, [V, I]),
+    "cnmfe_host_register": (I, [V, ctypes.c_size_t]),
+    "cnmfe_host_unregister": (I, [V]),
     "cnmfe_get_temporal": (I, [V, V, V, V, V, V]),
     "cnmfe_sync": (I, [V]),
     "cnmfe_timer_begin": (I, [V]),

@@ -5,6 +5,9 @@
 #include <cmath>
 #include <cstring>
 #include <vector>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "internal.h"
 #include "kernels_video.cuh"
 #include "kernels_ring.cuh"
@@ -70,8 +73,15 @@ struct Scratch {
         if (bytes <= cap) return 0;
         if (base) cudaFree(base);
         base = nullptr; cap = 0;
-        CNMFE_CUDA_OK(cudaMalloc((void**)&base, bytes));
-        cap = bytes;
+        // head-room: the need moves by a few bytes with nnz(A) from call to call, and re-allocating a multi-GB arena
+        // costs tens of milliseconds
+        size_t want = bytes + std::max<size_t>(bytes / 32, (size_t)64 << 20);
+        if (cudaMalloc((void**)&base, want) != cudaSuccess) {
+            (void)cudaGetLastError();
+            want = bytes;
+            CNMFE_CUDA_OK(cudaMalloc((void**)&base, want));
+        }
+        cap = want;
         return 0;
     }
     void reset() { off = 0; }
@@ -120,6 +130,18 @@ struct cnmfe_ctx {
 };
 
 namespace {
+
+// host-side section timer: CNMFE_HOST_PROFILE=1 prints the wall time between ticks (diagnostics only)
+struct HostTick {
+    bool on; std::chrono::steady_clock::time_point t;
+    HostTick() : on(getenv("CNMFE_HOST_PROFILE") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void operator()(const char* what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[cnmfe host] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 
 void phase_begin(cnmfe_ctx* c) { cudaEventRecord(c->pe0, c->st); }
 void phase_end(cnmfe_ctx* c, int which) {
@@ -482,31 +504,40 @@ extern "C" int cnmfe_upload_block_dev(cnmfe_ctx* c, int ip, const void* Y, int d
 
 extern "C" int cnmfe_set_neurons(cnmfe_ctx* c, int K, const int64_t* jc, const int64_t* ir, const double* pr,
                                  const double* C) {
-    if (!c || K < 0 || (K > 0 && (!jc || !ir || !pr || !C))) { set_error("cnmfe_set_neurons: bad arguments"); return -1; }
+    // a NULL (jc,ir,pr) triple or a NULL C keeps what the context already holds for that part (K must then match)
+    const bool keepA = !jc && !ir && !pr, keepC = !C;
+    if (!c || K < 0 || (K > 0 && !keepA && (!jc || !ir || !pr))) { set_error("cnmfe_set_neurons: bad arguments"); return -1; }
+    if (K > 0 && (keepA || keepC) && K != c->K) {
+        set_error("cnmfe_set_neurons: NULL part with K=%d but the context holds K=%d", K, c->K); return -1;
+    }
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
     static const int64_t zero = 0;
     if (K == 0) { c->A.set(0, &zero, nullptr, nullptr); c->K = 0; return 0; }
-    c->A.set(K, jc, ir, pr);
+    if (!keepA) c->A.set(K, jc, ir, pr);
     if (K != c->K) { c->have_spatial = false; }
     c->K = K;
     if (ensure_K(c, K)) return -1;
-    return upload_KT(c, C, K, c->C);
+    return keepC ? 0 : upload_KT(c, C, K, c->C);
 }
 
 extern "C" int cnmfe_set_prev(cnmfe_ctx* c, int K, const int64_t* jc, const int64_t* ir, const double* pr,
                               const double* C) {
-    if (!c || K < 0 || (K > 0 && (!jc || !ir || !pr || !C))) { set_error("cnmfe_set_prev: bad arguments"); return -1; }
+    const bool keepA = !jc && !ir && !pr, keepC = !C;
+    if (!c || K < 0 || (K > 0 && !keepA && (!jc || !ir || !pr))) { set_error("cnmfe_set_prev: bad arguments"); return -1; }
+    if (K > 0 && (keepA || keepC) && K != c->Kprev) {
+        set_error("cnmfe_set_prev: NULL part with K=%d but the context holds K=%d", K, c->Kprev); return -1;
+    }
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
     static const int64_t zero = 0;
     if (K == 0) { c->Aprev.set(0, &zero, nullptr, nullptr); c->Kprev = 0; return 0; }
-    c->Aprev.set(K, jc, ir, pr);
+    if (!keepA) c->Aprev.set(K, jc, ir, pr);
     c->Kprev = K;
     if ((size_t)K > c->Kprev_cap) {
         if (c->Cprev) cudaFree(c->Cprev);
         CNMFE_CUDA_OK(cudaMalloc((void**)&c->Cprev, (size_t)K * c->T * 8));
         c->Kprev_cap = K;
     }
-    return upload_KT(c, C, K, c->Cprev);
+    return keepC ? 0 : upload_KT(c, C, K, c->Cprev);
 }
 
 extern "C" int cnmfe_set_search(cnmfe_ctx* c, int K, const int64_t* jc, const int64_t* ir) {
@@ -641,12 +672,15 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         if (!P.owned) continue;
         if (!P.uploaded) { set_error("update_background: block %d not uploaded", ip); return -1; }
         LocalSparse L;
+        HostTick tick;
         build_local(c, P, c->A, SEL_SUM_BLOCK, ROWS_BLOCK, nullptr, &L);
+        tick("bg build_local");
         const int Kb = L.K();
         if (Kb == 0 && !flag_first) continue;   // update_background_parallel.m:188-199
         if (Kb > 4096) { set_error("update_background: %d neurons touch block %d; the solver's neuron bitmap handles <= 4096 per block", Kb, ip); return -1; }
         if (c->scr.reserve(bg_scratch_bytes(c, P, Kb, L.col.size()))) return -1;
         c->scr.reset();
+        tick("bg reserve");
         const RingGeom& g = P.geom;
         phase_begin(c);
         TAKE_OR_FAIL(d_ptr, to_dev(c, L.ptr));
@@ -672,6 +706,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         int pmax = 0;
         CNMFE_CUDA_OK(cudaMemcpyAsync(&pmax, c->d_pmax, 4, cudaMemcpyDeviceToHost, c->st));
         CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+        tick("bg uploads+pmax");
         int kf = 1;
         if (c->opt.bg_acceleration) {
             long long nmax = 100LL * pmax;
@@ -706,6 +741,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
                         if (act[p]) alist.push_back(p);
                     }
         phase_end(c, 6);
+        tick("bg active list");
         if (alist.empty()) continue;
         TAKE_OR_FAIL(d_alist, to_dev(c, alist));
         // projections needed by the neuron corrections
@@ -720,6 +756,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
             LAUNCH(ring_make_N_kernel, P.db, 64, 0, c->st, d_N, Kb, d_ptr, d_col, d_val, d_Vsel, (size_t)P.db);
         }
         phase_end(c, 2);
+        tick("bg projections");
         // second moments
         phase_begin(c);
         const size_t ND = (size_t)ring_num_disp(c->rr);
@@ -737,6 +774,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
                    c->ngroups, d_S2, ND);
         }
         phase_end(c, 0);
+        tick("bg second moments");
         // assemble + solve
         phase_begin(c);
         RingSolveArgs a;
@@ -750,6 +788,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         LAUNCH(ring_solve_kernel, (unsigned)alist.size(), RING_SOLVE_THREADS, smem, c->st, a);
         CNMFE_CUDA_OK(cudaGetLastError());
         phase_end(c, 1);
+        tick("bg ring solve");
         P.w_uniform = false;
     }
     c->first_bg = false;
@@ -1128,6 +1167,17 @@ extern "C" int cnmfe_update_temporal_finish(cnmfe_ctx* c) {
 extern "C" int cnmfe_update_temporal(cnmfe_ctx* c) {
     if (cnmfe_update_temporal_patches(c)) return -1;
     return cnmfe_update_temporal_finish(c);
+}
+
+extern "C" int cnmfe_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) { set_error("cnmfe_host_register: null"); return -1; }
+    CNMFE_CUDA_OK(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return 0;
+}
+extern "C" int cnmfe_host_unregister(void* p) {
+    if (!p) { set_error("cnmfe_host_unregister: null"); return -1; }
+    CNMFE_CUDA_OK(cudaHostUnregister(p));
+    return 0;
 }
 
 extern "C" int cnmfe_set_trace_major(cnmfe_ctx* c, int on) {

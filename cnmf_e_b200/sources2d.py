@@ -115,7 +115,11 @@ class Sources2D:
         self.C_prev = np.zeros((0, self.T))
         self.W = {}
         self.b0 = {}
-        self._ring_synced = {}
+        self._ring_synced = {}      # patch -> (W, b0) objects whose contents the device holds
+        self._dev = {}              # "A" / "C" / "A_prev" / "C_prev" -> host object whose contents the device holds
+        self._pinned = {}           # name -> page-locked reusable host buffer (ring weights)
+        self.h2d_bytes = 0          # bytes this object has sent to / fetched from the device (state, not the video)
+        self.d2h_bytes = 0
         self.b = {}
         self.f = {}
         self.b0_new = np.zeros((self.d1, self.d2))
@@ -127,6 +131,9 @@ class Sources2D:
     # ------------------------------------------------------------------ lifetime
     def close(self):
         if getattr(self, "_h", None):
+            for buf in self._pinned.values():
+                self._lib.cnmfe_host_unregister(_ptr(buf))
+            self._pinned = {}
             self._lib.cnmfe_destroy(self._h)
             self._h = None
 
@@ -197,18 +204,69 @@ class Sources2D:
         return (np.ascontiguousarray(A.indptr, dtype=np.int64), np.ascontiguousarray(A.indices, dtype=np.int64),
                 np.ascontiguousarray(A.data, dtype=np.float64))
 
+    # Host <-> device coherence.  Arrays this class hands out (pull_*) are read-only, so "same object" means "same
+    # contents": a part whose host object is the one the device was last synchronised with is not sent again.  Code
+    # that must edit in place makes a writable copy and assigns it back (a new object => re-sent), or calls
+    # invalidate().
+    def invalidate(self):
+        self._dev = {}
+        self._ring_synced = {}
+
+    @staticmethod
+    def _freeze(x):
+        if sp.issparse(x):
+            for part in (x.data, x.indices, x.indptr):
+                part.setflags(write=False)
+        else:
+            x.setflags(write=False)
+        return x
+
+    @staticmethod
+    def _frozen(x):
+        return (not x.data.flags.writeable) if sp.issparse(x) else (not x.flags.writeable)
+
+    def _mark(self, name, obj):
+        """The device now holds the contents of `obj` (only trusted while obj stays read-only)."""
+        self._dev[name] = obj
+
+    def _current(self, name, obj):
+        return self._dev.get(name) is obj and self._frozen(obj)
+
+    def _push_pair(self, setter, nameA, A, nameC, C):
+        K = A.shape[1]
+        C = np.asarray(C)
+        assert C.shape == (K, self.T), "%s must be K x T" % nameC
+        sendA, sendC = not self._current(nameA, A), not self._current(nameC, C)
+        if not (sendA or sendC):
+            return
+        jc = ir = pr = Cc = None
+        if sendA or K == 0:
+            jc, ir, pr = self._csc(A)
+        if sendC:
+            Cc = np.ascontiguousarray(C, dtype=np.float64)
+        L.check(setter(self._h, K, _ptr(jc), _ptr(ir), _ptr(pr), _ptr(Cc)))
+        self.h2d_bytes += sum(x.nbytes for x in (jc, ir, pr, Cc) if x is not None)
+        self._mark(nameA, A)
+        self._mark(nameC, C)
+
     def push_neurons(self):
-        jc, ir, pr = self._csc(self.A)
-        C = np.ascontiguousarray(self.C, dtype=np.float64)
-        K = self.A.shape[1]
-        assert C.shape == (K, self.T), "C must be K x T"
-        L.check(self._lib.cnmfe_set_neurons(self._h, K, _ptr(jc), _ptr(ir), _ptr(pr), _ptr(C)))
+        self._push_pair(self._lib.cnmfe_set_neurons, "A", self.A, "C", self.C)
 
     def push_prev(self):
-        jc, ir, pr = self._csc(self.A_prev)
-        C = np.ascontiguousarray(self.C_prev, dtype=np.float64)
-        K = self.A_prev.shape[1]
-        L.check(self._lib.cnmfe_set_prev(self._h, K, _ptr(jc), _ptr(ir), _ptr(pr), _ptr(C)))
+        self._push_pair(self._lib.cnmfe_set_prev, "A_prev", self.A_prev, "C_prev", self.C_prev)
+
+    def _pinned_buffer(self, name, shape):
+        """Reusable page-locked float64 host buffer (the ring weights are ~250 MB per 512x512 patch: a fresh pageable
+        array per pull costs more in page faults than the copy itself)."""
+        buf = self._pinned.get(name)
+        if buf is not None and buf.shape == tuple(shape):
+            return buf
+        if buf is not None:
+            self._lib.cnmfe_host_unregister(_ptr(buf))
+        buf = np.zeros(shape)
+        if buf.nbytes >= (1 << 20) and self._lib.cnmfe_host_register(_ptr(buf), buf.nbytes) == 0:
+            self._pinned[name] = buf
+        return buf
 
     def push_ring(self):
         if str(self.options["background_model"]).lower() in ("svd", "nmf"):
@@ -228,12 +286,14 @@ class Sources2D:
                 continue
             # arrays handed out by pull_ring are read-only: an unchanged identity means the device copy is current
             # (the ring weights are ~250 MB at 512x512; re-sending them on every call would dominate the step)
-            if self._ring_synced.get(i) == (id(W), id(b0)):
+            s = self._ring_synced.get(i)
+            if s is not None and s[0] is W and s[1] is b0:
                 continue
             Wf = None if W is None else np.ascontiguousarray(W, dtype=np.float64)   # (d_patch, nnb) C-order == nnb x d_patch col-major
             b0f = None if b0 is None else np.ascontiguousarray(b0, dtype=np.float64)
             L.check(self._lib.cnmfe_set_ring(self._h, i, _ptr(Wf), _ptr(b0f)))
-            self._ring_synced[i] = (id(W), id(b0))
+            self.h2d_bytes += sum(x.nbytes for x in (Wf, b0f) if x is not None)
+            self._ring_synced[i] = (W, b0)
 
     def pull_ring(self):
         if str(self.options["background_model"]).lower() in ("svd", "nmf"):
@@ -250,19 +310,17 @@ class Sources2D:
             dp = (p[1] - p[0] + 1) * (p[3] - p[2] + 1)
             if int(self.options.get("bg_ssub", 1)) > 1:
                 d1s, d2s, nnb, _, _ = self.ssub_dims(i)
-                W = np.empty((d1s * d2s, nnb))
-                b0 = np.empty(dp)
-                L.check(self._lib.cnmfe_get_ring(self._h, i, _ptr(W), _ptr(b0)))
-                W.setflags(write=False); b0.setflags(write=False)
-                self.W[i], self.b0[i] = W, b0
-                self._ring_synced[i] = (id(W), id(b0))
-                continue
-            W = np.empty((dp, self.nnb))
+                wshape = (d1s * d2s, nnb)
+            else:
+                wshape = (dp, self.nnb)
+            # W lands in a page-locked buffer that the NEXT pull_ring overwrites (copy it to keep an old fit)
+            W = self._pinned_buffer(("W", i), wshape).view()
             b0 = np.empty(dp)
             L.check(self._lib.cnmfe_get_ring(self._h, i, _ptr(W), _ptr(b0)))
+            self.d2h_bytes += W.nbytes + b0.nbytes
             W.setflags(write=False); b0.setflags(write=False)
             self.W[i], self.b0[i] = W, b0
-            self._ring_synced[i] = (id(W), id(b0))
+            self._ring_synced[i] = (W, b0)
 
     def ssub_dims(self, i):
         """(d1s, d2s, nnb, r_shift, c_shift) of the coarse ring grid of patch i (bg_ssub > 1)."""
@@ -323,8 +381,12 @@ class Sources2D:
         if sync_host:
             self.pull_ring()
             self.b0_new = self.reconstruct_b0()
-            self.A_prev = self.A.copy()
-            self.C_prev = np.array(self.C, copy=True)
+            # obj.A_prev = obj.A; obj.C_prev = obj.C (update_background_parallel.m:316-317): read-only state is shared,
+            # not copied; the device took the same snapshot
+            self.A_prev = self.A if self._frozen(self.A) else self._freeze(self.A.copy())
+            self.C_prev = self.C if self._frozen(self.C) else self._freeze(np.array(self.C, copy=True))
+            self._mark("A_prev", self.A_prev)
+            self._mark("C_prev", self.C_prev)
 
     def update_spatial_parallel(self, use_parallel=True, update_sn=False, IND=None, sync_host=True):
         """update_spatial_parallel(obj, use_parallel, update_sn).  IND: (d,K) boolean search mask
@@ -345,6 +407,7 @@ class Sources2D:
         ir = np.ascontiguousarray(INDc.indices, dtype=np.int64)
         self._ind_jc, self._ind_ir = jc, ir
         L.check(self._lib.cnmfe_set_search(self._h, INDc.shape[1], _ptr(jc), _ptr(ir)))
+        self.h2d_bytes += jc.nbytes + ir.nbytes
         L.check(self._lib.cnmfe_update_spatial_ex(self._h, int(bool(update_sn))))
         if update_sn:
             snm = np.zeros((self.d1, self.d2), order="F")
@@ -353,16 +416,19 @@ class Sources2D:
         if sync_host:
             vals = np.zeros(ir.size)
             L.check(self._lib.cnmfe_get_spatial(self._h, _ptr(vals)))
+            self.d2h_bytes += vals.nbytes
             vals = self._allreduce_sum(vals)
             A_new = sp.csc_matrix((vals, ir.copy(), jc.copy()), shape=INDc.shape)
             A_new.eliminate_zeros()
             if self.post_process_fn is not None:
                 A_new = sp.csc_matrix(self.post_process_fn(A_new))
-            self.A = A_new
+            self.A = self._freeze(A_new)
             if self.P.get("Ymean") is not None:
                 self.b0_new = self.P["Ymean"] - (self.A @ self.C.mean(axis=1)).reshape(self.d1, self.d2, order="F")
             if self.world_size > 1 or self.post_process_fn is not None:
                 self.push_neurons()
+            else:
+                self._mark("A", self.A)      # the device kept exactly these values
 
     def update_temporal_parallel(self, use_parallel=True, use_c_hat=True, sync_host=True):
         """update_temporal_parallel(obj, use_parallel, use_c_hat)."""
@@ -386,7 +452,8 @@ class Sources2D:
         L.check(self._lib.cnmfe_get_spatial(self._h, _ptr(vals)))
         A_new = sp.csc_matrix((vals, ir.copy(), jc.copy()), shape=(self.d1 * self.d2, jc.size - 1))
         A_new.eliminate_zeros()
-        self.A = A_new
+        self.A = self._freeze(A_new)
+        self._mark("A", self.A)
 
     def exchange_spatial(self):
         """Multi-GPU: every rank solved the rows of its own patches; one all-reduce (disjoint supports => a gather) of
@@ -404,7 +471,9 @@ class Sources2D:
         kp = np.zeros((K, 2))
         nsn = np.zeros(K)
         L.check(self._lib.cnmfe_get_temporal(self._h, _ptr(C), _ptr(Cr), _ptr(S), _ptr(kp), _ptr(nsn)))
-        self.C, self.C_raw, self.S = C, Cr, S
+        self.d2h_bytes += C.nbytes + Cr.nbytes + S.nbytes + kp.nbytes + nsn.nbytes
+        self.C, self.C_raw, self.S = self._freeze(C), self._freeze(Cr), self._freeze(S)
+        self._mark("C", self.C)
         self.P["kernel_pars"], self.P["neuron_sn"] = kp, nsn
         if self.P.get("Ymean") is not None:
             self.b0_new = self.P["Ymean"] - (self.A @ self.C.mean(axis=1)).reshape(self.d1, self.d2, order="F")

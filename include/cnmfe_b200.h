@@ -104,7 +104,8 @@ int cnmfe_upload_block(cnmfe_ctx* ctx, int ipatch, const void* Y, int dtype);
 /* same, Y already in device memory (frame-major nr_block*nc_block per frame, as MATLAB lays it out) */
 int cnmfe_upload_block_dev(cnmfe_ctx* ctx, int ipatch, const void* Y_dev, int dtype);
 
-/* obj.A (d x K sparse), obj.C (K x T)   (Sources2D.m:11-13) */
+/* obj.A (d x K sparse), obj.C (K x T)   (Sources2D.m:11-13).  For both setters: a NULL (jc, ir, pr) triple or a NULL C
+ * keeps the part the context already holds (K must match) -- lets a caller re-send only what changed */
 int cnmfe_set_neurons(cnmfe_ctx* ctx, int K, const int64_t* A_jc, const int64_t* A_ir, const double* A_pr,
                       const double* C);
 /* obj.A_prev, obj.C_prev (Sources2D.m:14-15); cnmfe_update_background snapshots them itself (:316-317) */
@@ -156,6 +157,10 @@ int cnmfe_set_use_c_hat(cnmfe_ctx* ctx, int use_c_hat);
 /* Layout of the K x T arrays (C, C_prev, C_raw, S) at this boundary: 0 (default) = MATLAB column-major (k fastest);
  * 1 = trace-contiguous [K][T] (NumPy C order; what the device uses) -- saves two transpositions per array per call */
 int cnmfe_set_trace_major(cnmfe_ctx* ctx, int on);
+/* Page-lock / release a caller-owned host range (cudaHostRegister) so the big transfers (ring weights, video blocks)
+ * run at PCIe rate; optional -- every entry point also takes pageable memory */
+int cnmfe_host_register(void* p, size_t bytes);
+int cnmfe_host_unregister(void* p);
 /* obj.C, obj.C_raw, obj.S (K x T col-major), obj.P.kernel_pars (2 x K), obj.P.neuron_sn (K); any may be NULL */
 int cnmfe_get_temporal(cnmfe_ctx* ctx, double* C, double* C_raw, double* S, double* kernel_pars,
                        double* neuron_sn);
