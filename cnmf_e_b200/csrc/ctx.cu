@@ -782,8 +782,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         a.nsel = nsel; a.a_ptr = d_ptr; a.a_col = d_col; a.a_val = d_val; a.N = d_N; a.K = Kb; a.Csum = d_Csum;
         a.active = d_active; a.active_list = d_alist; a.n_active = (int)alist.size(); a.W = P.W; a.db = (size_t)P.db; a.ND = ND;
         const int NMAX = c->nnb + 1;
-        size_t smem = ((size_t)(NMAX + 1) * (NMAX + 2) / 2 + 384 + 2 * (size_t)(NMAX + 1) +
-                       2 * (size_t)(NMAX + 1) * RING_KSET + RING_KSET) * 8 + (7 * (size_t)(NMAX + 1) + RING_KALL) * 4 + 64;
+        size_t smem = ring_solve_smem_bytes(NMAX);
         CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LAUNCH(ring_solve_kernel, (unsigned)alist.size(), RING_SOLVE_THREADS, smem, c->st, a);
         CNMFE_CUDA_OK(cudaGetLastError());

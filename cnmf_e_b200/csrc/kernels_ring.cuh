@@ -177,82 +177,105 @@ struct RingSolveArgs {
 };
 
 #define RING_SOLVE_THREADS 256
-#define RING_KSET 16
+#define RING_KSET 8
 #define RING_KALL 128
-// One CTA per active patch pixel: assemble the (n+1)x(n+1) normal equations, ridge, Cholesky, write weights.
+#define RING_NIDX 128        // index space of the augmented system: 0..n-1 ring pixels, n ones row, n1 = n+1 rhs/centre
+#define RING_XSTRIDE 10
+#define RING_XBUF (16 * RING_XSTRIDE)
+// One CTA per active patch pixel: assemble the (n+1)x(n+1) normal equations, ridge, factorise, write weights.
 // fit_ring_model.m:92-108:  X=[Bf(ring,:);1]; w=(X*X'+1e-5*trace(X*X')*I)\(X*y'); W(m,ring)=w(1:end-1)+1e-100
 //
 // The lower triangle of the AUGMENTED matrix [G; rhs'] (row n1 = right-hand side, so the forward substitution falls
 // out of the factorisation) lives in REGISTERS: 256 threads form a 16 x 16 grid, thread (ti,tj) owns the elements
 // (i, j) = (ti + 16a, tj + 16b), b <= a < 8.  Each elimination step broadcasts column k through shared memory and
 // every thread updates its own 36 registers; the step is templated on k/16 so finished register blocks are skipped.
+//
+// Per-index vectors (means, sums, neuron rows, the published column) are stored PERMUTED, entry i = t + 16a at
+// [t * RING_XSTRIDE + a], so that the 8 entries a thread needs for its rows (t = ti) or its columns (t = tj) are
+// contiguous: 16-byte shared loads, conflict-free with the stride of 10 doubles.
+//
+// Everything is written so that NO per-element masking is needed:
+//   index n  (ones row)  carries  Ybar = -1, S1 = 0, S1c = nsel  and no pixel (raw moment = 0),
+//   index n1 (rhs row)   carries  the centre pixel's values,
+//   indices > n1 (padding) carry zeros,
+// and then  Cov(i,j) = raw(i,j) - Ybar_j*S1_i - Ybar_i*S1c_j  gives the ring covariances, the ones row/column
+// (S1c_j, nsel) and the right-hand side in one formula; the neuron correction  A_j.N_i + A_i.N_j  works the same way
+// with A_n = 0, N_n = Csum.  Strictly-upper entries of the diagonal register tiles and the (n1, n1) entry collect
+// finite values that nothing reads.
 struct RingRegs { double g[8][8]; };
 
-// Right-looking elimination with ONE barrier per column: the owners of column k publish its UNSCALED entries x_i and the
-// pivot g_kk (double-buffered), then every thread applies G(i,j) -= (x_i / g_kk) * x_j to its registers.  The column of
-// the Cholesky factor is L(i,k) = x_i * (1/sqrt(g_kk)) (LAPACK dpotf2 scales by the reciprocal pivot); the registers keep
-// x_i and the pivots are stored in piv[] so that the scaling is applied once, when L is written out.
+__device__ __forceinline__ int ring_perm(int i) { return (i & 15) * RING_XSTRIDE + (i >> 4); }
+__device__ const double ring_zero_moment = 0.0;
+
+__host__ __device__ inline size_t ring_solve_smem_bytes(int NMAX) {
+    size_t dbl = 2 * RING_XBUF + 128 + 3 * RING_XBUF + 2 * (size_t)RING_KSET * RING_XBUF + RING_KSET + 16 + RING_NIDX /* qoff */ +
+                 (size_t)(NMAX + 1) * (NMAX + 2) / 2 + 2;
+    size_t ints = 5 * (size_t)RING_NIDX + RING_KALL;
+    return dbl * 8 + ints * 4 + 64;
+}
+
+// Right-looking LDL' elimination with ONE barrier per column: the owners of column k publish its UNSCALED entries x_i
+// (zeros for i <= k) and the reciprocal pivot 1/d_k (double-buffered), then every thread applies
+// G(i,j) -= (x_i / d_k) * x_j to its registers.  The registers keep x_i; rd[] keeps the reciprocal pivots, so the unit
+// factor M(i,k) = x_i / d_k is formed once, when it is written out.
 template <int KA>
-__device__ __forceinline__ void ring_chol_block(RingRegs& R, int n1, int ti, int tj, double* xbuf, double* piv) {
+__device__ __forceinline__ void ring_chol_block(RingRegs& R, int n1, int ti, int tj, double* xbuf, double* rd) {
     const int kend = min(16 * KA + 15, n1 - 1);
+    constexpr int A0 = KA & ~1;          // first (even) register index loaded: keeps the 16-byte alignment
     for (int k = 16 * KA; k <= kend; ++k) {
         const int kr = k & 15;
-        double* xb = xbuf + (k & 1) * 128;
+        double* xb = xbuf + (k & 1) * RING_XBUF;
         if (tj == kr) {
+            double* dst = xb + ti * RING_XSTRIDE;
 #pragma unroll
-            for (int a = KA; a < 8; ++a) {
-                const int i = ti + 16 * a;
-                if (i > k && i <= n1) xb[i] = R.g[a][KA];
-            }
-            if (ti == kr) { piv[k] = R.g[KA][KA]; xb[127] = 1.0 / R.g[KA][KA]; }
+            for (int a = KA; a < 8; ++a) dst[a] = (ti + 16 * a > k) ? R.g[a][KA] : 0.0;
+            if (ti == kr) { const double r = 1.0 / R.g[KA][KA]; rd[k] = r; xb[8] = r; }   // slot 8 of thread-row 0: padding
         }
         __syncthreads();
-        const double rinv = xb[127];
+        const double rinv = xb[8];
         double ci[8], cj[8];
+        const double2* si = reinterpret_cast<const double2*>(xb + ti * RING_XSTRIDE);
+        const double2* sj = reinterpret_cast<const double2*>(xb + tj * RING_XSTRIDE);
 #pragma unroll
-        for (int a = KA; a < 8; ++a) {
-            const int i = ti + 16 * a, j = tj + 16 * a;
-            ci[a] = (i > k && i <= n1) ? xb[i] * rinv : 0.0;
-            cj[a] = (j > k && j < n1) ? xb[j] : 0.0;
+        for (int a = A0; a < 8; a += 2) {
+            const double2 vi = si[a >> 1], vj = sj[a >> 1];
+            ci[a] = vi.x * rinv; ci[a + 1] = vi.y * rinv;
+            cj[a] = vj.x; cj[a + 1] = vj.y;
         }
 #pragma unroll
         for (int a = KA; a < 8; ++a)
 #pragma unroll
-            for (int b = KA; b <= a; ++b) {
-                // column k itself (b == KA && tj == kr) is final: keep x_i there
-                R.g[a][b] = fma(-ci[a], cj[b], R.g[a][b]);
-            }
+            for (int b = KA; b <= a; ++b) R.g[a][b] = fma(-ci[a], cj[b], R.g[a][b]);
     }
 }
 
 __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingSolveArgs a) {
     extern __shared__ double smem[];
     const RingGeom& g = a.g;
-    const int dp = g.nr * g.nc;
     const int p = a.active_list[blockIdx.x];
     const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
     const int pr = p % g.nr + g.pr_off, pc = p / g.nr + g.pc_off;
     const size_t qm = (size_t)pc * g.nrb + pr;
     const int NMAX = g.nnb + 1;
     // shared layout
-    double* L = smem;                                         // packed lower (after the factorisation), (NMAX+1)(NMAX+2)/2
-    double* colk = L + (size_t)(NMAX + 1) * (NMAX + 2) / 2;   // 256: double-buffered column, later the solution
-    double* piv = colk + 256;                                 // 128: pivots g_kk, later 1/sqrt(g_kk)
-    double* ym = piv + 128;                                  // NMAX+1   (index n = the centre pixel m)
-    double* s1c = ym + NMAX + 1;                              // NMAX+1
-    double* Ar = s1c + NMAX + 1;                              // (NMAX+1) * RING_KSET
-    double* Nr = Ar + (size_t)(NMAX + 1) * RING_KSET;         // (NMAX+1) * RING_KSET
-    double* cs = Nr + (size_t)(NMAX + 1) * RING_KSET;         // RING_KSET
-    int* qi = reinterpret_cast<int*>(cs + RING_KSET);         // NMAX+1  block pixel index (index n = m)
-    int* slot = qi + NMAX + 1;
-    int* sdr = slot + NMAX + 1;                               // index n: 0
-    int* sdc = sdr + NMAX + 1;
-    int* kall = sdc + NMAX + 1;                               // RING_KALL
-    int* ap0 = kall + RING_KALL;                              // NMAX+1  A-row extents of the ring pixels / centre
-    int* ap1 = ap0 + NMAX + 1;
-    int* rows_with = ap1 + NMAX + 1;                          // NMAX+1  ring pixels that carry neuron entries
+    double* colk = smem;                                      // 2*RING_XBUF: double-buffered column, later the solution
+    double* rd = colk + 2 * RING_XBUF;                        // 128: reciprocal pivots 1/d_k
+    double* ymp = rd + 128;                                   // permuted per-index vectors (see above)
+    double* S1p = ymp + RING_XBUF;
+    double* s1cp = S1p + RING_XBUF;
+    double* XA = s1cp + RING_XBUF;                            // RING_KSET x RING_XBUF: A rows of the indices
+    double* XN = XA + RING_KSET * RING_XBUF;                  // RING_KSET x RING_XBUF: N rows of the indices
+    double* cs = XN + RING_KSET * RING_XBUF;                  // RING_KSET (+ 16 partial traces)
+    double* trs = cs + RING_KSET;
+    long long* qoff = reinterpret_cast<long long*>(trs + 16); // RING_NIDX: block pixel index * ND
+    double* L = reinterpret_cast<double*>(qoff + RING_NIDX);  // packed rows of the unit factor, (NMAX+1)(NMAX+2)/2
+    int* qi = reinterpret_cast<int*>(L + (size_t)(NMAX + 1) * (NMAX + 2) / 2 + 2);   // RING_NIDX block pixel index
+    int* slot = qi + RING_NIDX;
+    int* elin = slot + RING_NIDX;                             // dc*(4rr+1)+dr: displacement ids are differences of these
+    int* ap0 = elin + RING_NIDX;                              // A-row extents of the indices
+    int* ap1 = ap0 + RING_NIDX;
+    int* kall = ap1 + RING_NIDX;                              // RING_KALL
     __shared__ int s_n, s_nk;
-    __shared__ double s_tr;
     // valid ring neighbours (inside the FOV), compacted in slot order: parallel ballot scan over <= 8 warps
     {
         const int lane = tid & 31, wid = tid >> 5;
@@ -266,76 +289,85 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
         }
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (lane == 0) s_wcnt[wid] = __popc(m);
+        if (tid < RING_NIDX) { qi[tid] = (int)qm; elin[tid] = 0; }
         __syncthreads();
         int base = 0;
         for (int w = 0; w < wid; ++w) base += s_wcnt[w];
         if (ok) {
             const int pos = base + __popc(m & ((1u << lane) - 1));
-            qi[pos] = (pc + dc) * g.nrb + (pr + dr); slot[pos] = tid; sdr[pos] = dr; sdc[pos] = dc;
+            qi[pos] = (pc + dc) * g.nrb + (pr + dr); slot[pos] = tid; elin[pos] = dc * (4 * g.rr + 1) + dr;
         }
         if (tid == 0) {
             int n = 0;
             for (int w = 0; w < 8; ++w) n += s_wcnt[w];
-            qi[n] = (int)qm; sdr[n] = 0; sdc[n] = 0;
             s_n = n;
         }
     }
     __syncthreads();
     const int n = s_n, n1 = n + 1;
-    for (int i = tid; i <= n; i += blockDim.x) {
-        double y = a.Ymean[qi[i]];
-        ym[i] = y;
-        s1c[i] = a.S1[qi[i]] - a.nsel * y;
-        ap0[i] = a.a_ptr[qi[i]];
-        ap1[i] = a.a_ptr[qi[i] + 1];
+    if (tid < RING_NIDX) {
+        const int i = tid;
+        double y = 0.0, s1 = 0.0, s1c = 0.0;
+        int p0 = 0, p1 = 0;
+        long long qo = 0;
+        if (i < n || i == n1) {
+            const int q = qi[i];
+            y = a.Ymean[q]; s1 = a.S1[q]; s1c = s1 - a.nsel * y;
+            p0 = a.a_ptr[q]; p1 = a.a_ptr[q + 1];
+            qo = (long long)q * (long long)a.ND;
+        } else if (i == n) {
+            y = -1.0; s1 = 0.0; s1c = a.nsel;
+        }
+        const int pp = ring_perm(i);
+        ymp[pp] = y; S1p[pp] = s1; s1cp[pp] = s1c;
+        ap0[i] = p0; ap1[i] = p1; qoff[i] = qo;
     }
     __syncthreads();
-    // --- assemble into registers.  Rows 0..n-1: ring pixels; row n: ones; row n1: right-hand side (pixel m = index n
-    //     of the qi/ym/s1c arrays).  Cov(x, y) of the centred video for "pixel indices" x, y in [0, n]:
-    //     S2c = S2 - nsel*Yb_x*Yb_y - Yb_y*S1c_x - Yb_x*S1c_y,  S1c = S1 - nsel*Yb
+    // --- assemble into registers: Cov(i,j) = raw(i,j) - Ybar_j*S1_i - Ybar_i*S1c_j, raw = second moment of the pixel
+    //     pair (0 where an index carries no pixel).  The moment of a pair sits at S2[base*ND + |e_i - e_j|], base = the
+    //     pixel the displacement starts from (canonical half plane <=> e_i - e_j >= 0).
     RingRegs R;
-    // address of the raw second moment of "pixel indices" (x, y) (canonical orientation chosen branch-free)
-    auto s2ptr = [&](int x, int y) -> const double* {
-        int ddr = sdr[x] - sdr[y], ddc = sdc[x] - sdc[y];   // displacement from pixel y to pixel x
-        bool canon = (ddc > 0) || (ddc == 0 && ddr >= 0);
-        int base = canon ? qi[y] : qi[x];
-        int id = canon ? ring_disp_id(ddr, ddc, g.rr) : ring_disp_id(-ddr, -ddc, g.rr);
-        return a.S2 + (size_t)base * a.ND + id;
-    };
+    {
+        double ymj[8], s1cj[8];
+        int ej[8];
 #pragma unroll
-    for (int aa = 0; aa < 8; ++aa) {
-        const int i = ti + 16 * aa;
-        const double* ptr[8];
-        double raw[8];
-#pragma unroll
-        for (int bb = 0; bb <= aa; ++bb) {
-            const int j = tj + 16 * bb;
-            const bool pair = (j <= i) && (j < n) && (i < n || i == n1);
-            ptr[bb] = pair ? s2ptr(i < n ? i : n, j) : a.S2;
+        for (int b = 0; b < 8; b += 2) {
+            const double2 v = reinterpret_cast<const double2*>(ymp + tj * RING_XSTRIDE)[b >> 1];
+            const double2 w = reinterpret_cast<const double2*>(s1cp + tj * RING_XSTRIDE)[b >> 1];
+            ymj[b] = v.x; ymj[b + 1] = v.y; s1cj[b] = w.x; s1cj[b + 1] = w.y;
         }
 #pragma unroll
-        for (int bb = 0; bb <= aa; ++bb) raw[bb] = __ldg(ptr[bb]);
+        for (int b = 0; b < 8; ++b) ej[b] = elin[tj + 16 * b];
 #pragma unroll
-        for (int bb = 0; bb <= aa; ++bb) {
-            const int j = tj + 16 * bb;
-            double v = 0.0;
-            if (j <= i && i <= n1 && j <= n) {
-                const int x = (i < n) ? i : n;   // row n1 (rhs) pairs the centre pixel (index n) with p_j
-                if ((i < n || i == n1) && j < n) v = raw[bb] - a.nsel * ym[x] * ym[j] - ym[j] * s1c[x] - ym[x] * s1c[j];
-                else if (i == n) v = (j < n) ? s1c[j] : a.nsel;   // ones row
-                else v = s1c[n];                                    // i == n1, j == n: sum Bf(m)
+        for (int aa = 0; aa < 8; ++aa) {
+            const int i = ti + 16 * aa;
+            const bool vi = (i < n) || (i == n1);
+            const int ei = elin[i];
+            const long long qoi = qoff[i];
+            const double* ptr[8];
+            double raw[8];
+#pragma unroll
+            for (int bb = 0; bb <= aa; ++bb) {
+                const int j = tj + 16 * bb;
+                const int lin = ei - ej[bb];
+                const long long off = (lin >= 0 ? qoff[j] : qoi) + (long long)abs(lin);
+                ptr[bb] = (vi && j < n) ? a.S2 + off : &ring_zero_moment;
             }
-            R.g[aa][bb] = v;
+#pragma unroll
+            for (int bb = 0; bb <= aa; ++bb) raw[bb] = __ldg(ptr[bb]);
+            const double ymi = ymp[ti * RING_XSTRIDE + aa], s1i = S1p[ti * RING_XSTRIDE + aa];
+#pragma unroll
+            for (int bb = 0; bb <= aa; ++bb) R.g[aa][bb] = fma(-ymi, s1cj[bb], fma(-ymj[bb], s1i, raw[bb]));
         }
     }
     // --- neuron corrections: Cov_Bf = Cov_Y - N_x.A_y - A_x.N_y ; sum_sel Bf(x) = S1c_x - A_x.Csum
-    // distinct neurons touching the ring pixels / the centre (deterministic scan order), handled RING_KSET at a time
-    // distinct neurons: bitmap over local neuron ids (K <= 4096), compacted in ascending id order (deterministic)
+    // distinct neurons touching the ring pixels / the centre: bitmap over local neuron ids (K <= 4096), compacted in
+    // ascending id order (deterministic), handled RING_KSET at a time
     __shared__ unsigned s_bits[128];
     if (tid < 128) s_bits[tid] = 0u;
     __syncthreads();
-    for (int y = tid; y <= n; y += blockDim.x)
-        for (int e = ap0[y]; e < ap1[y]; ++e) { int k = a.a_col[e]; atomicOr(&s_bits[(k >> 5) & 127], 1u << (k & 31)); }
+    if (tid < RING_NIDX)
+        for (int e = ap0[tid]; e < ap1[tid]; ++e) { int k = a.a_col[e]; atomicOr(&s_bits[(k >> 5) & 127], 1u << (k & 31)); }
     __syncthreads();
     if (tid < 32) {
         int base = 0;
@@ -356,110 +388,102 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
     const int nall = s_nk;
     for (int kbase = 0; kbase < nall; kbase += RING_KSET) {
         const int* kset = kall + kbase;
-        __syncthreads();
         const int nk = min(RING_KSET, nall - kbase);
-        for (int x = tid; x < (n + 1) * RING_KSET; x += blockDim.x) { Ar[x] = 0.0; }
-        for (int x = tid; x < (n + 1) * nk; x += blockDim.x) {
-            int y = x / nk, z = x - y * nk;
-            Nr[y * RING_KSET + z] = a.N[(size_t)qi[y] * a.K + kset[z]];
-        }
-        if (tid < nk) cs[tid] = a.Csum[kset[tid]];
         __syncthreads();
-        for (int y = tid; y <= n; y += blockDim.x)
-            for (int e = ap0[y]; e < ap1[y]; ++e) {
-                int k = a.a_col[e];
-                for (int z = 0; z < nk; ++z) if (kset[z] == k) Ar[y * RING_KSET + z] = a.a_val[e];
+        for (int x = tid; x < 2 * RING_KSET * RING_XBUF; x += blockDim.x) XA[x] = 0.0;   // XA and XN are adjacent
+        __syncthreads();
+        for (int x = tid; x < RING_NIDX * nk; x += blockDim.x) {
+            const int y = x & (RING_NIDX - 1), z = x >> 7;
+            if (y < n || y == n1) XN[z * RING_XBUF + ring_perm(y)] = a.N[(size_t)qi[y] * a.K + kset[z]];
+            else if (y == n) XN[z * RING_XBUF + ring_perm(y)] = a.Csum[kset[z]];
+        }
+        if (tid < RING_NIDX)
+            for (int e = ap0[tid]; e < ap1[tid]; ++e) {
+                const int k = a.a_col[e];
+                for (int z = 0; z < nk; ++z) if (kset[z] == k) XA[z * RING_XBUF + ring_perm(tid)] = a.a_val[e];
             }
         __syncthreads();
-        // rows/columns of this thread that carry neuron entries (index n = centre pixel, needed by row n1)
-        unsigned rmask = 0u, cmask = 0u;
+        for (int z = 0; z < nk; ++z) {
+            const double* xa = XA + z * RING_XBUF;
+            const double* xn = XN + z * RING_XBUF;
+            double aj[8], nj[8];
 #pragma unroll
-        for (int aa = 0; aa < 8; ++aa) {
-            int i = ti + 16 * aa, j = tj + 16 * aa;
-            if (i == n1) i = n;
-            if (i <= n && ap1[i] > ap0[i]) rmask |= 1u << aa;
-            if (j <= n && ap1[j] > ap0[j]) cmask |= 1u << aa;
-        }
-        const bool centre_has = ap1[n] > ap0[n];
-#pragma unroll
-        for (int aa = 0; aa < 8; ++aa)
-#pragma unroll
-            for (int bb = 0; bb <= aa; ++bb) {
-                const int i = ti + 16 * aa, j = tj + 16 * bb;
-                const bool touch = ((rmask >> aa) & 1u) || ((cmask >> bb) & 1u) || (i == n1 && centre_has);
-                if (touch && j <= i && i <= n1 && j <= n) {
-                    double c = 0.0;
-                    if (i < n) {
-                        for (int z = 0; z < nk; ++z)
-                            c += Ar[j * RING_KSET + z] * Nr[i * RING_KSET + z] + Ar[i * RING_KSET + z] * Nr[j * RING_KSET + z];
-                    } else if (i == n) {
-                        if (j < n) for (int z = 0; z < nk; ++z) c += Ar[j * RING_KSET + z] * cs[z];
-                    } else {
-                        if (j < n) {
-                            for (int z = 0; z < nk; ++z)
-                                c += Ar[n * RING_KSET + z] * Nr[j * RING_KSET + z] + Ar[j * RING_KSET + z] * Nr[n * RING_KSET + z];
-                        } else {
-                            for (int z = 0; z < nk; ++z) c += Ar[n * RING_KSET + z] * cs[z];
-                        }
-                    }
-                    R.g[aa][bb] -= c;
-                }
+            for (int b = 0; b < 8; b += 2) {
+                const double2 v = reinterpret_cast<const double2*>(xa + tj * RING_XSTRIDE)[b >> 1];
+                const double2 w = reinterpret_cast<const double2*>(xn + tj * RING_XSTRIDE)[b >> 1];
+                aj[b] = v.x; aj[b + 1] = v.y; nj[b] = w.x; nj[b + 1] = w.y;
             }
+#pragma unroll
+            for (int aa = 0; aa < 8; ++aa) {
+                const double ai = xa[ti * RING_XSTRIDE + aa], ni = xn[ti * RING_XSTRIDE + aa];
+#pragma unroll
+                for (int bb = 0; bb <= aa; ++bb) R.g[aa][bb] = fma(-aj[bb], ni, fma(-ai, nj[bb], R.g[aa][bb]));
+            }
+        }
     }
-    // --- ridge: trace over the n1 x n1 system (diagonal owners are the threads with ti == tj)
+    // --- ridge: trace over the n1 x n1 system (diagonal owners are the threads with ti == tj), summed in a fixed order
     {
-        double tr = 0.0;
         if (ti == tj) {
+            double tr = 0.0;
 #pragma unroll
             for (int aa = 0; aa < 8; ++aa) if (ti + 16 * aa < n1) tr += R.g[aa][aa];
+            trs[ti] = tr;
         }
         __syncthreads();
-        if (tid == 0) s_tr = 0.0;
-        __syncthreads();
-        if (ti == tj) atomicAdd(&s_tr, tr);
-        __syncthreads();
-        const double lam = s_tr * 1e-5;
+        double tot = 0.0;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) tot += trs[t];
+        const double lam = tot * 1e-5;
         if (ti == tj) {
 #pragma unroll
             for (int aa = 0; aa < 8; ++aa) if (ti + 16 * aa < n1) R.g[aa][aa] += lam;
         }
     }
-    // --- Cholesky of the augmented matrix
-    ring_chol_block<0>(R, n1, ti, tj, colk, piv);
-    if (n1 > 16) ring_chol_block<1>(R, n1, ti, tj, colk, piv);
-    if (n1 > 32) ring_chol_block<2>(R, n1, ti, tj, colk, piv);
-    if (n1 > 48) ring_chol_block<3>(R, n1, ti, tj, colk, piv);
-    if (n1 > 64) ring_chol_block<4>(R, n1, ti, tj, colk, piv);
-    if (n1 > 80) ring_chol_block<5>(R, n1, ti, tj, colk, piv);
-    if (n1 > 96) ring_chol_block<6>(R, n1, ti, tj, colk, piv);
-    if (n1 > 112) ring_chol_block<7>(R, n1, ti, tj, colk, piv);
+    // --- LDL' of the augmented matrix
+    ring_chol_block<0>(R, n1, ti, tj, colk, rd);
+    if (n1 > 16) ring_chol_block<1>(R, n1, ti, tj, colk, rd);
+    if (n1 > 32) ring_chol_block<2>(R, n1, ti, tj, colk, rd);
+    if (n1 > 48) ring_chol_block<3>(R, n1, ti, tj, colk, rd);
+    if (n1 > 64) ring_chol_block<4>(R, n1, ti, tj, colk, rd);
+    if (n1 > 80) ring_chol_block<5>(R, n1, ti, tj, colk, rd);
+    if (n1 > 96) ring_chol_block<6>(R, n1, ti, tj, colk, rd);
+    if (n1 > 112) ring_chol_block<7>(R, n1, ti, tj, colk, rd);
     __syncthreads();
-    // --- write out L (scaling column k by 1/sqrt(g_kk)), back substitution L' w = z (z = row n1) by one warp
-    for (int k = tid; k < n1; k += blockDim.x) piv[k] = 1.0 / sqrt(piv[k]);
-    __syncthreads();
+    // --- write out the strictly-lower part of the unit factor M(i,j) = x_ij / d_j (rows packed); row n1 is then
+    //     y = D^-1 M^-1 rhs, and M' w = y is solved by one warp
 #pragma unroll
     for (int aa = 0; aa < 8; ++aa)
 #pragma unroll
         for (int bb = 0; bb <= aa; ++bb) {
             const int i = ti + 16 * aa, j = tj + 16 * bb;
-            // diagonal: L(j,j) = sqrt(g_jj) = g_jj * (1/sqrt(g_jj));  below: x_i * (1/sqrt(g_jj))
-            if (j <= i && i <= n1 && j < n1) L[(size_t)i * (i + 1) / 2 + j] = R.g[aa][bb] * piv[j];
+            if (j < i && i <= n1) L[(size_t)i * (i + 1) / 2 + j] = R.g[aa][bb] * rd[j];
         }
     __syncthreads();
-    double* rdiag = piv;   // 1/L(k,k) = 1/sqrt(g_kk)
     if (tid < 32) {
-        // lane l keeps z_i for i = l + 32 m (m < 4) in registers; step k broadcasts w_k by shuffle
-        double z[4];
+        // lane l keeps y_i for i = l + 32 m (m < 4) in registers; step k broadcasts w_k by shuffle and subtracts
+        // M(k, i) * w_k from the entries i < k; row k-1 is fetched while step k runs
+        double z[4], rc[4];
+        const double* rown = L + (size_t)n1 * (n1 + 1) / 2;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) { int i = tid + 32 * m; z[m] = (i < n1) ? L[(size_t)n1 * (n1 + 1) / 2 + i] : 0.0; }
-        for (int k = n1 - 1; k >= 0; --k) {
-            const double* row = L + (size_t)k * (k + 1) / 2;
+        for (int m = 0; m < 4; ++m) { const int i = tid + 32 * m; z[m] = (i < n1) ? rown[i] : 0.0; }
+        {
+            const double* row = L + (size_t)n * (n + 1) / 2;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { const int i = tid + 32 * m; rc[m] = (i < n) ? row[i] : 0.0; }
+        }
+        for (int k = n; k >= 0; --k) {
+            double rn[4] = {0.0, 0.0, 0.0, 0.0};
+            if (k > 0) {
+                const double* row = L + (size_t)(k - 1) * k / 2;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) { const int i = tid + 32 * m; if (i < k - 1) rn[m] = row[i]; }
+            }
             const int km = k >> 5;
-            double zk = km == 0 ? z[0] : (km == 1 ? z[1] : (km == 2 ? z[2] : z[3]));
-            const double wk = __shfl_sync(0xffffffffu, zk, k & 31) * rdiag[k];
+            const double zk = km == 0 ? z[0] : (km == 1 ? z[1] : (km == 2 ? z[2] : z[3]));
+            const double wk = __shfl_sync(0xffffffffu, zk, k & 31);
             if (tid == (k & 31)) colk[k] = wk;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) { int i = tid + 32 * m; if (i < k) z[m] -= row[i] * wk; }
+            for (int m = 0; m < 4; ++m) { z[m] = fma(-rc[m], wk, z[m]); rc[m] = rn[m]; }
         }
     }
     __syncthreads();
