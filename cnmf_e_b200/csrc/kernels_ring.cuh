@@ -182,6 +182,7 @@ struct RingSolveArgs {
 #define RING_NIDX 128        // index space of the augmented system: 0..n-1 ring pixels, n ones row, n1 = n+1 rhs/centre
 #define RING_XSTRIDE 10
 #define RING_XBUF (16 * RING_XSTRIDE)
+#define RING_TT (16 * 17)     // one 16 x 16 diagonal tile of the unit factor, row stride 17
 // One CTA per active patch pixel: assemble the (n+1)x(n+1) normal equations, ridge, factorise, write weights.
 // fit_ring_model.m:92-108:  X=[Bf(ring,:);1]; w=(X*X'+1e-5*trace(X*X')*I)\(X*y'); W(m,ring)=w(1:end-1)+1e-100
 //
@@ -208,44 +209,114 @@ __device__ __forceinline__ int ring_perm(int i) { return (i & 15) * RING_XSTRIDE
 __device__ const double ring_zero_moment = 0.0;
 
 __host__ __device__ inline size_t ring_solve_smem_bytes(int NMAX) {
-    size_t dbl = 2 * RING_XBUF + 128 + 3 * RING_XBUF + 2 * (size_t)RING_KSET * RING_XBUF + RING_KSET + 16 + RING_NIDX /* qoff */ +
-                 (size_t)(NMAX + 1) * (NMAX + 2) / 2 + 2;
+    (void)NMAX;
+    size_t dbl = 4 * RING_XBUF + 128 + 3 * RING_XBUF + 2 * (size_t)RING_KSET * RING_XBUF + RING_KSET + 16 + RING_NIDX /* qoff */ +
+                 8 * RING_TT /* diagonal tiles of the unit factor */ + 2 * RING_NIDX /* zs, ws */;
     size_t ints = 5 * (size_t)RING_NIDX + RING_KALL;
     return dbl * 8 + ints * 4 + 64;
 }
 
-// Right-looking LDL' elimination with ONE barrier per column: the owners of column k publish its UNSCALED entries x_i
-// (zeros for i <= k) and the reciprocal pivot 1/d_k (double-buffered), then every thread applies
-// G(i,j) -= (x_i / d_k) * x_j to its registers.  The registers keep x_i; rd[] keeps the reciprocal pivots, so the unit
-// factor M(i,k) = x_i / d_k is formed once, when it is written out.
+// Right-looking LDL' elimination, TWO columns per barrier.  Thread (ti, tj) = (tid & 15, tid >> 4): a warp holds the
+// column residues tj = 2w (lanes 0-15) and 2w+1 (lanes 16-31), every row residue ti once per half -- so the columns
+// (k, k+1), k even, belong to ONE warp.  That warp factorises the 2-column panel with shuffles (pivot d_k, the entry
+// x_{k+1,k}, column k+1 after the update by column k, pivot d_{k+1}) and publishes both UNSCALED columns x_i (zeros for
+// i <= column) plus the reciprocal pivots; after the barrier every thread applies the rank-2 update
+// G(i,j) -= (x1_i / d_k) * x1_j + (x2_i / d_{k+1}) * x2_j to its registers.  Because the published column has a zero at
+// its own index, the registers of a finished column keep the unscaled x_i; rd[] keeps 1/d, so the unit factor
+// M(i,k) = x_i / d_k is formed when it is needed.
 template <int KA>
-__device__ __forceinline__ void ring_chol_block(RingRegs& R, int n1, int ti, int tj, double* xbuf, double* rd) {
+__device__ __forceinline__ void ring_ldl_block(RingRegs& R, int n1, int ti, int tj, double* xbuf, double* rd) {
     const int kend = min(16 * KA + 15, n1 - 1);
     constexpr int A0 = KA & ~1;          // first (even) register index loaded: keeps the 16-byte alignment
-    for (int k = 16 * KA; k <= kend; ++k) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4;
+    for (int k = 16 * KA; k <= kend; k += 2) {
         const int kr = k & 15;
-        double* xb = xbuf + (k & 1) * RING_XBUF;
-        if (tj == kr) {
-            double* dst = xb + ti * RING_XSTRIDE;
+        double* xb = xbuf + ((k >> 1) & 1) * (2 * RING_XBUF);
+        if (warp == (kr >> 1)) {
+            const bool second = (k + 1 <= kend);
+            double x[8];
 #pragma unroll
-            for (int a = KA; a < 8; ++a) dst[a] = (ti + 16 * a > k) ? R.g[a][KA] : 0.0;
-            if (ti == kr) { const double r = 1.0 / R.g[KA][KA]; rd[k] = r; xb[8] = r; }   // slot 8 of thread-row 0: padding
+            for (int a = KA; a < 8; ++a) x[a] = R.g[a][KA];
+            const double d1 = __shfl_sync(0xffffffffu, x[KA], kr);
+            const double m = __shfl_sync(0xffffffffu, x[KA], kr + 1);     // x_{k+1,k}
+            const double r1 = 1.0 / d1;
+#pragma unroll
+            for (int a = KA; a < 8; ++a) {
+                const double lo = __shfl_sync(0xffffffffu, x[a], ti);     // column-k entry of this thread's row
+                const bool live = (ti + 16 * a > k);
+                if (half) x[a] = live ? fma(-(lo * r1), m, x[a]) : x[a];
+            }
+            const double d2 = __shfl_sync(0xffffffffu, x[KA], 16 + ((kr + 1) & 15));
+            const double r2 = second ? 1.0 / d2 : 0.0;
+            double* dst = xb + half * RING_XBUF + ti * RING_XSTRIDE;
+            const int kk = k + half;
+            const bool on = (half == 0) || second;
+#pragma unroll
+            for (int a = KA; a < 8; ++a) dst[a] = (on && ti + 16 * a > kk) ? x[a] : 0.0;
+            if (lane == 0) { xb[8] = r1; xb[9] = r2; rd[k] = r1; rd[k + 1] = r2; }   // slots 8, 9 of thread-row 0: padding
         }
         __syncthreads();
-        const double rinv = xb[8];
-        double ci[8], cj[8];
-        const double2* si = reinterpret_cast<const double2*>(xb + ti * RING_XSTRIDE);
-        const double2* sj = reinterpret_cast<const double2*>(xb + tj * RING_XSTRIDE);
+        const double2 rv = *reinterpret_cast<const double2*>(xb + 8);
+        double cj1[8], cj2[8];
+        {
+            const double2* s1 = reinterpret_cast<const double2*>(xb + tj * RING_XSTRIDE);
+            const double2* s2 = reinterpret_cast<const double2*>(xb + RING_XBUF + tj * RING_XSTRIDE);
 #pragma unroll
-        for (int a = A0; a < 8; a += 2) {
-            const double2 vi = si[a >> 1], vj = sj[a >> 1];
-            ci[a] = vi.x * rinv; ci[a + 1] = vi.y * rinv;
-            cj[a] = vj.x; cj[a + 1] = vj.y;
+            for (int a = A0; a < 8; a += 2) {
+                const double2 v1 = s1[a >> 1], v2 = s2[a >> 1];
+                cj1[a] = v1.x; cj1[a + 1] = v1.y; cj2[a] = v2.x; cj2[a + 1] = v2.y;
+            }
         }
+        const double2* si1 = reinterpret_cast<const double2*>(xb + ti * RING_XSTRIDE);
+        const double2* si2 = reinterpret_cast<const double2*>(xb + RING_XBUF + ti * RING_XSTRIDE);
 #pragma unroll
-        for (int a = KA; a < 8; ++a)
+        for (int a2 = A0; a2 < 8; a2 += 2) {
+            const double2 v1 = si1[a2 >> 1], v2 = si2[a2 >> 1];
+            const double c1[2] = {v1.x * rv.x, v1.y * rv.x}, c2[2] = {v2.x * rv.y, v2.y * rv.y};
 #pragma unroll
-            for (int b = KA; b <= a; ++b) R.g[a][b] = fma(-ci[a], cj[b], R.g[a][b]);
+            for (int h = 0; h < 2; ++h) {
+                const int a = a2 + h;
+                if (a < KA) continue;
+#pragma unroll
+                for (int b = KA; b <= a; ++b) R.g[a][b] = fma(-c2[h], cj2[b], fma(-c1[h], cj1[b], R.g[a][b]));
+            }
+        }
+    }
+}
+
+// back substitution M' w = y, one 16-unknown block at a time (descending): warp 0 solves the diagonal tile with
+// shuffles, then every thread subtracts its register entries M(16A+ti, tj+16b) * w from the unknowns below (b < A),
+// reduced over ti inside the half-warp.
+template <int A>
+__device__ __forceinline__ void ring_backsub_block(const RingRegs& R, int n, int ti, int tj, const double* Tt,
+                                                   const double* rd, double* zs, double* ws) {
+    if (16 * A > n) return;                      // uniform: no unknown in this block
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        const int l = lane & 15;
+        const double* tile = Tt + A * RING_TT;
+        double col[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) col[k] = tile[k * 17 + l];
+        double z = zs[16 * A + l];
+#pragma unroll
+        for (int k = 15; k >= 1; --k) {
+            const double wk = __shfl_sync(0xffffffffu, z, k);
+            if (l < k) z = fma(-col[k], wk, z);
+        }
+        if (lane < 16) ws[16 * A + l] = z;
+    }
+    __syncthreads();
+    if (A > 0) {
+        const double wv = ws[16 * A + ti];
+#pragma unroll
+        for (int b = 0; b < A; ++b) {
+            double pz = R.g[A][b] * wv;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) pz += __shfl_xor_sync(0xffffffffu, pz, o);
+            if (ti == 0) zs[tj + 16 * b] = fma(-pz, rd[tj + 16 * b], zs[tj + 16 * b]);
+        }
+        __syncthreads();
     }
 }
 
@@ -253,13 +324,13 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
     extern __shared__ double smem[];
     const RingGeom& g = a.g;
     const int p = a.active_list[blockIdx.x];
-    const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+    const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
     const int pr = p % g.nr + g.pr_off, pc = p / g.nr + g.pc_off;
     const size_t qm = (size_t)pc * g.nrb + pr;
     const int NMAX = g.nnb + 1;
     // shared layout
-    double* colk = smem;                                      // 2*RING_XBUF: double-buffered column, later the solution
-    double* rd = colk + 2 * RING_XBUF;                        // 128: reciprocal pivots 1/d_k
+    double* colk = smem;                                      // 2 x (2*RING_XBUF): double-buffered column pair
+    double* rd = colk + 4 * RING_XBUF;                        // 128: reciprocal pivots 1/d_k
     double* ymp = rd + 128;                                   // permuted per-index vectors (see above)
     double* S1p = ymp + RING_XBUF;
     double* s1cp = S1p + RING_XBUF;
@@ -268,8 +339,10 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
     double* cs = XN + RING_KSET * RING_XBUF;                  // RING_KSET (+ 16 partial traces)
     double* trs = cs + RING_KSET;
     long long* qoff = reinterpret_cast<long long*>(trs + 16); // RING_NIDX: block pixel index * ND
-    double* L = reinterpret_cast<double*>(qoff + RING_NIDX);  // packed rows of the unit factor, (NMAX+1)(NMAX+2)/2
-    int* qi = reinterpret_cast<int*>(L + (size_t)(NMAX + 1) * (NMAX + 2) / 2 + 2);   // RING_NIDX block pixel index
+    double* Tt = reinterpret_cast<double*>(qoff + RING_NIDX); // 8 diagonal tiles of the unit factor
+    double* zs = Tt + 8 * RING_TT;                            // RING_NIDX: running right-hand side of the back substitution
+    double* wsol = zs + RING_NIDX;                            // RING_NIDX: solution
+    int* qi = reinterpret_cast<int*>(wsol + RING_NIDX);       // RING_NIDX block pixel index
     int* slot = qi + RING_NIDX;
     int* elin = slot + RING_NIDX;                             // dc*(4rr+1)+dr: displacement ids are differences of these
     int* ap0 = elin + RING_NIDX;                              // A-row extents of the indices
@@ -289,7 +362,7 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
         }
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (lane == 0) s_wcnt[wid] = __popc(m);
-        if (tid < RING_NIDX) { qi[tid] = (int)qm; elin[tid] = 0; }
+        if (tid < RING_NIDX) { qi[tid] = (int)qm; elin[tid] = 0; rd[tid] = 0.0; }   // rd beyond the last column stays 0 (read by the tiles)
         __syncthreads();
         int base = 0;
         for (int w = 0; w < wid; ++w) base += s_wcnt[w];
@@ -440,54 +513,40 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
         }
     }
     // --- LDL' of the augmented matrix
-    ring_chol_block<0>(R, n1, ti, tj, colk, rd);
-    if (n1 > 16) ring_chol_block<1>(R, n1, ti, tj, colk, rd);
-    if (n1 > 32) ring_chol_block<2>(R, n1, ti, tj, colk, rd);
-    if (n1 > 48) ring_chol_block<3>(R, n1, ti, tj, colk, rd);
-    if (n1 > 64) ring_chol_block<4>(R, n1, ti, tj, colk, rd);
-    if (n1 > 80) ring_chol_block<5>(R, n1, ti, tj, colk, rd);
-    if (n1 > 96) ring_chol_block<6>(R, n1, ti, tj, colk, rd);
-    if (n1 > 112) ring_chol_block<7>(R, n1, ti, tj, colk, rd);
+    ring_ldl_block<0>(R, n1, ti, tj, colk, rd);
+    if (n1 > 16) ring_ldl_block<1>(R, n1, ti, tj, colk, rd);
+    if (n1 > 32) ring_ldl_block<2>(R, n1, ti, tj, colk, rd);
+    if (n1 > 48) ring_ldl_block<3>(R, n1, ti, tj, colk, rd);
+    if (n1 > 64) ring_ldl_block<4>(R, n1, ti, tj, colk, rd);
+    if (n1 > 80) ring_ldl_block<5>(R, n1, ti, tj, colk, rd);
+    if (n1 > 96) ring_ldl_block<6>(R, n1, ti, tj, colk, rd);
+    if (n1 > 112) ring_ldl_block<7>(R, n1, ti, tj, colk, rd);
     __syncthreads();
-    // --- write out the strictly-lower part of the unit factor M(i,j) = x_ij / d_j (rows packed); row n1 is then
-    //     y = D^-1 M^-1 rhs, and M' w = y is solved by one warp
-#pragma unroll
-    for (int aa = 0; aa < 8; ++aa)
-#pragma unroll
-        for (int bb = 0; bb <= aa; ++bb) {
-            const int i = ti + 16 * aa, j = tj + 16 * bb;
-            if (j < i && i <= n1) L[(size_t)i * (i + 1) / 2 + j] = R.g[aa][bb] * rd[j];
-        }
+    // --- row n1 of the registers is now the unscaled forward-substituted right-hand side: y_j = x_{n1,j} / d_j.
+    //     Diagonal tiles of the unit factor M(i,j) = x_ij / d_j go to shared memory; M' w = y is solved block-wise.
+    if (tid < RING_NIDX) zs[tid] = 0.0;
     __syncthreads();
-    if (tid < 32) {
-        // lane l keeps y_i for i = l + 32 m (m < 4) in registers; step k broadcasts w_k by shuffle and subtracts
-        // M(k, i) * w_k from the entries i < k; row k-1 is fetched while step k runs
-        double z[4], rc[4];
-        const double* rown = L + (size_t)n1 * (n1 + 1) / 2;
+    {
+        const int a0 = n1 >> 4, t0 = n1 & 15;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) { const int i = tid + 32 * m; z[m] = (i < n1) ? rown[i] : 0.0; }
-        {
-            const double* row = L + (size_t)n * (n + 1) / 2;
+        for (int aa = 0; aa < 8; ++aa) {
+            Tt[aa * RING_TT + ti * 17 + tj] = (ti > tj) ? R.g[aa][aa] * rd[16 * aa + tj] : 0.0;
+            if (aa == a0 && ti == t0) {
 #pragma unroll
-            for (int m = 0; m < 4; ++m) { const int i = tid + 32 * m; rc[m] = (i < n) ? row[i] : 0.0; }
-        }
-        for (int k = n; k >= 0; --k) {
-            double rn[4] = {0.0, 0.0, 0.0, 0.0};
-            if (k > 0) {
-                const double* row = L + (size_t)(k - 1) * k / 2;
-#pragma unroll
-                for (int m = 0; m < 4; ++m) { const int i = tid + 32 * m; if (i < k - 1) rn[m] = row[i]; }
+                for (int bb = 0; bb <= aa; ++bb) { const int j = tj + 16 * bb; if (j < n1) zs[j] = R.g[aa][bb] * rd[j]; }
             }
-            const int km = k >> 5;
-            const double zk = km == 0 ? z[0] : (km == 1 ? z[1] : (km == 2 ? z[2] : z[3]));
-            const double wk = __shfl_sync(0xffffffffu, zk, k & 31);
-            if (tid == (k & 31)) colk[k] = wk;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) { z[m] = fma(-rc[m], wk, z[m]); rc[m] = rn[m]; }
         }
     }
     __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) a.W[(size_t)p * g.nnb + slot[i]] = colk[i] + 1e-100;
+    ring_backsub_block<7>(R, n, ti, tj, Tt, rd, zs, wsol);
+    ring_backsub_block<6>(R, n, ti, tj, Tt, rd, zs, wsol);
+    ring_backsub_block<5>(R, n, ti, tj, Tt, rd, zs, wsol);
+    ring_backsub_block<4>(R, n, ti, tj, Tt, rd, zs, wsol);
+    ring_backsub_block<3>(R, n, ti, tj, Tt, rd, zs, wsol);
+    ring_backsub_block<2>(R, n, ti, tj, Tt, rd, zs, wsol);
+    ring_backsub_block<1>(R, n, ti, tj, Tt, rd, zs, wsol);
+    ring_backsub_block<0>(R, n, ti, tj, Tt, rd, zs, wsol);
+    for (int i = tid; i < n; i += blockDim.x) a.W[(size_t)p * g.nnb + slot[i]] = wsol[i] + 1e-100;
 }
 
 // uniform ring initialisation (initComponents_parallel.m:213-236): W[i][p] = 1/#valid neighbours

@@ -162,3 +162,17 @@ def test_fast_temporal_use_c_hat_false(built_lib):
     _close(gpu.C, orc.C)
     assert np.array_equal(gpu.S > 0, orc.S > 0)
     gpu.close()
+
+
+def test_background_ring18_parity(built_lib):
+    """Ring radius 18 (120 neighbours: the 121 x 121 systems of BASELINE configs[1], all eight 16-column blocks of the
+    register-resident LDL' solver) against the oracle: first run (all pixels) and steady state (active pixels only)."""
+    D, orc, gpu = _make(56, 48, 500, 4, (56, 48), 18, seed=5)
+    orc.update_background_parallel()
+    gpu.update_background_parallel()
+    _check_bg(orc, gpu)
+    _sync_from_oracle(orc, gpu)
+    orc.update_background_parallel()
+    gpu.update_background_parallel()
+    _check_bg(orc, gpu)
+    gpu.close()
