@@ -750,8 +750,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         if (!d_N) { set_error("scratch exhausted"); return -1; }
         if (Kb > 0) {
             CNMFE_CUDA_OK(cudaMemsetAsync(d_N, 0, (size_t)P.db * Kb * 8, c->st));
-            long long nw = (long long)((P.nrb + PROJ_PQ - 1) / PROJ_PQ) * P.ncb;
-            LAUNCH(proj_mc_kernel, (unsigned)((nw + 7) / 8), 256, 0, c->st, P.Yt, P.Ymean, P.nrb, P.ncb, T, c->Tpad,
+            launch_proj_mc(c->st, P.Yt, P.Ymean, P.nrb, P.ncb, T, c->Tpad,
                    kf, d_Cc, Kb, d_bbox, d_N);
             LAUNCH(ring_make_N_kernel, P.db, 64, 0, c->st, d_N, Kb, d_ptr, d_col, d_val, d_Vsel, (size_t)P.db);
         }
@@ -942,8 +941,7 @@ extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
         phase_begin(c);
         CNMFE_CUDA_OK(cudaMemsetAsync(d_D, 0, (size_t)P.db * Ks * 8, c->st));
         {
-            long long nw = (long long)((P.nrb + PROJ_PQ - 1) / PROJ_PQ) * P.ncb;
-            LAUNCH(proj_mc_kernel, (unsigned)((nw + 7) / 8), 256, 0, c->st, P.Yt, P.Ymean, P.nrb, P.ncb, T, c->Tpad, 1,
+            launch_proj_mc(c->st, P.Yt, P.Ymean, P.nrb, P.ncb, T, c->Tpad, 1,
                    d_Cc, Ks, d_bbox, d_D);
         }
         if (Kp > 0) LAUNCH(spatial_make_D_kernel, P.db, 64, 0, c->st, d_D, Ks, d_pptr, d_pcol, d_pval, d_P2);
@@ -1094,7 +1092,7 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
         { dim3 gg(Kt, (Kt + 127) / 128); LAUNCH(temporal_V_kernel, gg, 128, 0, c->st, d_cptr, d_crow, d_cval, Kt, d_V); }
         phase_end(c, 6);
         phase_begin(c);
-        { dim3 gg(Kt, (T + 511) / 512); LAUNCH(proj_bt_kernel, gg, 256, 0, c->st, P.Yt, P.Ymean, P.nrb, T, c->Tpad, d_B, Kt, d_bbox, d_U); }
+        launch_proj_bt(c->st, P.Yt, P.Ymean, P.nrb, T, c->Tpad, d_B, Kt, d_bbox, d_U);
         { dim3 gg((T + 255) / 256, Kt); LAUNCH(add_small_matmul_kernel, gg, 256, 0, c->st, d_U, Kt, T, d_cst, d_AWA, Kp, d_Ccp); }
         phase_end(c, 2);
         // V -> CSR (host), sweeps

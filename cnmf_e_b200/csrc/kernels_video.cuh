@@ -188,6 +188,275 @@ proj_bt_kernel(const uint16_t* __restrict__ Yt, const double* __restrict__ Ymean
     if (t + 1 < T) U[(size_t)k * T + t + 1] = a1;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tiled versions of the two projections (all frames, kf = 1).  u16 -> double without I2F: the bit pattern
+// 0x43300000'0000yyyy is the double 2^52 + y, so (that - 2^52) is y exactly; then - Ymean as in the reference.
+__device__ __forceinline__ double u16_to_f64(unsigned y) {
+    return __hiloint2double(0x43300000, (int)y) - 4503599627370496.0;
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Centred projection, tiled: one CTA = an 8 x 8 pixel tile; the video rows of the tile are staged chunk by chunk
+// (PMC_TC frames, double-buffered cp.async) into shared memory, padded so that the 64 pixels read the same frames
+// without bank conflicts.  A lane owns the pixels (l, l + 32) of the tile and PMC_NB neurons: per 4 frames it does two
+// 8-byte shared loads, 2 x PMC_NB 16-byte warp-uniform loads of the traces and 64 DFMA.  The 8 warps split the
+// neuron groups of the tile and, when there are fewer than 8 groups, the frames of each chunk; the partial sums meet
+// in shared memory at the end (fixed order).  Same contract as proj_mc_kernel (Mc dense [db][K], zeroed by the caller,
+// written only inside the neuron boxes); needs T even (16-byte trace loads).
+#define PMC_TC 256
+#define PMC_ROWB (PMC_TC * 2 + 8)
+#define PMC_NB 8
+#define PMC_STAGE (64 * PMC_ROWB)
+__global__ void __launch_bounds__(256, 2)
+proj_mc_tile_kernel(const uint16_t* __restrict__ Yt, const double* __restrict__ Ymean, int nrb, int ncb, int T, int Tpad,
+                    const double* __restrict__ Cc, int K, const int* __restrict__ bbox, double* __restrict__ Mc) {
+    extern __shared__ __align__(16) unsigned char pmc_smem[];
+    __shared__ int s_list[64];
+    __shared__ int s_cnt;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles_r = (nrb + 7) >> 3;
+    const int r0 = (blockIdx.x % tiles_r) * 8, c0 = (blockIdx.x / tiles_r) * 8;
+    const int r1 = min(nrb - 1, r0 + 7), c1 = min(ncb - 1, c0 + 7);
+    if (warp == 0) {
+        int cnt = 0;
+        for (int kk = 0; kk < K; kk += 32) {
+            const int k = kk + lane;
+            bool hit = false;
+            if (k < K) {
+                const int* b = bbox + 4 * k;
+                hit = (c1 >= b[2] && c0 <= b[3] && r1 >= b[0] && r0 <= b[1]);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const int pos = cnt + __popc(m & ((1u << lane) - 1));
+                if (pos < 64) s_list[pos] = k;
+            }
+            cnt += __popc(m);
+        }
+        if (lane == 0) s_cnt = min(cnt, 64);
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    if (cnt == 0) return;
+    const int G = (cnt + PMC_NB - 1) / PMC_NB;
+    const int TS = G == 1 ? 8 : (G == 2 ? 4 : (G <= 4 ? 2 : 1));
+    const int Gp = 8 / TS;
+    const int grp = warp % Gp, slice = warp / Gp;
+    const bool active = grp < G;
+    // the lane's two pixels
+    int pq[2]; double ym[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        const int r = min(r0 + (i & 7), nrb - 1), c = min(c0 + (i >> 3), ncb - 1);
+        pq[h] = c * nrb + r;
+        ym[h] = Ymean[pq[h]];
+    }
+    const double* crow[PMC_NB];
+#pragma unroll
+    for (int j = 0; j < PMC_NB; ++j) crow[j] = Cc + (size_t)s_list[min(grp * PMC_NB + j, cnt - 1)] * T;
+    double acc[2][PMC_NB];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < PMC_NB; ++j) acc[h][j] = 0.0;
+    // staging: thread -> (row = pass * 4 + tid / 64, 8-byte column = tid % 64)
+    const int srow = tid >> 6, scol = tid & 63;
+    auto stage = [&](int ch, int buf) {
+        const int t0 = ch * PMC_TC;
+        if (t0 + scol * 4 < Tpad) {
+            unsigned char* dst = pmc_smem + buf * PMC_STAGE + scol * 8;
+#pragma unroll 4
+            for (int ps = 0; ps < 16; ++ps) {
+                const int i = ps * 4 + srow;
+                const int r = min(r0 + (i & 7), nrb - 1), c = min(c0 + (i >> 3), ncb - 1);
+                cp_async8(dst + i * PMC_ROWB, Yt + (size_t)(c * nrb + r) * Tpad + t0 + scol * 4);
+            }
+        }
+        cp_async_commit();
+    };
+    const int nch = (Tpad + PMC_TC - 1) / PMC_TC;
+    stage(0, 0);
+    for (int ch = 0; ch < nch; ++ch) {
+        if (ch + 1 < nch) { stage(ch + 1, (ch + 1) & 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncthreads();
+        if (active) {
+            const int t0 = ch * PMC_TC;
+            const int nfr = min(PMC_TC, Tpad - t0);
+            const int ta = slice * nfr / TS, tb = (slice + 1) * nfr / TS;
+            const unsigned char* base = pmc_smem + (ch & 1) * PMC_STAGE;
+            const unsigned char* rowA = base + lane * PMC_ROWB;
+            const unsigned char* rowB = base + (lane + 32) * PMC_ROWB;
+            for (int t = ta; t < tb; t += 4) {
+                const uint2 ya = *reinterpret_cast<const uint2*>(rowA + t * 2);
+                const uint2 yb = *reinterpret_cast<const uint2*>(rowB + t * 2);
+                double y[2][4];
+                y[0][0] = u16_to_f64(ya.x & 0xffffu) - ym[0]; y[0][1] = u16_to_f64(ya.x >> 16) - ym[0];
+                y[0][2] = u16_to_f64(ya.y & 0xffffu) - ym[0]; y[0][3] = u16_to_f64(ya.y >> 16) - ym[0];
+                y[1][0] = u16_to_f64(yb.x & 0xffffu) - ym[1]; y[1][1] = u16_to_f64(yb.x >> 16) - ym[1];
+                y[1][2] = u16_to_f64(yb.y & 0xffffu) - ym[1]; y[1][3] = u16_to_f64(yb.y >> 16) - ym[1];
+                const int tg = t0 + t;
+                if (tg + 4 <= T) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        double2 cv[PMC_NB];
+#pragma unroll
+                        for (int j = 0; j < PMC_NB; ++j) cv[j] = __ldg(reinterpret_cast<const double2*>(crow[j] + tg + 2 * u));
+#pragma unroll
+                        for (int j = 0; j < PMC_NB; ++j) {
+                            acc[0][j] = fma(y[0][2 * u], cv[j].x, acc[0][j]);
+                            acc[1][j] = fma(y[1][2 * u], cv[j].x, acc[1][j]);
+                            acc[0][j] = fma(y[0][2 * u + 1], cv[j].y, acc[0][j]);
+                            acc[1][j] = fma(y[1][2 * u + 1], cv[j].y, acc[1][j]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        if (tg + f < T) {
+#pragma unroll
+                            for (int j = 0; j < PMC_NB; ++j) {
+                                const double cvv = __ldg(crow[j] + tg + f);
+                                acc[0][j] = fma(y[0][f], cvv, acc[0][j]);
+                                acc[1][j] = fma(y[1][f], cvv, acc[1][j]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // partial sums -> shared memory [warp][pixel][PMC_NB]; summed over the frame slices in ascending order
+    double* red = reinterpret_cast<double*>(pmc_smem);
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < PMC_NB; ++j) red[((size_t)warp * 64 + lane + 32 * h) * PMC_NB + j] = acc[h][j];
+    __syncthreads();
+    const int px = tid & 63;
+    const int pr = r0 + (px & 7), pc = c0 + (px >> 3);
+    if (pr >= nrb || pc >= ncb) return;
+    const size_t q = (size_t)pc * nrb + pr;
+    for (int g = tid >> 6; g < G; g += 4) {
+        for (int j = 0; j < PMC_NB; ++j) {
+            const int li = g * PMC_NB + j;
+            if (li >= cnt) break;
+            const int k = s_list[li];
+            const int* b = bbox + 4 * k;
+            if (pc < b[2] || pc > b[3] || pr < b[0] || pr > b[1]) continue;
+            double v = 0.0;
+            for (int sl = 0; sl < TS; ++sl) v += red[((size_t)(sl * Gp + g) * 64 + px) * PMC_NB + j];
+            Mc[q * K + k] = v;
+        }
+    }
+}
+
+// Temporal projection, list version: one CTA = (neuron k, PBT_FRAMES frames).  The non-zero pixels of B(:,k) inside
+// the neuron box are compacted (in box order) into shared memory, then every thread streams its 8 frames of those
+// pixel rows with four 16-byte loads in flight.  Same summation order as proj_bt_kernel.
+#define PBT_FRAMES 2048
+#define PBT_SEG 2048
+__global__ void __launch_bounds__(256)
+proj_bt_list_kernel(const uint16_t* __restrict__ Yt, const double* __restrict__ Ymean, int nrb, int T, int Tpad,
+                    const double* __restrict__ B, int K, const int* __restrict__ bbox, double* __restrict__ U) {
+    __shared__ int s_q[PBT_SEG];
+    __shared__ double s_w[PBT_SEG];
+    __shared__ double s_m[PBT_SEG];
+    __shared__ int s_wcnt[8];
+    const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = blockIdx.y * PBT_FRAMES + tid * 8;
+    const int* b = bbox + 4 * k;
+    const int br0 = b[0], br1 = b[1], bc0 = b[2], bc1 = b[3];
+    const int hgt = br1 - br0 + 1, npix = (br1 >= br0 && bc1 >= bc0) ? hgt * (bc1 - bc0 + 1) : 0;
+    double acc[8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) acc[f] = 0.0;
+    const bool live = t < Tpad;
+    for (int s0 = 0; s0 < npix; s0 += PBT_SEG) {
+        const int seg = min(PBT_SEG, npix - s0);
+        __syncthreads();
+        int n = 0;
+        for (int i0 = 0; i0 < seg; i0 += 256) {
+            const int i = i0 + tid;
+            double w = 0.0; int q = 0;
+            if (i < seg) {
+                const int x = s0 + i;
+                q = (bc0 + x / hgt) * nrb + br0 + x % hgt;
+                w = B[(size_t)q * K + k];
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, w != 0.0);
+            if (lane == 0) s_wcnt[warp] = __popc(m);
+            __syncthreads();
+            int pre = 0, tot = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < 8; ++w2) { const int cw = s_wcnt[w2]; if (w2 < warp) pre += cw; tot += cw; }
+            if (w != 0.0) {
+                const int pos = n + pre + __popc(m & ((1u << lane) - 1));
+                s_q[pos] = q; s_w[pos] = w; s_m[pos] = Ymean[q];
+            }
+            n += tot;
+            __syncthreads();
+        }
+        if (live) {
+            int e = 0;
+            for (; e + 4 <= n; e += 4) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(Yt + (size_t)s_q[e + u] * Tpad + t));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double w = s_w[e + u], ym = s_m[e + u];
+                    const unsigned ws[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        acc[2 * h] = fma(w, u16_to_f64(ws[h] & 0xffffu) - ym, acc[2 * h]);
+                        acc[2 * h + 1] = fma(w, u16_to_f64(ws[h] >> 16) - ym, acc[2 * h + 1]);
+                    }
+                }
+            }
+            for (; e < n; ++e) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(Yt + (size_t)s_q[e] * Tpad + t));
+                const double w = s_w[e], ym = s_m[e];
+                const unsigned ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    acc[2 * h] = fma(w, u16_to_f64(ws[h] & 0xffffu) - ym, acc[2 * h]);
+                    acc[2 * h + 1] = fma(w, u16_to_f64(ws[h] >> 16) - ym, acc[2 * h + 1]);
+                }
+            }
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int f = 0; f < 8; ++f) if (t + f < T) U[(size_t)k * T + t + f] = acc[f];
+    }
+}
+
+// host-side dispatch: the tiled kernels cover the all-frames case; frame-subsampled fits (kf > 1) and odd T use the
+// warp-per-pixel-group kernels above
+inline void launch_proj_mc(cudaStream_t st, const uint16_t* Yt, const double* Ymean, int nrb, int ncb, int T, int Tpad,
+                           int kf, const double* Cc, int K, const int* bbox, double* Mc) {
+    if (kf == 1 && (T & 1) == 0) {
+        cudaFuncSetAttribute(proj_mc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PMC_STAGE);
+        const unsigned tiles = (unsigned)(((nrb + 7) / 8) * ((ncb + 7) / 8));
+        LAUNCH(proj_mc_tile_kernel, tiles, 256, 2 * PMC_STAGE, st, Yt, Ymean, nrb, ncb, T, Tpad, Cc, K, bbox, Mc);
+    } else {
+        long long nw = (long long)((nrb + PROJ_PQ - 1) / PROJ_PQ) * ncb;
+        LAUNCH(proj_mc_kernel, (unsigned)((nw + 7) / 8), 256, 0, st, Yt, Ymean, nrb, ncb, T, Tpad, kf, Cc, K, bbox, Mc);
+    }
+}
+inline void launch_proj_bt(cudaStream_t st, const uint16_t* Yt, const double* Ymean, int nrb, int T, int Tpad,
+                           const double* B, int K, const int* bbox, double* U) {
+    dim3 gg(K, (T + PBT_FRAMES - 1) / PBT_FRAMES);
+    LAUNCH(proj_bt_list_kernel, gg, 256, 0, st, Yt, Ymean, nrb, T, Tpad, B, K, bbox, U);
+}
+
 // U[k][t] += cst[k] + sum_j M[k][j] * X[j][t]   (small dense correction)
 __global__ void add_small_matmul_kernel(double* __restrict__ U, int K, int T, const double* __restrict__ cst,
                                         const double* __restrict__ M, int J, const double* __restrict__ X) {
