@@ -29,7 +29,11 @@ void set_error(const char* fmt, ...);
         ++cnmfe::g_launch_count;                                  \
     } while (0)
 
+// NOTE: every warp-collective helper starts with __syncwarp().  After divergent code (e.g. an `if (threadIdx.x == 0)`
+// section) the lanes of a warp are not guaranteed to have re-converged; shuffles issued by a divergent warp take the
+// compiler's slow path (BRA.DIV: one lane group at a time), which cost 10x in the OASIS scans.
 __device__ __forceinline__ double warp_sum(double v) {
+    __syncwarp();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -56,6 +60,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 __device__ __forceinline__ double block_max(double v, double* red) {
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncwarp();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     __syncthreads();

@@ -2,6 +2,8 @@
 // One CTA per trace (persistent CTAs pull work items); all math double.  See oasis.cuh for reference citations.
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
+#include <cstdio>
 #include <vector>
 #include "oasis_methods.cuh"
 #include "internal.h"
@@ -86,6 +88,7 @@ deconv_batch_kernel(const double* __restrict__ Y, int T, int N, cnmfe_deconv_opt
     TraceWS ws;
     double *x, *ybuf;
     carve_ws(arena, slot_bytes, blockIdx.x, T, &ws, &x, &ybuf);
+    if (threadIdx.x == 0) sh.prof = nullptr;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(ticket, 1u);
@@ -141,6 +144,7 @@ getsn_batch_kernel(const double* __restrict__ Y, int T, int N, double* __restric
     TraceWS ws;
     double *x, *ybuf;
     carve_ws(arena, slot_bytes, blockIdx.x, T, &ws, &x, &ybuf);
+    if (threadIdx.x == 0) sh.prof = nullptr;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(ticket, 1u);
@@ -159,6 +163,7 @@ struct HalsArgs {
     double* C; double* C_raw; double* S; double* sn; double* pars;
     int* done; unsigned int* ticket; const int* order;
     char* arena; size_t slot_bytes;
+    unsigned long long* prof;   // 16 counters or nullptr
 };
 
 // One work item = (sweep, neuron).  Items are handed out in the reference's sequential order; an item waits until
@@ -170,6 +175,9 @@ __global__ void __launch_bounds__(CNMFE_BLOCK) hals_temporal_kernel(HalsArgs a) 
     TraceWS ws;
     double *x, *ybuf;
     carve_ws(a.arena, a.slot_bytes, blockIdx.x, a.T, &ws, &x, &ybuf);
+    if (threadIdx.x == 0) { sh.prof = a.prof; sh.t0 = clock64(); for (int i = 0; i < 16; ++i) sh.pc[i] = 0ull; }
+    long long k_c0 = clock64(); unsigned long long k_g0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_g0));
     const int T = a.T;
     const unsigned int total = (unsigned)a.maxIter * (unsigned)a.n_update;
     for (;;) {
@@ -180,6 +188,8 @@ __global__ void __launch_bounds__(CNMFE_BLOCK) hals_temporal_kernel(HalsArgs a) 
         if (item >= total) break;
         const int sweep = item / a.n_update, k = a.order[item % a.n_update];
         const int r0 = a.Vptr[k], r1 = a.Vptr[k + 1];
+        CNMFE_PROF(&sh, 10);
+        if (sh.prof) { if (threadIdx.x == 0) sh.pc[14] += 1ull; __syncwarp(); }
         if (threadIdx.x == 0) {
             for (int e = r0; e < r1; ++e) {
                 int j = a.Vidx[e];
@@ -190,6 +200,7 @@ __global__ void __launch_bounds__(CNMFE_BLOCK) hals_temporal_kernel(HalsArgs a) 
             __threadfence();
         }
         __syncthreads();
+        CNMFE_PROF(&sh, 0);
         const double aak = a.aa[k];
         // ck_raw = C(k,:) + (U(k,:) - V(k,:)*C)/aa(k)   (HALS_temporal.m:62)
         for (int t = threadIdx.x; t < T; t += blockDim.x) {
@@ -198,6 +209,7 @@ __global__ void __launch_bounds__(CNMFE_BLOCK) hals_temporal_kernel(HalsArgs a) 
             x[t] = __ldcg(a.C + (size_t)k * T + t) + (a.U[(size_t)k * T + t] - acc) / aak;
         }
         __syncthreads();
+        CNMFE_PROF(&sh, 1);
         const bool last = (sweep == a.maxIter - 1);
         if (!a.deconv_flag) {
             double mn = INFINITY;
@@ -211,7 +223,9 @@ __global__ void __launch_bounds__(CNMFE_BLOCK) hals_temporal_kernel(HalsArgs a) 
         } else {
             double med = block_median(x, T, &sh);
             double b = block_mean_below(x, T, med, &sh);       // HALS_temporal.m:78
+            CNMFE_PROF(&sh, 2);
             double sn_psd = block_getsn(x, T, ws.scr, &sh);     // :79
+            CNMFE_PROF(&sh, 3);
             for (int t = threadIdx.x; t < T; t += blockDim.x) x[t] -= b;
             __syncthreads();
             DeconvOut out;
@@ -236,7 +250,18 @@ __global__ void __launch_bounds__(CNMFE_BLOCK) hals_temporal_kernel(HalsArgs a) 
         }
         __threadfence();
         __syncthreads();
+        CNMFE_PROF(&sh, 10);
         if (threadIdx.x == 0) atomicAdd(a.done + k, 1);
+    }
+    if (threadIdx.x == 0 && a.prof) {
+        for (int i = 0; i < 12; ++i) atomicAdd(&a.prof[i], sh.pc[i]);
+        atomicAdd(&a.prof[14], sh.pc[14]); atomicAdd(&a.prof[15], sh.pc[15]);
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0 && a.prof) {
+        unsigned long long k_g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_g1));
+        a.prof[12] = (unsigned long long)(clock64() - k_c0);
+        a.prof[13] = k_g1 - k_g0;
     }
 }
 
@@ -330,8 +355,25 @@ int hals_temporal_dev(const double* U, const int* Vptr, const int* Vidx, const d
     a.C = C; a.C_raw = C_raw; a.S = S; a.sn = sn; a.pars = pars;
     a.done = done; a.ticket = ticket; a.order = order_scratch;
     a.arena = arena->base; a.slot_bytes = arena->slot_bytes;
+    a.prof = nullptr;
+    static const bool profile = getenv("CNMFE_HALS_PROFILE") != nullptr;   // diagnostics: per-phase cycles of thread 0
+    if (profile) {
+        CNMFE_CUDA_OK(cudaMalloc((void**)&a.prof, 16 * 8));
+        CNMFE_CUDA_OK(cudaMemsetAsync(a.prof, 0, 16 * 8, st));
+    }
     LAUNCH(hals_temporal_kernel, slots, CNMFE_BLOCK, 0, st, a);
     CNMFE_CUDA_OK(cudaGetLastError());
+    if (profile) {
+        unsigned long long h[16];
+        CNMFE_CUDA_OK(cudaStreamSynchronize(st));
+        CNMFE_CUDA_OK(cudaMemcpy(h, a.prof, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(a.prof);
+        static const char* nm[16] = {"wait deps", "gemv", "median+mean", "getsn", "quantile", "cold scan", "solution", "fminbnd",
+                                     "rebuild pools", "warm run", "other", "pow table", "", "", "items", "foopsi iters"};
+        fprintf(stderr, "[cnmfe hals profile] K=%d T=%d slots=%d:", K, T, slots);
+        for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%.0fk", nm[i], h[14] ? (double)h[i] / (double)h[14] / 1e3 : 0.0);
+        fprintf(stderr, " cycles/item; items=%llu iters/item=%.2f block0 clock64=%llu globaltimer_ns=%llu\n", h[14], h[14] ? (double)h[15] / (double)h[14] : 0.0, h[12], h[13]);
+    }
     return 0;
 }
 

@@ -41,7 +41,23 @@ struct BlockShared {
     int hist[256];
     int ibc[4];
     double dbc[4];
+    unsigned long long* prof;   // optional per-phase cycle counters (CNMFE_HALS_PROFILE diagnostics), else nullptr
+    long long t0;
+    unsigned long long pc[16];  // per-CTA accumulators, flushed to prof[] when the kernel ends
 };
+
+// diagnostics: add the cycles since the previous mark to counter i (thread 0 only; no-op unless profiling is on)
+#define CNMFE_PROF(sh, i)                                                                     \
+    do {                                                                                      \
+        if ((sh)->prof) {                                                                     \
+            if (threadIdx.x == 0) {                                                           \
+                long long _t = clock64();                                                     \
+                (sh)->pc[i] += (unsigned long long)(_t - (sh)->t0);                           \
+                (sh)->t0 = _t;                                                                \
+            }                                                                                 \
+            __syncwarp();   /* re-converge warp 0: a divergent warp takes the slow shuffle path */ \
+        }                                                                                     \
+    } while (0)
 
 __host__ __device__ inline int nextpow2_int(int L) {
     int n = 1;
@@ -364,7 +380,8 @@ __device__ void block_oasis_ar1_solution(const TraceWS& ws, int n, double g, int
 // to the first event (a new pool is accepted, or a back-track merge is needed) is committed.  Decisions and values are
 // identical to the element-by-element loop; only the divisions/table look-ups are parallelised.
 __device__ int warp_oasis_ar1_cold(const double* __restrict__ y, int T, double g, double lam, double smin,
-                                   TraceWS& ws) {
+                                   TraceWS& ws, unsigned long long* prof = nullptr) {
+    __syncwarp();   // enter converged (see common.cuh: divergent warps take the slow shuffle path)
     const int lane = threadIdx.x & 31;
     const double pen = lam * (1.0 - g);
     const double* gp = ws.gp;
@@ -373,17 +390,38 @@ __device__ int warp_oasis_ar1_cold(const double* __restrict__ y, int T, double g
     int top = 0, i = 1, lt = 1;
     double vt = val(0), wt = 1.0;
     if (lane == 0) pt[0] = 0;
-    double rp = 0.0;   // back-track threshold of the pool below the top (valid when top > 0)
+    // the pool below the top is cached in registers (valid when top > 0): v, w, l, g^l, g^(2l) and its back-track
+    // threshold rp = max(0, v/w * g^l) + smin
+    double bv = 0.0, bw = 1.0, bg1 = 0.0, bg2 = 0.0, rp = 0.0;
+    int bl = 0;
+    // operands of the NEXT window under the no-event continuation (i + m, lt + m), loaded while this window's
+    // sequential prefix runs
+    int pf_i = -1, pf_lt = -1;
+    double pf_y = 0.0, pf_e1 = 0.0, pf_e2 = 0.0;
     while (i < T) {
         const int m = min(32, T - i);
         const int idx = i + lane;
         const bool in = lane < m;
-        const double yj = in ? val(idx) : 0.0;
-        const double e1 = in ? gp[lt + lane] : 0.0;
-        const double e2 = in ? gp[2 * (lt + lane)] : 0.0;
+        double yj, e1, e2;
+        if (pf_i == i && pf_lt == lt) { yj = pf_y; e1 = pf_e1; e2 = pf_e2; }
+        else {
+            yj = in ? val(idx) : 0.0;
+            e1 = in ? gp[lt + lane] : 0.0;
+            e2 = in ? gp[2 * (lt + lane)] : 0.0;
+        }
+        {
+            const int ni = i + m, nlt = lt + m, nidx = ni + lane;
+            const bool nin = nidx < T;
+            pf_y = nin ? val(nidx) : 0.0;
+            pf_e1 = nin ? gp[nlt + lane] : 0.0;
+            pf_e2 = nin ? gp[2 * (nlt + lane)] : 0.0;
+            pf_i = ni; pf_lt = nlt;
+        }
         const double aj = yj * e1;
+        // running (v, w) in the reference's sequential order; lanes >= m contribute exact zeros
         double v = vt, w = wt, vj = 0.0, wj = 1.0, vj1 = 0.0, wj1 = 1.0;
-        for (int mm = 0; mm < m; ++mm) {
+#pragma unroll
+        for (int mm = 0; mm < 32; ++mm) {
             const double am = __shfl_sync(0xffffffffu, aj, mm);
             const double bm = __shfl_sync(0xffffffffu, e2, mm);
             if (lane == mm) { vj = v; wj = w; }
@@ -401,12 +439,14 @@ __device__ int warp_oasis_ar1_cold(const double* __restrict__ y, int T, double g
         }
         const int e = __ffs(ev) - 1;
         if (mf & (1u << e)) {
-            // elements 0..e-1 absorbed, element e starts a new pool
-            vt = __shfl_sync(0xffffffffu, vj, e);
-            wt = __shfl_sync(0xffffffffu, wj, e);
-            lt += e;
-            if (lane == 0) { pv[top] = vt; pw[top] = wt; pl[top] = lt; pt[top + 1] = i + e; }
-            rp = fmax(0.0, vt / wt * gp[lt]) + smin;
+            // elements 0..e-1 absorbed, element e starts a new pool; the finished pool becomes the cached one below
+            bv = __shfl_sync(0xffffffffu, vj, e);
+            bw = __shfl_sync(0xffffffffu, wj, e);
+            bg1 = __shfl_sync(0xffffffffu, e1, e);      // g^(lt + e)
+            bg2 = __shfl_sync(0xffffffffu, e2, e);      // g^(2 (lt + e))
+            bl = lt + e;
+            if (lane == 0) { pv[top] = bv; pw[top] = bw; pl[top] = bl; pt[top + 1] = i + e; }
+            rp = fmax(0.0, bv / bw * bg1) + smin;
             ++top;
             vt = __shfl_sync(0xffffffffu, yj, e);
             wt = 1.0; lt = 1;
@@ -419,18 +459,17 @@ __device__ int warp_oasis_ar1_cold(const double* __restrict__ y, int T, double g
             i += e + 1;
             __syncwarp();
             while (top > 0) {
-                const double vp = pv[top - 1], wp = pw[top - 1];
-                const int lp = pl[top - 1];
-                if (vt / wt < fmax(0.0, vp / wp * gp[lp]) + smin) {
-                    vt = vp + vt * gp[lp];
-                    wt = wp + wt * gp[2 * lp];
-                    lt = lp + lt;
+                if (vt / wt < rp) {
+                    vt = bv + vt * bg1;
+                    wt = bw + wt * bg2;
+                    lt = bl + lt;
                     --top;
+                    if (top > 0) {
+                        bv = pv[top - 1]; bw = pw[top - 1]; bl = pl[top - 1];
+                        bg1 = gp[bl]; bg2 = gp[2 * bl];
+                        rp = fmax(0.0, bv / bw * bg1) + smin;
+                    }
                 } else break;
-            }
-            if (top > 0) {
-                const double vp = pv[top - 1], wp = pw[top - 1];
-                rp = fmax(0.0, vp / wp * gp[pl[top - 1]]) + smin;
             }
         }
         __syncwarp();
@@ -443,16 +482,20 @@ __device__ int warp_oasis_ar1_cold(const double* __restrict__ y, int T, double g
 // Cold oasisAR1(y, g, lam, smin): pools + solution into ws.c / ws.s.  Returns pool count.
 __device__ int block_oasis_ar1(const double* y, int T, double g, double lam, double smin, TraceWS& ws,
                                BlockShared* sh) {
+    CNMFE_PROF(sh, 10);
     block_pow_table(g, T, ws.gp);
     __syncthreads();
+    CNMFE_PROF(sh, 11);
     if (threadIdx.x < 32) {
-        int n = warp_oasis_ar1_cold(y, T, g, lam, smin, ws);
+        int n = warp_oasis_ar1_cold(y, T, g, lam, smin, ws, sh->prof);
         if (threadIdx.x == 0) sh->ibc[2] = n;
     }
     __syncthreads();
     const int n = sh->ibc[2];
     __syncthreads();
+    CNMFE_PROF(sh, 5);
     block_oasis_ar1_solution(ws, n, g, T, ws.c, ws.s);
+    CNMFE_PROF(sh, 6);
     return n;
 }
 
@@ -570,7 +613,9 @@ __device__ double block_update_g(const double* y, int T, int* n_io, double lam, 
     double ml = 0.0;
     for (int p = threadIdx.x; p < n; p += blockDim.x) ml = fmax(ml, (double)ws.pl[p]);
     int maxl = (int)block_max(ml, sh->red);
+    CNMFE_PROF(sh, 10);
     double g = block_fminbnd_rss(y, n, lam, maxl, g_lo, g_hi, ws, sh);
+    CNMFE_PROF(sh, 7);
     // rebuild pools: v from the returned g, w from the LAST evaluated kernel (ws.hh), foopsi_oasisAR1.m:153-162
     const double lg = log(g), pen = lam * (1.0 - g);
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -582,9 +627,13 @@ __device__ double block_update_g(const double* y, int T, int* n_io, double lam, 
         if (lane == 0) { ws.pv[p] = dot; ws.pw[p] = ws.hh[l - 1]; }
     }
     __syncthreads();
+    CNMFE_PROF(sh, 8);
     block_pow_table(g, T, ws.gp);
+    CNMFE_PROF(sh, 11);
     n = block_oasis_ar1_run(ws, n, smin, sh);
+    CNMFE_PROF(sh, 9);
     block_oasis_ar1_solution(ws, n, g, T, ws.c, ws.s);
+    CNMFE_PROF(sh, 6);
     *n_io = n;
     return g;
 }
@@ -606,11 +655,14 @@ __device__ void block_foopsi_ar1(const double* __restrict__ y, int T, double g, 
         n = block_oasis_ar1(y, T, g, lam, smin, ws, sh);
         if (optimize_g && n > 0) g = block_update_g(y, T, &n, lam, smin, g_lo, g_hi, ws, sh);
     } else {
+        CNMFE_PROF(sh, 10);
         b = block_quantile(y, T, 0.15, sh);
+        CNMFE_PROF(sh, 4);
         for (int i = threadIdx.x; i < T; i += blockDim.x) ws.yb[i] = y[i] - b;
         __syncthreads();
         n = block_oasis_ar1(ws.yb, T, g, lam, smin, ws, sh);
         for (int m = 0; m < maxIter; ++m) {
+            if (sh->prof) { if (threadIdx.x == 0) sh->pc[15] += 1ull; __syncwarp(); }
             double a = 0.0;
             for (int i = threadIdx.x; i < T; i += blockDim.x) a += y[i] - ws.c[i];
             b = block_sum(a, sh->red) / (double)T;
@@ -676,6 +728,7 @@ __device__ int block_oasis_ar2(const double* __restrict__ y, int T, double g1, d
     }
     __syncthreads();
     if (threadIdx.x < 32) {
+        __syncwarp();   // enter converged
         const int lane = threadIdx.x;
         double* v = ws.pv; double* w = ws.pw; int* t = ws.pt; int* l = ws.pl;
         int top = 0;   // stack [0..top]; pool 0 is never merged (scan starts at the 2nd pool)
