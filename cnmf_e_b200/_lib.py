@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcnmfe_b200.so")
+LIB_PATH = os.environ.get("CNMFE_B200_LIB") or os.path.join(_HERE, "libcnmfe_b200.so")   # env override: development A/B builds only
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int_p = ctypes.POINTER(ctypes.c_int)

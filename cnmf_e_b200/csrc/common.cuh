@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cmath>
 
+#ifndef CNMFE_BLOCK
 #define CNMFE_BLOCK 256
+#endif
 
 namespace cnmfe {
 
@@ -32,6 +34,11 @@ void set_error(const char* fmt, ...);
 // NOTE: every warp-collective helper starts with __syncwarp().  After divergent code (e.g. an `if (threadIdx.x == 0)`
 // section) the lanes of a warp are not guaranteed to have re-converged; shuffles issued by a divergent warp take the
 // compiler's slow path (BRA.DIV: one lane group at a time), which cost 10x in the OASIS scans.
+// Warp index as a value the compiler can see is warp-uniform (broadcast from lane 0).  A branch on it keeps the shuffles
+// inside the branch on the fast path; a branch on threadIdx.x >> 5 (or threadIdx.x < 32) makes the compiler wrap each of
+// them in divergence guards (WARPSYNC / ENDCOLLECTIVE): 1.6x the instructions of ring_solve_kernel's panel factorisation.
+__device__ __forceinline__ int warp_id_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ double warp_sum(double v) {
     __syncwarp();
 #pragma unroll
@@ -41,7 +48,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // Block-wide sum; result valid in all threads. `red` = shared double[32].
 __device__ __forceinline__ double block_sum(double v, double* red) {
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31, wid = warp_id_uniform();
     v = warp_sum(v);
     __syncthreads();
     if (lane == 0) red[wid] = v;
@@ -59,7 +66,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 }
 
 __device__ __forceinline__ double block_max(double v, double* red) {
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31, wid = warp_id_uniform();
     __syncwarp();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -780,12 +780,32 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         a.g = g; a.off_r = c->d_off_r; a.off_c = c->d_off_c; a.S2 = d_S2; a.S1 = d_S1; a.Ymean = P.Ymean;
         a.nsel = nsel; a.a_ptr = d_ptr; a.a_col = d_col; a.a_val = d_val; a.N = d_N; a.K = Kb; a.Csum = d_Csum;
         a.active = d_active; a.active_list = d_alist; a.n_active = (int)alist.size(); a.W = P.W; a.db = (size_t)P.db; a.ND = ND;
+        a.prof = nullptr;
+        static const bool ring_profile = getenv("CNMFE_RING_PROFILE") != nullptr;
+        if (ring_profile) {
+            CNMFE_CUDA_OK(cudaMalloc((void**)&a.prof, 64));
+            CNMFE_CUDA_OK(cudaMemsetAsync(a.prof, 0, 64, c->st));
+        }
         const int NMAX = c->nnb + 1;
         size_t smem = ring_solve_smem_bytes(NMAX);
-        CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LAUNCH(ring_solve_kernel, (unsigned)alist.size(), RING_SOLVE_THREADS, smem, c->st, a);
+        if (ring_profile) {
+            CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LAUNCH(ring_solve_kernel<true>, (unsigned)alist.size(), RING_SOLVE_THREADS, smem, c->st, a);
+        } else {
+            CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LAUNCH(ring_solve_kernel<false>, (unsigned)alist.size(), RING_SOLVE_THREADS, smem, c->st, a);
+        }
         CNMFE_CUDA_OK(cudaGetLastError());
         phase_end(c, 1);
+        if (ring_profile) {
+            unsigned long long h[8];
+            CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+            CNMFE_CUDA_OK(cudaMemcpy(h, a.prof, 64, cudaMemcpyDeviceToHost));
+            cudaFree(a.prof);
+            const double np_ = (double)alist.size();
+            fprintf(stderr, "[cnmfe ring profile] pixels=%zu cycles/pixel: setup=%.0f assemble=%.0f neuron-scan=%.0f(+bitmap) compact=%.0f corrections=%.0f ridge=%.0f ldl=%.0f backsub+store=%.0f; neurons/pixel=%.2f\n",
+                    alist.size(), h[0] / np_, h[1] / np_, h[2] / np_, 0.0, h[3] / np_, h[4] / np_, h[5] / np_, h[6] / np_, h[7] / np_);
+        }
         tick("bg ring solve");
         P.w_uniform = false;
     }

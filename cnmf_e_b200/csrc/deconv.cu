@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <vector>
+#include <algorithm>
 #include "oasis_methods.cuh"
 #include "internal.h"
 
@@ -78,17 +79,31 @@ void trace_arena_free(TraceArena* a) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
+extern __shared__ __align__(16) unsigned char cnmfe_dyn_smem[];
+
+// launch shape of the per-trace kernels: dynamic shared memory for the Welch FFT and the resident-CTA cap that goes with it
+template <typename Kern>
+static int trace_launch_shape(Kern kern, int T, int device, int want, int* slots, size_t* smem) {
+    *smem = trace_fft_smem_bytes(T);
+    int s = default_trace_slots(device);
+    if (*smem) {
+        CNMFE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+        s = s / 4 * 3;   // 64 KB + static per CTA: 3 CTAs per SM
+    }
+    *slots = s > want ? want : s;
+    return 0;
+}
 __global__ void __launch_bounds__(CNMFE_BLOCK)
 deconv_batch_kernel(const double* __restrict__ Y, int T, int N, cnmfe_deconv_opts o, const double* __restrict__ sn_in,
                     const double* __restrict__ pars_in, int mode, double* __restrict__ c_out,
                     double* __restrict__ s_out, double* __restrict__ craw_out, double* __restrict__ outs,
-                    char* arena, size_t slot_bytes, unsigned int* ticket) {
+                    char* arena, size_t slot_bytes, unsigned int* ticket, int fft_smem) {
     __shared__ BlockShared sh;
     __shared__ unsigned int s_item;
     TraceWS ws;
     double *x, *ybuf;
     carve_ws(arena, slot_bytes, blockIdx.x, T, &ws, &x, &ybuf);
-    if (threadIdx.x == 0) sh.prof = nullptr;
+    if (threadIdx.x == 0) { sh.prof = nullptr; sh.zfft = fft_smem ? reinterpret_cast<double2*>(cnmfe_dyn_smem) : nullptr; }
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(ticket, 1u);
@@ -138,13 +153,13 @@ deconv_batch_kernel(const double* __restrict__ Y, int T, int N, cnmfe_deconv_opt
 
 __global__ void __launch_bounds__(CNMFE_BLOCK)
 getsn_batch_kernel(const double* __restrict__ Y, int T, int N, double* __restrict__ sn, char* arena,
-                   size_t slot_bytes, unsigned int* ticket) {
+                   size_t slot_bytes, unsigned int* ticket, int fft_smem) {
     __shared__ BlockShared sh;
     __shared__ unsigned int s_item;
     TraceWS ws;
     double *x, *ybuf;
     carve_ws(arena, slot_bytes, blockIdx.x, T, &ws, &x, &ybuf);
-    if (threadIdx.x == 0) sh.prof = nullptr;
+    if (threadIdx.x == 0) { sh.prof = nullptr; sh.zfft = fft_smem ? reinterpret_cast<double2*>(cnmfe_dyn_smem) : nullptr; }
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(ticket, 1u);
@@ -163,19 +178,21 @@ struct HalsArgs {
     double* C; double* C_raw; double* S; double* sn; double* pars;
     int* done; unsigned int* ticket; const int* order;
     char* arena; size_t slot_bytes;
+    int fft_smem;               // 1: GetSn's FFT buffer lives in dynamic shared memory
     unsigned long long* prof;   // 16 counters or nullptr
+    unsigned long long* prof_items;   // [maxIter * n_update][4] = start, deps ready, end (globaltimer ns), foopsi iterations
 };
 
 // One work item = (sweep, neuron).  Items are handed out in the reference's sequential order; an item waits until
 // the neurons it overlaps (V(k,j) != 0) have reached the state the sequential loop would have seen
 // (HALS_temporal.m:59-62: neuron k reads rows j<k of THIS sweep and rows j>k of the PREVIOUS sweep).
-__global__ void __launch_bounds__(CNMFE_BLOCK) hals_temporal_kernel(HalsArgs a) {
+__global__ void __launch_bounds__(CNMFE_BLOCK, 512 / CNMFE_BLOCK) hals_temporal_kernel(HalsArgs a) {
     __shared__ BlockShared sh;
     __shared__ unsigned int s_item;
     TraceWS ws;
     double *x, *ybuf;
     carve_ws(a.arena, a.slot_bytes, blockIdx.x, a.T, &ws, &x, &ybuf);
-    if (threadIdx.x == 0) { sh.prof = a.prof; sh.t0 = clock64(); for (int i = 0; i < 16; ++i) sh.pc[i] = 0ull; }
+    if (threadIdx.x == 0) { sh.zfft = a.fft_smem ? reinterpret_cast<double2*>(cnmfe_dyn_smem) : nullptr; sh.prof = a.prof; sh.t0 = clock64(); for (int i = 0; i < 16; ++i) sh.pc[i] = 0ull; }
     long long k_c0 = clock64(); unsigned long long k_g0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_g0));
     const int T = a.T;
@@ -189,7 +206,14 @@ __global__ void __launch_bounds__(CNMFE_BLOCK) hals_temporal_kernel(HalsArgs a) 
         const int sweep = item / a.n_update, k = a.order[item % a.n_update];
         const int r0 = a.Vptr[k], r1 = a.Vptr[k + 1];
         CNMFE_PROF(&sh, 10);
-        if (sh.prof) { if (threadIdx.x == 0) sh.pc[14] += 1ull; __syncwarp(); }
+        if (sh.prof) {
+            if (threadIdx.x == 0) {
+                sh.pc[14] += 1ull;
+                unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+                a.prof_items[4 * (size_t)item] = g; a.prof_items[4 * (size_t)item + 3] = sh.pc[15];
+            }
+            __syncwarp();
+        }
         if (threadIdx.x == 0) {
             for (int e = r0; e < r1; ++e) {
                 int j = a.Vidx[e];
@@ -201,6 +225,10 @@ __global__ void __launch_bounds__(CNMFE_BLOCK) hals_temporal_kernel(HalsArgs a) 
         }
         __syncthreads();
         CNMFE_PROF(&sh, 0);
+        if (sh.prof) {
+            if (threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); a.prof_items[4 * (size_t)item + 1] = g; }
+            __syncwarp();
+        }
         const double aak = a.aa[k];
         // ck_raw = C(k,:) + (U(k,:) - V(k,:)*C)/aa(k)   (HALS_temporal.m:62)
         for (int t = threadIdx.x; t < T; t += blockDim.x) {
@@ -251,6 +279,13 @@ __global__ void __launch_bounds__(CNMFE_BLOCK) hals_temporal_kernel(HalsArgs a) 
         __threadfence();
         __syncthreads();
         CNMFE_PROF(&sh, 10);
+        if (sh.prof) {
+            if (threadIdx.x == 0) {
+                unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+                a.prof_items[4 * (size_t)item + 2] = g; a.prof_items[4 * (size_t)item + 3] = sh.pc[15] - a.prof_items[4 * (size_t)item + 3];
+            }
+            __syncwarp();
+        }
         if (threadIdx.x == 0) atomicAdd(a.done + k, 1);
     }
     if (threadIdx.x == 0 && a.prof) {
@@ -306,12 +341,12 @@ int deconv_batch_dev(const double* Y, int T, int N, const cnmfe_deconv_opts& o, 
     if (ensure_ticket()) return -1;
     int dev = 0;
     cudaGetDevice(&dev);
-    int slots = default_trace_slots(dev);
-    if (slots > N) slots = N;
+    int slots; size_t smem;
+    if (trace_launch_shape(deconv_batch_kernel, T, dev, N, &slots, &smem)) return -1;
     if (trace_arena_reserve(arena, T, slots > arena->nslots ? slots : arena->nslots)) return -1;
     CNMFE_CUDA_OK(cudaMemsetAsync(g_ticket, 0, 4, st));
-    LAUNCH(deconv_batch_kernel, slots, CNMFE_BLOCK, 0, st, Y, T, N, o, sn_in, pars_in, mode, c, s, craw_out, outs,
-           arena->base, arena->slot_bytes, g_ticket);
+    LAUNCH(deconv_batch_kernel, slots, CNMFE_BLOCK, smem, st, Y, T, N, o, sn_in, pars_in, mode, c, s, craw_out, outs,
+           arena->base, arena->slot_bytes, g_ticket, smem ? 1 : 0);
     CNMFE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -322,11 +357,11 @@ int getsn_batch_dev(const double* Y, int T, int N, double* sn, TraceArena* arena
     if (ensure_ticket()) return -1;
     int dev = 0;
     cudaGetDevice(&dev);
-    int slots = default_trace_slots(dev);
-    if (slots > N) slots = N;
+    int slots; size_t smem;
+    if (trace_launch_shape(getsn_batch_kernel, T, dev, N, &slots, &smem)) return -1;
     if (trace_arena_reserve(arena, T, slots > arena->nslots ? slots : arena->nslots)) return -1;
     CNMFE_CUDA_OK(cudaMemsetAsync(g_ticket, 0, 4, st));
-    LAUNCH(getsn_batch_kernel, slots, CNMFE_BLOCK, 0, st, Y, T, N, sn, arena->base, arena->slot_bytes, g_ticket);
+    LAUNCH(getsn_batch_kernel, slots, CNMFE_BLOCK, smem, st, Y, T, N, sn, arena->base, arena->slot_bytes, g_ticket, smem ? 1 : 0);
     CNMFE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -339,8 +374,8 @@ int hals_temporal_dev(const double* U, const int* Vptr, const int* Vidx, const d
     if (T < 32) { set_error("HALS_temporal: T=%d too short", T); return -1; }
     int dev = 0;
     cudaGetDevice(&dev);
-    int slots = default_trace_slots(dev);
-    if (slots > K) slots = K;
+    int slots; size_t smem;
+    if (trace_launch_shape(hals_temporal_kernel, T, dev, K, &slots, &smem)) return -1;
     if (trace_arena_reserve(arena, T, slots > arena->nslots ? slots : arena->nslots)) return -1;
     // order_scratch: K ints + 1 (n_update at [K])
     LAUNCH(hals_order_kernel, 1, 32, 0, st, aa, K, maxIter, order_scratch, done, ticket, order_scratch + K);
@@ -355,13 +390,16 @@ int hals_temporal_dev(const double* U, const int* Vptr, const int* Vidx, const d
     a.C = C; a.C_raw = C_raw; a.S = S; a.sn = sn; a.pars = pars;
     a.done = done; a.ticket = ticket; a.order = order_scratch;
     a.arena = arena->base; a.slot_bytes = arena->slot_bytes;
-    a.prof = nullptr;
+    a.fft_smem = smem ? 1 : 0;
+    a.prof = nullptr; a.prof_items = nullptr;
     static const bool profile = getenv("CNMFE_HALS_PROFILE") != nullptr;   // diagnostics: per-phase cycles of thread 0
     if (profile) {
         CNMFE_CUDA_OK(cudaMalloc((void**)&a.prof, 16 * 8));
         CNMFE_CUDA_OK(cudaMemsetAsync(a.prof, 0, 16 * 8, st));
+        CNMFE_CUDA_OK(cudaMalloc((void**)&a.prof_items, (size_t)maxIter * n_update * 32));
+        CNMFE_CUDA_OK(cudaMemsetAsync(a.prof_items, 0, (size_t)maxIter * n_update * 32, st));
     }
-    LAUNCH(hals_temporal_kernel, slots, CNMFE_BLOCK, 0, st, a);
+    LAUNCH(hals_temporal_kernel, slots, CNMFE_BLOCK, smem, st, a);
     CNMFE_CUDA_OK(cudaGetLastError());
     if (profile) {
         unsigned long long h[16];
@@ -373,6 +411,47 @@ int hals_temporal_dev(const double* U, const int* Vptr, const int* Vidx, const d
         fprintf(stderr, "[cnmfe hals profile] K=%d T=%d slots=%d:", K, T, slots);
         for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%.0fk", nm[i], h[14] ? (double)h[i] / (double)h[14] / 1e3 : 0.0);
         fprintf(stderr, " cycles/item; items=%llu iters/item=%.2f block0 clock64=%llu globaltimer_ns=%llu\n", h[14], h[14] ? (double)h[15] / (double)h[14] : 0.0, h[12], h[13]);
+        // critical path: walk back from the item that finished last through the dependency that released it
+        {
+            const size_t total = (size_t)maxIter * n_update;
+            std::vector<unsigned long long> it(total * 4);
+            CNMFE_CUDA_OK(cudaMemcpy(it.data(), a.prof_items, total * 32, cudaMemcpyDeviceToHost));
+            cudaFree(a.prof_items);
+            std::vector<int> vptr(K + 1), order(n_update);
+            CNMFE_CUDA_OK(cudaMemcpy(vptr.data(), Vptr, (K + 1) * 4, cudaMemcpyDeviceToHost));
+            std::vector<int> vidx(vptr[K]);
+            CNMFE_CUDA_OK(cudaMemcpy(vidx.data(), Vidx, vidx.size() * 4, cudaMemcpyDeviceToHost));
+            CNMFE_CUDA_OK(cudaMemcpy(order.data(), order_scratch, n_update * 4, cudaMemcpyDeviceToHost));
+            std::vector<int> pos(K, -1);
+            for (int i = 0; i < n_update; ++i) pos[order[i]] = i;
+            unsigned long long t0 = ~0ull, t1 = 0; size_t last = 0;
+            double sum_exec = 0, max_exec = 0;
+            for (size_t i = 0; i < total; ++i) {
+                t0 = std::min(t0, it[4 * i]);
+                if (it[4 * i + 2] > t1) { t1 = it[4 * i + 2]; last = i; }
+                double ex = (double)(it[4 * i + 2] - it[4 * i + 1]);
+                sum_exec += ex; max_exec = std::max(max_exec, ex);
+            }
+            fprintf(stderr, "[cnmfe hals profile] span %.3f ms, mean exec %.3f ms, max exec %.3f ms; critical chain (sweep,k: wait ms, exec ms, iters):", (t1 - t0) / 1e6, sum_exec / total / 1e6, max_exec / 1e6);
+            size_t cur = last;
+            for (int hop = 0; hop < 64; ++hop) {
+                const int sweep = (int)(cur / n_update), k = order[cur % n_update];
+                fprintf(stderr, " (%d,%d: %.2f %.2f %llu)", sweep, k, (it[4 * cur + 1] - it[4 * cur]) / 1e6, (it[4 * cur + 2] - it[4 * cur + 1]) / 1e6, it[4 * cur + 3]);
+                // the dependency that finished last
+                long long best = -1; unsigned long long bt = 0;
+                for (int e = vptr[k]; e < vptr[k + 1]; ++e) {
+                    const int j = vidx[e];
+                    if (pos[j] < 0) continue;
+                    const int need = (pos[j] < pos[k]) ? sweep + 1 : sweep;   // completions of j required
+                    if (need <= 0) continue;
+                    const size_t dep = (size_t)(need - 1) * n_update + pos[j];
+                    if (it[4 * dep + 2] >= bt) { bt = it[4 * dep + 2]; best = (long long)dep; }
+                }
+                if (best < 0) break;
+                cur = (size_t)best;
+            }
+            fprintf(stderr, "\n");
+        }
     }
     return 0;
 }

@@ -174,6 +174,7 @@ struct RingSolveArgs {
     const int* active_list; int n_active;
     double* W;   // [dp][nnb]
     size_t db, ND;
+    unsigned long long* prof;   // diagnostics (CNMFE_RING_PROFILE): 8 per-phase cycle counters of thread 0, else nullptr
 };
 
 #define RING_SOLVE_THREADS 256
@@ -228,7 +229,7 @@ template <int KA>
 __device__ __forceinline__ void ring_ldl_block(RingRegs& R, int n1, int ti, int tj, double* xbuf, double* rd) {
     const int kend = min(16 * KA + 15, n1 - 1);
     constexpr int A0 = KA & ~1;          // first (even) register index loaded: keeps the 16-byte alignment
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4;
+    const int lane = threadIdx.x & 31, warp = warp_id_uniform()   /* no divergence guards around the panel shuffles */, half = lane >> 4;
     for (int k = 16 * KA; k <= kend; k += 2) {
         const int kr = k & 15;
         double* xb = xbuf + ((k >> 1) & 1) * (2 * RING_XBUF);
@@ -291,7 +292,7 @@ template <int A>
 __device__ __forceinline__ void ring_backsub_block(const RingRegs& R, int n, int ti, int tj, const double* Tt,
                                                    const double* rd, double* zs, double* ws) {
     if (16 * A > n) return;                      // uniform: no unknown in this block
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_id_uniform();
     if (warp == 0) {
         const int l = lane & 15;
         const double* tile = Tt + A * RING_TT;
@@ -320,6 +321,7 @@ __device__ __forceinline__ void ring_backsub_block(const RingRegs& R, int n, int
     }
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingSolveArgs a) {
     extern __shared__ double smem[];
     const RingGeom& g = a.g;
@@ -328,6 +330,8 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
     const int pr = p % g.nr + g.pr_off, pc = p / g.nr + g.pc_off;
     const size_t qm = (size_t)pc * g.nrb + pr;
     const int NMAX = g.nnb + 1;
+    long long pt0 = PROF ? clock64() : 0;
+#define RING_PROF(i) do { if (PROF && tid == 0) { long long _t = clock64(); atomicAdd(a.prof + (i), (unsigned long long)(_t - pt0)); pt0 = _t; } } while (0)
     // shared layout
     double* colk = smem;                                      // 2 x (2*RING_XBUF): double-buffered column pair
     double* rd = colk + 4 * RING_XBUF;                        // 128: reciprocal pivots 1/d_k
@@ -399,6 +403,7 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
     // --- assemble into registers: Cov(i,j) = raw(i,j) - Ybar_j*S1_i - Ybar_i*S1c_j, raw = second moment of the pixel
     //     pair (0 where an index carries no pixel).  The moment of a pair sits at S2[base*ND + |e_i - e_j|], base = the
     //     pixel the displacement starts from (canonical half plane <=> e_i - e_j >= 0).
+    RING_PROF(0);
     RingRegs R;
     {
         double ymj[8], s1cj[8];
@@ -436,13 +441,14 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
     // --- neuron corrections: Cov_Bf = Cov_Y - N_x.A_y - A_x.N_y ; sum_sel Bf(x) = S1c_x - A_x.Csum
     // distinct neurons touching the ring pixels / the centre: bitmap over local neuron ids (K <= 4096), compacted in
     // ascending id order (deterministic), handled RING_KSET at a time
+    RING_PROF(1);
     __shared__ unsigned s_bits[128];
     if (tid < 128) s_bits[tid] = 0u;
     __syncthreads();
     if (tid < RING_NIDX)
         for (int e = ap0[tid]; e < ap1[tid]; ++e) { int k = a.a_col[e]; atomicOr(&s_bits[(k >> 5) & 127], 1u << (k & 31)); }
     __syncthreads();
-    if (tid < 32) {
+    if (warp_id_uniform() == 0) {
         int base = 0;
         for (int w0 = 0; w0 < 128; w0 += 32) {
             const unsigned bits = s_bits[w0 + tid];
@@ -459,6 +465,8 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
     }
     __syncthreads();
     const int nall = s_nk;
+    RING_PROF(2);
+    if (PROF && tid == 0) atomicAdd(a.prof + 7, (unsigned long long)nall);
     for (int kbase = 0; kbase < nall; kbase += RING_KSET) {
         const int* kset = kall + kbase;
         const int nk = min(RING_KSET, nall - kbase);
@@ -494,6 +502,7 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
             }
         }
     }
+    RING_PROF(3);
     // --- ridge: trace over the n1 x n1 system (diagonal owners are the threads with ti == tj), summed in a fixed order
     {
         if (ti == tj) {
@@ -512,6 +521,7 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
             for (int aa = 0; aa < 8; ++aa) if (ti + 16 * aa < n1) R.g[aa][aa] += lam;
         }
     }
+    RING_PROF(4);
     // --- LDL' of the augmented matrix
     ring_ldl_block<0>(R, n1, ti, tj, colk, rd);
     if (n1 > 16) ring_ldl_block<1>(R, n1, ti, tj, colk, rd);
@@ -522,6 +532,7 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
     if (n1 > 96) ring_ldl_block<6>(R, n1, ti, tj, colk, rd);
     if (n1 > 112) ring_ldl_block<7>(R, n1, ti, tj, colk, rd);
     __syncthreads();
+    RING_PROF(5);
     // --- row n1 of the registers is now the unscaled forward-substituted right-hand side: y_j = x_{n1,j} / d_j.
     //     Diagonal tiles of the unit factor M(i,j) = x_ij / d_j go to shared memory; M' w = y is solved block-wise.
     if (tid < RING_NIDX) zs[tid] = 0.0;
@@ -547,6 +558,8 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
     ring_backsub_block<1>(R, n, ti, tj, Tt, rd, zs, wsol);
     ring_backsub_block<0>(R, n, ti, tj, Tt, rd, zs, wsol);
     for (int i = tid; i < n; i += blockDim.x) a.W[(size_t)p * g.nnb + slot[i]] = wsol[i] + 1e-100;
+    RING_PROF(6);
+#undef RING_PROF
 }
 
 // uniform ring initialisation (initComponents_parallel.m:213-236): W[i][p] = 1/#valid neighbours

@@ -218,7 +218,7 @@ proj_mc_tile_kernel(const uint16_t* __restrict__ Yt, const double* __restrict__ 
     extern __shared__ __align__(16) unsigned char pmc_smem[];
     __shared__ int s_list[64];
     __shared__ int s_cnt;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = warp_id_uniform();
     const int tiles_r = (nrb + 7) >> 3;
     const int r0 = (blockIdx.x % tiles_r) * 8, c0 = (blockIdx.x / tiles_r) * 8;
     const int r1 = min(nrb - 1, r0 + 7), c1 = min(ncb - 1, c0 + 7);

@@ -41,6 +41,9 @@ struct BlockShared {
     int hist[256];
     int ibc[4];
     double dbc[4];
+    double2 stage[32];          // cold scan: (a_m, b_m) of the current window, read back as broadcast 16-byte loads
+    double2 snap[32];           // cold scan: running (v, w) before element m
+    double2* zfft;              // GetSn FFT buffer in dynamic shared memory (nfft complex), or nullptr -> global scratch
     unsigned long long* prof;   // optional per-phase cycle counters (CNMFE_HALS_PROFILE diagnostics), else nullptr
     long long t0;
     unsigned long long pc[16];  // per-CTA accumulators, flushed to prof[] when the kernel ends
@@ -69,6 +72,12 @@ __host__ __device__ inline int welch_nfft(int T) {
     int L = (int)floor((double)T / 4.5);
     int n = nextpow2_int(L);
     return n < 256 ? 256 : n;
+}
+
+// dynamic shared memory of the per-trace kernels: the Welch FFT buffer when it fits 64 KB (3 CTAs/SM), else 0
+__host__ __device__ inline size_t trace_fft_smem_bytes(int T) {
+    size_t b = (size_t)welch_nfft(T) * 16;
+    return b <= 65536 ? b : 0;
 }
 
 __host__ __device__ inline size_t trace_scratch_doubles(int T) {
@@ -102,15 +111,23 @@ __device__ double select_kth(const double* __restrict__ x, int n, int k, BlockSh
             if ((key & mask) == prefix) atomicAdd(&sh->hist[(int)((key >> shift) & 255ull)], 1);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int kk = sh->ibc[0], cum = 0, b = 0;
-            for (b = 0; b < 256; ++b) {
-                int h = sh->hist[b];
-                if (cum + h > kk) break;
-                cum += h;
+        if (warp_id_uniform() == 0) {
+            // warp 0: lane owns 8 consecutive bins; exactly one lane contains rank kk
+            const int lane = threadIdx.x, kk = sh->ibc[0];
+            int h[8], tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { h[j] = sh->hist[8 * lane + j]; tot += h[j]; }
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            int cum = incl - tot;
+            if (cum <= kk && kk < incl) {
+                int b = 0;
+#pragma unroll
+                for (b = 0; b < 7; ++b) { if (cum + h[b] > kk) break; cum += h[b]; }
+                sh->ibc[0] = kk - cum;
+                sh->ibc[1] = 8 * lane + b;
             }
-            sh->ibc[0] = kk - cum;
-            sh->ibc[1] = b;
         }
         __syncthreads();
         unsigned long long b = (unsigned long long)sh->ibc[1];
@@ -121,10 +138,23 @@ __device__ double select_kth(const double* __restrict__ x, int n, int k, BlockSh
     return dkey_inv(prefix);
 }
 
+// (k+1)-th smallest given a = the k-th smallest (0-based): a again if it has a duplicate at rank k+1, else the
+// smallest element above a.  One pass instead of a second 8-pass select.
+__device__ double select_next(const double* __restrict__ x, int n, int k, double a, BlockShared* sh) {
+    double le = 0.0, mn = INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = x[i];
+        if (v <= a) le += 1.0; else mn = fmin(mn, v);
+    }
+    le = block_sum(le, sh->red);            // exact: integer counts < 2^53
+    mn = -block_max(-mn, sh->red);
+    return ((int)le >= k + 2) ? a : mn;
+}
+
 __device__ double block_median(const double* x, int n, BlockShared* sh) {
     if (n & 1) return select_kth(x, n, n / 2, sh);
     double a = select_kth(x, n, n / 2 - 1, sh);
-    double b = select_kth(x, n, n / 2, sh);
+    double b = select_next(x, n, n / 2 - 1, a, sh);
     return (a + b) / 2.0;
 }
 
@@ -136,7 +166,7 @@ __device__ double block_quantile(const double* x, int n, double p, BlockShared* 
     int lo = (int)floor(pos);
     double fr = pos - (double)lo;
     double a = select_kth(x, n, lo - 1, sh);
-    double b = select_kth(x, n, lo, sh);
+    double b = select_next(x, n, lo - 1, a, sh);
     return a + fr * (b - a);
 }
 
@@ -184,7 +214,7 @@ __device__ double block_getsn(const double* __restrict__ x, int N, double* scr, 
     const int nfft = welch_nfft(N);
     int logn = 0;
     while ((1 << logn) < nfft) ++logn;
-    double2* z = reinterpret_cast<double2*>(scr);
+    double2* z = sh->zfft ? sh->zfft : reinterpret_cast<double2*>(scr);
     double2* tw = reinterpret_cast<double2*>(scr + 2 * (size_t)nfft);
     double* acc = scr + 3 * (size_t)nfft;
     const int f0 = nfft / 4, nf = nfft / 4 + 1;
@@ -380,7 +410,7 @@ __device__ void block_oasis_ar1_solution(const TraceWS& ws, int n, double g, int
 // to the first event (a new pool is accepted, or a back-track merge is needed) is committed.  Decisions and values are
 // identical to the element-by-element loop; only the divisions/table look-ups are parallelised.
 __device__ int warp_oasis_ar1_cold(const double* __restrict__ y, int T, double g, double lam, double smin,
-                                   TraceWS& ws, unsigned long long* prof = nullptr) {
+                                   TraceWS& ws, double2* stage, double2* snap) {
     __syncwarp();   // enter converged (see common.cuh: divergent warps take the slow shuffle path)
     const int lane = threadIdx.x & 31;
     const double pen = lam * (1.0 - g);
@@ -418,17 +448,24 @@ __device__ int warp_oasis_ar1_cold(const double* __restrict__ y, int T, double g
             pf_i = ni; pf_lt = nlt;
         }
         const double aj = yj * e1;
-        // running (v, w) in the reference's sequential order; lanes >= m contribute exact zeros
-        double v = vt, w = wt, vj = 0.0, wj = 1.0, vj1 = 0.0, wj1 = 1.0;
+        // running (v, w) in the reference's sequential order; lanes >= m contribute exact zeros.  The window's operands
+        // go through shared memory so every lane reads them back as one broadcast 16-byte load per element, and lane mm
+        // stores the running pair it needs (4 instructions per element instead of 14 with shuffles + selects).
+        __syncwarp();
+        stage[lane] = make_double2(aj, e2);
+        __syncwarp();
+        double v = vt, w = wt;
 #pragma unroll
         for (int mm = 0; mm < 32; ++mm) {
-            const double am = __shfl_sync(0xffffffffu, aj, mm);
-            const double bm = __shfl_sync(0xffffffffu, e2, mm);
-            if (lane == mm) { vj = v; wj = w; }
-            v = v + am;
-            w = w + bm;
-            if (lane == mm) { vj1 = v; wj1 = w; }
+            const double2 ab = stage[mm];
+            if (lane == mm) snap[mm] = make_double2(v, w);
+            v = v + ab.x;
+            w = w + ab.y;
         }
+        __syncwarp();
+        const double2 own = snap[lane];
+        const double vj = own.x, wj = own.y;
+        const double vj1 = vj + aj, wj1 = wj + e2;   // the same additions the chain performed for this element
         const bool fwd = in && (yj >= vj / wj * e1 + smin);
         const bool back = in && !fwd && (top > 0) && (vj1 / wj1 < rp);
         const unsigned mf = __ballot_sync(0xffffffffu, fwd), mb = __ballot_sync(0xffffffffu, back);
@@ -486,8 +523,8 @@ __device__ int block_oasis_ar1(const double* y, int T, double g, double lam, dou
     block_pow_table(g, T, ws.gp);
     __syncthreads();
     CNMFE_PROF(sh, 11);
-    if (threadIdx.x < 32) {
-        int n = warp_oasis_ar1_cold(y, T, g, lam, smin, ws, sh->prof);
+    if (warp_id_uniform() == 0) {
+        int n = warp_oasis_ar1_cold(y, T, g, lam, smin, ws, sh->stage, sh->snap);
         if (threadIdx.x == 0) sh->ibc[2] = n;
     }
     __syncthreads();
@@ -507,9 +544,17 @@ __device__ void block_cumsum_sq(const double* h, double* hh, int m1, BlockShared
     for (int j = b; j < e; ++j) a += h[j] * h[j];
     part[threadIdx.x] = a;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double run = 0.0;
-        for (int i = 0; i < (int)blockDim.x; ++i) { double x = part[i]; part[i] = run; run += x; }
+    if (warp_id_uniform() == 0) {
+        // exclusive scan of the blockDim partials: lane = blockDim/32 consecutive partials, then a warp scan
+        const int lane = threadIdx.x, per2 = (int)blockDim.x >> 5, b0 = lane * per2;
+        double sl = 0.0;
+        for (int i = 0; i < per2; ++i) sl += part[b0 + i];
+        double incl = sl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        double run = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) run = 0.0;
+        for (int i = 0; i < per2; ++i) { double x = part[b0 + i]; part[b0 + i] = run; run += x; }
     }
     __syncthreads();
     a = part[threadIdx.x];
@@ -727,7 +772,7 @@ __device__ int block_oasis_ar2(const double* __restrict__ y, int T, double g1, d
         }
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
+    if (warp_id_uniform() == 0) {
         __syncwarp();   // enter converged
         const int lane = threadIdx.x;
         double* v = ws.pv; double* w = ws.pw; int* t = ws.pt; int* l = ws.pl;

@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include "common.cuh"
 #include "internal.h"
 
@@ -33,9 +34,11 @@ constexpr int STAGES = 3;
 constexpr int A_BYTES = MR * MC * KSTAGE;                 // 16384
 constexpr int B_BYTES = NB * KSTAGE;                      // 14336
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // 61440
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int EPI_STRIDE = 17;                            // doubles per pixel row of the epilogue transpose buffer (16 + pad)
+constexpr int EPI_BYTES = 4 * 32 * EPI_STRIDE * 8;        // one 32 x 16 buffer per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
 constexpr int TMEM_COLS = 512;
-constexpr int COL_HH = 0, COL_MID = 128, COL_LL = 256;
+constexpr int COL_HH = 0, COL_MID = NB, COL_LL = 2 * NB;   // [hh | hl+lh | ll]: adjacent, so one N = 2*NB MMA spans two of them
 constexpr int THREADS = 192;
 constexpr int MAX_K_BYTES = 16384;                        // frames per pass so that hl+lh < 2^31
 }  // namespace tc
@@ -70,6 +73,24 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// multicast variant: the box lands at the same shared offset of every CTA in ctaMask and completes tx on the mbarrier at
+// the same offset of each of them
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        :
+        : "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
@@ -88,6 +109,11 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t da, uint64_t db
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// arrive on the mbarrier at this offset in every CTA of ctaMask once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -102,9 +128,28 @@ struct TcParams {
     int kb0, kb1;               // K-stage range of this pass
     int accumulate;             // epilogue: S2 += (second and later passes)
     long long nitems;
+    long long ngroups;          // cluster work items (each = CL CTA items)
     double* S2;
 };
 
+// Work item of CTA `rank` in cluster work item g -> (r0, c0, cB): tile-major, neighbour column fastest, so the CL CTAs of
+// a cluster share the pixel tile.  (A neighbour-column-major order -- every B column read from DRAM once per band of tile
+// rows -- was measured and is slower: 32.7 vs 29.0 ms; the kernel is not DRAM/L2 bound.)
+template <int CL>
+__device__ __forceinline__ bool tc_decode(const TcParams& P, long long g, int rank, int* r0, int* c0, int* cB) {
+    using namespace tc;
+    const long long item = g * CL + rank;
+    const int j = (int)(item % P.nbc);
+    const long long tile = item / P.nbc;
+    const int tr = (int)(tile % P.ntr), tcx = (int)(tile / P.ntr);
+    *r0 = tr * MR; *c0 = tcx * MC; *cB = *c0 + j;
+    return true;
+}
+
+// CL = CTAs per cluster.  The CL CTAs of a cluster work on the SAME pixel tile with CL consecutive neighbour columns, so
+// the A tile (the larger operand) is fetched from L2 once per cluster: every CTA loads 1/CL of it and multicasts the slice
+// to all of them.  The kernel is bound by the L2 -> SM fill rate (60 KB per 896 MMA cycles at CL = 1), not by the MMAs.
+template <int CL>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 ring_s2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -119,10 +164,11 @@ ring_s2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     uint64_t* tmem_full = bars + 2 * STAGES;   // [1]
     uint64_t* tmem_empty = tmem_full + 1;      // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+    double* epi_buf = reinterpret_cast<double*>(tiles + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), CL); }
         mbar_init(smem_u32(tmem_full), 1);
         mbar_init(smem_u32(tmem_empty), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -135,28 +181,37 @@ ring_s2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();            // peers' barriers are initialised before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const int nkb = P.kb1 - P.kb0;
+    // work distribution: a cluster takes CL consecutive items (same tile, neighbour columns j .. j+CL-1; nbc % CL == 0)
+    const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
+    const long long g0 = blockIdx.x / CL, gstep = gridDim.x / CL;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
+    constexpr int A_SLICE = A_BYTES / CL;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-                const int j = (int)(item % P.nbc);
-                const long long tile = item / P.nbc;
-                const int tr = (int)(tile % P.ntr), tcx = (int)(tile / P.ntr);
-                const int r0 = tr * MR, c0 = tcx * MC, cB = c0 + j;
+            for (long long g = g0; g < P.ngroups; g += gstep) {
+                int r0, c0, cB;
+                if (!tc_decode<CL>(P, g, crank, &r0, &c0, &cB)) continue;
                 const int rB0 = max(0, r0 - BSHIFT);
                 for (int kb = P.kb0; kb < P.kb1; ++kb) {
                     mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
                     const uint32_t fb = smem_u32(full_bar + stage);
                     uint8_t* st = tiles + stage * STAGE_BYTES;
                     mbar_expect_tx(fb, STAGE_BYTES);
-                    tma_load_3d(smem_u32(st), &tmA_hi, fb, kb * KSTAGE, r0, c0);
-                    tma_load_3d(smem_u32(st + A_BYTES), &tmA_lo, fb, kb * KSTAGE, r0, c0);
+                    if (CL > 1) {
+                        tma_load_3d_mc(smem_u32(st + crank * A_SLICE), &tmA_hi, fb, kb * KSTAGE, r0, c0 + crank * (MC / CL), CMASK);
+                        tma_load_3d_mc(smem_u32(st + A_BYTES + crank * A_SLICE), &tmA_lo, fb, kb * KSTAGE, r0, c0 + crank * (MC / CL), CMASK);
+                    } else {
+                        tma_load_3d(smem_u32(st), &tmA_hi, fb, kb * KSTAGE, r0, c0);
+                        tma_load_3d(smem_u32(st + A_BYTES), &tmA_lo, fb, kb * KSTAGE, r0, c0);
+                    }
                     tma_load_3d(smem_u32(st + 2 * A_BYTES), &tmB_hi, fb, kb * KSTAGE, rB0, cB);
                     tma_load_3d(smem_u32(st + 2 * A_BYTES + B_BYTES), &tmB_lo, fb, kb * KSTAGE, rB0, cB);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -169,9 +224,15 @@ ring_s2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 (2) @4, a/b format U8 (0), K-major,
             // N>>3 @17, M>>4 @24
             const uint32_t idesc = (2u << 4) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // B_hi and B_lo are adjacent in the stage (NB rows = 14 swizzle atoms each), so a descriptor at B_hi with
+            // N = 2*NB reads [B_hi; B_lo]:  A_hi x [B_hi;B_lo] -> [hh | hl]  and  A_lo x [B_hi;B_lo] -> [lh | ll], the
+            // second one placed NB columns further so that lh lands on hl.  Two MMAs per K-step instead of four: each A
+            // tile is fetched from shared memory once per K-step (operand reads 22 KB instead of 30 KB per 32 frames).
+            const uint32_t idesc2 = (2u << 4) | ((uint32_t)((2 * NB) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (long long item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+            for (long long g = g0; g < P.ngroups; g += gstep) {
+                { int r0, c0, cB; if (!tc_decode<CL>(P, g, crank, &r0, &c0, &cB)) continue; }
                 mbar_wait(smem_u32(tmem_empty), acc_phase ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = 0; kb < nkb; ++kb) {
@@ -183,14 +244,20 @@ ring_s2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         const uint64_t dAh = make_desc_sw128(sa + ks * 32);
                         const uint64_t dAl = make_desc_sw128(sa + A_BYTES + ks * 32);
                         const uint64_t dBh = make_desc_sw128(sa + 2 * A_BYTES + ks * 32);
-                        const uint64_t dBl = make_desc_sw128(sa + 2 * A_BYTES + B_BYTES + ks * 32);
-                        const uint32_t acc = (kb | ks) ? 1u : 0u;
-                        mma_i8(tmem_base + COL_HH, dAh, dBh, idesc, acc);
-                        mma_i8(tmem_base + COL_MID, dAh, dBl, idesc, acc);
-                        mma_i8(tmem_base + COL_MID, dAl, dBh, idesc, 1u);
-                        mma_i8(tmem_base + COL_LL, dAl, dBl, idesc, acc);
+                        if ((kb | ks) == 0) {
+                            // first K-step of the item initialises the three accumulators separately
+                            const uint64_t dBl = make_desc_sw128(sa + 2 * A_BYTES + B_BYTES + ks * 32);
+                            mma_i8(tmem_base + COL_HH, dAh, dBh, idesc, 0u);
+                            mma_i8(tmem_base + COL_MID, dAh, dBl, idesc, 0u);
+                            mma_i8(tmem_base + COL_MID, dAl, dBh, idesc, 1u);
+                            mma_i8(tmem_base + COL_LL, dAl, dBl, idesc, 0u);
+                        } else {
+                            mma_i8(tmem_base + COL_HH, dAh, dBh, idesc2, 1u);
+                            mma_i8(tmem_base + COL_MID, dAl, dBh, idesc2, 1u);
+                        }
                     }
-                    umma_commit(smem_u32(empty_bar + stage));     // frees the smem stage when these MMAs retire
+                    // frees the smem stage (in every CTA that multicasts into it) when these MMAs retire
+                    if (CL > 1) umma_commit_mc(smem_u32(empty_bar + stage), CMASK); else umma_commit(smem_u32(empty_bar + stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(smem_u32(tmem_full));                 // accumulators complete
@@ -201,19 +268,24 @@ ring_s2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         // ------------------------------------------------------------------ epilogue: warps 2..5 -> TMEM lane quadrant warp%4
         const int quad = warp & 3;
         uint32_t acc_phase = 0;
-        for (long long item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-            const int j = (int)(item % P.nbc);
-            const long long tile = item / P.nbc;
-            const int tr = (int)(tile % P.ntr), tcx = (int)(tile / P.ntr);
-            const int r0 = tr * MR, c0 = tcx * MC, cB = c0 + j;
+ for (long long g = g0; g < P.ngroups; g += gstep) {
+            int r0, c0, cB;
+            if (!tc_decode<CL>(P, g, crank, &r0, &c0, &cB)) continue;
             const int rB0 = max(0, r0 - BSHIFT);
-            const int rp = r0 + lane, cp = c0 + quad;          // this thread's pixel (TMEM lane = lane + 32*quad)
+            const int cp = c0 + quad;                          // this warp's pixel column; TMEM lane = pixel row r0 + lane
             const int dc = cB - cp;
-            const bool pix_ok = (rp < P.nrb) && (cp < P.ncb) && (cB < P.ncb) && (dc >= 0) && (dc <= 2 * P.rr);
+            const bool warp_ok = (cp < P.ncb) && (cB < P.ncb) && (dc >= 0) && (dc <= 2 * P.rr);   // warp-uniform
             mbar_wait(smem_u32(tmem_full), acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-            double* out = P.S2 + ((size_t)cp * P.nrb + rp) * (size_t)P.ND;
+            // The 16 accumulator columns a thread reads per step are 16 consecutive displacements of ITS pixel, i.e.
+            // 128 contiguous bytes of that pixel's S2 row -- but across the lanes the rows are ND*8 bytes apart.  The
+            // values are therefore transposed through shared memory so that a half-warp writes one pixel's run:
+            // every store instruction covers two 128-byte runs instead of 32 scattered 8-byte words.
+            double* stg = epi_buf + (warp - 2) * (32 * EPI_STRIDE);
+            const int hx = lane & 15, hp = lane >> 4;
+            const int id0 = (dc == 0) ? 0 : (2 * P.rr + 1) + (dc - 1) * (4 * P.rr + 1) + 2 * P.rr;   // disp id = id0 + dr
+            if (warp_ok)
 #pragma unroll 1
             for (int cc = 0; cc < NB; cc += 16) {
                 uint32_t hh[16], mid[16], ll[16];
@@ -221,18 +293,24 @@ ring_s2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 tmem_ld16(taddr + COL_MID + cc, mid);
                 tmem_ld16(taddr + COL_LL + cc, ll);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (pix_ok) {
 #pragma unroll
-                    for (int x = 0; x < 16; ++x) {
-                        const int rn = rB0 + cc + x;
-                        const int dr = rn - rp;
-                        if (rn < P.nrb && dr >= -2 * P.rr && dr <= 2 * P.rr && (dc > 0 || dr >= 0)) {
-                            long long v = ((long long)(int)hh[x] << 16) + ((long long)(int)mid[x] << 8) + (long long)(int)ll[x];
-                            double* o = out + tc_disp_id(dr, dc, P.rr);
-                            if (P.accumulate) *o += (double)v; else *o = (double)v;
-                        }
+                for (int x = 0; x < 16; ++x) {
+                    const long long v = ((long long)(int)hh[x] << 16) + ((long long)(int)mid[x] << 8) + (long long)(int)ll[x];
+                    stg[lane * EPI_STRIDE + x] = (double)v;
+                }
+                __syncwarp();
+                const int rn = rB0 + cc + hx;                  // neighbour row of this lane's column
+#pragma unroll 4
+                for (int it = 0; it < 16; ++it) {
+                    const int px = 2 * it + hp, rp = r0 + px;
+                    const int dr = rn - rp;
+                    if (rp < P.nrb && rn < P.nrb && dr >= -2 * P.rr && dr <= 2 * P.rr && (dc > 0 || dr >= 0)) {
+                        double* o = P.S2 + ((size_t)cp * P.nrb + rp) * (size_t)P.ND + (id0 + dr);
+                        const double val = stg[px * EPI_STRIDE + hx];
+                        if (P.accumulate) *o += val; else *o = val;
                     }
                 }
+                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -242,6 +320,7 @@ ring_s2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();            // no CTA leaves while a peer may still signal its barriers
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                      : "memory");
@@ -288,29 +367,46 @@ int ring_s2_tensor(const uint8_t* hi, const uint8_t* lo, int nrb, int ncb, int T
     // neighbour rows needed: [r0-2rr, r0+MR-1+2rr] must lie inside [r0-BSHIFT, r0-BSHIFT+NB-1]
     if (2 * rr > BSHIFT || MR - 1 + 2 * rr > NB - 1 - BSHIFT) return 1;
     if (Tpad % KSTAGE != 0) return 1;
-    CUtensorMap mAh, mAl, mBh, mBl;
-    if (make_map(&mAh, hi, Tpad, nrb, ncb, MR, MC) || make_map(&mAl, lo, Tpad, nrb, ncb, MR, MC) ||
-        make_map(&mBh, hi, Tpad, nrb, ncb, NB, 1) || make_map(&mBl, lo, Tpad, nrb, ncb, NB, 1))
-        return -1;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_s2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
     TcParams P;
     P.nrb = nrb; P.ncb = ncb; P.rr = rr; P.ND = tc_num_disp(rr);
     P.ntr = (nrb + MR - 1) / MR; P.ntc = (ncb + MC - 1) / MC; P.nbc = MC + 2 * rr;
     P.nitems = (long long)P.ntr * P.ntc * P.nbc;
     P.S2 = S2;
+    // cluster size: 2 when the neighbour-column count allows it (measured: 1 -> 29.2 ms, 2 -> 28.6 ms, 4 -> 32.9 ms: fewer
+    // co-resident clusters).  CNMFE_TC_CLUSTER=1|2|4 overrides for A/B measurements.
+    int CL = (P.nbc % 2 == 0) ? 2 : 1;
+    if (const char* e = getenv("CNMFE_TC_CLUSTER")) { int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && P.nbc % v == 0) CL = v; }
+    CUtensorMap mAh, mAl, mBh, mBl;
+    if (make_map(&mAh, hi, Tpad, nrb, ncb, MR, MC / CL) || make_map(&mAl, lo, Tpad, nrb, ncb, MR, MC / CL) ||
+        make_map(&mBh, hi, Tpad, nrb, ncb, NB, 1) || make_map(&mBl, lo, Tpad, nrb, ncb, NB, 1))
+        return -1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams) =
+        CL == 4 ? ring_s2_tc_kernel<4> : (CL == 2 ? ring_s2_tc_kernel<2> : ring_s2_tc_kernel<1>);
+    CNMFE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    // persistent grid: as many clusters as can be co-resident (1 CTA per SM)
+    int nclusters = sms / CL;
+    if (CL > 1) {
+        cfg.gridDim = dim3((unsigned)(nclusters * CL));
+        int maxc = 0;
+        if (cudaOccupancyMaxActiveClusters(&maxc, kern, &cfg) == cudaSuccess && maxc > 0 && maxc < nclusters) nclusters = maxc;
+    }
+    P.ngroups = P.nitems / CL;
+    if (P.ngroups < nclusters) nclusters = (int)P.ngroups;
+    cfg.gridDim = dim3((unsigned)(nclusters * CL));
     const int nkb_total = Tpad / KSTAGE, per_pass = MAX_K_BYTES / KSTAGE;
     for (int kb0 = 0, pass = 0; kb0 < nkb_total; kb0 += per_pass, ++pass) {
         P.kb0 = kb0; P.kb1 = kb0 + per_pass < nkb_total ? kb0 + per_pass : nkb_total;
         P.accumulate = pass > 0;
-        long long grid = P.nitems < sms ? P.nitems : sms;
-        ring_s2_tc_kernel<<<(unsigned)grid, THREADS, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, P);
+        CNMFE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mAh, mAl, mBh, mBl, P));
         ++g_launch_count;
         CNMFE_CUDA_OK(cudaGetLastError());
     }
