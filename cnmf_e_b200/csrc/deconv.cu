@@ -81,14 +81,19 @@ void trace_arena_free(TraceArena* a) {
 // ------------------------------------------------------------------------------------------------ kernels
 extern __shared__ __align__(16) unsigned char cnmfe_dyn_smem[];
 
-// launch shape of the per-trace kernels: dynamic shared memory for the Welch FFT and the resident-CTA cap that goes with it
+// launch shape of the per-trace kernels: dynamic shared memory (see trace_smem_layout) and the resident-CTA cap that goes
+// with it; *mode is the bit mask the kernel passes to trace_smem_bind
 template <typename Kern>
-static int trace_launch_shape(Kern kern, int T, int device, int want, int* slots, size_t* smem) {
-    *smem = trace_fft_smem_bytes(T);
+static int trace_launch_shape(Kern kern, int T, int device, int want, bool want_stage, int* slots, size_t* smem, int* mode) {
+    const TraceSmem L = trace_smem_layout(T, want_stage);
+    *smem = L.total;
+    *mode = (L.fft ? 1 : 0) | (L.stage ? 2 : 0);
     int s = default_trace_slots(device);
     if (*smem) {
         CNMFE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
-        s = s / 4 * 3;   // 64 KB + static per CTA: 3 CTAs per SM
+        int per_sm = (int)((227 * 1024) / (*smem + 6 * 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm < 4) s = s / 4 * per_sm;
     }
     *slots = s > want ? want : s;
     return 0;
@@ -103,7 +108,7 @@ deconv_batch_kernel(const double* __restrict__ Y, int T, int N, cnmfe_deconv_opt
     TraceWS ws;
     double *x, *ybuf;
     carve_ws(arena, slot_bytes, blockIdx.x, T, &ws, &x, &ybuf);
-    if (threadIdx.x == 0) { sh.prof = nullptr; sh.zfft = fft_smem ? reinterpret_cast<double2*>(cnmfe_dyn_smem) : nullptr; }
+    if (threadIdx.x == 0) { sh.prof = nullptr; trace_smem_bind(&sh, cnmfe_dyn_smem, T, fft_smem); }
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(ticket, 1u);
@@ -159,7 +164,7 @@ getsn_batch_kernel(const double* __restrict__ Y, int T, int N, double* __restric
     TraceWS ws;
     double *x, *ybuf;
     carve_ws(arena, slot_bytes, blockIdx.x, T, &ws, &x, &ybuf);
-    if (threadIdx.x == 0) { sh.prof = nullptr; sh.zfft = fft_smem ? reinterpret_cast<double2*>(cnmfe_dyn_smem) : nullptr; }
+    if (threadIdx.x == 0) { sh.prof = nullptr; trace_smem_bind(&sh, cnmfe_dyn_smem, T, fft_smem); }
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(ticket, 1u);
@@ -178,7 +183,7 @@ struct HalsArgs {
     double* C; double* C_raw; double* S; double* sn; double* pars;
     int* done; unsigned int* ticket; const int* order;
     char* arena; size_t slot_bytes;
-    int fft_smem;               // 1: GetSn's FFT buffer lives in dynamic shared memory
+    int fft_smem;               // dynamic shared memory mode (trace_smem_bind): bit 0 Welch FFT buffer, bit 1 update_g staging
     unsigned long long* prof;   // 16 counters or nullptr
     unsigned long long* prof_items;   // [maxIter * n_update][4] = start, deps ready, end (globaltimer ns), foopsi iterations
 };
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(CNMFE_BLOCK, 512 / CNMFE_BLOCK) hals_temporal_
     TraceWS ws;
     double *x, *ybuf;
     carve_ws(a.arena, a.slot_bytes, blockIdx.x, a.T, &ws, &x, &ybuf);
-    if (threadIdx.x == 0) { sh.zfft = a.fft_smem ? reinterpret_cast<double2*>(cnmfe_dyn_smem) : nullptr; sh.prof = a.prof; sh.t0 = clock64(); for (int i = 0; i < 16; ++i) sh.pc[i] = 0ull; }
+    if (threadIdx.x == 0) { trace_smem_bind(&sh, cnmfe_dyn_smem, a.T, a.fft_smem); sh.prof = a.prof; sh.t0 = clock64(); for (int i = 0; i < 32; ++i) sh.pc[i] = 0ull; }
     long long k_c0 = clock64(); unsigned long long k_g0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_g0));
     const int T = a.T;
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(CNMFE_BLOCK, 512 / CNMFE_BLOCK) hals_temporal_
     }
     if (threadIdx.x == 0 && a.prof) {
         for (int i = 0; i < 12; ++i) atomicAdd(&a.prof[i], sh.pc[i]);
-        atomicAdd(&a.prof[14], sh.pc[14]); atomicAdd(&a.prof[15], sh.pc[15]);
+        for (int i = 14; i < 32; ++i) atomicAdd(&a.prof[i], sh.pc[i]);
     }
     if (threadIdx.x == 0 && blockIdx.x == 0 && a.prof) {
         unsigned long long k_g1;
@@ -341,12 +346,12 @@ int deconv_batch_dev(const double* Y, int T, int N, const cnmfe_deconv_opts& o, 
     if (ensure_ticket()) return -1;
     int dev = 0;
     cudaGetDevice(&dev);
-    int slots; size_t smem;
-    if (trace_launch_shape(deconv_batch_kernel, T, dev, N, &slots, &smem)) return -1;
+    int slots, smode; size_t smem;
+    if (trace_launch_shape(deconv_batch_kernel, T, dev, N, o.optimize_pars != 0, &slots, &smem, &smode)) return -1;
     if (trace_arena_reserve(arena, T, slots > arena->nslots ? slots : arena->nslots)) return -1;
     CNMFE_CUDA_OK(cudaMemsetAsync(g_ticket, 0, 4, st));
     LAUNCH(deconv_batch_kernel, slots, CNMFE_BLOCK, smem, st, Y, T, N, o, sn_in, pars_in, mode, c, s, craw_out, outs,
-           arena->base, arena->slot_bytes, g_ticket, smem ? 1 : 0);
+           arena->base, arena->slot_bytes, g_ticket, smode);
     CNMFE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -357,11 +362,11 @@ int getsn_batch_dev(const double* Y, int T, int N, double* sn, TraceArena* arena
     if (ensure_ticket()) return -1;
     int dev = 0;
     cudaGetDevice(&dev);
-    int slots; size_t smem;
-    if (trace_launch_shape(getsn_batch_kernel, T, dev, N, &slots, &smem)) return -1;
+    int slots, smode; size_t smem;
+    if (trace_launch_shape(getsn_batch_kernel, T, dev, N, false, &slots, &smem, &smode)) return -1;
     if (trace_arena_reserve(arena, T, slots > arena->nslots ? slots : arena->nslots)) return -1;
     CNMFE_CUDA_OK(cudaMemsetAsync(g_ticket, 0, 4, st));
-    LAUNCH(getsn_batch_kernel, slots, CNMFE_BLOCK, smem, st, Y, T, N, sn, arena->base, arena->slot_bytes, g_ticket, smem ? 1 : 0);
+    LAUNCH(getsn_batch_kernel, slots, CNMFE_BLOCK, smem, st, Y, T, N, sn, arena->base, arena->slot_bytes, g_ticket, smode);
     CNMFE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -374,8 +379,8 @@ int hals_temporal_dev(const double* U, const int* Vptr, const int* Vidx, const d
     if (T < 32) { set_error("HALS_temporal: T=%d too short", T); return -1; }
     int dev = 0;
     cudaGetDevice(&dev);
-    int slots; size_t smem;
-    if (trace_launch_shape(hals_temporal_kernel, T, dev, K, &slots, &smem)) return -1;
+    int slots, smode; size_t smem;
+    if (trace_launch_shape(hals_temporal_kernel, T, dev, K, deconv_flag && o.optimize_pars, &slots, &smem, &smode)) return -1;
     if (trace_arena_reserve(arena, T, slots > arena->nslots ? slots : arena->nslots)) return -1;
     // order_scratch: K ints + 1 (n_update at [K])
     LAUNCH(hals_order_kernel, 1, 32, 0, st, aa, K, maxIter, order_scratch, done, ticket, order_scratch + K);
@@ -390,19 +395,19 @@ int hals_temporal_dev(const double* U, const int* Vptr, const int* Vidx, const d
     a.C = C; a.C_raw = C_raw; a.S = S; a.sn = sn; a.pars = pars;
     a.done = done; a.ticket = ticket; a.order = order_scratch;
     a.arena = arena->base; a.slot_bytes = arena->slot_bytes;
-    a.fft_smem = smem ? 1 : 0;
+    a.fft_smem = smode;
     a.prof = nullptr; a.prof_items = nullptr;
     static const bool profile = getenv("CNMFE_HALS_PROFILE") != nullptr;   // diagnostics: per-phase cycles of thread 0
     if (profile) {
-        CNMFE_CUDA_OK(cudaMalloc((void**)&a.prof, 16 * 8));
-        CNMFE_CUDA_OK(cudaMemsetAsync(a.prof, 0, 16 * 8, st));
+        CNMFE_CUDA_OK(cudaMalloc((void**)&a.prof, 32 * 8));
+        CNMFE_CUDA_OK(cudaMemsetAsync(a.prof, 0, 32 * 8, st));
         CNMFE_CUDA_OK(cudaMalloc((void**)&a.prof_items, (size_t)maxIter * n_update * 32));
         CNMFE_CUDA_OK(cudaMemsetAsync(a.prof_items, 0, (size_t)maxIter * n_update * 32, st));
     }
     LAUNCH(hals_temporal_kernel, slots, CNMFE_BLOCK, smem, st, a);
     CNMFE_CUDA_OK(cudaGetLastError());
     if (profile) {
-        unsigned long long h[16];
+        unsigned long long h[32];
         CNMFE_CUDA_OK(cudaStreamSynchronize(st));
         CNMFE_CUDA_OK(cudaMemcpy(h, a.prof, sizeof(h), cudaMemcpyDeviceToHost));
         cudaFree(a.prof);
@@ -411,6 +416,9 @@ int hals_temporal_dev(const double* U, const int* Vptr, const int* Vidx, const d
         fprintf(stderr, "[cnmfe hals profile] K=%d T=%d slots=%d:", K, T, slots);
         for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%.0fk", nm[i], h[14] ? (double)h[i] / (double)h[14] / 1e3 : 0.0);
         fprintf(stderr, " cycles/item; items=%llu iters/item=%.2f block0 clock64=%llu globaltimer_ns=%llu\n", h[14], h[14] ? (double)h[15] / (double)h[14] : 0.0, h[12], h[13]);
+        if (h[20]) fprintf(stderr, "[cnmfe hals profile] rss_g: %.1f evals/item, per eval: h table %.0f, cumsum %.0f, pools: 8-lane %.0f + cta-long %.0f + warp %.0f, sum %.0f cycles; mean maxl %.0f, mean pools %.0f, mean long pools %.2f\n",
+                           (double)h[20] / h[14], (double)h[16] / h[20], (double)h[17] / h[20], (double)h[24] / h[20], (double)h[25] / h[20], (double)h[18] / h[20], (double)h[19] / h[20],
+                           (double)h[21] / h[20], (double)h[22] / h[20], (double)h[26] / h[20]);
         // critical path: walk back from the item that finished last through the dependency that released it
         {
             const size_t total = (size_t)maxIter * n_update;

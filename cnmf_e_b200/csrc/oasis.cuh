@@ -41,12 +41,21 @@ struct BlockShared {
     int hist[256];
     int ibc[4];
     double dbc[4];
+    double part[CNMFE_BLOCK];   // block scan partials (cumsum of the update_g kernel table)
     double2 stage[32];          // cold scan: (a_m, b_m) of the current window, read back as broadcast 16-byte loads
     double2 snap[32];           // cold scan: running (v, w) before element m
     double2* zfft;              // GetSn FFT buffer in dynamic shared memory (nfft complex), or nullptr -> global scratch
+    double* ysm;                // update_g: shared-memory copy of the trace being fitted (aliases zfft), or nullptr
+    double* hsm;                // update_g: kernel table h = g^(0..maxl) and its cumsum of squares when maxl < hcap,
+    double* hhsm;               //           else ws.h / ws.hh are used
+    int* ptsm;                  // update_g: pool starts / lengths when n <= pcap, else ws.pt / ws.pl
+    int* plsm;
+    int hcap, pcap;
+    int nlong, long_thr;        // update_g: pools longer than long_thr, in ascending pool order (handled by the whole CTA)
+    int longp[128];
     unsigned long long* prof;   // optional per-phase cycle counters (CNMFE_HALS_PROFILE diagnostics), else nullptr
     long long t0;
-    unsigned long long pc[16];  // per-CTA accumulators, flushed to prof[] when the kernel ends
+    unsigned long long pc[32];  // per-CTA accumulators, flushed to prof[] when the kernel ends
 };
 
 // diagnostics: add the cycles since the previous mark to counter i (thread 0 only; no-op unless profiling is on)
@@ -74,10 +83,37 @@ __host__ __device__ inline int welch_nfft(int T) {
     return n < 256 ? 256 : n;
 }
 
-// dynamic shared memory of the per-trace kernels: the Welch FFT buffer when it fits 64 KB (3 CTAs/SM), else 0
-__host__ __device__ inline size_t trace_fft_smem_bytes(int T) {
-    size_t b = (size_t)welch_nfft(T) * 16;
-    return b <= 65536 ? b : 0;
+// Dynamic shared memory of the per-trace kernels.  Two users that never overlap in time share it:
+//   GetSn      the Welch FFT buffer (nfft complex doubles) when it fits 64 KB;
+//   update_g   a copy of the trace (T doubles), the kernel table h and its cumsum (TRACE_HCAP doubles each) and the pool
+//              starts/lengths (TRACE_PCAP ints each): fminbnd evaluates rss_g ~9 times per FOOPSI iteration; every
+//              evaluation reads the trace twice and chases pool -> length -> cumsum look-ups, and from L2 those
+//              dependent latencies were 85 % of rss_g.
+#define TRACE_HCAP 1024
+#define TRACE_PCAP 1024
+struct TraceSmem { size_t total, y_bytes; int fft, stage; };
+__host__ __device__ inline TraceSmem trace_smem_layout(int T, bool want_stage) {
+    TraceSmem L;
+    const size_t fb = (size_t)welch_nfft(T) * 16;
+    L.fft = fb <= 65536 ? 1 : 0;
+    L.y_bytes = (((size_t)T * 8) + 15) / 16 * 16;
+    const size_t sb = L.y_bytes + 2 * (size_t)TRACE_HCAP * 8 + 2 * (size_t)TRACE_PCAP * 4;
+    L.stage = (want_stage && sb <= 106496) ? 1 : 0;   // <= 104 KB: two CTAs per SM
+    L.total = L.fft ? fb : 0;
+    if (L.stage && sb > L.total) L.total = sb;
+    return L;
+}
+// called by thread 0 of a per-trace kernel (mode bit 0: fft, bit 1: stage)
+__device__ inline void trace_smem_bind(BlockShared* sh, unsigned char* dyn, int T, int mode) {
+    const TraceSmem L = trace_smem_layout(T, true);
+    sh->zfft = (mode & 1) ? reinterpret_cast<double2*>(dyn) : nullptr;
+    sh->ysm = (mode & 2) ? reinterpret_cast<double*>(dyn) : nullptr;
+    sh->hsm = (mode & 2) ? reinterpret_cast<double*>(dyn + L.y_bytes) : nullptr;
+    sh->hhsm = (mode & 2) ? sh->hsm + TRACE_HCAP : nullptr;
+    sh->ptsm = (mode & 2) ? reinterpret_cast<int*>(sh->hhsm + TRACE_HCAP) : nullptr;
+    sh->plsm = (mode & 2) ? sh->ptsm + TRACE_PCAP : nullptr;
+    sh->hcap = (mode & 2) ? TRACE_HCAP : 0;
+    sh->pcap = (mode & 2) ? TRACE_PCAP : 0;
 }
 
 __host__ __device__ inline size_t trace_scratch_doubles(int T) {
@@ -353,13 +389,17 @@ __device__ int block_oasis_ar1_run(TraceWS& ws, int n, double smin, BlockShared*
         int top = 0;
         double vt = v[0], wt = w[0];
         int lt = l[0];
+        // incoming pool i + 1 is loaded while pool i is processed (stores only touch indices <= top < i + 1)
+        double nv = (n > 1) ? v[1] : 0.0, nwt = (n > 1) ? w[1] : 1.0;
+        int nl = (n > 1) ? l[1] : 0, ntt = (n > 1) ? t[1] : 0;
         for (int i = 1; i < n; ++i) {
-            double vi = v[i], wi = w[i];
-            int li = l[i];
+            const double vi = nv, wi = nwt;
+            const int li = nl, ti = ntt;
+            if (i + 1 < n) { nv = v[i + 1]; nwt = w[i + 1]; nl = l[i + 1]; ntt = t[i + 1]; }
             if (vi / wi >= vt / wt * gp[lt] + smin) {
                 v[top] = vt; w[top] = wt; l[top] = lt;
                 ++top;
-                t[top] = t[i];
+                t[top] = ti;
                 vt = vi; wt = wi; lt = li;
                 continue;
             }
@@ -562,28 +602,122 @@ __device__ void block_cumsum_sq(const double* h, double* hh, int m1, BlockShared
     __syncthreads();
 }
 
+#define RSS_SHORT_POOL 256
+#define RSS_LONG_POOL 768
 // rss_g of update_g (foopsi_oasisAR1.m:165-178).  Leaves ws.h / ws.hh holding this g's tables.
-__device__ double block_rss_g(const double* __restrict__ y, int n, double g, double lam, int maxl, TraceWS& ws,
+__device__ double block_rss_g(const double* y, int n, double g, double lam, int maxl, TraceWS& ws,
                               BlockShared* sh) {
     const double lg = log(g), pen = lam * (1.0 - g);
     __syncthreads();
-    for (int j = threadIdx.x; j <= maxl; j += blockDim.x) ws.h[j] = exp(lg * (double)j);
+    CNMFE_PROF(sh, 7);
+    if (sh->ysm) y = sh->ysm;                                    // staged by block_update_g
+    const bool hs = (maxl < sh->hcap), ps = (n <= sh->pcap);
+    double* const htab = hs ? sh->hsm : ws.h;
+    double* const hhtab = hs ? sh->hhsm : ws.hh;
+    const int* const ptab = ps ? sh->ptsm : ws.pt;
+    const int* const ltab = ps ? sh->plsm : ws.pl;
+    if (sh->prof) { if (threadIdx.x == 0) { sh->pc[20] += 1ull; sh->pc[21] += (unsigned long long)maxl; sh->pc[22] += (unsigned long long)n; } __syncwarp(); }
+    for (int j = threadIdx.x; j <= maxl; j += blockDim.x) htab[j] = exp(lg * (double)j);
     __syncthreads();
-    block_cumsum_sq(ws.h, ws.hh, maxl + 1, sh, ws.scr);
+    CNMFE_PROF(sh, 16);
+    block_cumsum_sq(htab, hhtab, maxl + 1, sh, sh->part);
+    CNMFE_PROF(sh, 17);
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     double rss = 0.0;
-    for (int p = warp; p < n; p += nw) {
-        int t0 = ws.pt[p], l = ws.pl[p];
-        double dot = 0.0;
-        for (int j = lane; j < l; j += 32) dot += (y[t0 + j] - pen) * ws.h[j];
-        dot = warp_sum(dot);
-        double tv = fmax(dot / ws.hh[l - 1], 0.0);
-        for (int j = lane; j < l; j += 32) {
-            double r = y[t0 + j] - tv * ws.h[j];
+    // Pools are short on average (T / n ~ 25-50 samples) and there are hundreds of them, so a warp per pool spends its
+    // time in per-pool latencies (metadata load -> data load -> shuffle tree -> division -> second pass).  Short pools are
+    // therefore handled FOUR per warp (8 lanes each: 64-byte coalesced reads, 3-step reduction); long ones take a warp.
+    {
+        const int grp = lane >> 3, gl = lane & 7;
+        for (int p0 = warp * 4; p0 < n; p0 += nw * 4) {
+            const int p = p0 + grp;
+            int l = 0, t0 = 0;
+            if (p < n) { l = ltab[p]; t0 = ptab[p]; }
+            const int le = (l <= RSS_SHORT_POOL) ? l : 0;
+            // loads of four steps are issued together, the sums keep the one-at-a-time order
+            double dot = 0.0;
+            {
+                int j = gl;
+                for (; j + 24 < le; j += 32) {
+                    const double y0 = y[t0 + j], y1 = y[t0 + j + 8], y2 = y[t0 + j + 16], y3 = y[t0 + j + 24];
+                    const double h0 = htab[j], h1 = htab[j + 8], h2 = htab[j + 16], h3 = htab[j + 24];
+                    dot += (y0 - pen) * h0; dot += (y1 - pen) * h1; dot += (y2 - pen) * h2; dot += (y3 - pen) * h3;
+                }
+                for (; j < le; j += 8) dot += (y[t0 + j] - pen) * htab[j];
+            }
+            __syncwarp();
+            dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            if (le > 0) {
+                const double tv = fmax(dot / hhtab[l - 1], 0.0);
+                int j = gl;
+                for (; j + 24 < le; j += 32) {
+                    const double y0 = y[t0 + j], y1 = y[t0 + j + 8], y2 = y[t0 + j + 16], y3 = y[t0 + j + 24];
+                    const double h0 = htab[j], h1 = htab[j + 8], h2 = htab[j + 16], h3 = htab[j + 24];
+                    const double r0 = y0 - tv * h0, r1 = y1 - tv * h1, r2 = y2 - tv * h2, r3 = y3 - tv * h3;
+                    rss += r0 * r0; rss += r1 * r1; rss += r2 * r2; rss += r3 * r3;
+                }
+                for (; j < le; j += 8) {
+                    const double r = y[t0 + j] - tv * htab[j];
+                    rss += r * r;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    CNMFE_PROF(sh, 24);
+    // very long pools (quiet stretches: thousands of samples) by the whole CTA, one after the other: a single warp would
+    // chain l/128 load batches of the kernel table from L2
+    for (int k = 0; k < sh->nlong; ++k) {
+        const int p = sh->longp[k];
+        const int t0 = ptab[p], l = ltab[p];
+        double d = 0.0;
+        for (int j = threadIdx.x; j < l; j += blockDim.x) d += (y[t0 + j] - pen) * htab[j];
+        d = block_sum(d, sh->red);
+        const double tv = fmax(d / hhtab[l - 1], 0.0);
+        for (int j = threadIdx.x; j < l; j += blockDim.x) {
+            const double r = y[t0 + j] - tv * htab[j];
             rss += r * r;
         }
     }
-    return block_sum(rss, sh->red);
+    CNMFE_PROF(sh, 25);
+    if (sh->prof) { if (threadIdx.x == 0) sh->pc[26] += (unsigned long long)sh->nlong; __syncwarp(); }
+    const int long_thr = sh->long_thr;
+    for (int p = warp; p < n; p += nw) {
+        int t0 = ptab[p], l = ltab[p];
+        if (l <= RSS_SHORT_POOL || l > long_thr) continue;
+        double dot = 0.0;
+        {
+            int j = lane;
+            for (; j + 96 < l; j += 128) {
+                const double y0 = y[t0 + j], y1 = y[t0 + j + 32], y2 = y[t0 + j + 64], y3 = y[t0 + j + 96];
+                const double h0 = htab[j], h1 = htab[j + 32], h2 = htab[j + 64], h3 = htab[j + 96];
+                dot += (y0 - pen) * h0; dot += (y1 - pen) * h1; dot += (y2 - pen) * h2; dot += (y3 - pen) * h3;
+            }
+            for (; j < l; j += 32) dot += (y[t0 + j] - pen) * htab[j];
+        }
+        dot = warp_sum(dot);
+        double tv = fmax(dot / hhtab[l - 1], 0.0);
+        {
+            int j = lane;
+            for (; j + 96 < l; j += 128) {
+                const double y0 = y[t0 + j], y1 = y[t0 + j + 32], y2 = y[t0 + j + 64], y3 = y[t0 + j + 96];
+                const double h0 = htab[j], h1 = htab[j + 32], h2 = htab[j + 64], h3 = htab[j + 96];
+                const double r0 = y0 - tv * h0, r1 = y1 - tv * h1, r2 = y2 - tv * h2, r3 = y3 - tv * h3;
+                rss += r0 * r0; rss += r1 * r1; rss += r2 * r2; rss += r3 * r3;
+            }
+            for (; j < l; j += 32) {
+                double r = y[t0 + j] - tv * htab[j];
+                rss += r * r;
+            }
+        }
+    }
+    __syncthreads();
+    CNMFE_PROF(sh, 18);
+    rss = block_sum(rss, sh->red);
+    CNMFE_PROF(sh, 19);
+    return rss;
 }
 
 // MATLAB fminbnd on rss_g over [ax,bx]; returns xf (all threads run the scalar logic redundantly).
@@ -658,6 +792,32 @@ __device__ double block_update_g(const double* y, int T, int* n_io, double lam, 
     double ml = 0.0;
     for (int p = threadIdx.x; p < n; p += blockDim.x) ml = fmax(ml, (double)ws.pl[p]);
     int maxl = (int)block_max(ml, sh->red);
+    if (sh->ysm) {
+        for (int i = threadIdx.x; i < T; i += blockDim.x) sh->ysm[i] = y[i];
+        if (n <= sh->pcap)
+            for (int p = threadIdx.x; p < n; p += blockDim.x) { sh->ptsm[p] = ws.pt[p]; sh->plsm[p] = ws.pl[p]; }
+        __syncthreads();
+    }
+    // pools longer than RSS_LONG_POOL, sorted (the order fixes the order of the additions -> deterministic)
+    if (threadIdx.x == 0) sh->nlong = 0;
+    __syncthreads();
+    for (int p = threadIdx.x; p < n; p += blockDim.x)
+        if (ws.pl[p] > RSS_LONG_POOL) { const int k = atomicAdd(&sh->nlong, 1); if (k < 128) sh->longp[k] = p; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nl = sh->nlong;
+        if (nl > 128) { nl = 0; sh->long_thr = 0x7fffffff; }     // cannot list them all: the warp path takes every length
+        else sh->long_thr = RSS_LONG_POOL;
+        for (int i = 1; i < nl; ++i) {
+            const int v = sh->longp[i];
+            int j = i - 1;
+            while (j >= 0 && sh->longp[j] > v) { sh->longp[j + 1] = sh->longp[j]; --j; }
+            sh->longp[j + 1] = v;
+        }
+        sh->nlong = nl;
+    }
+    __syncthreads();
+    const double* const hh_last = (maxl < sh->hcap) ? sh->hhsm : ws.hh;   // where the last rss_g evaluation left cumsum(h.^2)
     CNMFE_PROF(sh, 10);
     double g = block_fminbnd_rss(y, n, lam, maxl, g_lo, g_hi, ws, sh);
     CNMFE_PROF(sh, 7);
@@ -669,7 +829,7 @@ __device__ double block_update_g(const double* y, int T, int* n_io, double lam, 
         double dot = 0.0;
         for (int j = lane; j < l; j += 32) dot += (y[t0 + j] - pen) * exp(lg * (double)j);
         dot = warp_sum(dot);
-        if (lane == 0) { ws.pv[p] = dot; ws.pw[p] = ws.hh[l - 1]; }
+        if (lane == 0) { ws.pv[p] = dot; ws.pw[p] = hh_last[l - 1]; }
     }
     __syncthreads();
     CNMFE_PROF(sh, 8);
