@@ -788,7 +788,20 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         }
         const int NMAX = c->nnb + 1;
         size_t smem = ring_solve_smem_bytes(NMAX);
+        {
+            // shared-memory carve-out: just enough for the two CTAs per SM the register file allows; the rest stays L1, which
+            // the moment gathers of the assembly phase live on (measured at 54.5 KB/CTA: carve-out 50 % 39.3 ms, 60 % 41.4,
+            // 75 % 43.3, 100 % 53 ms; below two CTAs' worth 61 ms).  CNMFE_RING_CARVEOUT=percent overrides (A/B knob).
+            int pct = (int)((2 * (smem + 2048) * 100 + 228 * 1024 - 1) / (228 * 1024));
+            if (const char* e = getenv("CNMFE_RING_CARVEOUT")) pct = atoi(e);
+            CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        }
         if (ring_profile) {
+            int occ = 0;
+            cudaFuncSetAttribute(ring_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_solve_kernel<false>, RING_SOLVE_THREADS, smem);
+            fprintf(stderr, "[cnmfe ring profile] dynamic smem %zu B, occupancy %d CTAs/SM\n", smem, occ);
             CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             LAUNCH(ring_solve_kernel<true>, (unsigned)alist.size(), RING_SOLVE_THREADS, smem, c->st, a);
         } else {

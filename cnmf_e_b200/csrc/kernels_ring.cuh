@@ -211,8 +211,9 @@ __device__ const double ring_zero_moment = 0.0;
 
 __host__ __device__ inline size_t ring_solve_smem_bytes(int NMAX) {
     (void)NMAX;
-    size_t dbl = 4 * RING_XBUF + 128 + 3 * RING_XBUF + 2 * (size_t)RING_KSET * RING_XBUF + RING_KSET + 16 + RING_NIDX /* qoff */ +
-                 8 * RING_TT /* diagonal tiles of the unit factor */ + 2 * RING_NIDX /* zs, ws */;
+    static_assert(8 * RING_TT <= 2 * RING_KSET * RING_XBUF, "the diagonal tiles alias the neuron-correction buffers");
+    size_t dbl = 4 * RING_XBUF + 128 + 3 * RING_XBUF + 2 * (size_t)RING_KSET * RING_XBUF /* XA, XN; later the diagonal tiles */ +
+                 RING_KSET + 16 + RING_NIDX /* qoff */ + 2 * RING_NIDX /* zs, ws */;
     size_t ints = 5 * (size_t)RING_NIDX + RING_KALL;
     return dbl * 8 + ints * 4 + 64;
 }
@@ -343,8 +344,10 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
     double* cs = XN + RING_KSET * RING_XBUF;                  // RING_KSET (+ 16 partial traces)
     double* trs = cs + RING_KSET;
     long long* qoff = reinterpret_cast<long long*>(trs + 16); // RING_NIDX: block pixel index * ND
-    double* Tt = reinterpret_cast<double*>(qoff + RING_NIDX); // 8 diagonal tiles of the unit factor
-    double* zs = Tt + 8 * RING_TT;                            // RING_NIDX: running right-hand side of the back substitution
+    double* Tt = XA;                                          // 8 diagonal tiles of the unit factor: written after the factorisation,
+                                                              // when the correction buffers XA / XN are dead (less shared memory
+                                                              // per CTA = more L1 for the moment gathers: 39 -> ms measured)
+    double* zs = reinterpret_cast<double*>(qoff + RING_NIDX); // RING_NIDX: running right-hand side of the back substitution
     double* wsol = zs + RING_NIDX;                            // RING_NIDX: solution
     int* qi = reinterpret_cast<int*>(wsol + RING_NIDX);       // RING_NIDX block pixel index
     int* slot = qi + RING_NIDX;
