@@ -382,12 +382,34 @@ def run_ours(args):
     achieved = int8_ops / gram_s / 1e12
     roofline = dict(bound="tensor", kernel="ring second moments S2 (%s)" % ("tcgen05 INT8" if lib.cnmfe_last_gram_was_tensor(obj._h) else "SIMT u64"),
                     achieved=achieved, peak=2.0 * bf16, unit="TOP/s (int8 dense)", frac=achieved / (2.0 * bf16),
-                    traffic=(88.4e9 * (T / 10000.0) if (lib.cnmfe_last_gram_was_tensor(obj._h) and ss == 1) else None),
-                    traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/r1_ncu_full_gram.csv), scaled by T/10000",
+                    traffic=(89.47e9 * (T / 10000.0) if (lib.cnmfe_last_gram_was_tensor(obj._h) and ss == 1) else None),
+                    traffic_source="dram__bytes_read.sum (84.24 GB) + dram__bytes_write.sum (5.23 GB) of one ncu --set full capture (profiles/r1_ncu_full_gram.csv), scaled by T/10000",
                     peak_source=peak_src, ms_per_launch=1e3 * gram_s,
                     algorithmic_ops_per_launch=int8_ops,
                     hbm_iteration=dict(algorithmic_bytes=3.0 * d1 * d2 * T * 2 / world, gbs=3.0 * d1 * d2 * T * 2 / world / (t_max / args.steps) / 1e9,
                                        peak_gbs=peaks.get("hbm_gbs", 6650.0)))
+    # ---- the other kernels of the step, each against the bound that applies to it (live per-phase CUDA-event times)
+    ph = [float(x) / args.steps / 1e3 for x in phases]          # seconds per step
+    nnb1 = 121 if ss == 1 else None
+    others = {}
+    if nnb1 and ph[1] > 0:
+        dpx = float(sum(int(b[1] - b[0] + 1) * int(b[3] - b[2] + 1) for b in nblk))
+        sol_bytes = dpx * (nnb1 * (nnb1 + 1) / 2 + nnb1) * 8.0      # moment gather + weights out, all pixels active
+        sol_flop = dpx * (2.0 * nnb1 ** 3 / 6.0 + 2.0 * nnb1 ** 2)  # LDL' + two triangular solves (fp64)
+        others["ring_solve_kernel"] = dict(ms=1e3 * ph[1], bound="shared-memory operand bandwidth / latency (fp64, not tensor)",
+                                           algorithmic_bytes=sol_bytes, hbm_gbs=sol_bytes / ph[1] / 1e9,
+                                           hbm_frac=sol_bytes / ph[1] / 1e9 / peaks.get("hbm_gbs", 6650.0),
+                                           fp64_tflops=sol_flop / ph[1] / 1e12, fp64_frac_of_36_tf=sol_flop / ph[1] / 36.0e12,
+                                           evidence="profiles/r1_ncu_full_solve.csv: LDS wavefronts 50 % of peak, fp64 pipe 27 %, barrier stalls 39 %")
+    if ph[2] > 0:
+        pb = 3.0 * d1 * d2 * T * 2 / world
+        others["projections (proj_mc_tile x2, proj_bt_list)"] = dict(ms=1e3 * ph[2], bound="hbm", algorithmic_bytes=pb, gbs=pb / ph[2] / 1e9,
+                                                                    frac=pb / ph[2] / 1e9 / peaks.get("hbm_gbs", 6650.0),
+                                                                    note="three streaming passes over the resident uint16 video (SURVEY 8d: 3*d*T*2 B)")
+    if ph[4] > 0:
+        others["hals_temporal_kernel"] = dict(ms=1e3 * ph[4], bound="dependency chain (5 sweeps x overlapping-neuron chain of exact sequential OASIS fits)",
+                                              note="CNMFE_HALS_PROFILE=1 prints the critical chain; see profiles/README_r1.md")
+    roofline["other_kernels"] = others
     # ---- CPU baseline, bounded sample, rank 0
     cores = os.cpu_count()
     cpu = None

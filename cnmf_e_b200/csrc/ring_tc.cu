@@ -11,7 +11,8 @@
 // Per item the K loop streams all frames: TMA (3-D boxes {128 B of t, rows, cols}, SWIZZLE_128B) -> 3-stage smem ring
 // -> 16 MMAs per stage (4 K-steps of 32 B x 4 byte-plane products) into three accumulators (hh, hl+lh, ll), then the
 // epilogue warps read TMEM (tcgen05.ld 32x32b), combine in int64 and write the (pixel, displacement) run.
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..5 = epilogue (one TMEM lane quadrant each).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..9 = epilogue (TMEM lane quadrant warp % 4,
+// two warps per quadrant splitting the columns: the accumulators are single-buffered, so the epilogue is a pipeline bubble).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -35,11 +36,12 @@ constexpr int A_BYTES = MR * MC * KSTAGE;                 // 16384
 constexpr int B_BYTES = NB * KSTAGE;                      // 14336
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // 61440
 constexpr int EPI_STRIDE = 17;                            // doubles per pixel row of the epilogue transpose buffer (16 + pad)
-constexpr int EPI_BYTES = 4 * 32 * EPI_STRIDE * 8;        // one 32 x 16 buffer per epilogue warp
+constexpr int EPI_WARPS = 8;                              // two per TMEM lane quadrant: they split the accumulator columns
+constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_STRIDE * 8; // one 32 x 16 buffer per epilogue warp
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
 constexpr int TMEM_COLS = 512;
 constexpr int COL_HH = 0, COL_MID = NB, COL_LL = 2 * NB;   // [hh | hl+lh | ll]: adjacent, so one N = 2*NB MMA spans two of them
-constexpr int THREADS = 192;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int MAX_K_BYTES = 16384;                        // frames per pass so that hl+lh < 2^31
 }  // namespace tc
 
@@ -170,7 +172,7 @@ ring_s2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), CL); }
         mbar_init(smem_u32(tmem_full), 1);
-        mbar_init(smem_u32(tmem_empty), 4);
+        mbar_init(smem_u32(tmem_empty), EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -265,8 +267,10 @@ ring_s2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: warps 2..5 -> TMEM lane quadrant warp%4
+        // ------------------------------------------------------------------ epilogue: warps 2..9 -> TMEM lane quadrant warp%4
         const int quad = warp & 3;
+        // the two warps of a quadrant split the NB accumulator columns (16-column steps): [0, 64) and [64, NB)
+        const int cc_begin = ((warp - 2) >> 2) ? 64 : 0, cc_end = ((warp - 2) >> 2) ? NB : 64;
         uint32_t acc_phase = 0;
  for (long long g = g0; g < P.ngroups; g += gstep) {
             int r0, c0, cB;
@@ -287,7 +291,7 @@ ring_s2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             const int id0 = (dc == 0) ? 0 : (2 * P.rr + 1) + (dc - 1) * (4 * P.rr + 1) + 2 * P.rr;   // disp id = id0 + dr
             if (warp_ok)
 #pragma unroll 1
-            for (int cc = 0; cc < NB; cc += 16) {
+            for (int cc = cc_begin; cc < cc_end; cc += 16) {
                 uint32_t hh[16], mid[16], ll[16];
                 tmem_ld16(taddr + COL_HH + cc, hh);
                 tmem_ld16(taddr + COL_MID + cc, mid);
