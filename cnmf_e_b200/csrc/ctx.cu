@@ -43,6 +43,15 @@ struct HostCsc {
 
 struct Rect { int r0, r1, c0, c1; };   // 0-based inclusive, FOV coordinates
 
+struct LocalSparse {
+    std::vector<int> ids;                       // local -> global neuron
+    std::vector<int> ptr, col; std::vector<double> val;      // rows by pixel (block or patch pixel index)
+    std::vector<int> cptr, crow; std::vector<double> cval;   // columns by local neuron (rows sorted)
+    std::vector<int> bbox;                      // [K][4] r0,r1,c0,c1 in block coords (tight)
+    std::vector<int64_t> entry_src;             // csc entry index of each row-entry (for IND bookkeeping)
+    int K() const { return (int)ids.size(); }
+};
+
 struct Patch {
     Rect patch, block;
     int nr, nc, nrb, ncb, dp, db;
@@ -55,17 +64,12 @@ struct Patch {
     // spatial result bookkeeping
     std::vector<int64_t> ind_entry;   // for each pattern entry (patch CSR order): index into the user's IND csc
     RingGeom geom;
+    // local view of A_prev on the block (SEL_SUM_BLOCK, ROWS_BLOCK): built by the ring BG update (A_prev = A there) and reused
+    // by the spatial and temporal updates of the same iteration
+    LocalSparse lp_cache; bool lp_valid = false;
 };
 
 // Local (per patch) sparse view of a d x K matrix.
-struct LocalSparse {
-    std::vector<int> ids;                       // local -> global neuron
-    std::vector<int> ptr, col; std::vector<double> val;      // rows by pixel (block or patch pixel index)
-    std::vector<int> cptr, crow; std::vector<double> cval;   // columns by local neuron (rows sorted)
-    std::vector<int> bbox;                      // [K][4] r0,r1,c0,c1 in block coords (tight)
-    std::vector<int64_t> entry_src;             // csc entry index of each row-entry (for IND bookkeeping)
-    int K() const { return (int)ids.size(); }
-};
 
 struct Scratch {
     char* base = nullptr; size_t cap = 0, off = 0;
@@ -104,8 +108,8 @@ struct cnmfe_ctx {
     int* d_groups = nullptr; int ngroups = 0;
     std::vector<Patch> patches;
     cnmfe_options opt;
-    cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr;   // st2: second-moment kernel, overlapped with the host planning of the BG update
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr, ge0 = nullptr, ge1 = nullptr;
     float phase_ms[7] = {0, 0, 0, 0, 0, 0, 0};
     int last_gram_tensor = 0;
     int use_c_hat = 1;            // update_temporal_parallel(obj, use_parallel, use_c_hat)
@@ -245,67 +249,78 @@ enum RowSpace { ROWS_BLOCK, ROWS_BLOCK_PATCHONLY, ROWS_PATCH };
 // row lists use.  vals == nullptr -> M's own values.
 void build_local(const cnmfe_ctx* c, const Patch& P, const HostCsc& M, SelMode sel, RowSpace rows,
                  const HostCsc* vals, LocalSparse* L) {
-    const int d1 = c->d1;
+    // Host planning runs between kernels on the critical path of every update call, so it is written flat: no per-neuron
+    // containers, no 64-bit division per entry (the rows of a CSC column are sorted, so the FOV column of an entry only
+    // ever moves forward), values of `vals` found by a sorted merge instead of a binary search per entry.
+    const int64_t d1 = c->d1;
     L->ids.clear();
     const int nrows = (rows == ROWS_PATCH) ? P.dp : P.db;
-    std::vector<std::vector<std::pair<int, double>>> tmp;   // per local neuron: (pixel, value)
-    std::vector<std::vector<int64_t>> tmp_src;
-    auto in_rect = [](const Rect& R, int r, int cc) { return r >= R.r0 && r <= R.r1 && cc >= R.c0 && cc <= R.c1; };
+    const size_t nnz = M.ir.size();
+    static thread_local std::vector<int> lidx;          // local row index of each entry of the current column, -1 = dropped
+    L->cptr.assign(1, 0); L->crow.clear(); L->cval.clear(); L->bbox.clear();
+    L->crow.reserve(nnz); L->cval.reserve(nnz);
+    static thread_local std::vector<int64_t> csrc;      // csc entry index of each kept column entry
+    csrc.clear(); csrc.reserve(nnz);
+    const int nrw = (rows == ROWS_PATCH) ? P.nr : P.nrb;
     for (int k = 0; k < M.K; ++k) {
+        const int64_t e0 = M.jc[k], e1 = M.jc[k + 1];
+        if ((size_t)(e1 - e0) > lidx.size()) lidx.resize((size_t)(e1 - e0));
         double sum = 0.0;
         bool any = false;
-        for (int64_t e = M.jc[k]; e < M.jc[k + 1]; ++e) {
-            int r = (int)(M.ir[e] % d1), cc = (int)(M.ir[e] / d1);
-            bool inb = in_rect(P.block, r, cc), inp = in_rect(P.patch, r, cc);
+        int64_t cc = 0, base = 0;                       // FOV column of the current entry and its first linear index
+        for (int64_t e = e0; e < e1; ++e) {
+            const int64_t row = M.ir[e];
+            if (row < base || row >= base + d1) { cc = row / d1; base = cc * d1; }
+            const int r = (int)(row - base), ci = (int)cc;
+            const bool inb = r >= P.block.r0 && r <= P.block.r1 && ci >= P.block.c0 && ci <= P.block.c1;
+            const bool inp = r >= P.patch.r0 && r <= P.patch.r1 && ci >= P.patch.c0 && ci <= P.patch.c1;
             if (sel == SEL_SUM_BLOCK && inb) sum += M.pr[e];
             if (sel == SEL_SUM_HALO && inb && !inp) sum += M.pr[e];
             if (sel == SEL_ANY_PATCH && inp) any = true;
+            int idx = -1;
+            if (rows == ROWS_PATCH) { if (inp) idx = (ci - P.patch.c0) * P.nr + (r - P.patch.r0); }
+            else if (rows == ROWS_BLOCK_PATCHONLY) { if (inp) idx = (ci - P.block.c0) * P.nrb + (r - P.block.r0); }
+            else { if (inb) idx = (ci - P.block.c0) * P.nrb + (r - P.block.r0); }
+            lidx[(size_t)(e - e0)] = idx;
         }
-        bool take = (sel == SEL_ANY_PATCH) ? any : (sum > 0.0);
+        const bool take = (sel == SEL_ANY_PATCH) ? any : (sum > 0.0);
         if (!take) continue;
-        std::vector<std::pair<int, double>> ent;
-        std::vector<int64_t> src;
-        for (int64_t e = M.jc[k]; e < M.jc[k + 1]; ++e) {
-            int r = (int)(M.ir[e] % d1), cc = (int)(M.ir[e] / d1);
-            bool inb = in_rect(P.block, r, cc), inp = in_rect(P.patch, r, cc);
-            int idx;
-            if (rows == ROWS_PATCH) { if (!inp) continue; idx = (cc - P.patch.c0) * P.nr + (r - P.patch.r0); }
-            else if (rows == ROWS_BLOCK_PATCHONLY) { if (!inp) continue; idx = (cc - P.block.c0) * P.nrb + (r - P.block.r0); }
-            else { if (!inb) continue; idx = (cc - P.block.c0) * P.nrb + (r - P.block.r0); }
-            double v = vals ? vals->lookup(k, M.ir[e]) : M.pr[e];
-            ent.emplace_back(idx, v);
-            src.push_back(e);
+        // entries are already sorted by local index because ir is sorted and the index map is monotone in (c, r)
+        int r0 = 1 << 30, r1 = -1, c0 = 1 << 30, c1 = -1;
+        int64_t vp = vals ? vals->jc[k] : 0;
+        const int64_t vend = vals ? vals->jc[k + 1] : 0;
+        for (int64_t e = e0; e < e1; ++e) {
+            const int idx = lidx[(size_t)(e - e0)];
+            if (idx < 0) continue;
+            double v;
+            if (vals) {
+                const int64_t row = M.ir[e];
+                while (vp < vend && vals->ir[vp] < row) ++vp;
+                v = (vp < vend && vals->ir[vp] == row) ? vals->pr[vp] : 0.0;
+            } else v = M.pr[e];
+            L->crow.push_back(idx); L->cval.push_back(v); csrc.push_back(e);
+            int r = idx % nrw, ci = idx / nrw;
+            if (rows == ROWS_PATCH) { r += P.patch.r0 - P.block.r0; ci += P.patch.c0 - P.block.c0; }
+            r0 = std::min(r0, r); r1 = std::max(r1, r); c0 = std::min(c0, ci); c1 = std::max(c1, ci);
         }
         L->ids.push_back(k);
-        tmp.push_back(std::move(ent));
-        tmp_src.push_back(std::move(src));
+        L->cptr.push_back((int)L->crow.size());
+        if (r1 < 0) { r0 = 0; r1 = -1; c0 = 0; c1 = -1; }
+        L->bbox.push_back(r0); L->bbox.push_back(r1); L->bbox.push_back(c0); L->bbox.push_back(c1);
     }
     const int K = L->K();
-    // columns (entries are already sorted by pixel because ir is sorted and the index map is monotone in (c, r))
-    L->cptr.assign(K + 1, 0); L->crow.clear(); L->cval.clear(); L->bbox.assign((size_t)K * 4, 0);
-    const int nrw = (rows == ROWS_PATCH) ? P.nr : P.nrb;
-    for (int k = 0; k < K; ++k) {
-        int r0 = 1 << 30, r1 = -1, c0 = 1 << 30, c1 = -1;
-        for (auto& pv : tmp[k]) {
-            L->crow.push_back(pv.first); L->cval.push_back(pv.second);
-            int r = pv.first % nrw, cc = pv.first / nrw;
-            if (rows == ROWS_PATCH) { r += P.patch.r0 - P.block.r0; cc += P.patch.c0 - P.block.c0; }
-            r0 = std::min(r0, r); r1 = std::max(r1, r); c0 = std::min(c0, cc); c1 = std::max(c1, cc);
-        }
-        L->cptr[k + 1] = (int)L->crow.size();
-        if (r1 < 0) { r0 = 0; r1 = -1; c0 = 0; c1 = -1; }
-        L->bbox[4 * k] = r0; L->bbox[4 * k + 1] = r1; L->bbox[4 * k + 2] = c0; L->bbox[4 * k + 3] = c1;
-    }
     // rows by pixel (ascending local neuron id inside each row)
     L->ptr.assign(nrows + 1, 0);
-    for (int k = 0; k < K; ++k) for (auto& pv : tmp[k]) L->ptr[pv.first + 1]++;
+    const size_t nkept = L->crow.size();
+    for (size_t x = 0; x < nkept; ++x) L->ptr[L->crow[x] + 1]++;
     for (int i = 0; i < nrows; ++i) L->ptr[i + 1] += L->ptr[i];
-    L->col.assign(L->ptr[nrows], 0); L->val.assign(L->ptr[nrows], 0.0); L->entry_src.assign(L->ptr[nrows], 0);
-    std::vector<int> fill(L->ptr.begin(), L->ptr.end() - 1);
+    L->col.assign(nkept, 0); L->val.assign(nkept, 0.0); L->entry_src.assign(nkept, 0);
+    static thread_local std::vector<int> fill;
+    fill.assign(L->ptr.begin(), L->ptr.end() - 1);
     for (int k = 0; k < K; ++k)
-        for (size_t x = 0; x < tmp[k].size(); ++x) {
-            int pos = fill[tmp[k][x].first]++;
-            L->col[pos] = k; L->val[pos] = tmp[k][x].second; L->entry_src[pos] = tmp_src[k][x];
+        for (int x = L->cptr[k]; x < L->cptr[k + 1]; ++x) {
+            const int pos = fill[L->crow[x]]++;
+            L->col[pos] = k; L->val[pos] = L->cval[x]; L->entry_src[pos] = csrc[x];
         }
 }
 
@@ -369,7 +384,7 @@ extern "C" int cnmfe_create(cnmfe_ctx** out, int d1, int d2, int T, int npatch, 
         return -1;
     }
     c->sn.assign((size_t)d1 * d2, 1.0);
-    cudaStreamCreate(&c->st);
+    cudaStreamCreate(&c->st); cudaStreamCreate(&c->st2); cudaEventCreate(&c->ge0); cudaEventCreate(&c->ge1);
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1); cudaEventCreate(&c->pe0); cudaEventCreate(&c->pe1);
     cudaMalloc((void**)&c->d_off_r, c->nnb * 4); cudaMalloc((void**)&c->d_off_c, c->nnb * 4);
     cudaMemcpy(c->d_off_r, c->off_r.data(), c->nnb * 4, cudaMemcpyHostToDevice);
@@ -437,6 +452,9 @@ extern "C" void cnmfe_destroy(cnmfe_ctx* c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->pe0) cudaEventDestroy(c->pe0);
     if (c->pe1) cudaEventDestroy(c->pe1);
+    if (c->ge0) cudaEventDestroy(c->ge0);
+    if (c->ge1) cudaEventDestroy(c->ge1);
+    if (c->st2) cudaStreamDestroy(c->st2);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
 }
@@ -529,6 +547,7 @@ extern "C" int cnmfe_set_prev(cnmfe_ctx* c, int K, const int64_t* jc, const int6
     }
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
     static const int64_t zero = 0;
+    for (Patch& Pq : c->patches) Pq.lp_valid = false;
     if (K == 0) { c->Aprev.set(0, &zero, nullptr, nullptr); c->Kprev = 0; return 0; }
     if (!keepA) c->Aprev.set(K, jc, ir, pr);
     c->Kprev = K;
@@ -657,6 +676,7 @@ static int update_temporal_patches_svd(cnmfe_ctx* c);
 
 extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
     if (!c) { set_error("cnmfe_update_background: null ctx"); return -1; }
+    for (Patch& Pq : c->patches) Pq.lp_valid = false;
     if (c->opt.background_model == 1) return update_background_svd(c);
     if (c->opt.background_model == 2) {
         set_error("update_background: the nmf model calls the Statistics-toolbox nnmf with a RANDOM initialisation (fit_nmf_model.m:19); fit it in MATLAB and hand b, f over with cnmfe_set_bf -- the nmf BG subtraction of the spatial/temporal updates is built");
@@ -671,9 +691,10 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         Patch& P = c->patches[ip];
         if (!P.owned) continue;
         if (!P.uploaded) { set_error("update_background: block %d not uploaded", ip); return -1; }
-        LocalSparse L;
+        LocalSparse& L = P.lp_cache;     // = the local view of A_prev once this call returns (A_prev <- A below)
         HostTick tick;
         build_local(c, P, c->A, SEL_SUM_BLOCK, ROWS_BLOCK, nullptr, &L);
+        P.lp_valid = true;
         tick("bg build_local");
         const int Kb = L.K();
         if (Kb == 0 && !flag_first) continue;   // update_background_parallel.m:188-199
@@ -682,6 +703,42 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         c->scr.reset();
         tick("bg reserve");
         const RingGeom& g = P.geom;
+        // frames used for the weights (fit_ring_model.m:59-90)
+        const bool first_run = P.w_uniform;
+        CNMFE_CUDA_OK(cudaMemsetAsync(c->d_pmax, 0, 4, c->st));
+        LAUNCH(ring_pmax_kernel, (P.dp + 255) / 256, 256, 0, c->st, g, c->d_off_r, c->d_off_c, P.W, c->d_pmax);
+        int pmax = 0;
+        CNMFE_CUDA_OK(cudaMemcpyAsync(&pmax, c->d_pmax, 4, cudaMemcpyDeviceToHost, c->st));
+        CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+        int kf = 1;
+        if (c->opt.bg_acceleration) {
+            long long nmax = 100LL * pmax;
+            long long nk = std::min<long long>(T, nmax);
+            if (nk < 1) nk = 1;
+            kf = (int)(T / nk);
+            if (kf < 1) kf = 1;
+        }
+        // second moments: they depend only on the resident video and the frame stride, so the kernel (the longest of the
+        // call) starts NOW on a side stream and the host planning below (uploads, active pixels, neuron grams) overlaps it
+        const size_t ND = (size_t)ring_num_disp(c->rr);
+        double* d_S2 = c->scr.take<double>(ND * P.db);
+        if (!d_S2) { set_error("scratch exhausted"); return -1; }
+        {
+            CNMFE_CUDA_OK(cudaEventRecord(c->ge0, c->st2));
+            int tc_rc = 1;
+            if (c->opt.use_tensor_gram && kf == 1)
+                tc_rc = ring_s2_tensor(P.hi, P.lo, P.nrb, P.ncb, T, c->Tpad, c->rr, d_S2, c->st2);
+            if (tc_rc < 0) return -1;
+            c->last_gram_tensor = (tc_rc == 0);
+            if (tc_rc != 0) {
+                long long nw = (long long)((P.nrb + 3) / 4) * P.ncb;
+                dim3 gg((unsigned)((nw + 7) / 8), c->ngroups);
+                LAUNCH(ring_s2_simt_kernel, gg, 256, 0, c->st2, P.Yt, P.nrb, P.ncb, T, c->Tpad, kf, c->rr, c->d_groups,
+                       c->ngroups, d_S2, ND);
+            }
+            CNMFE_CUDA_OK(cudaEventRecord(c->ge1, c->st2));
+        }
+        tick("bg pmax + launch of the second moments");
         phase_begin(c);
         TAKE_OR_FAIL(d_ptr, to_dev(c, L.ptr));
         TAKE_OR_FAIL(d_col, to_dev(c, L.col));
@@ -699,22 +756,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         TAKE_OR_FAIL(d_active, c->scr.take<unsigned char>(P.dp));
         if (Kb > 0)
             LAUNCH(gather_center_rows_kernel, Kb, 256, 0, c->st, c->C, d_ids, Kb, T, d_Cc, d_Cmean);
-        // frames used for the weights (fit_ring_model.m:59-90)
-        const bool first_run = P.w_uniform;
-        CNMFE_CUDA_OK(cudaMemsetAsync(c->d_pmax, 0, 4, c->st));
-        LAUNCH(ring_pmax_kernel, (P.dp + 255) / 256, 256, 0, c->st, g, c->d_off_r, c->d_off_c, P.W, c->d_pmax);
-        int pmax = 0;
-        CNMFE_CUDA_OK(cudaMemcpyAsync(&pmax, c->d_pmax, 4, cudaMemcpyDeviceToHost, c->st));
-        CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
-        tick("bg uploads+pmax");
-        int kf = 1;
-        if (c->opt.bg_acceleration) {
-            long long nmax = 100LL * pmax;
-            long long nk = std::min<long long>(T, nmax);
-            if (nk < 1) nk = 1;
-            kf = (int)(T / nk);
-            if (kf < 1) kf = 1;
-        }
+        tick("bg uploads");
         const double nsel = (double)((T - 1) / kf + 1);
         double* d_S1 = P.Ysum;
         if (kf != 1) {
@@ -732,7 +774,9 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         CNMFE_CUDA_OK(cudaMemcpyAsync(act.data(), d_active, P.dp, cudaMemcpyDeviceToHost, c->st));
         CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
         std::vector<int> alist;
-        // 16 x 16 pixel tiles: concurrently solved pixels share their ring rows of the moment table in L2
+        alist.reserve(P.dp);
+        // 16 x 16 pixel tiles: concurrently solved pixels share their ring rows of the moment table in L2 (a device-side
+        // warp-aggregated compaction was tried: its scrambled group order cost the solver 3 %)
         for (int tc0 = 0; tc0 < P.nc; tc0 += 16)
             for (int tr0 = 0; tr0 < P.nr; tr0 += 16)
                 for (int cc = tc0; cc < std::min(P.nc, tc0 + 16); ++cc)
@@ -740,10 +784,11 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
                         int p = cc * P.nr + rr_;
                         if (act[p]) alist.push_back(p);
                     }
+        if (alist.empty()) { CNMFE_CUDA_OK(cudaStreamSynchronize(c->st2)); continue; }
+        TAKE_OR_FAIL(d_alist, to_dev(c, alist));
         phase_end(c, 6);
         tick("bg active list");
-        if (alist.empty()) continue;
-        TAKE_OR_FAIL(d_alist, to_dev(c, alist));
+        CNMFE_CUDA_OK(cudaStreamWaitEvent(c->st, c->ge1, 0));   // what follows needs the SMs (and then the moments)
         // projections needed by the neuron corrections
         phase_begin(c);
         double* d_N = c->scr.take<double>((size_t)P.db * std::max(Kb, 1));
@@ -756,30 +801,19 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         }
         phase_end(c, 2);
         tick("bg projections");
-        // second moments
-        phase_begin(c);
-        const size_t ND = (size_t)ring_num_disp(c->rr);
-        double* d_S2 = c->scr.take<double>(ND * P.db);
-        if (!d_S2) { set_error("scratch exhausted"); return -1; }
-        int tc_rc = 1;
-        if (c->opt.use_tensor_gram && kf == 1)
-            tc_rc = ring_s2_tensor(P.hi, P.lo, P.nrb, P.ncb, T, c->Tpad, c->rr, d_S2, c->st);
-        if (tc_rc < 0) return -1;
-        c->last_gram_tensor = (tc_rc == 0);
-        if (tc_rc != 0) {
-            long long nw = (long long)((P.nrb + 3) / 4) * P.ncb;
-            dim3 gg((unsigned)((nw + 7) / 8), c->ngroups);
-            LAUNCH(ring_s2_simt_kernel, gg, 256, 0, c->st, P.Yt, P.nrb, P.ncb, T, c->Tpad, kf, c->rr, c->d_groups,
-                   c->ngroups, d_S2, ND);
+        // second moments: done (see above); their time is read from the side stream's events
+        {
+            float gms = 0;
+            CNMFE_CUDA_OK(cudaEventSynchronize(c->ge1));
+            CNMFE_CUDA_OK(cudaEventElapsedTime(&gms, c->ge0, c->ge1));
+            c->phase_ms[0] += gms;
         }
-        phase_end(c, 0);
-        tick("bg second moments");
         // assemble + solve
         phase_begin(c);
         RingSolveArgs a;
         a.g = g; a.off_r = c->d_off_r; a.off_c = c->d_off_c; a.S2 = d_S2; a.S1 = d_S1; a.Ymean = P.Ymean;
         a.nsel = nsel; a.a_ptr = d_ptr; a.a_col = d_col; a.a_val = d_val; a.N = d_N; a.K = Kb; a.Csum = d_Csum;
-        a.active = d_active; a.active_list = d_alist; a.n_active = (int)alist.size(); a.W = P.W; a.db = (size_t)P.db; a.ND = ND;
+        a.active = d_active; a.active_list = d_alist; a.n_active = (int)alist.size(); a.n_active_dev = nullptr; a.W = P.W; a.db = (size_t)P.db; a.ND = ND;
         a.prof = nullptr;
         static const bool ring_profile = getenv("CNMFE_RING_PROFILE") != nullptr;
         if (ring_profile) {
@@ -815,9 +849,10 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
             CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
             CNMFE_CUDA_OK(cudaMemcpy(h, a.prof, 64, cudaMemcpyDeviceToHost));
             cudaFree(a.prof);
-            const double np_ = (double)alist.size();
-            fprintf(stderr, "[cnmfe ring profile] pixels=%zu cycles/pixel: setup=%.0f assemble=%.0f neuron-scan=%.0f(+bitmap) compact=%.0f corrections=%.0f ridge=%.0f ldl=%.0f backsub+store=%.0f; neurons/pixel=%.2f\n",
-                    alist.size(), h[0] / np_, h[1] / np_, h[2] / np_, 0.0, h[3] / np_, h[4] / np_, h[5] / np_, h[6] / np_, h[7] / np_);
+            const int nact = (int)alist.size();
+            const double np_ = (double)std::max(nact, 1);
+            fprintf(stderr, "[cnmfe ring profile] pixels=%d cycles/pixel: setup=%.0f assemble=%.0f neuron-scan=%.0f(+bitmap) compact=%.0f corrections=%.0f ridge=%.0f ldl=%.0f backsub+store=%.0f; neurons/pixel=%.2f\n",
+                    nact, h[0] / np_, h[1] / np_, h[2] / np_, 0.0, h[3] / np_, h[4] / np_, h[5] / np_, h[6] / np_, h[7] / np_);
         }
         tick("bg ring solve");
         P.w_uniform = false;
@@ -866,12 +901,18 @@ extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
         Patch& P = c->patches[ip];
         if (!P.owned) continue;
         if (!P.uploaded) { set_error("update_spatial: block %d not uploaded", ip); return -1; }
-        LocalSparse LS, LP;
+        LocalSparse LS, LPown;
+        HostTick tick;
         build_local(c, P, c->IND, SEL_ANY_PATCH, ROWS_PATCH, &c->A, &LS);
+        tick("sp build_local IND");
         const int Ks = LS.K();
         if (Ks == 0 && !update_sn) continue;   // update_spatial_parallel.m:121-124
-        build_local(c, P, c->Aprev, c->opt.replicate_spatial_aprev_quirk ? SEL_SUM_HALO : SEL_SUM_BLOCK, ROWS_BLOCK,
-                    nullptr, &LP);
+        const bool lp_cached = P.lp_valid && !c->opt.replicate_spatial_aprev_quirk;
+        if (!lp_cached)
+            build_local(c, P, c->Aprev, c->opt.replicate_spatial_aprev_quirk ? SEL_SUM_HALO : SEL_SUM_BLOCK, ROWS_BLOCK,
+                        nullptr, &LPown);
+        const LocalSparse& LP = lp_cached ? P.lp_cache : LPown;
+        tick("sp build_local Aprev");
         const int Kp = LP.K();
         const size_t nent = LS.col.size();
         size_t need = pad256((size_t)P.db * Ks * 8) + pad256((size_t)Ks * T * 8) + pad256((size_t)std::max(Kp, 1) * T * 8) +
@@ -924,6 +965,7 @@ extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
             }
         }
         phase_end(c, 6);
+        tick("sp uploads+small grams");
         // ---- optional explicit rows of the BG-subtracted video (update_sn: GetSn per pixel, :191-194; lars: energy)
         if (update_sn || lars) {
             phase_begin(c);
@@ -993,6 +1035,7 @@ extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
                    Ks, d_iptr, d_icol, d_pptr, d_pcol, d_pval, d_P2, d_U);
         }
         phase_end(c, 2);
+        tick("sp projections");
         phase_begin(c);
         CNMFE_CUDA_OK(cudaMemsetAsync(c->d_err, 0, 4, c->st));
         LAUNCH(spatial_solve_kernel, (P.dp + 127) / 128, 128, 0, c->st, P.dp, d_iptr, d_icol, d_U, d_V, Ks, d_sn,
@@ -1005,9 +1048,13 @@ extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
         CNMFE_CUDA_OK(cudaGetLastError());
         if (err) { set_error("update_spatial: more than %d search masks overlap one pixel", SPATIAL_MAXROW); return -1; }
         for (size_t e = 0; e < nent; ++e) c->A_on_IND[LS.entry_src[e]] = anew[e];
+        tick("sp solve+readback");
     }
     c->have_spatial = true;
-    return cnmfe_set_spatial(c, c->A_on_IND.data());
+    HostTick tick2;
+    const int rc = cnmfe_set_spatial(c, c->A_on_IND.data());
+    tick2("sp set_spatial (A <- IND)");
+    return rc;
 }
 
 // obj.A = A_new on the pattern (zeros dropped), update_spatial_parallel.m:321-335
@@ -1049,8 +1096,10 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
         Patch& P = c->patches[ip];
         if (!P.owned) continue;
         if (!P.uploaded) { set_error("update_temporal: block %d not uploaded", ip); return -1; }
-        LocalSparse LA, LP;
+        LocalSparse LA, LPown;
+        HostTick tick;
         build_local(c, P, c->A, SEL_SUM_BLOCK, ROWS_BLOCK_PATCHONLY, nullptr, &LA);
+        tick("tp build_local A");
         const int Kt = LA.K();
         if (Kt == 0) continue;   // update_temporal_parallel.m:123-126
         if (!c->use_c_hat) {
@@ -1064,7 +1113,9 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
             for (size_t e = 0; e < LA.col.size(); ++e)
                 if (!(LA.val[e] / amax[LA.col[e]] >= 0.5)) LA.val[e] = 0.0;
         }
-        build_local(c, P, c->Aprev, SEL_SUM_BLOCK, ROWS_BLOCK, nullptr, &LP);
+        if (!P.lp_valid) build_local(c, P, c->Aprev, SEL_SUM_BLOCK, ROWS_BLOCK, nullptr, &LPown);
+        const LocalSparse& LP = P.lp_valid ? P.lp_cache : LPown;
+        tick("tp build_local Aprev");
         const int Kp = LP.K();
         size_t need = (c->opt.bg_ssub > 1 ? 4 : 1) * pad256((size_t)P.db * Kt * 8) + 4 * pad256((size_t)Kt * T * 8) + pad256((size_t)std::max(Kp, 1) * T * 8) +
                       2 * pad256((size_t)Kt * Kt * 12 + 64) + pad256((size_t)Kt * std::max(Kp, 1) * 8) +
@@ -1124,10 +1175,12 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
                d_cst);
         { dim3 gg(Kt, (Kt + 127) / 128); LAUNCH(temporal_V_kernel, gg, 128, 0, c->st, d_cptr, d_crow, d_cval, Kt, d_V); }
         phase_end(c, 6);
+        tick("tp uploads+B build");
         phase_begin(c);
         launch_proj_bt(c->st, P.Yt, P.Ymean, P.nrb, T, c->Tpad, d_B, Kt, d_bbox, d_U);
         { dim3 gg((T + 255) / 256, Kt); LAUNCH(add_small_matmul_kernel, gg, 256, 0, c->st, d_U, Kt, T, d_cst, d_AWA, Kp, d_Ccp); }
         phase_end(c, 2);
+        tick("tp projection");
         // V -> CSR (host), sweeps
         phase_begin(c);
         std::vector<double> V((size_t)Kt * Kt);
@@ -1160,6 +1213,7 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
                               &c->arena, c->st)) return -1;
         { dim3 gg((T + 255) / 256, Kt); LAUNCH(temporal_merge_kernel, gg, 256, 0, c->st, d_Crawl, d_V, Kt, T, d_ids, c->num, c->den); }
         phase_end(c, 4);
+        tick("tp sweeps");
         CNMFE_CUDA_OK(cudaGetLastError());
     }
     CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));

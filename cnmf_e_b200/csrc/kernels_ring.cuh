@@ -172,6 +172,7 @@ struct RingSolveArgs {
     const double* N; int K; const double* Csum;
     const unsigned char* active;
     const int* active_list; int n_active;
+    const int* n_active_dev;    // device-side count of active_list (the grid covers all patch pixels), or nullptr: n_active
     double* W;   // [dp][nnb]
     size_t db, ND;
     unsigned long long* prof;   // diagnostics (CNMFE_RING_PROFILE): 8 per-phase cycle counters of thread 0, else nullptr
@@ -326,6 +327,7 @@ template <bool PROF>
 __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingSolveArgs a) {
     extern __shared__ double smem[];
     const RingGeom& g = a.g;
+    if ((int)blockIdx.x >= (a.n_active_dev ? *a.n_active_dev : a.n_active)) return;
     const int p = a.active_list[blockIdx.x];
     const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
     const int pr = p % g.nr + g.pr_off, pc = p / g.nr + g.pc_off;
