@@ -764,10 +764,6 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
             if (!d_S1) { set_error("scratch exhausted"); return -1; }
             LAUNCH(row_sum_strided_kernel, (P.db * 32 + 255) / 256, 256, 0, c->st, P.Yt, P.db, T, c->Tpad, kf, d_S1);
         }
-        if (Kb > 0) {
-            dim3 gg(Kb, Kb);
-            LAUNCH(small_gram_kernel, gg, 128, 0, c->st, d_Cc, Kb, d_Cc, Kb, T, kf, d_Vsel, d_Csum);
-        }
         LAUNCH(ring_active_b0_kernel, (P.dp + 255) / 256, 256, 0, c->st, g, c->d_off_r, c->d_off_c, P.W, d_sumA,
                P.Ymean, d_ptr, d_col, d_val, d_Cmean, first_run ? 1 : 0, d_active, P.b0);
         std::vector<unsigned char> act(P.dp);
@@ -794,6 +790,9 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         double* d_N = c->scr.take<double>((size_t)P.db * std::max(Kb, 1));
         if (!d_N) { set_error("scratch exhausted"); return -1; }
         if (Kb > 0) {
+            // (only the light kernels above share the SMs with the second-moment kernel; this Gram of the traces waits for it)
+            dim3 gg(Kb, Kb);
+            LAUNCH(small_gram_kernel, gg, 128, 0, c->st, d_Cc, Kb, d_Cc, Kb, T, kf, d_Vsel, d_Csum);
             CNMFE_CUDA_OK(cudaMemsetAsync(d_N, 0, (size_t)P.db * Kb * 8, c->st));
             launch_proj_mc(c->st, P.Yt, P.Ymean, P.nrb, P.ncb, T, c->Tpad,
                    kf, d_Cc, Kb, d_bbox, d_N);
@@ -1059,9 +1058,9 @@ extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
 
 // obj.A = A_new on the pattern (zeros dropped), update_spatial_parallel.m:321-335
 extern "C" int cnmfe_set_spatial(cnmfe_ctx* c, const double* vals) {
-    if (!c || !vals) { set_error("cnmfe_set_spatial: null"); return -1; }
+    if (!c || (!vals && !c->IND.ir.empty())) { set_error("cnmfe_set_spatial: null"); return -1; }   // empty pattern (K = 0): nothing to read
     if (c->IND.K != c->K) { set_error("cnmfe_set_spatial: search mask has %d columns, A has %d", c->IND.K, c->K); return -1; }
-    if (vals != c->A_on_IND.data()) c->A_on_IND.assign(vals, vals + c->IND.ir.size());
+    if (vals && vals != c->A_on_IND.data()) c->A_on_IND.assign(vals, vals + c->IND.ir.size());
     HostCsc An;
     An.K = c->K;
     An.jc.assign(c->K + 1, 0);
@@ -1076,7 +1075,7 @@ extern "C" int cnmfe_set_spatial(cnmfe_ctx* c, const double* vals) {
 }
 
 extern "C" int cnmfe_get_spatial(cnmfe_ctx* c, double* A_on_IND) {
-    if (!c || !A_on_IND) { set_error("cnmfe_get_spatial: null"); return -1; }
+    if (!c || (!A_on_IND && !c->A_on_IND.empty())) { set_error("cnmfe_get_spatial: null"); return -1; }
     if (!c->have_spatial) { set_error("cnmfe_get_spatial: no spatial update has run"); return -1; }
     std::copy(c->A_on_IND.begin(), c->A_on_IND.end(), A_on_IND);
     return 0;

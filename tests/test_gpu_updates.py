@@ -176,3 +176,28 @@ def test_background_ring18_parity(built_lib):
     gpu.update_background_parallel()
     _check_bg(orc, gpu)
     gpu.close()
+
+
+def test_no_neurons(built_lib):
+    """K = 0: the first BG update still fits the ring weights on the raw video (fit_ring_model.m:25-29, first run = all pixels
+    active); a second one skips the patch (update_background_parallel.m:188-199); spatial / temporal are no-ops."""
+    from oracle import gen, cnmfe as OC
+    from cnmf_e_b200.sources2d import Sources2D
+    d1, d2, T, rr = 40, 36, 300, 6
+    D = gen.make_synthetic(d1, d2, T, 3, seed=5, nblob=2)
+    orc = OC.OracleSources2D(D["Y"], (d1, d2), ring_radius=rr)
+    gpu = Sources2D(d1, d2, T, (d1, d2), ring_radius=rr)
+    gpu.load_video(D["Y"])
+    for o in (orc, gpu):
+        o.A, o.C = sp.csc_matrix((d1 * d2, 0)), np.zeros((0, T))
+        o.P["sn"] = np.full((d1, d2), 10.0)
+    orc.update_background_parallel()
+    gpu.update_background_parallel()
+    _check_bg(orc, gpu)
+    W1 = gpu.ring_as_sparse(0).toarray().copy()
+    gpu.update_background_parallel()                       # not the first run any more, no neurons: patch skipped
+    assert np.array_equal(gpu.ring_as_sparse(0).toarray(), W1)
+    IND = sp.csc_matrix((d1 * d2, 0), dtype=bool)
+    gpu.update_spatial_parallel(IND=IND)
+    gpu.update_temporal_parallel()
+    assert gpu.A.shape == (d1 * d2, 0) and gpu.C.shape == (0, T)
