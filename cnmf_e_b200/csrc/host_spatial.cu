@@ -1,0 +1,193 @@
+// host_spatial.cu -- the two per-neuron routines that bracket every spatial update in the reference:
+//   determine_search_location(A, 'ellipse', params)   ca_source_extraction/utilities/determine_search_location.m:57-92
+//   post_process_spatial / connectivity_constraint    @Sources2D/post_process_spatial.m:19-32, endoscope/connectivity_constraint.m
+// They are host code in the reference too (MATLAB, per neuron on a small crop); here they are plain C++ on the CSC matrix so that
+// the host mirror / MEX gateway need not leave the library between cnmfe_update_spatial calls.  No CUDA in this file.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <vector>
+#include "common.cuh"
+#include "internal.h"
+
+using cnmfe::set_error;
+
+// connectivity_constraint(img, thr, sz): ai_open = imopen(img, strel('square', sz)); temp = ai_open > max(img)*thr;
+// l = bwlabel(temp, 4); img(l ~= l(ind_max)) = 0  with ind_max = first arg-max of img (column-major).
+// MATLAB's flat morphology ignores pixels outside the image (erosion pads +Inf, dilation -Inf).  Note the reference's
+// behaviour when the arg-max pixel is NOT in the opened mask: l(ind_max) = 0, so every labelled component is removed and the
+// unlabelled remainder is kept -- replicated.
+extern "C" int cnmfe_connectivity_constraint(int d1, int d2, int K, const int64_t* jc, const int64_t* ir, double* pr,
+                                             double thr, int sz) {
+    if (d1 <= 0 || d2 <= 0 || K < 0 || !jc || (K > 0 && jc[K] > 0 && (!ir || !pr))) { set_error("cnmfe_connectivity_constraint: bad arguments"); return -1; }
+    if (sz < 1 || (sz & 1) == 0) { set_error("cnmfe_connectivity_constraint: sz must be odd (strel('square', sz) centred)"); return -1; }
+    const int h = sz / 2, margin = 2 * h;
+    std::vector<double> img, ero, opn;
+    std::vector<unsigned char> mask, keep;
+    std::vector<int> stack;
+    for (int k = 0; k < K; ++k) {
+        const int64_t e0 = jc[k], e1 = jc[k + 1];
+        // bounding box, maximum and its first position (entries are sorted by linear index = column-major order)
+        int r0 = d1, r1 = -1, c0 = d2, c1 = -1;
+        double vmax = 0.0;
+        int64_t imax = 0;
+        bool have = false, anynz = false;
+        for (int64_t e = e0; e < e1; ++e) {
+            const double v = pr[e];
+            if (v == 0.0) continue;
+            anynz = true;
+            const int r = (int)(ir[e] % d1), c = (int)(ir[e] / d1);
+            r0 = std::min(r0, r); r1 = std::max(r1, r); c0 = std::min(c0, c); c1 = std::max(c1, c);
+            if (!have || v > vmax) { vmax = v; imax = ir[e]; have = true; }
+        }
+        if (!anynz) continue;
+        // max(img(:)) over the FULL image: implicit zeros count when every stored value is negative
+        if (vmax < 0.0 && (int64_t)d1 * d2 > (e1 - e0)) { vmax = 0.0; /* arg-max = first implicit zero */
+            int64_t pos = 0, e = e0;
+            while (e < e1 && ir[e] == pos && pr[e] != 0.0) { ++pos; ++e; }   // first linear index that is zero
+            imax = pos;
+        }
+        const int R0 = std::max(0, r0 - margin), R1 = std::min(d1 - 1, r1 + margin);
+        const int C0 = std::max(0, c0 - margin), C1 = std::min(d2 - 1, c1 + margin);
+        const int nr = R1 - R0 + 1, nc = C1 - C0 + 1;
+        img.assign((size_t)nr * nc, 0.0);
+        for (int64_t e = e0; e < e1; ++e) {
+            const int r = (int)(ir[e] % d1), c = (int)(ir[e] / d1);
+            if (r >= R0 && r <= R1 && c >= C0 && c <= C1) img[(size_t)(c - C0) * nr + (r - R0)] = pr[e];
+        }
+        // pixels of the FOV outside the crop are zeros (the crop has a 2h margin); pixels outside the FOV do not count
+        auto at = [&](const std::vector<double>& a, int r, int c, bool* inside) -> double {
+            *inside = (r >= 0 && r < d1 && c >= 0 && c < d2);
+            if (!*inside) return 0.0;
+            if (r < R0 || r > R1 || c < C0 || c > C1) return 0.0;
+            return a[(size_t)(c - C0) * nr + (r - R0)];
+        };
+        ero.assign(img.size(), 0.0);
+        for (int c = C0; c <= C1; ++c)
+            for (int r = R0; r <= R1; ++r) {
+                double m = std::numeric_limits<double>::infinity();
+                for (int dc = -h; dc <= h; ++dc)
+                    for (int dr = -h; dr <= h; ++dr) {
+                        bool in;
+                        const double v = at(img, r + dr, c + dc, &in);
+                        if (in) m = std::min(m, v);
+                    }
+                ero[(size_t)(c - C0) * nr + (r - R0)] = m;
+            }
+        opn.assign(img.size(), 0.0);
+        for (int c = C0; c <= C1; ++c)
+            for (int r = R0; r <= R1; ++r) {
+                double m = -std::numeric_limits<double>::infinity();
+                for (int dc = -h; dc <= h; ++dc)
+                    for (int dr = -h; dr <= h; ++dr) {
+                        bool in;
+                        const double v = at(ero, r + dr, c + dc, &in);
+                        if (in) m = std::max(m, v);
+                    }
+                opn[(size_t)(c - C0) * nr + (r - R0)] = m;
+            }
+        const double level = vmax * thr;
+        mask.assign(img.size(), 0);
+        for (size_t i = 0; i < img.size(); ++i) mask[i] = opn[i] > level ? 1 : 0;
+        // component of the arg-max pixel (4-connected), or -- if that pixel is not in the mask -- the unlabelled remainder
+        const int rm = (int)(imax % d1), cm = (int)(imax / d1);
+        const bool max_in_crop = (rm >= R0 && rm <= R1 && cm >= C0 && cm <= C1);
+        const bool seeded = max_in_crop && mask[(size_t)(cm - C0) * nr + (rm - R0)];
+        keep.assign(img.size(), 0);
+        if (seeded) {
+            stack.clear();
+            stack.push_back((cm - C0) * nr + (rm - R0));
+            keep[stack.back()] = 1;
+            while (!stack.empty()) {
+                const int p = stack.back(); stack.pop_back();
+                const int r = p % nr, c = p / nr;
+                const int nb[4][2] = {{r - 1, c}, {r + 1, c}, {r, c - 1}, {r, c + 1}};
+                for (auto& q : nb) {
+                    if (q[0] < 0 || q[0] >= nr || q[1] < 0 || q[1] >= nc) continue;
+                    const int qi = q[1] * nr + q[0];
+                    if (mask[qi] && !keep[qi]) { keep[qi] = 1; stack.push_back(qi); }
+                }
+            }
+        } else {
+            for (size_t i = 0; i < img.size(); ++i) keep[i] = mask[i] ? 0 : 1;
+        }
+        for (int64_t e = e0; e < e1; ++e) {
+            const int r = (int)(ir[e] % d1), c = (int)(ir[e] / d1);
+            const bool inc = (r >= R0 && r <= R1 && c >= C0 && c <= C1);
+            // outside the crop the mask is false: kept only in the "unlabelled remainder" case (those entries are zeros anyway)
+            const bool kp = inc ? (keep[(size_t)(c - C0) * nr + (r - R0)] != 0) : !seeded;
+            if (!kp) pr[e] = 0.0;
+        }
+    }
+    return 0;
+}
+
+// determine_search_location(A, 'ellipse', params): ellipse around the centre of mass, axes = principal components of the
+// footprint with variances clamped to [min_size^2, max_size^2], expanded by `dist`.  Output: CSC pattern (sorted rows).
+// out_ir must hold K * (2*ceil(dist*max_size) + 1)^2 entries (the ellipse never leaves that box).
+extern "C" int cnmfe_search_location_ellipse(int d1, int d2, int K, const int64_t* jc, const int64_t* ir, const double* pr,
+                                             double min_size, double max_size, double dist, int64_t* out_jc,
+                                             int64_t* out_ir, int64_t cap) {
+    if (d1 <= 0 || d2 <= 0 || K < 0 || !jc || !out_jc || (K > 0 && !out_ir)) { set_error("cnmfe_search_location_ellipse: bad arguments"); return -1; }
+    if (!(dist > 0.0) || !std::isfinite(dist)) { set_error("cnmfe_search_location_ellipse: dist must be finite and positive (dist = Inf means the whole FOV: pass a full mask instead)"); return -1; }
+    const int reach = (int)std::ceil(dist * std::max(max_size, min_size));
+    int64_t n = 0;
+    out_jc[0] = 0;
+    for (int k = 0; k < K; ++k) {
+        const int64_t e0 = jc[k], e1 = jc[k + 1];
+        double s = 0.0, sx = 0.0, sy = 0.0;
+        for (int64_t e = e0; e < e1; ++e) {
+            const double a = pr ? pr[e] : 1.0;
+            s += a;
+            sx += a * (double)(ir[e] % d1 + 1);
+            sy += a * (double)(ir[e] / d1 + 1);
+        }
+        double cx, cy, vxx = 0.0, vxy = 0.0, vyy = 0.0;
+        if (s == 0.0) {
+            // ind_empty: A(1, k) = 1  (determine_search_location.m:51-55)
+            cx = 1.0; cy = 1.0;
+        } else {
+            cx = sx / s; cy = sy / s;
+            // com.m:27-29 clamps
+            if (cx < 0.0) cx = 0.0;
+            if (cy < 0.0) cy = 0.0;
+            if (cx > d1) cx = d1;
+            if (cy > d2) cy = d2;
+            for (int64_t e = e0; e < e1; ++e) {
+                const double a = pr ? pr[e] : 1.0;
+                const double dx = (double)(ir[e] % d1 + 1) - cx, dy = (double)(ir[e] / d1 + 1) - cy;
+                vxx += a * dx * dx; vxy += a * dx * dy; vyy += a * dy * dy;
+            }
+            vxx /= s; vxy /= s; vyy /= s;
+        }
+        // eigen-decomposition of [[vxx, vxy], [vxy, vyy]], ascending eigenvalues (MATLAB eig of a symmetric matrix)
+        const double half = 0.5 * (vxx + vyy), dif = 0.5 * (vxx - vyy);
+        const double rad = std::sqrt(dif * dif + vxy * vxy);
+        const double l1 = half - rad, l2 = half + rad;
+        double v1x, v1y, v2x, v2y;
+        if (vxy == 0.0) {
+            if (vxx <= vyy) { v1x = 1; v1y = 0; v2x = 0; v2y = 1; } else { v1x = 0; v1y = 1; v2x = 1; v2y = 0; }
+        } else {
+            // eigenvector of l2: (vxy, l2 - vxx); of l1: orthogonal
+            double ex = vxy, ey = l2 - vxx;
+            const double nn = std::sqrt(ex * ex + ey * ey);
+            ex /= nn; ey /= nn;
+            v2x = ex; v2y = ey; v1x = -ey; v1y = ex;
+        }
+        const double d11 = std::min(max_size * max_size, std::max(min_size * min_size, l1));
+        const double d22 = std::min(max_size * max_size, std::max(min_size * min_size, l2));
+        const int rc = (int)std::floor(cx), cc = (int)std::floor(cy);     // 1-based centre, floor
+        for (int c = std::max(1, cc - reach); c <= std::min(d2, cc + reach + 1); ++c)
+            for (int r = std::max(1, rc - reach); r <= std::min(d1, rc + reach + 1); ++r) {
+                const double dx = (double)r - cx, dy = (double)c - cy;
+                const double p1 = dx * v1x + dy * v1y, p2 = dx * v2x + dy * v2y;
+                if (std::sqrt(p1 * p1 / d11 + p2 * p2 / d22) <= dist) {
+                    if (n >= cap) { set_error("cnmfe_search_location_ellipse: out_ir too small (%lld entries)", (long long)cap); return -1; }
+                    out_ir[n++] = (int64_t)(c - 1) * d1 + (r - 1);
+                }
+            }
+        out_jc[k + 1] = n;
+    }
+    return 0;
+}

@@ -388,6 +388,38 @@ class Sources2D:
             self._mark("A_prev", self.A_prev)
             self._mark("C_prev", self.C_prev)
 
+    # ---- host-side brackets of the spatial update (library C++: csrc/host_spatial.cu) ----------------------------------
+    def determine_search_location(self, A=None, min_size=3.0, max_size=8.0, dist=3.0):
+        """IND = determine_search_location(obj.A, 'ellipse', options) (utilities/determine_search_location.m:57-92): the
+        reference's default search_method, as a (d, K) boolean csc matrix.  Usable as `search_fn`."""
+        A = sp.csc_matrix(self.A if A is None else A, dtype=np.float64)
+        A.sort_indices()
+        K = A.shape[1]
+        jc = np.ascontiguousarray(A.indptr, dtype=np.int64)
+        ir = np.ascontiguousarray(A.indices, dtype=np.int64)
+        pr = np.ascontiguousarray(A.data, dtype=np.float64)
+        reach = int(np.ceil(dist * max(max_size, min_size)))
+        cap = max(1, K * (2 * reach + 2) ** 2)
+        ojc = np.zeros(K + 1, dtype=np.int64)
+        oir = np.zeros(cap, dtype=np.int64)
+        L.check(self._lib.cnmfe_search_location_ellipse(self.d1, self.d2, K, _ptr(jc), _ptr(ir), _ptr(pr), float(min_size),
+                                                        float(max_size), float(dist), _ptr(ojc), _ptr(oir), cap))
+        n = int(ojc[K])
+        return sp.csc_matrix((np.ones(n, dtype=bool), oir[:n].copy(), ojc), shape=(self.d1 * self.d2, K))
+
+    def post_process_spatial(self, A_new=None, thr=0.01, sz=5):
+        """A_ = post_process_spatial(obj, A_new) with spatial_constraints = struct('circular', false, 'connected', true)
+        (the CNMFSetParms default): connectivity_constraint per neuron.  Usable as `post_process_fn`."""
+        A = sp.csc_matrix(self.A if A_new is None else A_new, dtype=np.float64).copy()
+        A.sort_indices()
+        jc = np.ascontiguousarray(A.indptr, dtype=np.int64)
+        ir = np.ascontiguousarray(A.indices, dtype=np.int64)
+        pr = np.ascontiguousarray(A.data, dtype=np.float64)
+        L.check(self._lib.cnmfe_connectivity_constraint(self.d1, self.d2, A.shape[1], _ptr(jc), _ptr(ir), _ptr(pr), float(thr), int(sz)))
+        out = sp.csc_matrix((pr, ir, jc), shape=A.shape)
+        out.eliminate_zeros()
+        return out
+
     def update_spatial_parallel(self, use_parallel=True, update_sn=False, IND=None, sync_host=True):
         """update_spatial_parallel(obj, use_parallel, update_sn).  IND: (d,K) boolean search mask
         (determine_search_location output, update_spatial_parallel.m:66); defaults to self.search_fn(self)."""

@@ -164,6 +164,18 @@ int cnmfe_host_unregister(void* p);
 /* obj.C, obj.C_raw, obj.S (K x T col-major), obj.P.kernel_pars (2 x K), obj.P.neuron_sn (K); any may be NULL */
 int cnmfe_get_temporal(cnmfe_ctx* ctx, double* C, double* C_raw, double* S, double* kernel_pars,
                        double* neuron_sn);
+/* ---- host-side brackets of the spatial update (plain C++, no device work, ctx-free) ----
+ * post_process_spatial with spatial_constraints.connected (@Sources2D/post_process_spatial.m:19-32 ->
+ * endoscope/connectivity_constraint.m): per column of A (d1*d2 x K CSC) 5x5 grey opening, threshold thr*max (0.01),
+ * 4-connected labelling, keep the component of the arg-max pixel.  pr is edited in place: removed entries become 0. */
+int cnmfe_connectivity_constraint(int d1, int d2, int K, const int64_t* jc, const int64_t* ir, double* pr,
+                                  double thr, int sz);
+/* determine_search_location(A, 'ellipse', params) (utilities/determine_search_location.m:57-92): search mask as a CSC
+ * pattern (out_jc K+1, out_ir sorted).  out_ir needs cap >= K * (2*ceil(dist*max_size) + 2)^2 entries.
+ * Defaults of the reference: min_size 3, max_size 8, dist 3. */
+int cnmfe_search_location_ellipse(int d1, int d2, int K, const int64_t* jc, const int64_t* ir, const double* pr,
+                                  double min_size, double max_size, double dist, int64_t* out_jc, int64_t* out_ir,
+                                  int64_t cap);
 /* block the host until all queued device work of ctx is done */
 int cnmfe_sync(cnmfe_ctx* ctx);
 /* CUDA-event timing of the kernels on the ctx stream: begin/end bracket a region, returns milliseconds */

@@ -1,20 +1,36 @@
 function update_spatial_parallel(obj, use_parallel, update_sn) %#ok<INUSL>
-%% drop-in for ca_source_extraction/@Sources2D/update_spatial_parallel.m on B200 (update_sn = true is not built).
-if exist('update_sn', 'var') && ~isempty(update_sn) && update_sn
-    error('cnmfe:b200', 'update_sn=true is not available in the B200 path');
-end
+%% drop-in for ca_source_extraction/@Sources2D/update_spatial_parallel.m on B200.
+if ~exist('update_sn', 'var') || isempty(update_sn); update_sn = false; end
 h = cnmfe_b200_handle(obj);
 search_method = obj.options.search_method;
 if strcmpi(search_method, 'dilate'); obj.options.se = []; end
-IND = sparse(logical(determine_search_location(obj.A, search_method, obj.options)));   % stays MATLAB (:66)
+if strcmpi(search_method, 'ellipse') && ~isinf(obj.options.dist)
+    % library C++ (cnmfe_search_location_ellipse), same result as determine_search_location(obj.A, 'ellipse', options) (:66)
+    [jc, ir] = cnmfe_b200_mex('search_location', obj.A, obj.options.d1, obj.options.d2, obj.options.min_size, obj.options.max_size, obj.options.dist);
+    jj = zeros(numel(ir), 1); for k = 1:numel(jc)-1; jj(jc(k)+1:jc(k+1)) = k; end
+    IND = sparse(ir + 1, jj, true, size(obj.A,1), size(obj.A,2));
+else
+    IND = sparse(logical(determine_search_location(obj.A, search_method, obj.options)));   % 'dilate' stays MATLAB (:66)
+end
 cnmfe_b200_mex('set_neurons', h, obj.A, obj.C);
 cnmfe_b200_mex('set_prev', h, obj.A_prev, obj.C_prev);
 cnmfe_b200_mex('set_sn', h, obj.P.sn);
 cnmfe_b200_mex('set_search', h, IND);
-vals = cnmfe_b200_mex('update_spatial', h, nnz(IND));
+if update_sn
+    [vals, obj.P.sn] = cnmfe_b200_mex('update_spatial', h, nnz(IND), true, obj.options.d1, obj.options.d2);   % (:191-194, :337-339)
+else
+    vals = cnmfe_b200_mex('update_spatial', h, nnz(IND));
+end
 [ii, jj] = find(IND);
 A_new = sparse(ii, jj, vals, size(IND,1), size(IND,2));
-obj.A = obj.post_process_spatial(obj.reshape(A_new, 2));                                  % stays MATLAB (:341)
+sc = obj.options.spatial_constraints;
+if sc.connected && ~sc.circular
+    Atmp = cnmfe_b200_mex('post_process_spatial', A_new, obj.options.d1, obj.options.d2);    % connectivity_constraint per neuron (:341)
+    [ii2, jj2, vv2] = find(Atmp);                                                             % removed entries come back as explicit zeros
+    obj.A = sparse(ii2, jj2, vv2, size(Atmp,1), size(Atmp,2));
+else
+    obj.A = obj.post_process_spatial(obj.reshape(A_new, 2));                                  % circular_constraints stays MATLAB
+end
 if strcmpi(obj.options.background_model, 'ring')
     obj.b0_new = cell2mat(obj.P.Ymean) - obj.reshape(obj.A*mean(obj.C,2), 2);
 end

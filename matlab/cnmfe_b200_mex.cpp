@@ -8,6 +8,7 @@
 // Usage:  varargout = cnmfe_b200_mex(command, args...)   -- see matlab/@Sources2D/*.m for the call sites.
 #include <cstdint>
 #include <cstring>
+#include <cmath>
 #include <string>
 #include <vector>
 #include "mex.h"
@@ -117,10 +118,15 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         check(cnmfe_get_ring(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), mxGetPr(plhs[0]), mxGetPr(plhs[1])), cmd);
     } else if (c == "update_background") {
         check(cnmfe_update_background(ctx_of(prhs[1])), cmd);
-    } else if (c == "update_spatial") {   // vals = update_spatial(h, nnz(IND))  -> values on find(IND) order
-        check(cnmfe_update_spatial(ctx_of(prhs[1])), cmd);
+    } else if (c == "update_spatial") {   // [vals, sn] = update_spatial(h, nnz(IND), update_sn, d1, d2)  -> values on find(IND) order
+        const int usn = (nrhs > 3 && !mxIsEmpty(prhs[3])) ? (int)mxGetScalar(prhs[3]) : 0;
+        check(cnmfe_update_spatial_ex(ctx_of(prhs[1]), usn), cmd);
         plhs[0] = mxCreateDoubleMatrix((mwSize)mxGetScalar(prhs[2]), 1, mxREAL);
         check(cnmfe_get_spatial(ctx_of(prhs[1]), mxGetPr(plhs[0])), "get_spatial");
+        if (nlhs > 1) {                     // obj.P.sn after update_sn (update_spatial_parallel.m:191-194, :337-339)
+            plhs[1] = mxCreateDoubleMatrix((mwSize)mxGetScalar(prhs[4]), (mwSize)mxGetScalar(prhs[5]), mxREAL);
+            check(cnmfe_get_sn_map(ctx_of(prhs[1]), mxGetPr(plhs[1])), "get_sn_map");
+        }
     } else if (c == "set_spatial") {
         check(cnmfe_set_spatial(ctx_of(prhs[1]), mxGetPr(prhs[2])), cmd);
     } else if (c == "update_temporal") {   // [C, C_raw, S, kernel_pars, neuron_sn] = update_temporal(h, K, T)
@@ -146,6 +152,27 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     } else if (c == "get_sn") {   // sn = get_sn(Y (T x N))
         plhs[0] = mxCreateDoubleMatrix(mxGetN(prhs[1]), 1, mxREAL);
         check(cnmfe_get_sn(mxGetPr(prhs[1]), (int)mxGetM(prhs[1]), (int)mxGetN(prhs[1]), mxGetPr(plhs[0]), 0), cmd);
+    } else if (c == "post_process_spatial") {   // A_ = post_process_spatial(A sparse d x K, d1, d2): connectivity_constraint per neuron
+        const mwSize K = mxGetN(prhs[1]);
+        const mwIndex* jcm = mxGetJc(prhs[1]); const mwIndex* irm = mxGetIr(prhs[1]);
+        std::vector<int64_t> jc(jcm, jcm + K + 1), ir(irm, irm + jcm[K]);
+        plhs[0] = mxDuplicateArray(prhs[1]);               // same pattern; removed entries become explicit zeros
+        check(cnmfe_connectivity_constraint((int)mxGetScalar(prhs[2]), (int)mxGetScalar(prhs[3]), (int)K, jc.data(), ir.data(),
+                                            mxGetPr(plhs[0]), 0.01, 5), cmd);
+    } else if (c == "search_location") {   // [jc, ir] = search_location(A sparse d x K, d1, d2, min_size, max_size, dist): 0-based CSC pattern
+        const mwSize K = mxGetN(prhs[1]);
+        const mwIndex* jcm = mxGetJc(prhs[1]); const mwIndex* irm = mxGetIr(prhs[1]);
+        std::vector<int64_t> jc(jcm, jcm + K + 1), ir(irm, irm + jcm[K]);
+        const double mn = mxGetScalar(prhs[4]), mx = mxGetScalar(prhs[5]), dist = mxGetScalar(prhs[6]);
+        const int64_t reach = (int64_t)std::ceil(dist * (mx > mn ? mx : mn));
+        const int64_t cap = (int64_t)K * (2 * reach + 2) * (2 * reach + 2) + 1;
+        std::vector<int64_t> ojc(K + 1), oir((size_t)cap);
+        check(cnmfe_search_location_ellipse((int)mxGetScalar(prhs[2]), (int)mxGetScalar(prhs[3]), (int)K, jc.data(), ir.data(),
+                                            mxGetPr(prhs[1]), mn, mx, dist, ojc.data(), oir.data(), cap), cmd);
+        plhs[0] = mxCreateDoubleMatrix(K + 1, 1, mxREAL);
+        plhs[1] = mxCreateDoubleMatrix((mwSize)ojc[K], 1, mxREAL);
+        for (mwSize k = 0; k <= K; ++k) mxGetPr(plhs[0])[k] = (double)ojc[k];
+        for (int64_t e = 0; e < ojc[K]; ++e) mxGetPr(plhs[1])[e] = (double)oir[e];
     } else {
         mexErrMsgIdAndTxt("cnmfe:usage", "unknown command %s", cmd);
     }
