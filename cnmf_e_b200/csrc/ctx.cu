@@ -264,6 +264,11 @@ void build_local(const cnmfe_ctx* c, const Patch& P, const HostCsc& M, SelMode s
     const int nrw = (rows == ROWS_PATCH) ? P.nr : P.nrb;
     for (int k = 0; k < M.K; ++k) {
         const int64_t e0 = M.jc[k], e1 = M.jc[k + 1];
+        if (e1 == e0) continue;                          // no entries: never selected
+        // sorted rows: the FOV columns of this neuron span [first / d1, last / d1]; if that misses the block, no entry can be
+        // in the block or the patch -- skip without the per-entry pass (keeps the planning O(local nnz + K) when the FOV is
+        // tiled by many patches / sharded over GPUs)
+        if (M.ir[e0] <= M.ir[e1 - 1] && (M.ir[e1 - 1] / d1 < P.block.c0 || M.ir[e0] / d1 > P.block.c1)) continue;
         if ((size_t)(e1 - e0) > lidx.size()) lidx.resize((size_t)(e1 - e0));
         double sum = 0.0;
         bool any = false;
@@ -1322,6 +1327,40 @@ extern "C" int cnmfe_debug_second_moments(cnmfe_ctx* c, int ip, int use_tensor, 
     return 0;
 }
 extern "C" int cnmfe_last_gram_was_tensor(cnmfe_ctx* c) { return c ? c->last_gram_tensor : 0; }
+// Host planning under test on CPU: the block / patch-local view build_local() derives from a MATLAB CSC matrix.  No device
+// work.  sel: 0 sum-in-block > 0, 1 sum-in-halo > 0, 2 any-in-patch; rows: 0 block pixels, 1 block index of patch pixels only,
+// 2 patch pixels.  Output arrays must hold K (+1) / nrows + 1 / nnz entries; *n_local and *n_kept receive the used sizes.
+extern "C" int cnmfe_debug_local_view(int d1, int d2, const int* patch_pos, const int* block_pos, int K, const int64_t* jc,
+                                      const int64_t* ir, const double* pr, int sel, int rows, const int64_t* vjc,
+                                      const int64_t* vir, const double* vpr, int* n_local, int* n_kept, int* ids, int* ptr,
+                                      int* col, double* val, int64_t* entry_src, int* cptr, int* crow, double* cval, int* bbox) {
+    if (!patch_pos || !block_pos || !jc || !n_local || !n_kept || sel < 0 || sel > 2 || rows < 0 || rows > 2) { set_error("cnmfe_debug_local_view: bad arguments"); return -1; }
+    cnmfe_ctx c;
+    c.d1 = d1; c.d2 = d2;
+    Patch P;
+    P.patch = {patch_pos[0] - 1, patch_pos[1] - 1, patch_pos[2] - 1, patch_pos[3] - 1};
+    P.block = {block_pos[0] - 1, block_pos[1] - 1, block_pos[2] - 1, block_pos[3] - 1};
+    P.nr = P.patch.r1 - P.patch.r0 + 1; P.nc = P.patch.c1 - P.patch.c0 + 1;
+    P.nrb = P.block.r1 - P.block.r0 + 1; P.ncb = P.block.c1 - P.block.c0 + 1;
+    P.dp = P.nr * P.nc; P.db = P.nrb * P.ncb;
+    HostCsc M, V;
+    M.set(K, jc, ir, pr);
+    if (vjc) V.set(K, vjc, vir, vpr);
+    LocalSparse L;
+    build_local(&c, P, M, (SelMode)sel, (RowSpace)rows, vjc ? &V : nullptr, &L);
+    *n_local = L.K(); *n_kept = (int)L.col.size();
+    std::copy(L.ids.begin(), L.ids.end(), ids);
+    std::copy(L.ptr.begin(), L.ptr.end(), ptr);
+    std::copy(L.col.begin(), L.col.end(), col);
+    std::copy(L.val.begin(), L.val.end(), val);
+    std::copy(L.entry_src.begin(), L.entry_src.end(), entry_src);
+    std::copy(L.cptr.begin(), L.cptr.end(), cptr);
+    std::copy(L.crow.begin(), L.crow.end(), crow);
+    std::copy(L.cval.begin(), L.cval.end(), cval);
+    std::copy(L.bbox.begin(), L.bbox.end(), bbox);
+    return 0;
+}
+
 
 #include "ctx_svd.inc"
 #include "ctx_ssub.inc"

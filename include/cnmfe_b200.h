@@ -176,6 +176,12 @@ int cnmfe_connectivity_constraint(int d1, int d2, int K, const int64_t* jc, cons
 int cnmfe_search_location_ellipse(int d1, int d2, int K, const int64_t* jc, const int64_t* ir, const double* pr,
                                   double min_size, double max_size, double dist, int64_t* out_jc, int64_t* out_ir,
                                   int64_t cap);
+/* test hook (CPU, no device work): the block / patch-local view the host planning derives from a MATLAB CSC matrix
+ * (patch_pos / block_pos 1-based inclusive [r0 r1 c0 c1]); see csrc/ctx.cu build_local */
+int cnmfe_debug_local_view(int d1, int d2, const int* patch_pos, const int* block_pos, int K, const int64_t* jc,
+                           const int64_t* ir, const double* pr, int sel, int rows, const int64_t* vjc, const int64_t* vir,
+                           const double* vpr, int* n_local, int* n_kept, int* ids, int* ptr, int* col, double* val,
+                           int64_t* entry_src, int* cptr, int* crow, double* cval, int* bbox);
 /* block the host until all queued device work of ctx is done */
 int cnmfe_sync(cnmfe_ctx* ctx);
 /* CUDA-event timing of the kernels on the ctx stream: begin/end bracket a region, returns milliseconds */
