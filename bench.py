@@ -180,7 +180,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm
-SAMPLE = dict(d1=64, d2=64, T=1000, K=6, ring=RING)
+SAMPLE = dict(d1=96, d2=96, T=1500, K=12, ring=RING)   # ~5-12 s of CPU work per iteration on 8-16 host cores
 
 
 def cpu_reference_step(state=None):
