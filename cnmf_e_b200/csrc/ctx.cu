@@ -34,11 +34,6 @@ struct HostCsc {
         ir.assign(ir_, ir_ + jc_[K_]);
         if (pr_) pr.assign(pr_, pr_ + jc_[K_]); else pr.assign((size_t)jc_[K_], 1.0);
     }
-    double lookup(int k, int64_t row) const {
-        auto b = ir.begin() + jc[k], e = ir.begin() + jc[k + 1];
-        auto it = std::lower_bound(b, e, row);
-        return (it != e && *it == row) ? pr[it - ir.begin()] : 0.0;
-    }
 };
 
 struct Rect { int r0, r1, c0, c1; };   // 0-based inclusive, FOV coordinates

@@ -22,7 +22,6 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 
 // ------------------------------------------------------------------------------------------------ arena
-static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct SlotLayout {
     size_t yb, c, s, pv, pw, h, hh, gp, scr, sv, sw, x, ybuf, pt, pl, st, sl, total;

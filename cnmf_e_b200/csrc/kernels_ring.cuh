@@ -332,7 +332,6 @@ __global__ void __launch_bounds__(RING_SOLVE_THREADS, 2) ring_solve_kernel(RingS
     const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
     const int pr = p % g.nr + g.pr_off, pc = p / g.nr + g.pc_off;
     const size_t qm = (size_t)pc * g.nrb + pr;
-    const int NMAX = g.nnb + 1;
     long long pt0 = PROF ? clock64() : 0;
 #define RING_PROF(i) do { if (PROF && tid == 0) { long long _t = clock64(); atomicAdd(a.prof + (i), (unsigned long long)(_t - pt0)); pt0 = _t; } } while (0)
     // shared layout

@@ -195,7 +195,6 @@ __global__ void temporal_build_negWtA_kernel(RingGeom g, const int* __restrict__
     int db = g.nrb * g.ncb;
     if (q >= db) return;
     int r = q % g.nrb, c = q / g.nrb;
-    int dp = g.nr * g.nc;
     for (int i = 0; i < g.nnb; ++i) {
         int r2 = r - off_r[i], c2 = c - off_c[i];        // candidate centre pixel (block coords)
         int pr = r2 - g.pr_off, pc = c2 - g.pc_off;      // patch coords
