@@ -1247,6 +1247,48 @@ extern "C" int cnmfe_update_temporal_finish(cnmfe_ctx* c) {
     return 0;
 }
 
+// Multi-GPU variant of cnmfe_update_temporal_finish: this rank divides and deconvolves only the traces
+// [k0, k1) of the merged C_raw; the other rows of C, C_raw, S and of the per-trace outputs are zeroed, so that a SUM
+// all-reduce over ranks holding disjoint ranges assembles the full result (x + 0 is exact).  Buffers for that exchange:
+// cnmfe_temporal_state_buffers.  OPT-IN (Sources2D option shard_deconv): written without GPU time left in round 1 --
+// validate against the unsharded path on >= 2 GPUs before making it the default.
+extern "C" int cnmfe_update_temporal_finish_part(cnmfe_ctx* c, int k0, int k1) {
+    if (!c) { set_error("cnmfe_update_temporal_finish_part: null ctx"); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    const int T = c->T, K = c->K;
+    if (K == 0) return 0;
+    if (k0 < 0 || k1 > K || k0 > k1) { set_error("cnmfe_update_temporal_finish_part: range [%d, %d) outside [0, %d)", k0, k1, K); return -1; }
+    phase_begin(c);
+    const int n = k1 - k0;
+    for (double* buf : {c->C, c->Craw, c->S}) {
+        if (k0 > 0) CNMFE_CUDA_OK(cudaMemsetAsync(buf, 0, (size_t)k0 * T * 8, c->st));
+        if (k1 < K) CNMFE_CUDA_OK(cudaMemsetAsync(buf + (size_t)k1 * T, 0, (size_t)(K - k1) * T * 8, c->st));
+    }
+    CNMFE_CUDA_OK(cudaMemsetAsync(c->outs, 0, (size_t)K * 48, c->st));
+    if (n > 0) {
+        double* num = c->num + (size_t)k0 * T;
+        { dim3 gg((T + 255) / 256, n); LAUNCH(temporal_divide_kernel, gg, 256, 0, c->st, num, c->den + k0, n, T); }
+        if (c->opt.deconv_flag) {
+            if (deconv_batch_dev(num, T, n, c->opt.deconv, nullptr, nullptr, 1, c->C + (size_t)k0 * T, c->S + (size_t)k0 * T,
+                                 c->Craw + (size_t)k0 * T, c->outs + (size_t)k0 * 6, &c->arena, c->st)) return -1;
+        } else {
+            LAUNCH(rows_sub_min_kernel, n, 256, 0, c->st, num, T);
+            CNMFE_CUDA_OK(cudaMemcpyAsync(c->Craw + (size_t)k0 * T, num, (size_t)n * T * 8, cudaMemcpyDeviceToDevice, c->st));
+            CNMFE_CUDA_OK(cudaMemcpyAsync(c->C + (size_t)k0 * T, num, (size_t)n * T * 8, cudaMemcpyDeviceToDevice, c->st));
+        }
+    }
+    phase_end(c, 5);
+    CNMFE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// device buffers of obj.C, obj.C_raw, obj.S (K x T each, trace contiguous) and of the 6 per-trace outputs (K x 6)
+extern "C" int cnmfe_temporal_state_buffers(cnmfe_ctx* c, double** C_dev, double** Craw_dev, double** S_dev, double** outs_dev) {
+    if (!c || !C_dev || !Craw_dev || !S_dev || !outs_dev) { set_error("cnmfe_temporal_state_buffers: null"); return -1; }
+    *C_dev = c->C; *Craw_dev = c->Craw; *S_dev = c->S; *outs_dev = c->outs;
+    return 0;
+}
+
 extern "C" int cnmfe_update_temporal(cnmfe_ctx* c) {
     if (cnmfe_update_temporal_patches(c)) return -1;
     return cnmfe_update_temporal_finish(c);

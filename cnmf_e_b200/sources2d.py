@@ -13,6 +13,7 @@ Out of scope hooks, supplied by the caller exactly where 
   post_process_spatial(...)              -> `self.post_process_fn` (default identity)
 """
 import ctypes
+import os
 
 import numpy as np
 import scipy.sparse as sp
@@ -53,6 +54,14 @@ def patch_geometry(d1, d2, patch_dims, w_overlap):
     return patch_pos, block_pos
 
 
+def trace_range(K, rank, world_size):
+    """Contiguous block [k0, k1) of the K traces handled by `rank` when the final deconvTemporal is split over ranks
+    (sizes differ by at most one)."""
+    base, rem = divmod(int(K), int(world_size))
+    k0 = rank * base + min(rank, rem)
+    return k0, k0 + base + (1 if rank < rem else 0)
+
+
 def patch_owners(npatch, world_size):
     """Blocked patch -> rank assignment (patches in MATLAB linear order): rank r owns a contiguous run."""
     return np.array([(i * world_size) // npatch for i in range(npatch)], dtype=np.int64)
@@ -80,7 +89,9 @@ class Sources2D:
                             num_neighbors=num_neighbors, thresh_outlier=np.nan, spatial_algorithm="hals", maxIter=5,
                             deconv_flag=True, deconv_options=dict(type="ar1", method="foopsi", smin=-5,
                                                                   optimize_pars=True, optimize_b=True, max_tau=100),
-                            replicate_spatial_aprev_quirk=True, use_tensor_gram=True, nb=1)
+                            replicate_spatial_aprev_quirk=True, use_tensor_gram=True, nb=1,
+                            # multi-GPU: split the final deconvTemporal over ranks; opt-in until validated on >= 2 GPUs
+                            shard_deconv=bool(int(os.environ.get("CNMFE_SHARD_DECONV", "0"))))
         if options:
             self.options.update(options)
         self.patch_pos, self.block_pos = patch_geometry(self.d1, self.d2, patch_dims, ring_radius)
@@ -473,7 +484,13 @@ class Sources2D:
         L.check(self._lib.cnmfe_update_temporal_patches(self._h))
         if self.world_size > 1:
             self._allreduce_merge_buffers()
-        L.check(self._lib.cnmfe_update_temporal_finish(self._h))
+        if self.world_size > 1 and self.options.get("shard_deconv"):
+            K = self.A.shape[1]
+            k0, k1 = trace_range(K, self.rank, self.world_size)
+            L.check(self._lib.cnmfe_update_temporal_finish_part(self._h, k0, k1))
+            self._allreduce_temporal_state(K)
+        else:
+            L.check(self._lib.cnmfe_update_temporal_finish(self._h))
         if sync_host:
             self.pull_temporal()
 
@@ -563,6 +580,29 @@ class Sources2D:
             tn.copy_(a)
             td.copy_(b)
             torch.cuda.synchronize(self.device)
+
+    def _allreduce_temporal_state(self, K):
+        """After cnmfe_update_temporal_finish_part: every rank holds its own rows of C, C_raw, S and of the per-trace
+        outputs and zeros elsewhere; a SUM all-reduce (disjoint supports => a gather, x + 0 exact) completes them."""
+        import torch
+        import torch.distributed as dist
+        ptrs = [ctypes.c_void_p() for _ in range(4)]
+        L.check(self._lib.cnmfe_temporal_state_buffers(self._h, *[ctypes.byref(p) for p in ptrs]))
+        L.check(self._lib.cnmfe_sync(self._h))
+
+        class _Dev:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = dict(shape=(n,), typestr="<f8", data=(ptr, False), version=3)
+
+        for p, n in zip(ptrs, (K * self.T, K * self.T, K * self.T, K * 6)):
+            t = torch.as_tensor(_Dev(p.value, n), device=torch.device("cuda", self.device))
+            if dist.get_backend() == "nccl":
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            else:
+                a = t.cpu()
+                dist.all_reduce(a, op=dist.ReduceOp.SUM)
+                t.copy_(a)
+        torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------ timing helpers (bench.py)
     def phase_ms(self):

@@ -164,6 +164,11 @@ int cnmfe_host_unregister(void* p);
 /* obj.C, obj.C_raw, obj.S (K x T col-major), obj.P.kernel_pars (2 x K), obj.P.neuron_sn (K); any may be NULL */
 int cnmfe_get_temporal(cnmfe_ctx* ctx, double* C, double* C_raw, double* S, double* kernel_pars,
                        double* neuron_sn);
+/* Multi-GPU split of the final deconvTemporal (opt-in, see csrc/ctx.cu): this rank finishes only the traces
+ * [k0, k1) and zeroes the other rows of C, C_raw, S and of the per-trace outputs; a SUM all-reduce of the four device buffers
+ * over ranks with disjoint ranges then gives every rank the full result. */
+int cnmfe_update_temporal_finish_part(cnmfe_ctx* ctx, int k0, int k1);
+int cnmfe_temporal_state_buffers(cnmfe_ctx* ctx, double** C_dev, double** Craw_dev, double** S_dev, double** outs_dev);
 /* ---- host-side brackets of the spatial update (plain C++, no device work, ctx-free) ----
  * post_process_spatial with spatial_constraints.connected (@Sources2D/post_process_spatial.m:19-32 ->
  * endoscope/connectivity_constraint.m): per column of A (d1*d2 x K CSC) 5x5 grey opening, threshold thr*max (0.01),

@@ -74,3 +74,14 @@ def test_two_rank_merge_matches_single_process():
         p.join(300)
         assert p.exitcode == 0
     assert q.get(timeout=10) < 1e-9
+
+
+def test_trace_range_partition():
+    """Split of the final deconvTemporal over ranks (opt-in `shard_deconv`): contiguous, complete, balanced."""
+    from cnmf_e_b200.sources2d import trace_range
+    for K, w in [(300, 8), (7, 3), (2, 4), (0, 2), (2400, 8), (1000, 1)]:
+        r = [trace_range(K, i, w) for i in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == K
+        assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in r]
+        assert max(sizes) - min(sizes) <= 1
