@@ -49,6 +49,7 @@ SYMBOLS = {
     "cnmfe_hals_temporal_uv": (I, [V, V, I, I, V, I, ctypes.POINTER(DeconvOpts), V, V, V, V, I]),
     "cnmfe_update_temporal_finish_part": (I, [V, I, I]),
     "cnmfe_temporal_state_buffers": (I, [V, V, V, V, V]),
+    "cnmfe_graph_conn_comp": (I, [I, V, V, V, V]),
     "cnmfe_debug_local_view": (I, [I, I, V, V, I, V, V, V, I, I, V, V, V, V, V, V, V, V, V, V, V, V, V, V]),
     "cnmfe_connectivity_constraint": (I, [I, I, I, V, V, V, ctypes.c_double, I]),
     "cnmfe_search_location_ellipse": (I, [I, I, I, V, V, V, ctypes.c_double, ctypes.c_double, ctypes.c_double, V, V, ctypes.c_int64]),

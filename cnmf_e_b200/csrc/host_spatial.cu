@@ -1,6 +1,7 @@
-// host_spatial.cu -- the two per-neuron routines that bracket every spatial update in the reference:
+// host_spatial.cu -- host-side helpers of the reference that sit right next to the hot path:
 //   determine_search_location(A, 'ellipse', params)   ca_source_extraction/utilities/determine_search_location.m:57-92
 //   post_process_spatial / connectivity_constraint    @Sources2D/post_process_spatial.m:19-32, endoscope/connectivity_constraint.m
+//   graph_connected_comp                               utilities/graph_conn_comp_mex.cpp (the reference's only native file)
 // They are host code in the reference too (MATLAB, per neuron on a small crop); here they are plain C++ on the CSC matrix so that
 // the host mirror / MEX gateway need not leave the library between cnmfe_update_spatial calls.  No CUDA in this file.
 #include <algorithm>
@@ -189,5 +190,37 @@ extern "C" int cnmfe_search_location_ellipse(int d1, int d2, int K, const int64_
             }
         out_jc[k + 1] = n;
     }
+    return 0;
+}
+
+// [l, c] = graph_connected_comp(sA)  (ca_source_extraction/utilities/graph_connected_comp.m:26 -> the reference's only native
+// file, utilities/graph_conn_comp_mex.cpp): component labels 1..c of the nodes of a sparse adjacency matrix, numbered in the
+// order of their smallest node.  A node's neighbours are the rows stored in its COLUMN (the reference follows the CSC lists
+// only, so a non-symmetric matrix gives reachability from the seed and -- as there -- it is an error if that reaches a node
+// labelled earlier).  Used by the merge routines (merge_components.m:47, MergeNeighbors.m:60, quickMerge.m:71, ...);
+// SURVEY.md 8f row 4.
+extern "C" int cnmfe_graph_conn_comp(int n, const int64_t* jc, const int64_t* ir, uint32_t* labels, int* ncomp) {
+    if (n < 0 || !jc || !labels || !ncomp || (n > 0 && jc[n] > 0 && !ir)) { set_error("cnmfe_graph_conn_comp: bad arguments"); return -1; }
+    std::fill(labels, labels + n, 0u);
+    std::vector<int64_t> frontier;
+    frontier.reserve((size_t)n);
+    uint32_t cur = 0;
+    for (int64_t seed = 0; seed < n; ++seed) {
+        if (labels[seed]) continue;
+        ++cur;
+        labels[seed] = cur;
+        frontier.clear();
+        frontier.push_back(seed);
+        for (size_t head = 0; head < frontier.size(); ++head) {
+            const int64_t u = frontier[head];
+            for (int64_t e = jc[u]; e < jc[u + 1]; ++e) {
+                const int64_t v = ir[e];
+                if (v < 0 || v >= n) { set_error("cnmfe_graph_conn_comp: row index %lld outside [0, %d)", (long long)v, n); return -1; }
+                if (!labels[v]) { labels[v] = cur; frontier.push_back(v); }
+                else if (labels[v] != cur) { set_error("cnmfe_graph_conn_comp: mixed labeling %u <-> %u (adjacency not symmetric)", labels[v], cur); return -1; }
+            }
+        }
+    }
+    *ncomp = (int)cur;
     return 0;
 }

@@ -181,6 +181,10 @@ int cnmfe_connectivity_constraint(int d1, int d2, int K, const int64_t* jc, cons
 int cnmfe_search_location_ellipse(int d1, int d2, int K, const int64_t* jc, const int64_t* ir, const double* pr,
                                   double min_size, double max_size, double dist, int64_t* out_jc, int64_t* out_ir,
                                   int64_t cap);
+/* [l, c] = graph_connected_comp(sA) (utilities/graph_connected_comp.m:26 -> utilities/graph_conn_comp_mex.cpp, the
+ * reference's only native file; used by the merge routines): labels 1..c in the order of each component's smallest node.
+ * Host-side, ctx-free. */
+int cnmfe_graph_conn_comp(int n, const int64_t* jc, const int64_t* ir, uint32_t* labels, int* ncomp);
 /* test hook (CPU, no device work): the block / patch-local view the host planning derives from a MATLAB CSC matrix
  * (patch_pos / block_pos 1-based inclusive [r0 r1 c0 c1]); see csrc/ctx.cu build_local */
 int cnmfe_debug_local_view(int d1, int d2, const int* patch_pos, const int* block_pos, int K, const int64_t* jc,

@@ -96,3 +96,39 @@ def test_search_location_isotropic_known_answer(built_lib):
     m = IND.toarray().reshape(d1, d2, order="F")
     rr, cc = np.meshgrid(np.arange(d1), np.arange(d2), indexing="ij")
     assert np.array_equal(m, np.sqrt((rr - 20.0) ** 2 + (cc - 20.0) ** 2) / 3.0 <= 3.0)
+
+
+def test_graph_conn_comp_matches_scipy(built_lib):
+    """cnmfe_graph_conn_comp = the reference's graph_conn_comp_mex: labels 1..c ordered by each component's smallest node."""
+    import ctypes
+    from scipy.sparse.csgraph import connected_components
+    from cnmf_e_b200 import _lib as L
+    rng = np.random.default_rng(3)
+    for n, dens in [(1, 0.0), (12, 0.08), (60, 0.03), (200, 0.004)]:
+        M = sp.random(n, n, density=dens, random_state=int(rng.integers(1 << 30)), format="csc")
+        S = sp.csc_matrix(((M + M.T) != 0).astype(float))           # symmetric flag matrix, as the merge routines build it
+        S.sort_indices()
+        jc, ir = S.indptr.astype(np.int64), S.indices.astype(np.int64)
+        lab = np.zeros(n, np.uint32)
+        nc = ctypes.c_int(0)
+        L.check(built_lib.cnmfe_graph_conn_comp(n, jc.ctypes.data_as(ctypes.c_void_p), ir.ctypes.data_as(ctypes.c_void_p),
+                                                lab.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nc)))
+        c_ref, l_ref = connected_components(S, directed=False)
+        assert nc.value == c_ref
+        # same partition, and our numbering follows the smallest node of each component
+        first = {}
+        for i, l in enumerate(lab):
+            first.setdefault(int(l), i)
+        assert sorted(first) == list(range(1, c_ref + 1))
+        assert [first[l] for l in range(1, c_ref + 1)] == sorted(first.values())
+        for i in range(n):
+            for j in range(i + 1, n):
+                assert (lab[i] == lab[j]) == (l_ref[i] == l_ref[j])
+    # a non-symmetric matrix that reaches an earlier component is an error, as in the reference
+    A = sp.csc_matrix(np.array([[0, 0, 0], [0, 0, 0], [1, 0, 0.]]).T)   # column 2 lists row 0: node 2 -> node 0
+    A.sort_indices()
+    jc, ir = A.indptr.astype(np.int64), A.indices.astype(np.int64)
+    lab = np.zeros(3, np.uint32); nc = ctypes.c_int(0)
+    rc = built_lib.cnmfe_graph_conn_comp(3, jc.ctypes.data_as(ctypes.c_void_p), ir.ctypes.data_as(ctypes.c_void_p),
+                                         lab.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nc))
+    assert rc != 0 and b"mixed labeling" in built_lib.cnmfe_last_error()
