@@ -1,0 +1,40 @@
+"""CPU-only: host-side option parsing of the deconvolveCa mirror (OASIS_matlab/deconvolveCa.m:208-355: defaults, struct then
+name/value merge, rejected values) and error behaviour of compute entry points without a CUDA device."""
+import numpy as np
+import pytest
+
+
+def test_make_deconv_opts_defaults_and_merge(built_lib):
+    from cnmf_e_b200.oasis import make_deconv_opts
+    d, pars, sn = make_deconv_opts()
+    assert (d.type, d.method, d.maxIter, d.optimize_b, d.optimize_pars, d.has_tau_range) == (1, 1, 10, 0, 0, 0)   # ar1, constrained
+    # the demo's deconv_options (demo_large_data_1p.m:36-42) + the name/value pairs HALS_temporal adds (:92)
+    demo = dict(type="ar1", method="foopsi", smin=-5, optimize_pars=True, optimize_b=True, max_tau=100)
+    d, pars, sn = make_deconv_opts(demo, maxIter=20, sn=3.5, pars=[0.95])
+    assert (d.type, d.method, d.maxIter, d.optimize_b, d.optimize_pars) == (1, 0, 20, 1, 1)
+    assert (d.smin, d.max_tau) == (-5.0, 100.0) and sn == 3.5 and pars == [0.95]
+    # name/value pairs win over the struct (deconvolveCa.m:233-246)
+    d, _, _ = make_deconv_opts(demo, method="thresholded", type="ar2", tau_range=(2, 50))
+    assert (d.type, d.method, d.has_tau_range) == (2, 2, 1) and tuple(d.tau_range) == (2.0, 50.0)
+    d, _, _ = make_deconv_opts({"lambda": 2.5})
+    assert d.lam == 2.5
+
+
+def test_make_deconv_opts_rejects_unknown(built_lib):
+    from cnmf_e_b200.oasis import make_deconv_opts
+    for bad in (dict(type="ar3"), dict(method="mcmc"), dict(nonsense=1), dict(remove_large_residuals=True)):
+        with pytest.raises(ValueError):
+            make_deconv_opts(bad)
+    make_deconv_opts(dict(window=200, shift=100, extra_params=None))          # accepted and ignored, as by the reference's methods here
+
+
+def test_compute_entry_points_fail_loudly_without_gpu(built_lib):
+    """No CPU fallback: on a box without a CUDA device a compute call raises with the driver's message."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from cnmf_e_b200 import oasis as G, _lib as L
+    with pytest.raises(L.CnmfeError):
+        G.GetSn(np.random.default_rng(0).normal(size=(2, 500)))
+    with pytest.raises(L.CnmfeError):
+        G.deconvolveCa(np.random.default_rng(0).normal(size=500), dict(type="ar1", method="foopsi"))
