@@ -231,6 +231,41 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ----------------------------------------------------------------------------------------------- full-size invariants
+def full_size_checks(A, IND, C, S, kernel_pars, neuron_sn, smin_mult=5.0):
+    """Size-independent properties of one update iteration, evaluated on the FULL-size host results after the timed
+    region (never inside it; nothing here runs on the GPU):
+      spatial  A >= 0 and supp(A) inside the search mask (update_spatial_parallel.m:321-335, nnls);
+      temporal oasisAR1 pool algebra of the final deconvTemporal (oasisAR1.m:101-109): S >= 0, S_t = C_t - g C_{t-1} where
+               S_t > 0, C_t = g C_{t-1} elsewhere (t >= 1), and every spike >= smin = 5 sn (deconvolveCa.m:116-118).
+    Returns max violations (relative to the trace scale) -- reported, not asserted."""
+    import scipy.sparse as sp
+    out = {}
+    try:
+        A = sp.csc_matrix(A)
+        out["A_min"] = float(A.data.min()) if A.nnz else 0.0
+        outside = A.copy(); outside.data[:] = 1.0
+        ind = sp.csc_matrix(IND).astype(np.float64)
+        out["A_nnz_outside_search_mask"] = int((outside - outside.multiply(ind)).count_nonzero())
+        g = np.asarray(kernel_pars, dtype=np.float64).reshape(len(neuron_sn), -1)[:, 0]
+        C, S = np.asarray(C), np.asarray(S)
+        scale = np.maximum(np.abs(C).max(axis=1), 1e-300)
+        pred = g[:, None] * C[:, :-1]
+        resid = C[:, 1:] - pred - S[:, 1:]
+        out["S_min"] = float(S.min()) if S.size else 0.0
+        out["max_rel_AR1_residual"] = float((np.abs(resid) / scale[:, None]).max()) if resid.size else 0.0
+        spikes = S[:, 1:] > 0
+        smin = smin_mult * np.asarray(neuron_sn, dtype=np.float64)
+        viol = np.where(spikes, smin[:, None] - S[:, 1:], 0.0)
+        out["max_rel_spike_below_smin"] = float(max(0.0, (viol / scale[:, None]).max())) if viol.size else 0.0
+        out["n_spikes"] = int(spikes.sum())
+        out["ok"] = bool(out["A_min"] >= 0.0 and out["A_nnz_outside_search_mask"] == 0 and out["S_min"] >= 0.0
+                         and out["max_rel_AR1_residual"] < 1e-9 and out["max_rel_spike_below_smin"] < 1e-9)
+    except Exception as e:   # a reporting aid must never take the bench line down
+        out["error"] = repr(e)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -357,6 +392,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
     e2e_val = float(d1) * d2 * T / float(te_t.item())
+    checks = full_size_checks(obj.A, IND, obj.C, obj.S, obj.P.get("kernel_pars"), obj.P.get("neuron_sn")) if rank == 0 else None
     # bytes the Sources2D mirror actually moved (it re-sends only host state that changed since the last sync)
     h2d = (obj.h2d_bytes - h2d0) // nE + d1 * d2 * 8
     d2h = (obj.d2h_bytes - d2h0) // nE
@@ -424,6 +460,7 @@ def run_ours(args):
                 data="synthetic",
                 config=dict(workload="configs[1]: synthetic 1p %dx%dx%d uint16, %d neurons, ring-BG r=18 (120 nbrs, bg_ssub=BGSSUB), one %dx%d patch per GPU, nnls spatial, foopsi/ar1 OASIS (smin=-5, optimize_pars, optimize_b)".replace("BGSSUB", str(args.bg_ssub)) % (d1, d2, T, K, D1, D2_PER_GPU),
                             l2="inputs (%.1f GB resident video per GPU) larger than L2; no flush needed" % (float(sum(int(b[1] - b[0] + 1) * int(b[3] - b[2] + 1) for b in nblk)) * T * 2 / 1e9),
+                            full_size_checks=checks,
                             seed=SEED, device_ms_per_step=1e3 * t_dev / args.steps, wall_ms_per_step=1e3 * wall / args.steps,
                             call_wall_ms_per_step=dict(zip(["update_background", "update_spatial", "update_temporal"], [float(x) / args.steps for x in call_ms])),
                             phase_ms_per_step=dict(zip(["gram", "ring_solve", "projections", "spatial_solve", "temporal_sweeps", "deconvTemporal", "other"],

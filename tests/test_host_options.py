@@ -38,3 +38,20 @@ def test_compute_entry_points_fail_loudly_without_gpu(built_lib):
         G.GetSn(np.random.default_rng(0).normal(size=(2, 500)))
     with pytest.raises(L.CnmfeError):
         G.deconvolveCa(np.random.default_rng(0).normal(size=500), dict(type="ar1", method="foopsi"))
+
+
+def test_bench_full_size_checks_on_oracle_output():
+    """bench.py's post-run invariants (A >= 0 inside the mask, oasisAR1 pool algebra of C/S) hold for the oracle's iteration and
+    flag a corrupted trace."""
+    import bench
+    from oracle import gen, cnmfe as OC
+    D = gen.make_synthetic(48, 40, 600, 5, seed=3, nblob=2)
+    o = OC.OracleSources2D(D["Y"], (48, 40), ring_radius=6, options=dict(spatial_algorithm="nnls"))
+    o.A, o.C = D["A0"].copy(), D["C0"].copy()
+    o.P["sn"] = np.full((48, 40), 10.0)
+    o.update_background_parallel(); o.update_spatial_parallel(IND=D["IND"]); o.update_temporal_parallel()
+    kp = np.array([p[0] for p in o.P["kernel_pars"]])
+    r = bench.full_size_checks(o.A, D["IND"], o.C, o.S, kp, o.P["neuron_sn"])
+    assert r["ok"] and r["n_spikes"] > 0, r
+    C2 = o.C.copy(); C2[0, 10] += 1.0
+    assert not bench.full_size_checks(o.A, D["IND"], C2, o.S, kp, o.P["neuron_sn"])["ok"]
