@@ -27,3 +27,13 @@ def test_defaults_match_reference_parser(built_lib):
     o = _lib.Options()
     built_lib.cnmfe_options_defaults(ctypes.byref(o))
     assert o.maxIter_temporal == 5 and o.deconv_flag == 1 and o.spatial_algorithm == 0
+
+
+def test_mex_gateway_type_checks_against_the_header():
+    """matlab/cnmfe_b200_mex.cpp cannot be built here (no MATLAB), but it must stay in sync with the C ABI: compile it
+    (-fsyntax-only) against a stub mex.h and the real include/cnmfe_b200.h."""
+    import subprocess
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I" + os.path.join(ROOT, "tests", "stubs"),
+                        "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "matlab", "cnmfe_b200_mex.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
