@@ -52,6 +52,7 @@ SYMBOLS = {
     "cnmfe_graph_conn_comp": (I, [I, V, V, V, V]),
     "cnmfe_debug_local_view": (I, [I, I, V, V, I, V, V, V, I, I, V, V, V, V, V, V, V, V, V, V, V, V, V, V]),
     "cnmfe_connectivity_constraint": (I, [I, I, I, V, V, V, ctypes.c_double, I]),
+    "cnmfe_circular_constraints": (I, [I, I, I, V, V, V, V, V, V, ctypes.c_int64]),
     "cnmfe_search_location_ellipse": (I, [I, I, I, V, V, V, ctypes.c_double, ctypes.c_double, ctypes.c_double, V, V, ctypes.c_int64]),
     "cnmfe_create": (I, [ctypes.POINTER(V), I, I, I, I, V, V, V, I, I, I]),
     "cnmfe_destroy": (None, [V]),

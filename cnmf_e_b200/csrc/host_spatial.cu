@@ -124,6 +124,110 @@ extern "C" int cnmfe_connectivity_constraint(int d1, int d2, int K, const int64_
     return 0;
 }
 
+// circular_constraints(img) (endoscope/circular_constraints.m:1-54): on the bounding box of the non-zeros (skipped when it is
+// a single row or column) zero the pixels whose gradient points away from the peak and that are below a third of it, keep
+// the 4-connected component of the peak dilated by a 3 x 3 square, then a 3 x 3 median filter (zero padded, medfilt2).
+// MATLAB gradient(): central differences inside, one-sided at the borders, spacing 1.
+extern "C" int cnmfe_circular_constraints(int d1, int d2, int K, const int64_t* jc, const int64_t* ir, const double* pr,
+                                          int64_t* out_jc, int64_t* out_ir, double* out_pr, int64_t cap) {
+    if (d1 <= 0 || d2 <= 0 || K < 0 || !jc || !out_jc || (K > 0 && jc[K] > 0 && (!ir || !pr))) { set_error("cnmfe_circular_constraints: bad arguments"); return -1; }
+    std::vector<double> img, tmp;
+    std::vector<unsigned char> comp, dil;
+    std::vector<int> stack;
+    int64_t n = 0;
+    out_jc[0] = 0;
+    auto emit = [&](int64_t lin, double v) -> bool {
+        if (v == 0.0) return true;
+        if (n >= cap || !out_ir || !out_pr) return false;
+        out_ir[n] = lin; out_pr[n] = v; ++n;
+        return true;
+    };
+    for (int k = 0; k < K; ++k) {
+        const int64_t e0 = jc[k], e1 = jc[k + 1];
+        int r0 = d1, r1 = -1, c0 = d2, c1 = -1;
+        for (int64_t e = e0; e < e1; ++e) {
+            if (pr[e] == 0.0) continue;
+            const int r = (int)(ir[e] % d1), c = (int)(ir[e] / d1);
+            r0 = std::min(r0, r); r1 = std::max(r1, r); c0 = std::min(c0, c); c1 = std::max(c1, c);
+        }
+        const bool degenerate = (r1 < 0) || (r1 - r0 < 1) || (c1 - c0 < 1);       // empty, or a single row / column: unchanged
+        if (degenerate) {
+            for (int64_t e = e0; e < e1; ++e) if (!emit(ir[e], pr[e])) { set_error("cnmfe_circular_constraints: output too small"); return -1; }
+            out_jc[k + 1] = n;
+            continue;
+        }
+        const int nr = r1 - r0 + 1, nc = c1 - c0 + 1;
+        img.assign((size_t)nr * nc, 0.0);
+        for (int64_t e = e0; e < e1; ++e) {
+            const int r = (int)(ir[e] % d1), c = (int)(ir[e] / d1);
+            if (pr[e] != 0.0) img[(size_t)(c - c0) * nr + (r - r0)] = pr[e];
+        }
+        auto I = [&](int r, int c) -> double { return img[(size_t)c * nr + r]; };
+        // peak: first maximum in column-major order
+        double vmax = I(0, 0);
+        int y0 = 0, x0 = 0;
+        for (int c = 0; c < nc; ++c) for (int r = 0; r < nr; ++r) if (I(r, c) > vmax) { vmax = I(r, c); y0 = r; x0 = c; }
+        tmp = img;
+        for (int c = 0; c < nc; ++c)
+            for (int r = 0; r < nr; ++r) {
+                const double fx = (c == 0) ? I(r, 1) - I(r, 0) : (c == nc - 1) ? I(r, nc - 1) - I(r, nc - 2) : (I(r, c + 1) - I(r, c - 1)) / 2.0;
+                const double fy = (r == 0) ? I(1, c) - I(0, c) : (r == nr - 1) ? I(nr - 1, c) - I(nr - 2, c) : (I(r + 1, c) - I(r - 1, c)) / 2.0;
+                const double dot = fx * (double)(x0 - c) + fy * (double)(y0 - r);
+                if (dot < 0.0 && I(r, c) < vmax / 3.0) tmp[(size_t)c * nr + r] = 0.0;
+            }
+        img.swap(tmp);
+        // 4-connected component (non-zero pixels) of the peak, dilated by a 3 x 3 square
+        comp.assign(img.size(), 0);
+        if (I(y0, x0) != 0.0) {
+            stack.clear(); stack.push_back(x0 * nr + y0); comp[stack.back()] = 1;
+            while (!stack.empty()) {
+                const int p = stack.back(); stack.pop_back();
+                const int r = p % nr, c = p / nr;
+                const int nb[4][2] = {{r - 1, c}, {r + 1, c}, {r, c - 1}, {r, c + 1}};
+                for (auto& q : nb) {
+                    if (q[0] < 0 || q[0] >= nr || q[1] < 0 || q[1] >= nc) continue;
+                    const int qi = q[1] * nr + q[0];
+                    if (img[qi] != 0.0 && !comp[qi]) { comp[qi] = 1; stack.push_back(qi); }
+                }
+            }
+        } else {
+            // l(ind_max) = 0: "l == 0" is the zero background (cannot happen for a positive peak; kept for completeness)
+            for (size_t i = 0; i < img.size(); ++i) comp[i] = img[i] == 0.0 ? 1 : 0;
+        }
+        dil.assign(img.size(), 0);
+        for (int c = 0; c < nc; ++c)
+            for (int r = 0; r < nr; ++r) {
+                bool any = false;
+                for (int dc = -1; dc <= 1 && !any; ++dc)
+                    for (int dr = -1; dr <= 1 && !any; ++dr) {
+                        const int rr = r + dr, cc = c + dc;
+                        if (rr >= 0 && rr < nr && cc >= 0 && cc < nc && comp[(size_t)cc * nr + rr]) any = true;
+                    }
+                dil[(size_t)c * nr + r] = any ? 1 : 0;
+            }
+        for (size_t i = 0; i < img.size(); ++i) if (!dil[i]) img[i] = 0.0;
+        // medfilt2: 3 x 3 median, zeros outside the crop
+        tmp.assign(img.size(), 0.0);
+        for (int c = 0; c < nc; ++c)
+            for (int r = 0; r < nr; ++r) {
+                double w[9];
+                int m = 0;
+                for (int dc = -1; dc <= 1; ++dc)
+                    for (int dr = -1; dr <= 1; ++dr) {
+                        const int rr = r + dr, cc = c + dc;
+                        w[m++] = (rr >= 0 && rr < nr && cc >= 0 && cc < nc) ? I(rr, cc) : 0.0;
+                    }
+                std::nth_element(w, w + 4, w + 9);
+                tmp[(size_t)c * nr + r] = w[4];
+            }
+        for (int c = 0; c < nc; ++c)
+            for (int r = 0; r < nr; ++r)
+                if (!emit((int64_t)(c + c0) * d1 + (r + r0), tmp[(size_t)c * nr + r])) { set_error("cnmfe_circular_constraints: output too small"); return -1; }
+        out_jc[k + 1] = n;
+    }
+    return 0;
+}
+
 // determine_search_location(A, 'ellipse', params): ellipse around the centre of mass, axes = principal components of the
 // footprint with variances clamped to [min_size^2, max_size^2], expanded by `dist`.  Output: CSC pattern (sorted rows).
 // out_ir must hold K * (2*ceil(dist*max_size) + 1)^2 entries (the ellipse never leaves that box).

@@ -418,17 +418,36 @@ class Sources2D:
         n = int(ojc[K])
         return sp.csc_matrix((np.ones(n, dtype=bool), oir[:n].copy(), ojc), shape=(self.d1 * self.d2, K))
 
-    def post_process_spatial(self, A_new=None, thr=0.01, sz=5):
-        """A_ = post_process_spatial(obj, A_new) with spatial_constraints = struct('circular', false, 'connected', true)
-        (the CNMFSetParms default): connectivity_constraint per neuron.  Usable as `post_process_fn`."""
+    def post_process_spatial(self, A_new=None, thr=0.01, sz=5, connected=True, circular=False):
+        """A_ = post_process_spatial(obj, A_new) (@Sources2D/post_process_spatial.m:19-32); the CNMFSetParms default is
+        spatial_constraints = struct('circular', false, 'connected', true).  Usable as `post_process_fn`."""
         A = sp.csc_matrix(self.A if A_new is None else A_new, dtype=np.float64).copy()
         A.sort_indices()
+        K = A.shape[1]
         jc = np.ascontiguousarray(A.indptr, dtype=np.int64)
         ir = np.ascontiguousarray(A.indices, dtype=np.int64)
         pr = np.ascontiguousarray(A.data, dtype=np.float64)
-        L.check(self._lib.cnmfe_connectivity_constraint(self.d1, self.d2, A.shape[1], _ptr(jc), _ptr(ir), _ptr(pr), float(thr), int(sz)))
+        if connected:
+            L.check(self._lib.cnmfe_connectivity_constraint(self.d1, self.d2, K, _ptr(jc), _ptr(ir), _ptr(pr), float(thr), int(sz)))
         out = sp.csc_matrix((pr, ir, jc), shape=A.shape)
         out.eliminate_zeros()
+        if circular and K > 0:
+            out.sort_indices()
+            jc = np.ascontiguousarray(out.indptr, dtype=np.int64)
+            ir = np.ascontiguousarray(out.indices, dtype=np.int64)
+            pr = np.ascontiguousarray(out.data, dtype=np.float64)
+            # the result lives on the bounding boxes of the footprints
+            cap = 1
+            for k in range(K):
+                rows = ir[jc[k]:jc[k + 1]]
+                if rows.size:
+                    r, c = rows % self.d1, rows // self.d1
+                    cap += int((r.max() - r.min() + 1) * (c.max() - c.min() + 1))
+            ojc = np.zeros(K + 1, dtype=np.int64); oir = np.zeros(cap, dtype=np.int64); opr = np.zeros(cap)
+            L.check(self._lib.cnmfe_circular_constraints(self.d1, self.d2, K, _ptr(jc), _ptr(ir), _ptr(pr), _ptr(ojc), _ptr(oir),
+                                                         _ptr(opr), cap))
+            n = int(ojc[K])
+            out = sp.csc_matrix((opr[:n].copy(), oir[:n].copy(), ojc), shape=A.shape)
         return out
 
     def update_spatial_parallel(self, use_parallel=True, update_sn=False, IND=None, sync_host=True):

@@ -175,6 +175,11 @@ int cnmfe_temporal_state_buffers(cnmfe_ctx* ctx, double** C_dev, double** Craw_d
  * 4-connected labelling, keep the component of the arg-max pixel.  pr is edited in place: removed entries become 0. */
 int cnmfe_connectivity_constraint(int d1, int d2, int K, const int64_t* jc, const int64_t* ir, double* pr,
                                   double thr, int sz);
+/* post_process_spatial with spatial_constraints.circular (endoscope/circular_constraints.m): result as a new CSC matrix
+ * (the median filter can create non-zeros next to the footprint); cap >= sum over neurons of the bounding-box areas
+ * (<= d1*d2*K) -- the reference applies it after connectivity_constraint (post_process_spatial.m:24-30). */
+int cnmfe_circular_constraints(int d1, int d2, int K, const int64_t* jc, const int64_t* ir, const double* pr,
+                               int64_t* out_jc, int64_t* out_ir, double* out_pr, int64_t cap);
 /* determine_search_location(A, 'ellipse', params) (utilities/determine_search_location.m:57-92): search mask as a CSC
  * pattern (out_jc K+1, out_ir sorted).  out_ir needs cap >= K * (2*ceil(dist*max_size) + 2)^2 entries.
  * Defaults of the reference: min_size 3, max_size 8, dist 3. */

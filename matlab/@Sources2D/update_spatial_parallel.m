@@ -23,14 +23,18 @@ else
 end
 [ii, jj] = find(IND);
 A_new = sparse(ii, jj, vals, size(IND,1), size(IND,2));
-sc = obj.options.spatial_constraints;
-if sc.connected && ~sc.circular
-    Atmp = cnmfe_b200_mex('post_process_spatial', A_new, obj.options.d1, obj.options.d2);    % connectivity_constraint per neuron (:341)
-    [ii2, jj2, vv2] = find(Atmp);                                                             % removed entries come back as explicit zeros
-    obj.A = sparse(ii2, jj2, vv2, size(Atmp,1), size(Atmp,2));
-else
-    obj.A = obj.post_process_spatial(obj.reshape(A_new, 2));                                  % circular_constraints stays MATLAB
+sc = obj.options.spatial_constraints;                                                          % post_process_spatial (:341) in the library
+if sc.connected
+    Atmp = cnmfe_b200_mex('post_process_spatial', A_new, obj.options.d1, obj.options.d2);      % connectivity_constraint per neuron
+    [ii2, jj2, vv2] = find(Atmp);                                                               % removed entries come back as explicit zeros
+    A_new = sparse(ii2, jj2, vv2, size(Atmp,1), size(Atmp,2));
 end
+if sc.circular
+    [jc, ir, vv] = cnmfe_b200_mex('circular_constraints', A_new, obj.options.d1, obj.options.d2);   % circular_constraints per neuron
+    jj = zeros(numel(ir), 1); for k = 1:numel(jc)-1; jj(jc(k)+1:jc(k+1)) = k; end
+    A_new = sparse(ir + 1, jj, vv, size(A_new,1), size(A_new,2));
+end
+obj.A = A_new;
 if strcmpi(obj.options.background_model, 'ring')
     obj.b0_new = cell2mat(obj.P.Ymean) - obj.reshape(obj.A*mean(obj.C,2), 2);
 end

@@ -159,6 +159,28 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         plhs[0] = mxDuplicateArray(prhs[1]);               // same pattern; removed entries become explicit zeros
         check(cnmfe_connectivity_constraint((int)mxGetScalar(prhs[2]), (int)mxGetScalar(prhs[3]), (int)K, jc.data(), ir.data(),
                                             mxGetPr(plhs[0]), 0.01, 5), cmd);
+    } else if (c == "circular_constraints") {   // A_ = circular_constraints(A sparse d x K, d1, d2): circular_constraints.m per neuron
+        const mwSize K = mxGetN(prhs[1]);
+        const mwIndex* jcm = mxGetJc(prhs[1]); const mwIndex* irm = mxGetIr(prhs[1]);
+        std::vector<int64_t> jc(jcm, jcm + K + 1), ir(irm, irm + jcm[K]);
+        const int d1 = (int)mxGetScalar(prhs[2]), d2 = (int)mxGetScalar(prhs[3]);
+        int64_t cap = 1;                                   // the result lives on the bounding boxes of the footprints
+        for (mwSize k = 0; k < K; ++k) {
+            int r0 = d1, r1 = -1, c0 = d2, c1 = -1;
+            for (mwIndex e = jcm[k]; e < jcm[k + 1]; ++e) {
+                const int r = (int)(irm[e] % d1), cc = (int)(irm[e] / d1);
+                r0 = r < r0 ? r : r0; r1 = r > r1 ? r : r1; c0 = cc < c0 ? cc : c0; c1 = cc > c1 ? cc : c1;
+            }
+            if (r1 >= 0) cap += (int64_t)(r1 - r0 + 1) * (c1 - c0 + 1);
+        }
+        std::vector<int64_t> ojc(K + 1), oir((size_t)cap);
+        std::vector<double> opr((size_t)cap);
+        check(cnmfe_circular_constraints(d1, d2, (int)K, jc.data(), ir.data(), mxGetPr(prhs[1]), ojc.data(), oir.data(), opr.data(), cap), cmd);
+        plhs[0] = mxCreateDoubleMatrix(K + 1, 1, mxREAL);              // jc (0-based), ir (0-based), values
+        plhs[1] = mxCreateDoubleMatrix((mwSize)ojc[K], 1, mxREAL);
+        plhs[2] = mxCreateDoubleMatrix((mwSize)ojc[K], 1, mxREAL);
+        for (mwSize k = 0; k <= K; ++k) mxGetPr(plhs[0])[k] = (double)ojc[k];
+        for (int64_t e = 0; e < ojc[K]; ++e) { mxGetPr(plhs[1])[e] = (double)oir[e]; mxGetPr(plhs[2])[e] = opr[e]; }
     } else if (c == "search_location") {   // [jc, ir] = search_location(A sparse d x K, d1, d2, min_size, max_size, dist): 0-based CSC pattern
         const mwSize K = mxGetN(prhs[1]);
         const mwIndex* jcm = mxGetJc(prhs[1]); const mwIndex* irm = mxGetIr(prhs[1]);

@@ -28,14 +28,42 @@ def connectivity_constraint(img, thr=0.01, sz=5):
     return out
 
 
-def post_process_spatial(A, d1, d2, connected=True):
-    """A: (d1*d2, K) sparse.  post_process_spatial.m:19-32 with circular = false."""
+def circular_constraints(img):
+    """endoscope/circular_constraints.m:1-54 (show_imgs = false)."""
+    img = np.array(img, dtype=np.float64)
+    rr, cc = np.nonzero(img)
+    if rr.size == 0:
+        return img
+    rmin, rmax, cmin, cmax = rr.min(), rr.max(), cc.min(), cc.max()
+    if (rmax - rmin < 1) or (cmax - cmin < 1):
+        return img
+    sub = img[rmin:rmax + 1, cmin:cmax + 1].copy()
+    nr, nc = sub.shape
+    ind_max = int(np.argmax(sub.ravel(order="F")))
+    vmax = sub.ravel(order="F")[ind_max]
+    y0, x0 = ind_max % nr, ind_max // nr
+    x, y = np.meshgrid(np.arange(nc), np.arange(nr))
+    fy, fx = np.gradient(sub)                                             # MATLAB: [fx, fy] = gradient(img)
+    ind = ((fx * (x0 - x) + fy * (y0 - y)) < 0) & (sub < vmax / 3)
+    sub[ind] = 0
+    lab, _ = ndi.label(sub != 0, structure=[[0, 1, 0], [1, 1, 1], [0, 1, 0]])
+    keep = ndi.binary_dilation(lab == lab[y0, x0], structure=np.ones((3, 3), bool))
+    sub[~keep] = 0
+    sub = ndi.median_filter(sub, size=3, mode="constant", cval=0.0)      # medfilt2: zero padding
+    img[rmin:rmax + 1, cmin:cmax + 1] = sub
+    return img
+
+
+def post_process_spatial(A, d1, d2, connected=True, circular=False):
+    """A: (d1*d2, K) sparse.  post_process_spatial.m:19-32."""
     A = sp.csc_matrix(A, dtype=np.float64)
     cols = []
     for k in range(A.shape[1]):
         ai = np.asarray(A[:, k].todense()).reshape(d1, d2, order="F")
         if connected:
             ai = connectivity_constraint(ai)
+        if circular:
+            ai = circular_constraints(ai)
         cols.append(sp.csc_matrix(ai.reshape(-1, 1, order="F")))
     return sp.hstack(cols, format="csc") if cols else sp.csc_matrix((d1 * d2, 0))
 

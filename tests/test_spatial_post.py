@@ -132,3 +132,21 @@ def test_graph_conn_comp_matches_scipy(built_lib):
     rc = built_lib.cnmfe_graph_conn_comp(3, jc.ctypes.data_as(ctypes.c_void_p), ir.ctypes.data_as(ctypes.c_void_p),
                                          lab.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nc))
     assert rc != 0 and b"mixed labeling" in built_lib.cnmfe_last_error()
+
+
+def test_circular_constraints_matches_oracle(built_lib):
+    from oracle import spatial_post as OP
+    from cnmf_e_b200.sources2d import Sources2D
+    rng = np.random.default_rng(23)
+    for d1, d2, K in [(40, 36, 10), (25, 61, 6)]:
+        A = _footprints(rng, d1, d2, K)
+        A = sp.hstack([A, sp.csc_matrix((d1 * d2, 1))], format="csc")          # an empty neuron
+        line = np.zeros((d1, d2)); line[7, 3:9] = 1.0                           # a single row: left unchanged
+        A = sp.hstack([A, sp.csc_matrix(line.reshape(-1, 1, order="F"))], format="csc")
+        h = _Host(built_lib, d1, d2)
+        for connected in (False, True):
+            got = Sources2D.post_process_spatial(h, A, connected=connected, circular=True)
+            ref = OP.post_process_spatial(A, d1, d2, connected=connected, circular=True)
+            assert np.array_equal(got.toarray(), ref.toarray())
+        assert np.array_equal(Sources2D.post_process_spatial(h, A, connected=False, circular=True)[:, -1].toarray().ravel(),
+                              line.ravel(order="F"))
