@@ -53,6 +53,7 @@ SYMBOLS = {
     "cnmfe_debug_local_view": (I, [I, I, V, V, I, V, V, V, I, I, V, V, V, V, V, V, V, V, V, V, V, V, V, V]),
     "cnmfe_connectivity_constraint": (I, [I, I, I, V, V, V, ctypes.c_double, I]),
     "cnmfe_circular_constraints": (I, [I, I, I, V, V, V, V, V, V, ctypes.c_int64]),
+    "cnmfe_search_location_dilate": (I, [I, I, I, V, V, V, ctypes.c_double, I, I, V, V, ctypes.c_int64]),
     "cnmfe_search_location_ellipse": (I, [I, I, I, V, V, V, ctypes.c_double, ctypes.c_double, ctypes.c_double, V, V, ctypes.c_int64]),
     "cnmfe_create": (I, [ctypes.POINTER(V), I, I, I, I, V, V, V, I, I, I]),
     "cnmfe_destroy": (None, [V]),

@@ -297,6 +297,143 @@ extern "C" int cnmfe_search_location_ellipse(int d1, int d2, int K, const int64_
     return 0;
 }
 
+// determine_search_location(A, 'dilate', params) (utilities/determine_search_location.m:93-99): threshold_components
+// (utilities/threshold_components.m: 3 x 3 median, keep the pixels carrying `nrgthr` of the energy, 3 x 3 closing, largest-
+// energy 8-connected component; the LAST nb columns are copied unthresholded, as the reference does for its background
+// columns) followed by a dilation with strel('disk', bSiz, 0).  Output: CSC pattern of IND.  cap: sum over neurons of
+// (bbox height + 2 + 2 bSiz) * (bbox width + 2 + 2 bSiz) is always enough.
+extern "C" int cnmfe_search_location_dilate(int d1, int d2, int K, const int64_t* jc, const int64_t* ir, const double* pr,
+                                            double nrgthr, int nb, int bSiz, int64_t* out_jc, int64_t* out_ir, int64_t cap) {
+    if (d1 <= 0 || d2 <= 0 || K < 0 || !jc || !out_jc || nb < 0 || bSiz < 0 || (K > 0 && jc[K] > 0 && (!ir || !pr))) { set_error("cnmfe_search_location_dilate: bad arguments"); return -1; }
+    std::vector<double> img, med;
+    std::vector<unsigned char> bw, tmpb, sel;
+    std::vector<int> order, lab, stack;
+    int64_t n = 0;
+    out_jc[0] = 0;
+    for (int k = 0; k < K; ++k) {
+        const int64_t e0 = jc[k], e1 = jc[k + 1];
+        int r0 = d1, r1 = -1, c0 = d2, c1 = -1;
+        double colsum = 0.0;
+        for (int64_t e = e0; e < e1; ++e) {
+            colsum += pr[e];
+            if (pr[e] == 0.0) continue;
+            const int r = (int)(ir[e] % d1), c = (int)(ir[e] / d1);
+            r0 = std::min(r0, r); r1 = std::max(r1, r); c0 = std::min(c0, c); c1 = std::max(c1, c);
+        }
+        const bool empty_col = (colsum == 0.0);                    // ind_empty: A(1, k) = 1  (:51-55)
+        if (empty_col) { r0 = r1 = 0; c0 = c1 = 0; }
+        if (r1 < 0) { out_jc[k + 1] = n; continue; }              // stored values cancel to a non-zero sum but no non-zero entry: nothing
+        // crop with a margin of 2 (median spreads by 1, closing by 1 more), clipped to the FOV
+        const int R0 = std::max(0, r0 - 2), R1 = std::min(d1 - 1, r1 + 2), C0 = std::max(0, c0 - 2), C1 = std::min(d2 - 1, c1 + 2);
+        const int nr = R1 - R0 + 1, nc = C1 - C0 + 1;
+        img.assign((size_t)nr * nc, 0.0);
+        if (empty_col) img[(size_t)(0 - C0) * nr + (0 - R0)] = 1.0;
+        for (int64_t e = e0; e < e1; ++e) {
+            const int r = (int)(ir[e] % d1), c = (int)(ir[e] / d1);
+            if (r >= R0 && r <= R1 && c >= C0 && c <= C1) img[(size_t)(c - C0) * nr + (r - R0)] += pr[e];   // (+= : pixel 1 of an "empty" column)
+        }
+        auto inside = [&](int r, int c) { return r >= 0 && r < nr && c >= 0 && c < nc; };
+        const bool thresholded = (k < K - nb);
+        if (thresholded) {
+            // (i) medfilt2 3 x 3, zeros outside the image (pixels of the FOV outside the crop are zeros too)
+            med.assign(img.size(), 0.0);
+            for (int c = 0; c < nc; ++c)
+                for (int r = 0; r < nr; ++r) {
+                    double w[9]; int m = 0;
+                    for (int dc = -1; dc <= 1; ++dc) for (int dr = -1; dr <= 1; ++dr) w[m++] = inside(r + dr, c + dc) ? img[(size_t)(c + dc) * nr + (r + dr)] : 0.0;
+                    std::nth_element(w, w + 4, w + 9);
+                    med[(size_t)c * nr + r] = w[4];
+                }
+            // (ii) energy threshold: ascending stable sort of the squares (zeros first, they add nothing), running sum
+            order.clear();
+            for (int i = 0; i < (int)med.size(); ++i) if (med[i] != 0.0) order.push_back(i);
+            // FOV linear index order = (column, row) order; the crop index i = c * nr + r is monotone in it
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return med[a] * med[a] < med[b] * med[b]; });
+            double total = 0.0;
+            for (int i : order) total += med[i] * med[i];
+            bw.assign(img.size(), 0);
+            {
+                const double level = (1.0 - nrgthr) * total;
+                double run = 0.0;
+                bool on = false;
+                for (int i : order) {
+                    run += med[i] * med[i];
+                    if (!on && run > level) on = true;
+                    if (on) bw[i] = 1;
+                }
+            }
+            // (iii) imclose with a 3 x 3 square: dilation (outside = 0) then erosion (outside the FOV = 1; FOV pixels outside
+            //       the crop are 0 after the dilation because the margin is 2)
+            tmpb.assign(img.size(), 0);
+            for (int c = 0; c < nc; ++c)
+                for (int r = 0; r < nr; ++r) {
+                    unsigned char v = 0;
+                    for (int dc = -1; dc <= 1 && !v; ++dc) for (int dr = -1; dr <= 1 && !v; ++dr) if (inside(r + dr, c + dc) && bw[(size_t)(c + dc) * nr + (r + dr)]) v = 1;
+                    tmpb[(size_t)c * nr + r] = v;
+                }
+            for (int c = 0; c < nc; ++c)
+                for (int r = 0; r < nr; ++r) {
+                    unsigned char v = 1;
+                    for (int dc = -1; dc <= 1 && v; ++dc)
+                        for (int dr = -1; dr <= 1 && v; ++dr) {
+                            const int rr = r + dr, cc = c + dc;
+                            const int fr = rr + R0, fc = cc + C0;
+                            if (fr < 0 || fr >= d1 || fc < 0 || fc >= d2) continue;          // outside the FOV: ignored
+                            if (!inside(rr, cc) || !tmpb[(size_t)cc * nr + rr]) v = 0;        // FOV pixel outside the crop: 0
+                        }
+                    bw[(size_t)c * nr + r] = v;
+                }
+            // (iv) 8-connected components in column-major discovery order; keep the one with the largest energy (first on ties)
+            lab.assign(img.size(), 0);
+            int ncomp = 0, best = 0;
+            double best_e = -1.0;
+            for (int i = 0; i < (int)bw.size(); ++i) {
+                if (!bw[i] || lab[i]) continue;
+                ++ncomp;
+                stack.clear(); stack.push_back(i); lab[i] = ncomp;
+                double e = 0.0;
+                while (!stack.empty()) {
+                    const int p = stack.back(); stack.pop_back();
+                    e += med[p] * med[p];
+                    const int r = p % nr, c = p / nr;
+                    for (int dc = -1; dc <= 1; ++dc)
+                        for (int dr = -1; dr <= 1; ++dr) {
+                            if (!dr && !dc) continue;
+                            if (!inside(r + dr, c + dc)) continue;
+                            const int q = (c + dc) * nr + (r + dr);
+                            if (bw[q] && !lab[q]) { lab[q] = ncomp; stack.push_back(q); }
+                        }
+                }
+                if (e > best_e) { best_e = e; best = ncomp; }
+            }
+            sel.assign(img.size(), 0);
+            for (size_t i = 0; i < img.size(); ++i) sel[i] = (best > 0 && lab[i] == best && med[i] > 0.0) ? 1 : 0;   // Ath > 0 after the dilation test
+        } else {
+            sel.assign(img.size(), 0);
+            for (size_t i = 0; i < img.size(); ++i) sel[i] = img[i] > 0.0 ? 1 : 0;
+        }
+        // IND = imdilate(Ath, strel('disk', bSiz, 0)) > 0: a pixel is in if some selected positive pixel lies within the disk
+        const int b = bSiz;
+        const int DR0 = std::max(0, R0 - b), DR1 = std::min(d1 - 1, R1 + b), DC0 = std::max(0, C0 - b), DC1 = std::min(d2 - 1, C1 + b);
+        for (int fc = DC0; fc <= DC1; ++fc)
+            for (int fr = DR0; fr <= DR1; ++fr) {
+                bool hit = false;
+                for (int dc = -b; dc <= b && !hit; ++dc)
+                    for (int dr = -b; dr <= b && !hit; ++dr) {
+                        if (dr * dr + dc * dc > b * b) continue;
+                        const int rr = fr + dr - R0, cc = fc + dc - C0;
+                        if (inside(rr, cc) && sel[(size_t)cc * nr + rr]) hit = true;
+                    }
+                if (hit) {
+                    if (n >= cap || !out_ir) { set_error("cnmfe_search_location_dilate: out_ir too small (%lld entries)", (long long)cap); return -1; }
+                    out_ir[n++] = (int64_t)fc * d1 + fr;
+                }
+            }
+        out_jc[k + 1] = n;
+    }
+    return 0;
+}
+
 // [l, c] = graph_connected_comp(sA)  (ca_source_extraction/utilities/graph_connected_comp.m:26 -> the reference's only native
 // file, utilities/graph_conn_comp_mex.cpp): component labels 1..c of the nodes of a sparse adjacency matrix, numbered in the
 // order of their smallest node.  A node's neighbours are the rows stored in its COLUMN (the reference follows the CSC lists

@@ -400,15 +400,32 @@ class Sources2D:
             self._mark("C_prev", self.C_prev)
 
     # ---- host-side brackets of the spatial update (library C++: csrc/host_spatial.cu) ----------------------------------
-    def determine_search_location(self, A=None, min_size=3.0, max_size=8.0, dist=3.0):
-        """IND = determine_search_location(obj.A, 'ellipse', options) (utilities/determine_search_location.m:57-92): the
-        reference's default search_method, as a (d, K) boolean csc matrix.  Usable as `search_fn`."""
+    def determine_search_location(self, A=None, min_size=3.0, max_size=8.0, dist=3.0, method="ellipse", nrgthr=0.9999,
+                                  nb=1, bSiz=3):
+        """IND = determine_search_location(obj.A, method, options) (utilities/determine_search_location.m): 'ellipse' (:57-92,
+        the reference's default search_method) or 'dilate' (:93-99: threshold_components + imdilate with a disk of radius
+        bSiz), as a (d, K) boolean csc matrix.  Usable as `search_fn`."""
         A = sp.csc_matrix(self.A if A is None else A, dtype=np.float64)
         A.sort_indices()
         K = A.shape[1]
         jc = np.ascontiguousarray(A.indptr, dtype=np.int64)
         ir = np.ascontiguousarray(A.indices, dtype=np.int64)
         pr = np.ascontiguousarray(A.data, dtype=np.float64)
+        if str(method).lower() == "dilate":
+            cap = 1
+            for k in range(K):
+                rows = ir[jc[k]:jc[k + 1]]
+                h = w = 1
+                if rows.size:
+                    r, c = rows % self.d1, rows // self.d1
+                    h, w = int(r.max() - r.min() + 1), int(c.max() - c.min() + 1)
+                cap += (h + 4 + 2 * int(bSiz)) * (w + 4 + 2 * int(bSiz))
+            ojc = np.zeros(K + 1, dtype=np.int64)
+            oir = np.zeros(cap, dtype=np.int64)
+            L.check(self._lib.cnmfe_search_location_dilate(self.d1, self.d2, K, _ptr(jc), _ptr(ir), _ptr(pr), float(nrgthr), int(nb),
+                                                           int(bSiz), _ptr(ojc), _ptr(oir), cap))
+            n = int(ojc[K])
+            return sp.csc_matrix((np.ones(n, dtype=bool), oir[:n].copy(), ojc), shape=(self.d1 * self.d2, K))
         reach = int(np.ceil(dist * max(max_size, min_size)))
         cap = max(1, K * (2 * reach + 2) ** 2)
         ojc = np.zeros(K + 1, dtype=np.int64)

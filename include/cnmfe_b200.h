@@ -186,6 +186,11 @@ int cnmfe_circular_constraints(int d1, int d2, int K, const int64_t* jc, const i
 int cnmfe_search_location_ellipse(int d1, int d2, int K, const int64_t* jc, const int64_t* ir, const double* pr,
                                   double min_size, double max_size, double dist, int64_t* out_jc, int64_t* out_ir,
                                   int64_t cap);
+/* determine_search_location(A, 'dilate', params) (utilities/determine_search_location.m:93-99 -> threshold_components.m, then
+ * imdilate with strel('disk', bSiz, 0)).  Reference defaults: nrgthr 0.9999, nb 1 (the last nb columns are not thresholded),
+ * bSiz 3.  cap >= sum over neurons of (bbox height + 4 + 2 bSiz) * (bbox width + 4 + 2 bSiz). */
+int cnmfe_search_location_dilate(int d1, int d2, int K, const int64_t* jc, const int64_t* ir, const double* pr,
+                                 double nrgthr, int nb, int bSiz, int64_t* out_jc, int64_t* out_ir, int64_t cap);
 /* [l, c] = graph_connected_comp(sA) (utilities/graph_connected_comp.m:26 -> utilities/graph_conn_comp_mex.cpp, the
  * reference's only native file; used by the merge routines): labels 1..c in the order of each component's smallest node.
  * Host-side, ctx-free. */

@@ -4,13 +4,19 @@ if ~exist('update_sn', 'var') || isempty(update_sn); update_sn = false; end
 h = cnmfe_b200_handle(obj);
 search_method = obj.options.search_method;
 if strcmpi(search_method, 'dilate'); obj.options.se = []; end
+% determine_search_location(obj.A, search_method, options) (:66) in the library (host C++, same results)
 if strcmpi(search_method, 'ellipse') && ~isinf(obj.options.dist)
-    % library C++ (cnmfe_search_location_ellipse), same result as determine_search_location(obj.A, 'ellipse', options) (:66)
     [jc, ir] = cnmfe_b200_mex('search_location', obj.A, obj.options.d1, obj.options.d2, obj.options.min_size, obj.options.max_size, obj.options.dist);
+elseif strcmpi(search_method, 'dilate')
+    [jc, ir] = cnmfe_b200_mex('search_location_dilate', obj.A, obj.options.d1, obj.options.d2, obj.options.nrgthr, obj.options.nb, obj.options.bSiz);
+else
+    jc = [];
+end
+if ~isempty(jc)
     jj = zeros(numel(ir), 1); for k = 1:numel(jc)-1; jj(jc(k)+1:jc(k+1)) = k; end
     IND = sparse(ir + 1, jj, true, size(obj.A,1), size(obj.A,2));
 else
-    IND = sparse(logical(determine_search_location(obj.A, search_method, obj.options)));   % 'dilate' stays MATLAB (:66)
+    IND = sparse(logical(determine_search_location(obj.A, search_method, obj.options)));   % whole field of view
 end
 cnmfe_b200_mex('set_neurons', h, obj.A, obj.C);
 cnmfe_b200_mex('set_prev', h, obj.A_prev, obj.C_prev);

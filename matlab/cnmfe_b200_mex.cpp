@@ -159,6 +159,29 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         plhs[0] = mxDuplicateArray(prhs[1]);               // same pattern; removed entries become explicit zeros
         check(cnmfe_connectivity_constraint((int)mxGetScalar(prhs[2]), (int)mxGetScalar(prhs[3]), (int)K, jc.data(), ir.data(),
                                             mxGetPr(plhs[0]), 0.01, 5), cmd);
+    } else if (c == "search_location_dilate") {   // [jc, ir] = search_location_dilate(A sparse d x K, d1, d2, nrgthr, nb, bSiz): 0-based CSC pattern
+        const mwSize K = mxGetN(prhs[1]);
+        const mwIndex* jcm = mxGetJc(prhs[1]); const mwIndex* irm = mxGetIr(prhs[1]);
+        std::vector<int64_t> jc(jcm, jcm + K + 1), ir(irm, irm + jcm[K]);
+        const int d1 = (int)mxGetScalar(prhs[2]), d2 = (int)mxGetScalar(prhs[3]);
+        const double nrgthr = mxGetScalar(prhs[4]);
+        const int nb = (int)mxGetScalar(prhs[5]), bSiz = (int)mxGetScalar(prhs[6]);
+        int64_t cap = 1;
+        for (mwSize k = 0; k < K; ++k) {
+            int r0 = d1, r1 = -1, c0 = d2, c1 = -1;
+            for (mwIndex e = jcm[k]; e < jcm[k + 1]; ++e) {
+                const int r = (int)(irm[e] % d1), cc = (int)(irm[e] / d1);
+                r0 = r < r0 ? r : r0; r1 = r > r1 ? r : r1; c0 = cc < c0 ? cc : c0; c1 = cc > c1 ? cc : c1;
+            }
+            const int64_t hgt = r1 >= 0 ? r1 - r0 + 1 : 1, wid = r1 >= 0 ? c1 - c0 + 1 : 1;
+            cap += (hgt + 4 + 2 * bSiz) * (wid + 4 + 2 * bSiz);
+        }
+        std::vector<int64_t> ojc(K + 1), oir((size_t)cap);
+        check(cnmfe_search_location_dilate(d1, d2, (int)K, jc.data(), ir.data(), mxGetPr(prhs[1]), nrgthr, nb, bSiz, ojc.data(), oir.data(), cap), cmd);
+        plhs[0] = mxCreateDoubleMatrix(K + 1, 1, mxREAL);
+        plhs[1] = mxCreateDoubleMatrix((mwSize)ojc[K], 1, mxREAL);
+        for (mwSize k = 0; k <= K; ++k) mxGetPr(plhs[0])[k] = (double)ojc[k];
+        for (int64_t e = 0; e < ojc[K]; ++e) mxGetPr(plhs[1])[e] = (double)oir[e];
     } else if (c == "circular_constraints") {   // A_ = circular_constraints(A sparse d x K, d1, d2): circular_constraints.m per neuron
         const mwSize K = mxGetN(prhs[1]);
         const mwIndex* jcm = mxGetJc(prhs[1]); const mwIndex* irm = mxGetIr(prhs[1]);

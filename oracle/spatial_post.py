@@ -93,3 +93,56 @@ def determine_search_location(A, d1, d2, min_size=3.0, max_size=8.0, dist=3.0):
         ind = np.sqrt((cor @ V[:, 0]) ** 2 / d11 + (cor @ V[:, 1]) ** 2 / d22) <= dist
         cols.append(sp.csc_matrix(ind.reshape(-1, 1)))
     return sp.hstack(cols, format="csc").astype(bool) if cols else sp.csc_matrix((d, 0), dtype=bool)
+
+
+def threshold_components(A, d1, d2, nrgthr=0.9999, nb=1):
+    """utilities/threshold_components.m:1-62 (2-D): 3x3 median, energy threshold, 3x3 closing, largest-energy 8-connected
+    component; the last nb columns are copied unchanged (:24)."""
+    A = sp.csc_matrix(A, dtype=np.float64)
+    d, K = A.shape
+    cols = []
+    for i in range(K):
+        a = np.asarray(A[:, i].todense()).ravel()
+        if i >= K - nb:
+            cols.append(sp.csc_matrix(a.reshape(-1, 1)))
+            continue
+        At = ndi.median_filter(a.reshape(d1, d2, order="F"), size=3, mode="constant", cval=0.0).ravel(order="F")
+        e = At ** 2
+        ind = np.argsort(e, kind="stable")                                  # [temp, ind] = sort(A_temp.^2, 'ascend')
+        temp = np.cumsum(e[ind])
+        hit = np.nonzero(temp > (1 - nrgthr) * temp[-1])[0]
+        BW = np.zeros(d, bool)
+        if hit.size:
+            BW[ind[hit[0]:]] = True
+        BW = BW.reshape(d1, d2, order="F")
+        sq = np.ones((3, 3), bool)
+        dil = ndi.binary_dilation(BW, structure=sq, border_value=0)
+        BW = ndi.binary_erosion(dil, structure=sq, border_value=1)          # imclose: outside pixels never decide
+        # label in column-major discovery order (scipy scans row-major): label the transpose
+        Lt, num = ndi.label(BW.T, structure=np.ones((3, 3), bool))
+        Lab = Lt.T
+        out = np.zeros(d)
+        if num > 0:
+            nrg = np.array([np.sum(e[(Lab == l).ravel(order="F")]) for l in range(1, num + 1)])
+            ff = (Lab == (int(np.argmax(nrg)) + 1)).ravel(order="F")
+            out[ff] = At[ff]
+        cols.append(sp.csc_matrix(out.reshape(-1, 1)))
+    return sp.hstack(cols, format="csc") if cols else sp.csc_matrix((d, 0))
+
+
+def determine_search_location_dilate(A, d1, d2, nrgthr=0.9999, nb=1, bSiz=3):
+    """'dilate' method (determine_search_location.m:93-99) with expandCore = strel('disk', bSiz, 0)."""
+    A = sp.csc_matrix(A, dtype=np.float64).copy().tolil()
+    d, K = A.shape
+    empty = np.asarray(A.sum(axis=0)).ravel() == 0
+    for k in np.nonzero(empty)[0]:
+        A[0, k] = 1.0
+    Ath = threshold_components(A.tocsc(), d1, d2, nrgthr, nb)
+    rr, cc = np.meshgrid(np.arange(-bSiz, bSiz + 1), np.arange(-bSiz, bSiz + 1), indexing="ij")
+    disk = (rr ** 2 + cc ** 2) <= bSiz ** 2
+    cols = []
+    for i in range(K):
+        a = np.asarray(Ath[:, i].todense()).reshape(d1, d2, order="F")
+        dil = ndi.grey_dilation(a, footprint=disk, mode="constant", cval=-np.inf)
+        cols.append(sp.csc_matrix((dil > 0).reshape(-1, 1, order="F")))
+    return sp.hstack(cols, format="csc").astype(bool) if cols else sp.csc_matrix((d, 0), dtype=bool)

@@ -150,3 +150,24 @@ def test_circular_constraints_matches_oracle(built_lib):
             assert np.array_equal(got.toarray(), ref.toarray())
         assert np.array_equal(Sources2D.post_process_spatial(h, A, connected=False, circular=True)[:, -1].toarray().ravel(),
                               line.ravel(order="F"))
+
+
+def test_search_location_dilate_matches_oracle(built_lib):
+    from oracle import spatial_post as OP
+    from cnmf_e_b200.sources2d import Sources2D
+    rng = np.random.default_rng(41)
+    for d1, d2, K in [(44, 38, 9), (26, 58, 6)]:
+        A = _footprints(rng, d1, d2, K)
+        A = sp.hstack([A, sp.csc_matrix((d1 * d2, 1)), A[:, :1]], format="csc")     # an empty neuron; last column = "nb" column
+        h = _Host(built_lib, d1, d2)
+        for kw in (dict(), dict(nrgthr=0.99, nb=0, bSiz=4), dict(nb=2, bSiz=2)):
+            got = Sources2D.determine_search_location(h, A, method="dilate", **kw)
+            ref = OP.determine_search_location_dilate(A, d1, d2, **kw)
+            assert got.shape == ref.shape
+            diff = got.astype(np.int8) - ref.astype(np.int8)
+            assert diff.nnz == 0, "%d mask pixels differ (%s)" % (diff.nnz, kw)
+        # the thresholded mask contains the bulk of each real footprint
+        IND = Sources2D.determine_search_location(h, A, method="dilate")
+        for k in range(K):
+            a = A[:, k].toarray().ravel()
+            assert IND[:, k].toarray().ravel()[np.argmax(a)]
