@@ -469,12 +469,20 @@ class Sources2D:
 
     def update_spatial_parallel(self, use_parallel=True, update_sn=False, IND=None, sync_host=True):
         """update_spatial_parallel(obj, use_parallel, update_sn).  IND: (d,K) boolean search mask
-        (determine_search_location output, update_spatial_parallel.m:66); defaults to self.search_fn(self)."""
+        (determine_search_location output, update_spatial_parallel.m:66); defaults to self.search_fn(self) or, without a hook,
+        to the library's determine_search_location with options.search_method ('ellipse').  Post-processing
+        (post_process_spatial, :341) runs when post_process_fn is set, e.g. `obj.post_process_fn = obj.post_process_spatial`."""
         self._push_options()
         if IND is None:
-            if self.search_fn is None:
-                raise L.CnmfeError("no search mask: pass IND or set search_fn (determine_search_location stays in MATLAB)")
-            IND = self.search_fn(self)
+            # update_spatial_parallel.m:62-66: IND = determine_search_location(obj.A, options.search_method, options)
+            if self.search_fn is not None:
+                IND = self.search_fn(self)
+            else:
+                o = self.options
+                IND = self.determine_search_location(self.A, method=o.get("search_method", "ellipse"),
+                                                     min_size=o.get("min_size", 3.0), max_size=o.get("max_size", 8.0),
+                                                     dist=o.get("dist", 3.0), nrgthr=o.get("nrgthr", 0.9999),
+                                                     nb=o.get("nb", 1), bSiz=o.get("bSiz", 3))
         INDc = sp.csc_matrix(IND).astype(bool)
         INDc.sort_indices()
         if sync_host:
