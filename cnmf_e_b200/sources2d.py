@@ -399,6 +399,25 @@ class Sources2D:
             self._mark("A_prev", self.A_prev)
             self._mark("C_prev", self.C_prev)
 
+    def estimate_noise(self, Y, frame_range=None, chunk=32768):
+        """sn = estimate_noise(obj, frame_range, 'psd') (@Sources2D/Sources2D.m:328-379): per-pixel GetSn of the raw video on
+        frames [1, min(T, 3000)] by default (1-based inclusive, as in the reference).  Y: (d1, d2, T) host array (any dtype);
+        the rows go through the library's GetSn kernel in chunks.  Returns the (d1, d2) map and stores it in P['sn']."""
+        from . import oasis as G
+        Y = np.asarray(Y)
+        T = Y.shape[2]
+        if frame_range is None:
+            frame_range = (1, min(T, 3000))
+        f0, f1 = int(frame_range[0]) - 1, int(frame_range[1])
+        d = self.d1 * self.d2
+        sn = np.empty(d)
+        Yr = Y.reshape(d, T, order="F")                      # pixel index r + c*d1, MATLAB order
+        for p0 in range(0, d, int(chunk)):
+            rows = np.ascontiguousarray(Yr[p0:p0 + int(chunk), f0:f1], dtype=np.float64)
+            sn[p0:p0 + rows.shape[0]] = G.GetSn(rows, device=self.device)
+        self.P["sn"] = sn.reshape(self.d1, self.d2, order="F")
+        return self.P["sn"]
+
     # ---- host-side brackets of the spatial update (library C++: csrc/host_spatial.cu) ----------------------------------
     def determine_search_location(self, A=None, min_size=3.0, max_size=8.0, dist=3.0, method="ellipse", nrgthr=0.9999,
                                   nb=1, bSiz=3):
