@@ -237,8 +237,9 @@ class Sources2D:
         return (not x.data.flags.writeable) if sp.issparse(x) else (not x.flags.writeable)
 
     def _mark(self, name, obj):
-        """The device now holds the contents of `obj` (only trusted while obj stays read-only)."""
-        self._dev[name] = obj
+        """The device now holds the contents of `obj` -- remembered only if obj is read-only NOW (a writable array could be
+        modified and frozen later, which would make stale device state look current)."""
+        self._dev[name] = obj if self._frozen(obj) else None
 
     def _current(self, name, obj):
         return self._dev.get(name) is obj and self._frozen(obj)
