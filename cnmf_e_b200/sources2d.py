@@ -305,7 +305,9 @@ class Sources2D:
             b0f = None if b0 is None else np.ascontiguousarray(b0, dtype=np.float64)
             L.check(self._lib.cnmfe_set_ring(self._h, i, _ptr(Wf), _ptr(b0f)))
             self.h2d_bytes += sum(x.nbytes for x in (Wf, b0f) if x is not None)
-            self._ring_synced[i] = (W, b0)
+            # identity is only evidence of "unchanged" for read-only arrays (a writable one may be edited in place)
+            ro = all(x is None or not x.flags.writeable for x in (W, b0))
+            self._ring_synced[i] = (W, b0) if ro else None
 
     def pull_ring(self):
         if str(self.options["background_model"]).lower() in ("svd", "nmf"):

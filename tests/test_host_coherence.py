@@ -64,3 +64,19 @@ def test_trace_range_and_owner_partition_are_consistent():
         o = patch_owners(npatch, ws)
         assert sorted(set(o.tolist())) == list(range(ws))
     assert [trace_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+
+
+def test_ring_weights_resent_unless_read_only():
+    lib = _RecordingLib()
+    obj = _make(lib)
+    dp = obj.d1 * obj.d2
+    W, b0 = np.zeros((dp, max(obj.nnb, 1))), np.zeros(dp)
+    obj.W[0], obj.b0[0] = W, b0
+    obj.push_ring(); obj.push_ring()
+    assert lib.calls["cnmfe_set_ring"] == 2             # writable arrays: never assumed unchanged
+    W.setflags(write=False); b0.setflags(write=False)
+    obj.push_ring(); obj.push_ring()
+    assert lib.calls["cnmfe_set_ring"] == 3             # read-only and identical: sent once more, then trusted
+    obj.b0[0] = np.zeros(dp)
+    obj.push_ring()
+    assert lib.calls["cnmfe_set_ring"] == 4
