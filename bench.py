@@ -231,13 +231,16 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-# ----------------------------------------------------------------------------------------------- full-size invariants
-def full_size_checks(A, IND, C, S, kernel_pars, neuron_sn, smin_mult=5.0):
+# ----------------------------------------------------------------------------------------------- full-size checks
+def full_size_invariants(A, IND, C, S, kernel_pars, neuron_sn, smin_mult=5.0):
     """Size-independent properties of one update iteration, evaluated on the FULL-size host results after the timed
     region (never inside it; nothing here runs on the GPU):
       spatial  A >= 0 and supp(A) inside the search mask (update_spatial_parallel.m:321-335, nnls);
       temporal oasisAR1 pool algebra of the final deconvTemporal (oasisAR1.m:101-109): S >= 0, S_t = C_t - g C_{t-1} where
-               S_t > 0, C_t = g C_{t-1} elsewhere (t >= 1), and every spike >= smin = 5 sn (deconvolveCa.m:116-118).
+               S_t > 0, C_t = g C_{t-1} elsewhere (t >= 1); and the smin rule in the form the reference enforces it: the
+               forward test oasisAR1.m:64-65 compares v'/w' with (v/w) g^l + smin WITHOUT clipping v/w at 0 (only the
+               back-track test :82-83 has max(0, .)), so a pool that follows a NEGATIVE pool (c clipped to 0, :105) may
+               start with a spike below smin.  Exact invariant: S_t >= smin wherever S_t > 0 and C_{t-1} > 0.
     Returns max violations (relative to the trace scale) -- reported, not asserted."""
     import scipy.sparse as sp
     out = {}
@@ -256,13 +259,76 @@ def full_size_checks(A, IND, C, S, kernel_pars, neuron_sn, smin_mult=5.0):
         out["max_rel_AR1_residual"] = float((np.abs(resid) / scale[:, None]).max()) if resid.size else 0.0
         spikes = S[:, 1:] > 0
         smin = smin_mult * np.asarray(neuron_sn, dtype=np.float64)
-        viol = np.where(spikes, smin[:, None] - S[:, 1:], 0.0)
-        out["max_rel_spike_below_smin"] = float(max(0.0, (viol / scale[:, None]).max())) if viol.size else 0.0
+        after_positive = spikes & (C[:, :-1] > 0)
+        viol = np.where(after_positive, smin[:, None] - S[:, 1:], 0.0)
+        out["max_rel_spike_below_smin_after_positive_pool"] = float(max(0.0, (viol / scale[:, None]).max())) if viol.size else 0.0
         out["n_spikes"] = int(spikes.sum())
+        out["n_spikes_below_smin_after_clipped_pool"] = int((spikes & ~after_positive & (S[:, 1:] < smin[:, None])).sum())
         out["ok"] = bool(out["A_min"] >= 0.0 and out["A_nnz_outside_search_mask"] == 0 and out["S_min"] >= 0.0
-                         and out["max_rel_AR1_residual"] < 1e-9 and out["max_rel_spike_below_smin"] < 1e-9)
+                         and out["max_rel_AR1_residual"] < 1e-9 and out["max_rel_spike_below_smin_after_positive_pool"] < 1e-9)
     except Exception as e:   # a reporting aid must never take the bench line down
         out["error"] = repr(e)
+    return out
+
+
+def full_size_oracle_checks(obj, IND, n_pix=200, seed=1):
+    """One more update iteration through the host-buffer API after the timed region, each stage spot-checked against the float64
+    oracle re-deriving individual output rows from the raw video (oracle/spot.py): W rows (fit_ring_model.m:92-108), A rows
+    (update_spatial_parallel.m:157-166 + nnls_spatial.m) and ALL traces of the final deconvTemporal (deconvTemporal.m:62-84) on the
+    merged C_raw the CUDA path fed it.  Single rank, single patch form (configs[1])."""
+    import ctypes
+    import scipy.sparse as sp
+    from cnmf_e_b200 import _lib
+    from oracle import spot
+    out = {}
+    try:
+        lib = _lib.lib()
+        i = obj.owned_patches()[0]
+        T = obj.T
+
+        def rows_fn(idx):
+            idx = np.ascontiguousarray(idx, dtype=np.int32)
+            buf = np.empty((idx.size, T), dtype=np.uint16)
+            _lib.check(lib.cnmfe_debug_video_rows(obj._h, i, idx.size, idx.ctypes.data_as(ctypes.c_void_p), buf.ctypes.data_as(ctypes.c_void_p)))
+            return buf.astype(np.float64)
+
+        view = spot.PatchView(obj.d1, obj.d2, obj.patch_of(i), obj.block_of(i), obj.r_shift, obj.c_shift, rows_fn)
+        rng = np.random.default_rng(seed)
+        W_old = obj.W[i]                       # stays intact: pull_ring alternates between two buffers
+        A_bg, C_bg = obj.A, obj.C
+        pmax = int((np.asarray(W_old) > 0).sum(axis=1).max())
+        obj.update_background_parallel()
+        W_new, b0 = obj.W[i], obj.b0[i]
+        # sampled pixels: half from the refitted (active) set, half from the search masks
+        sumA = np.asarray(abs(sp.csr_matrix(A_bg)).sum(axis=1)).ravel()
+        changed = np.nonzero((np.asarray(W_new) != np.asarray(W_old)).any(axis=1))[0]
+        INDr = sp.csr_matrix(IND)
+        p = obj.patch_of(i)
+        rr_, cc_ = np.meshgrid(np.arange(p[0] - 1, p[1]), np.arange(p[2] - 1, p[3]), indexing="ij")
+        fov_of_patch_pixel = (rr_ + cc_ * obj.d1).ravel(order="F")
+        inmask = np.nonzero(np.asarray(INDr[fov_of_patch_pixel].sum(axis=1)).ravel() > 0)[0]
+        pix_a = rng.choice(changed, min(n_pix // 2, changed.size), replace=False) if changed.size else np.zeros(0, dtype=int)
+        pix_m = rng.choice(inmask, min(n_pix // 2, inmask.size), replace=False) if inmask.size else np.zeros(0, dtype=int)
+        pixels = np.concatenate([pix_a, pix_m]).astype(int)
+        out["ring_rows_vs_oracle"] = dict(spot.ring_rows(view, pixels, A_bg, C_bg, W_old, W_new, b0, pmax,
+                                                         bool(obj.options["bg_acceleration"])),
+                                          n_pixels_refit_by_gpu=int(changed.size), sumA_nonzero_pixels=int((sumA > 0).sum()))
+        obj.options["spatial_algorithm"] = "nnls"
+        obj.update_spatial_parallel(IND=IND)
+        single = obj.npatch == 1
+        out["spatial_rows_vs_oracle"] = spot.spatial_rows(view, pix_m, None if single else obj.A_prev, None if single else obj.C_prev,
+                                                          W_new, b0, C_bg, IND, obj.A) if single else dict(skipped="multi-patch")
+        obj.update_temporal_parallel()
+        K = obj.A.shape[1]
+        Craw_in = np.empty((K, T))
+        _lib.check(lib.cnmfe_get_merged_craw(obj._h, Craw_in.ctypes.data_as(ctypes.c_void_p)))
+        out["deconvTemporal_vs_oracle"] = spot.deconv_traces(Craw_in, obj.C, obj.S, obj.C_raw, obj.P["kernel_pars"],
+                                                            obj.options["deconv_options"])
+        out["ok"] = bool(all(v.get("ok", False) for v in out.values() if isinstance(v, dict) and "skipped" not in v))
+    except Exception as e:
+        import traceback
+        out["error"] = repr(e) + " | " + traceback.format_exc().splitlines()[-1]
+        out["ok"] = False
     return out
 
 
@@ -392,7 +458,12 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
     e2e_val = float(d1) * d2 * T / float(te_t.item())
-    checks = full_size_checks(obj.A, IND, obj.C, obj.S, obj.P.get("kernel_pars"), obj.P.get("neuron_sn")) if rank == 0 else None
+    checks = None
+    if rank == 0:
+        checks = full_size_invariants(obj.A, IND, obj.C, obj.S, obj.P.get("kernel_pars"), obj.P.get("neuron_sn"))
+        if world == 1 and not args.no_oracle_checks:
+            checks["oracle"] = full_size_oracle_checks(obj, IND)
+            checks["ok"] = bool(checks.get("ok", False) and checks["oracle"].get("ok", False))
     # bytes the Sources2D mirror actually moved (it re-sends only host state that changed since the last sync)
     h2d = (obj.h2d_bytes - h2d0) // nE + d1 * d2 * 8
     d2h = (obj.d2h_bytes - d2h0) // nE
@@ -521,6 +592,7 @@ def main():
     ap.add_argument("--frames", type=int, default=T_FULL)
     ap.add_argument("--tensor", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-oracle-checks", action="store_true", help="skip the post-timing oracle spot checks of the full-size results")
     ap.add_argument("--bg-ssub", type=int, default=1, help="options.bg_ssub of the ring model (configs[1] is quoted at 1)")
     ap.add_argument("--workload", default="iteration", choices=["iteration", "oasis"])
     ap.add_argument("--oasis-traces", type=int, default=5000)

@@ -585,6 +585,10 @@ extern "C" int cnmfe_set_ring(cnmfe_ctx* c, int ip, const double* W, const doubl
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
     if (c->opt.background_model == 0 && c->opt.bg_ssub > 1) return ssub_set_ring(c, ip, W, b0);
     Patch& P = c->patches[ip];
+    if (!W && b0) {   // only the offsets change: the weights (and the first-run state that goes with them) stay
+        if (P.owned) CNMFE_CUDA_OK(cudaMemcpy(P.b0, b0, (size_t)P.dp * 8, cudaMemcpyHostToDevice));
+        return 0;
+    }
     bool uniform = true;
     if (W) {
         // first-run test of fit_ring_model.m:25 / update_background_parallel.m:143 on row 1 (patch pixel 0)
@@ -1364,6 +1368,64 @@ extern "C" int cnmfe_debug_second_moments(cnmfe_ctx* c, int ip, int use_tensor, 
     return 0;
 }
 extern "C" int cnmfe_last_gram_was_tensor(cnmfe_ctx* c) { return c ? c->last_gram_tensor : 0; }
+
+// sn = estimate_noise(obj, frame_range, 'psd') (@Sources2D/Sources2D.m:328-379) from the RESIDENT video: per-pixel GetSn
+// (OASIS_matlab/functions/GetSn.m) of the raw frames [f0, f1] (1-based inclusive) for every pixel of the owned patches.
+extern "C" int cnmfe_estimate_noise(cnmfe_ctx* c, int f0, int f1, double* sn) {
+    if (!c || !sn) { set_error("cnmfe_estimate_noise: null"); return -1; }
+    if (f0 < 1 || f1 > c->T || f1 - f0 + 1 < 32) { set_error("cnmfe_estimate_noise: frame range [%d, %d] outside [1, %d] or shorter than 32", f0, f1, c->T); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    const int n = f1 - f0 + 1, CH = 4096;
+    if (c->scr.reserve(std::max(c->scr.cap, pad256((size_t)CH * n * 8) + pad256((size_t)CH * 8) + 4096))) return -1;
+    std::vector<double> tmp(CH);
+    for (int ip = 0; ip < c->npatch; ++ip) {
+        Patch& P = c->patches[ip];
+        if (!P.owned) continue;
+        if (!P.uploaded) { set_error("cnmfe_estimate_noise: block %d not uploaded", ip); return -1; }
+        c->scr.reset();
+        TAKE_OR_FAIL(d_rows, c->scr.take<double>((size_t)CH * n));
+        TAKE_OR_FAIL(d_sn, c->scr.take<double>(CH));
+        for (int p0 = 0; p0 < P.dp; p0 += CH) {
+            const int m = std::min(CH, P.dp - p0);
+            dim3 gg((n + 255) / 256, m);
+            LAUNCH(rows_u16_to_f64_kernel, gg, 256, 0, c->st, P.Yt, c->Tpad, P.nrb, P.geom.pr_off, P.geom.pc_off, P.nr, p0,
+                   f0 - 1, n, d_rows);
+            if (getsn_batch_dev(d_rows, n, m, d_sn, &c->arena, c->st)) return -1;
+            CNMFE_CUDA_OK(cudaMemcpyAsync(tmp.data(), d_sn, (size_t)m * 8, cudaMemcpyDeviceToHost, c->st));
+            CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+            for (int i = 0; i < m; ++i) {
+                const int p = p0 + i, r = p % P.nr + P.patch.r0, cc = p / P.nr + P.patch.c0;
+                sn[(size_t)cc * c->d1 + r] = tmp[i];
+            }
+        }
+    }
+    CNMFE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// merged C_raw = sum_p aa_p C_raw,p / sum_p aa_p (update_temporal_parallel.m:269-280) as it ENTERED the final deconvTemporal,
+// i.e. before deconvTemporal.m:84 subtracts the baseline; valid after cnmfe_update_temporal_finish[_part] (rows this rank
+// finished).  K x T in the boundary layout (cnmfe_set_trace_major).  Lets a checker re-run deconvolveCa on the same input.
+extern "C" int cnmfe_get_merged_craw(cnmfe_ctx* c, double* Craw_in) {
+    if (!c || !Craw_in) { set_error("cnmfe_get_merged_craw: null"); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    return download_KT(c, c->num, c->K, Craw_in);
+}
+
+// rows of the resident video (diagnostics / spot checks against the oracle): out[i][0..T) = Y(block pixel idx[i], :) of block
+// ipatch as uint16, idx = r + c * nr_block (0-based, block coordinates)
+extern "C" int cnmfe_debug_video_rows(cnmfe_ctx* c, int ip, int n, const int32_t* idx, uint16_t* out) {
+    if (!c || ip < 0 || ip >= c->npatch || n < 0 || (n > 0 && (!idx || !out))) { set_error("cnmfe_debug_video_rows: bad arguments"); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    Patch& P = c->patches[ip];
+    if (!P.owned || !P.uploaded) { set_error("cnmfe_debug_video_rows: block not resident"); return -1; }
+    CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < n; ++i) {
+        if (idx[i] < 0 || idx[i] >= P.db) { set_error("cnmfe_debug_video_rows: pixel %d outside the block", idx[i]); return -1; }
+        CNMFE_CUDA_OK(cudaMemcpy(out + (size_t)i * c->T, P.Yt + (size_t)idx[i] * c->Tpad, (size_t)c->T * 2, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
 // Host planning under test on CPU: the block / patch-local view build_local() derives from a MATLAB CSC matrix.  No device
 // work.  sel: 0 sum-in-block > 0, 1 sum-in-halo > 0, 2 any-in-patch; rows: 0 block pixels, 1 block index of patch pixels only,
 // 2 patch pixels.  Output arrays must hold K (+1) / nrows + 1 / nnz entries; *n_local and *n_kept receive the used sizes.

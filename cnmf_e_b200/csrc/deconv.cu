@@ -66,6 +66,7 @@ int default_trace_slots(int device) {
 
 int trace_arena_reserve(TraceArena* a, int T, int nslots) {
     size_t sb = trace_slot_bytes(T);
+    if (!a->ticket) CNMFE_CUDA_OK(cudaMalloc((void**)&a->ticket, 64));
     if (a->base && a->slot_bytes >= sb && a->nslots >= nslots && a->T == T) return 0;
     if (a->base) { cudaFree(a->base); a->base = nullptr; }
     CNMFE_CUDA_OK(cudaMalloc((void**)&a->base, sb * (size_t)nslots));
@@ -74,7 +75,8 @@ int trace_arena_reserve(TraceArena* a, int T, int nslots) {
 }
 void trace_arena_free(TraceArena* a) {
     if (a->base) cudaFree(a->base);
-    a->base = nullptr; a->nslots = 0; a->slot_bytes = 0;
+    if (a->ticket) cudaFree(a->ticket);
+    a->base = nullptr; a->nslots = 0; a->slot_bytes = 0; a->ticket = nullptr;
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -318,11 +320,6 @@ __global__ void hals_order_kernel(const double* aa, int K, int maxIter, int* ord
 }
 
 // ------------------------------------------------------------------------------------------------ host wrappers
-static unsigned int* g_ticket = nullptr;   // small device scratch shared by the batch launches
-static int ensure_ticket() {
-    if (!g_ticket) CNMFE_CUDA_OK(cudaMalloc((void**)&g_ticket, 64));
-    return 0;
-}
 
 int deconv_batch_dev(const double* Y, int T, int N, const cnmfe_deconv_opts& o, const double* sn_in,
                      const double* pars_in, int mode, double* c, double* s, double* craw_out, double* outs,
@@ -342,15 +339,14 @@ int deconv_batch_dev(const double* Y, int T, int N, const cnmfe_deconv_opts& o, 
         set_error("deconvolve: thresholded with optimize_b is not built (needs estimate_baseline_noise)");
         return -1;
     }
-    if (ensure_ticket()) return -1;
     int dev = 0;
     cudaGetDevice(&dev);
     int slots, smode; size_t smem;
     if (trace_launch_shape(deconv_batch_kernel, T, dev, N, o.optimize_pars != 0, &slots, &smem, &smode)) return -1;
     if (trace_arena_reserve(arena, T, slots > arena->nslots ? slots : arena->nslots)) return -1;
-    CNMFE_CUDA_OK(cudaMemsetAsync(g_ticket, 0, 4, st));
+    CNMFE_CUDA_OK(cudaMemsetAsync(arena->ticket, 0, 4, st));
     LAUNCH(deconv_batch_kernel, slots, CNMFE_BLOCK, smem, st, Y, T, N, o, sn_in, pars_in, mode, c, s, craw_out, outs,
-           arena->base, arena->slot_bytes, g_ticket, smode);
+           arena->base, arena->slot_bytes, arena->ticket, smode);
     CNMFE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -358,14 +354,13 @@ int deconv_batch_dev(const double* Y, int T, int N, const cnmfe_deconv_opts& o, 
 int getsn_batch_dev(const double* Y, int T, int N, double* sn, TraceArena* arena, cudaStream_t st) {
     if (N <= 0) return 0;
     if (T < 32) { set_error("GetSn: T=%d too short", T); return -1; }
-    if (ensure_ticket()) return -1;
     int dev = 0;
     cudaGetDevice(&dev);
     int slots, smode; size_t smem;
     if (trace_launch_shape(getsn_batch_kernel, T, dev, N, false, &slots, &smem, &smode)) return -1;
     if (trace_arena_reserve(arena, T, slots > arena->nslots ? slots : arena->nslots)) return -1;
-    CNMFE_CUDA_OK(cudaMemsetAsync(g_ticket, 0, 4, st));
-    LAUNCH(getsn_batch_kernel, slots, CNMFE_BLOCK, smem, st, Y, T, N, sn, arena->base, arena->slot_bytes, g_ticket, smode);
+    CNMFE_CUDA_OK(cudaMemsetAsync(arena->ticket, 0, 4, st));
+    LAUNCH(getsn_batch_kernel, slots, CNMFE_BLOCK, smem, st, Y, T, N, sn, arena->base, arena->slot_bytes, arena->ticket, smode);
     CNMFE_CUDA_OK(cudaGetLastError());
     return 0;
 }

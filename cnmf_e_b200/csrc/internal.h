@@ -13,6 +13,7 @@ struct TraceArena {
     size_t slot_bytes = 0;
     int nslots = 0;
     int T = 0;
+    unsigned int* ticket = nullptr;   // work-item counter of the batch kernels launched on this arena (one arena = one ctx or one call)
 };
 size_t trace_slot_bytes(int T);
 int trace_arena_reserve(TraceArena* a, int T, int nslots);   // (re)allocates when too small

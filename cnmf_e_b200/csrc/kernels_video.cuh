@@ -53,6 +53,17 @@ __global__ void row_sum_strided_kernel(const uint16_t* __restrict__ Yt, int d, i
     if (lane == 0) S1[warp] = (double)s;
 }
 
+// rows of the resident video as doubles: dst[i][0..n) = Yt[q0(i)][f0 .. f0+n), q(i) = (c0 + i / nr) * nrb + r0 + i % nr
+// (patch pixels of a block in MATLAB order).  grid = (ceil(n/256), rows).
+__global__ void rows_u16_to_f64_kernel(const uint16_t* __restrict__ Yt, int Tpad, int nrb, int r0, int c0, int nr, int first,
+                                       int f0, int n, double* __restrict__ dst) {
+    const int i = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int p = first + i;
+    const size_t q = (size_t)(c0 + p / nr) * nrb + r0 + p % nr;
+    dst[(size_t)i * n + t] = (double)Yt[q * Tpad + f0 + t];
+}
+
 // Gather rows of a [K][T] matrix: dst[i] = src[ids[i]]; also row means and centred copy.
 __global__ void gather_center_rows_kernel(const double* __restrict__ src, const int* __restrict__ ids, int n, int T,
                                           double* __restrict__ dst_centered, double* __restrict__ mean_out) {

@@ -27,6 +27,9 @@ _SPATIAL = {"hals": 0, "hals_thresh": 1, "nnls": 2, "lars": 3}
 def patch_geometry(d1, d2, patch_dims, w_overlap):
     """patch_pos / block_pos of endoscope/distribute_data.m:39,55-77,163-173 (1-based inclusive [r0 r1 c0 c1])."""
     min_w = 2 * w_overlap + 3
+    patch_dims = [max(int(p), min_w) for p in np.atleast_1d(patch_dims)]      # distribute_data.m:46
+    if len(patch_dims) == 1:
+        patch_dims = patch_dims * 2
 
     def idx(dn, pd, force_last):
         x = dn / pd
@@ -52,6 +55,20 @@ def patch_geometry(d1, d2, patch_dims, w_overlap):
             block_pos[m, n] = [max(1, pr[m] - w_overlap - 1), min(d1, pr[m + 1] + w_overlap),
                                max(1, pc[n] - w_overlap - 1), min(d2, pc[n + 1] + w_overlap)]
     return patch_pos, block_pos
+
+
+def block_indices(patch_pos, d1, d2, w_overlap):
+    """block_idx_r, block_idx_c of distribute_data.m:91-98 (1-based): every patch border x contributes x-1-w and x+w,
+    clamped to the FOV, sorted, unique (so even a single patch gives three blocks per dimension)."""
+    def one(pidx, dn):
+        b = set()
+        for x in pidx:
+            b.add(min(max(int(x) - 1 - w_overlap, 1), dn))
+            b.add(min(max(int(x) + w_overlap, 1), dn))
+        return np.array(sorted(b))
+    pr = sorted(set(int(x) for x in patch_pos[:, 0, 0]) | {int(patch_pos[-1, 0, 1])})
+    pc = sorted(set(int(x) for x in patch_pos[0, :, 2]) | {int(patch_pos[0, -1, 3])})
+    return one(pr, d1), one(pc, d2)
 
 
 def trace_range(K, rank, world_size):
@@ -129,6 +146,7 @@ class Sources2D:
         self._ring_synced = {}      # patch -> (W, b0) objects whose contents the device holds
         self._dev = {}              # "A" / "C" / "A_prev" / "C_prev" -> host object whose contents the device holds
         self._pinned = {}           # name -> page-locked reusable host buffer (ring weights)
+        self._ring_flip = {}        # patch -> which of its two pinned W buffers the last pull_ring filled
         self.h2d_bytes = 0          # bytes this object has sent to / fetched from the device (state, not the video)
         self.d2h_bytes = 0
         self.b = {}
@@ -327,8 +345,10 @@ class Sources2D:
                 wshape = (d1s * d2s, nnb)
             else:
                 wshape = (dp, self.nnb)
-            # W lands in a page-locked buffer that the NEXT pull_ring overwrites (copy it to keep an old fit)
-            W = self._pinned_buffer(("W", i), wshape).view()
+            # W lands in one of TWO page-locked buffers used in alternation, so the array handed out by the previous
+            # pull_ring (e.g. kept by the caller for a convergence check) stays intact for one more update
+            self._ring_flip[i] = 1 - self._ring_flip.get(i, 1)
+            W = self._pinned_buffer(("W", i, self._ring_flip[i]), wshape).view()
             b0 = np.empty(dp)
             L.check(self._lib.cnmfe_get_ring(self._h, i, _ptr(W), _ptr(b0)))
             self.d2h_bytes += W.nbytes + b0.nbytes
@@ -395,6 +415,8 @@ class Sources2D:
         if sync_host:
             self.pull_ring()
             self.b0_new = self.reconstruct_b0()
+            if self.world_size > 1:     # patches are disjoint: the sum over ranks assembles the full map (update_background_parallel.m:315)
+                self.b0_new = self._allreduce_sum(self.b0_new.ravel()).reshape(self.d1, self.d2)
             # obj.A_prev = obj.A; obj.C_prev = obj.C (update_background_parallel.m:316-317): read-only state is shared,
             # not copied; the device took the same snapshot
             self.A_prev = self.A if self._frozen(self.A) else self._freeze(self.A.copy())
@@ -402,24 +424,46 @@ class Sources2D:
             self._mark("A_prev", self.A_prev)
             self._mark("C_prev", self.C_prev)
 
-    def estimate_noise(self, Y, frame_range=None, chunk=32768):
+    def estimate_noise(self, Y=None, frame_range=None, chunk=32768, replicate_block_quirk=True):
         """sn = estimate_noise(obj, frame_range, 'psd') (@Sources2D/Sources2D.m:328-379): per-pixel GetSn of the raw video on
-        frames [1, min(T, 3000)] by default (1-based inclusive, as in the reference).  Y: (d1, d2, T) host array (any dtype);
-        the rows go through the library's GetSn kernel in chunks.  Returns the (d1, d2) map and stores it in P['sn']."""
+        frames [1, min(T, 3000)] by default (1-based inclusive, as in the reference).  Returns the (d1, d2) map; like the
+        reference it does NOT assign obj.P.sn (the caller does, demo_large_data_1p.m / initComponents_parallel.m).
+        Y = None (single rank): the rows are read from the video resident on the device (cnmfe_estimate_noise); Y = (d1, d2, T)
+        host array: its rows go through the library's GetSn kernel in chunks.
+        replicate_block_quirk: the reference assembles the map from the blocks of distribute_data.m:91-98 and deletes row /
+        column `end-1` (not `end`) of every non-last block (Sources2D.m:369-374), so the map position just before an interior
+        block border holds the value of the border pixel itself; replicated by default, False gives the plain per-pixel map."""
         from . import oasis as G
-        Y = np.asarray(Y)
-        T = Y.shape[2]
-        if frame_range is None:
-            frame_range = (1, min(T, 3000))
-        f0, f1 = int(frame_range[0]) - 1, int(frame_range[1])
         d = self.d1 * self.d2
-        sn = np.empty(d)
-        Yr = Y.reshape(d, T, order="F")                      # pixel index r + c*d1, MATLAB order
-        for p0 in range(0, d, int(chunk)):
-            rows = np.ascontiguousarray(Yr[p0:p0 + int(chunk), f0:f1], dtype=np.float64)
-            sn[p0:p0 + rows.shape[0]] = G.GetSn(rows, device=self.device)
-        self.P["sn"] = sn.reshape(self.d1, self.d2, order="F")
-        return self.P["sn"]
+        if Y is None:
+            if frame_range is None:
+                frame_range = (1, min(self.T, 3000))
+            if self.world_size != 1:
+                raise L.CnmfeError("estimate_noise from the resident video needs all patches on this rank; pass Y")
+            out = np.zeros((self.d1, self.d2), order="F")
+            L.check(self._lib.cnmfe_estimate_noise(self._h, int(frame_range[0]), int(frame_range[1]), _ptr(out)))
+            sn = np.ascontiguousarray(out)
+        else:
+            Y = np.asarray(Y)
+            T = Y.shape[2]
+            if frame_range is None:
+                frame_range = (1, min(T, 3000))
+            f0, f1 = int(frame_range[0]) - 1, int(frame_range[1])
+            snv = np.empty(d)
+            Yr = Y.reshape(d, T, order="F")                      # pixel index r + c*d1, MATLAB order
+            for p0 in range(0, d, int(chunk)):
+                rows = np.ascontiguousarray(Yr[p0:p0 + int(chunk), f0:f1], dtype=np.float64)
+                snv[p0:p0 + rows.shape[0]] = G.GetSn(rows, device=self.device)
+            sn = snv.reshape(self.d1, self.d2, order="F")
+        if replicate_block_quirk:
+            br, bc = block_indices(self.patch_pos, self.d1, self.d2, int(self.options["ring_radius"]))
+            rmap, cmap = np.arange(self.d1), np.arange(self.d2)
+            for b in br[1:-1]:
+                rmap[b - 2] = b - 1          # 0-based: position of pixel b-1 shows pixel b
+            for b in bc[1:-1]:
+                cmap[b - 2] = b - 1
+            sn = np.ascontiguousarray(sn[np.ix_(rmap, cmap)])
+        return sn
 
     # ---- host-side brackets of the spatial update (library C++: csrc/host_spatial.cu) ----------------------------------
     def determine_search_location(self, A=None, min_size=3.0, max_size=8.0, dist=3.0, method="ellipse", nrgthr=0.9999,
@@ -433,6 +477,13 @@ class Sources2D:
         jc = np.ascontiguousarray(A.indptr, dtype=np.int64)
         ir = np.ascontiguousarray(A.indices, dtype=np.int64)
         pr = np.ascontiguousarray(A.data, dtype=np.float64)
+        m = str(method).lower()
+        if m not in ("ellipse", "dilate") or (m == "ellipse" and np.isinf(dist)):
+            # determine_search_location.m:91 (ellipse with dist == Inf) and the `otherwise` branch (:100-101): IND = true(d, K),
+            # all-zero components excluded (:103-105)
+            full = np.ones((self.d1 * self.d2, K), dtype=bool)
+            full[:, np.asarray(A.sum(axis=0)).ravel() == 0] = False
+            return sp.csc_matrix(full)
         if str(method).lower() == "dilate":
             cap = 1
             for k in range(K):
@@ -532,7 +583,7 @@ class Sources2D:
             if self.post_process_fn is not None:
                 A_new = sp.csc_matrix(self.post_process_fn(A_new))
             self.A = self._freeze(A_new)
-            if self.P.get("Ymean") is not None:
+            if self.P.get("Ymean") is not None and self._is_ring():      # update_spatial_parallel.m:347-351
                 self.b0_new = self.P["Ymean"] - (self.A @ self.C.mean(axis=1)).reshape(self.d1, self.d2, order="F")
             if self.world_size > 1 or self.post_process_fn is not None:
                 self.push_neurons()
@@ -590,8 +641,11 @@ class Sources2D:
         self.C, self.C_raw, self.S = self._freeze(C), self._freeze(Cr), self._freeze(S)
         self._mark("C", self.C)
         self.P["kernel_pars"], self.P["neuron_sn"] = kp, nsn
-        if self.P.get("Ymean") is not None:
+        if self.P.get("Ymean") is not None and self._is_ring():          # update_temporal_parallel.m:291-295
             self.b0_new = self.P["Ymean"] - (self.A @ self.C.mean(axis=1)).reshape(self.d1, self.d2, order="F")
+
+    def _is_ring(self):
+        return str(self.options["background_model"]).lower() == "ring"
 
     # aliases named by BASELINE.json north_star
     update_background = update_background_parallel

@@ -117,8 +117,8 @@ int cnmfe_set_search(cnmfe_ctx* ctx, int K, const int64_t* IND_jc, const int64_t
 int cnmfe_set_sn(cnmfe_ctx* ctx, const double* sn);
 /* obj.W{ipatch}, obj.b0{ipatch}: ring weights in slot form, W[i + p*nnb] = weight of patch pixel p for ring
  * offset i (cnmfe_ring_offsets), i.e. an nnb x d_patch column-major matrix; entries whose neighbour falls outside
- * the FOV are ignored.  NULL W = uniform
- * initialisation (initComponents_parallel.m:213-236). */
+ * the FOV are ignored.  NULL W and NULL b0 = uniform initialisation (initComponents_parallel.m:213-236); NULL W with a
+ * b0 replaces only the offsets and keeps the weights. */
 int cnmfe_ring_offsets(cnmfe_ctx* ctx, int* nnb, int32_t* r_shift, int32_t* c_shift);
 int cnmfe_set_ring(cnmfe_ctx* ctx, int ipatch, const double* W_slots, const double* b0);
 int cnmfe_get_ring(cnmfe_ctx* ctx, int ipatch, double* W_slots, double* b0);
@@ -139,6 +139,10 @@ int cnmfe_update_spatial(cnmfe_ctx* ctx);
  * update_spatial_parallel.m:191-194) before the solve; read it back with cnmfe_get_sn_map (d1 x d2) */
 int cnmfe_update_spatial_ex(cnmfe_ctx* ctx, int update_sn);
 int cnmfe_get_sn_map(cnmfe_ctx* ctx, double* sn);
+/* sn = estimate_noise(obj, frame_range, 'psd') (@Sources2D/Sources2D.m:328-379) from the RESIDENT video: per-pixel GetSn of
+ * the raw frames [f0, f1] (1-based inclusive; the reference's default is [1, min(T, 3000)]) on the pixels of the owned patches;
+ * sn is d1 x d2 column-major, other pixels untouched.  The reference's block-border quirk (:369-374) is applied by the caller. */
+int cnmfe_estimate_noise(cnmfe_ctx* ctx, int f0, int f1, double* sn);
 /* A on the search pattern: values aligned with (IND_jc, IND_ir) given to cnmfe_set_search */
 int cnmfe_get_spatial(cnmfe_ctx* ctx, double* A_on_IND);
 /* replace obj.A by values on the search pattern (e.g. after the cross-GPU exchange of the patches' rows, or after
@@ -216,6 +220,11 @@ int cnmfe_last_phase_ms(cnmfe_ctx* ctx, float* ms7);
 int cnmfe_debug_second_moments(cnmfe_ctx* ctx, int ipatch, int use_tensor, double* out);
 /* 1 if the last cnmfe_update_background used the tensor-core kernel for the second moments */
 int cnmfe_last_gram_was_tensor(cnmfe_ctx* ctx);
+/* rows of the resident video: out[i][0..T) = Y(block pixel idx[i], :) of block ipatch, idx = r + c*nr_block (0-based) */
+int cnmfe_debug_video_rows(cnmfe_ctx* ctx, int ipatch, int n, const int32_t* idx, uint16_t* out);
+/* the merged C_raw (update_temporal_parallel.m:269-280) as it entered the final deconvTemporal (before deconvTemporal.m:84
+ * subtracts the baseline); K x T in the boundary layout.  A checker can re-run deconvolveCa on exactly this input. */
+int cnmfe_get_merged_craw(cnmfe_ctx* ctx, double* Craw_in);
 
 #ifdef __cplusplus
 }

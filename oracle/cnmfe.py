@@ -116,9 +116,11 @@ def is_first_run(W_old):
     return len(np.unique(np.asarray(W_old[0, :].todense()).ravel())) == 2
 
 
-def fit_ring_model(Y, A, C, W_old, thresh_outlier, sn=None, ind_patch=None, with_projection=True):
+def fit_ring_model(Y, A, C, W_old, thresh_outlier, sn=None, ind_patch=None, with_projection=True, pmax=None):
     """fit_ring_model.m:11-128.  Y: (d_blk,T) any dtype; A: (d_blk,K); C: (K,T); W_old: sparse (d_p,d_blk).
-    Returns W (CSR, same pattern as W_old) and b0 (d_p,)."""
+    Returns W (CSR, same pattern as W_old) and b0 (d_p,).
+    pmax (not in the reference): overrides max_m nnz(W_old(m,:) > 0) of :61 -- used by spot checks that hand over a few rows
+    of a large patch and must subsample frames exactly as the full call did."""
     Y = np.asarray(Y)
     d, T = Y.shape
     if A is None or np.size(A) == 0:
@@ -147,7 +149,8 @@ def fit_ring_model(Y, A, C, W_old, thresh_outlier, sn=None, ind_patch=None, with
         ind_outlier = tmp_Bf > (Bf_old + thresh_outlier * np.asarray(sn).reshape(-1, 1))
         tmp_Bf[ind_outlier] = Bf_old[ind_outlier]
         Bf[ind_patch, :] = tmp_Bf
-    pmax = int(np.max(np.asarray((W_old > 0).sum(axis=1)).ravel()))
+    if pmax is None:
+        pmax = int(np.max(np.asarray((W_old > 0).sum(axis=1)).ravel()))
     nmax = pmax * 100
     if use_outlier and nmax < T:
         temp = ind_outlier.sum(axis=0)
@@ -385,6 +388,42 @@ def HALS_temporal(Y, A, C, maxIter=1, deconv_options=None):
                     C_raw[k, :] = ck_raw
     res = dict(sn=sn, kernel_pars=kernel_pars) if deconv_flag else None
     return C, C_raw, res, S
+
+
+def estimate_noise(Y, patch_dims, w_overlap, frame_range=None):
+    """Sources2D.estimate_noise (@Sources2D/Sources2D.m:328-379), method 'psd': GetSn per pixel, evaluated block by block on
+    the block grid of distribute_data.m:91-98 (block_idx = sorted unique clamped patch borders -1-w / +w), INCLUDING the
+    reference's assembly quirk: row / column `end-1` of every non-last block is deleted (:369-374) although consecutive blocks
+    share their border row, so the kept border row appears twice and the row before it never does.  Y: (d1, d2, T)."""
+    d1, d2, T = Y.shape
+    if frame_range is None:
+        frame_range = (1, min(T, 3000))
+    patch_pos, _ = patch_geometry(d1, d2, patch_dims, w_overlap)
+    pr = sorted(set(int(x) for x in patch_pos[:, 0, 0]) | {int(patch_pos[-1, 0, 1])})
+    pc = sorted(set(int(x) for x in patch_pos[0, :, 2]) | {int(patch_pos[0, -1, 3])})
+    # patch_idx_r as distribute_data.m:56-67 built it: starts of the patches and the last row
+    def block_idx(pidx, dn):
+        b = []
+        for x in pidx:
+            b += [x - 1 - w_overlap, x + w_overlap]
+        b = [min(max(v, 1), dn) for v in b]
+        return sorted(set(b))
+    bir, bic = block_idx(pr, d1), block_idx(pc, d2)
+    nrb, ncb = len(bir) - 1, len(bic) - 1
+    cols = []
+    for n in range(ncb):
+        rows = []
+        for m in range(nrb):
+            r0, r1, c0, c1 = bir[m], bir[m + 1], bic[n], bic[n + 1]
+            Yp = Y[r0 - 1:r1, c0 - 1:c1, frame_range[0] - 1:frame_range[1]].astype(np.float64)
+            tmp = O.GetSn(Yp.reshape(-1, Yp.shape[2], order="F")).reshape(r1 - r0 + 1, c1 - c0 + 1, order="F")
+            if m != nrb - 1:
+                tmp = np.delete(tmp, -2, axis=0)
+            if n != ncb - 1:
+                tmp = np.delete(tmp, -2, axis=1)
+            rows.append(tmp)
+        cols.append(np.vstack(rows))
+    return np.hstack(cols)
 
 
 # ----------------------------------------------------------------------------- Sources2D restatement

@@ -4,13 +4,13 @@ spike support (indices where s>0) must be IDENTICAL."""
 import numpy as np
 import pytest
 
+import gpu_cases as GC
+
 pytestmark = pytest.mark.gpu
 
 
-def _traces(N=6, T=3000, noise=0.1, g=0.95, seed=13):
-    from oracle import oasis as O
-    Y, truth, sp = O.gen_data(gam=g, noise=noise, T=T, N=N, seed=seed)
-    return Y, truth, sp
+def _traces(name):
+    return GC.traces(name)
 
 
 def _compare(Y, opts, built_lib, rtol=1e-7):
@@ -32,7 +32,7 @@ def test_getsn_matches_oracle(built_lib):
     from cnmf_e_b200 import oasis as G
     from oracle import oasis as O
     for T in (1000, 3000, 10000, 20011):
-        Y, _, _ = _traces(N=3, T=T, noise=0.3)
+        Y, _, _ = _traces("ar1_getsn_%d" % T)
         sn = G.GetSn(Y)
         ref = O.GetSn(Y)
         assert np.allclose(sn, ref, rtol=1e-10), (T, sn, ref)
@@ -40,44 +40,42 @@ def test_getsn_matches_oracle(built_lib):
 
 def test_foopsi_ar1_demo_options(built_lib):
     """deconv_options of demos/demo_large_data_1p.m:41-47"""
-    Y, _, _ = _traces(noise=0.1)
+    Y, _, _ = _traces("ar1_n01")
     _compare(Y, dict(type="ar1", method="foopsi", smin=-5, optimize_pars=True, optimize_b=True, max_tau=100), built_lib)
 
 
 def test_foopsi_ar1_fixed_g_lambda(built_lib):
-    Y, _, _ = _traces(noise=0.3)
+    Y, _, _ = _traces("ar1_n03")
     _compare(Y, dict(type="ar1", method="foopsi", pars=[0.95], **{"lambda": 0.5}), built_lib)
     _compare(Y, dict(type="ar1", method="foopsi", pars=[0.95], smin=0.4, optimize_pars=True), built_lib)
 
 
 def test_constrained_ar1(built_lib):
-    Y, _, _ = _traces(noise=0.3)
+    Y, _, _ = _traces("ar1_n03")
     _compare(Y, dict(), built_lib)                                             # deconvolveCa.m:220 default method
     _compare(Y, dict(optimize_b=True, optimize_pars=True), built_lib, rtol=1e-6)
 
 
 def test_thresholded_ar1(built_lib):
-    Y, _, _ = _traces(noise=0.3)
+    Y, _, _ = _traces("ar1_n03")
     _compare(Y, dict(method="thresholded", optimize_pars=True), built_lib, rtol=1e-6)
 
 
 def test_foopsi_ar2(built_lib):
-    from oracle import oasis as O
-    Y, _, _ = O.gen_data([1.7, -0.712], 1.0, 3000, 30, 0.5, 0, 4, 3)
+    Y, _, _ = _traces("ar2_4")
     _compare(Y, dict(type="ar2", method="foopsi", pars=[1.7, -0.712], smin=-3), built_lib)
     _compare(Y, dict(type="ar2", method="foopsi", smin=-3), built_lib, rtol=1e-6)
 
 
 def test_thresholded_ar2(built_lib):
-    from oracle import oasis as O
-    Y, _, _ = O.gen_data([1.7, -0.712], 1.0, 3000, 30, 0.5, 0, 3, 3)
+    Y, _, _ = _traces("ar2_3")
     _compare(Y, dict(type="ar2", method="thresholded", pars=[1.7, -0.712]), built_lib)
 
 
 def test_pav_invariants_large(built_lib):
     """Size-independent properties at a BASELINE-scale T: s>=smin or 0, c_t = g c_{t-1} off spikes."""
     from cnmf_e_b200 import oasis as G
-    Y, _, _ = _traces(N=8, T=100000, noise=0.2)
+    Y, _, _ = _traces("ar1_long")
     r = G.deconvolveCa_batch(Y, dict(type="ar1", method="foopsi", pars=[0.95], smin=0.5))
     for n in range(Y.shape[0]):
         c, s = r["c"][n], r["s"][n]
@@ -90,8 +88,8 @@ def test_pav_invariants_large(built_lib):
 
 def test_hals_temporal_uv(built_lib):
     from cnmf_e_b200 import oasis as G
-    from oracle import cnmfe as OC, gen
-    D = gen.make_synthetic(48, 48, 1500, 8, seed=5, nblob=0, bg_amp=0.0)
+    from oracle import cnmfe as OC
+    D = GC.synthetic("hals_uv")
     Y = D["Y"].reshape(-1, 1500, order="F").astype(np.float64)
     Y = Y - Y.mean(axis=1, keepdims=True)
     A = D["A0"].toarray()

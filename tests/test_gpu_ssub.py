@@ -4,6 +4,8 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
+import gpu_cases as GC
+
 pytestmark = pytest.mark.gpu
 
 
@@ -13,13 +15,14 @@ def _close(a, b, tol=1e-7):
     assert err <= tol * scale, "max abs err %g (scale %g)" % (err, scale)
 
 
-@pytest.mark.parametrize("shape", [(60, 52, 500, 5, (60, 52), 2), (75, 64, 400, 7, (38, 32), 2), (48, 45, 300, 4, (48, 45), 3)])
+@pytest.mark.parametrize("shape", [("ssub_60x52", (60, 52), 2), ("ssub_75x64_patches", (38, 32), 2), ("ssub3_48x45", (48, 45), 3)])
 def test_bg_ssub_chain(built_lib, shape):
-    from oracle import gen, oasis as O
+    from oracle import oasis as O
     from oracle.ssub import OracleSources2DSsub
     from cnmf_e_b200.sources2d import Sources2D
-    d1, d2, T, K, patch, ssub = shape
-    D = gen.make_synthetic(d1, d2, T, K, seed=41, nblob=3)
+    case, patch, ssub = shape
+    D = GC.synthetic(case)
+    d1, d2, T = D["Y"].shape
     sn = O.GetSn(D["Y"].reshape(-1, T, order="F").astype(np.float64)).reshape(d1, d2, order="F")
     orc = OracleSources2DSsub(D["Y"], patch, ring_radius=10, bg_ssub=ssub, options=dict(spatial_algorithm="hals_thresh"))
     gpu = Sources2D(d1, d2, T, patch, ring_radius=10, options=dict(bg_ssub=ssub, spatial_algorithm="hals_thresh"))

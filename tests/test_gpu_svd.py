@@ -4,6 +4,8 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
+import gpu_cases as GC
+
 pytestmark = pytest.mark.gpu
 
 
@@ -13,13 +15,14 @@ def _close(a, b, tol=1e-7):
     assert err <= tol * scale, "max abs err %g (scale %g)" % (err, scale)
 
 
-@pytest.mark.parametrize("shape", [(48, 40, 500, 5, (48, 40), 1), (64, 60, 400, 8, (32, 30), 2)])
+@pytest.mark.parametrize("shape", [("svd_48x40", (48, 40), 1), ("svd_64x60_patches", (32, 30), 2)])
 def test_svd_background_chain(built_lib, shape):
-    from oracle import gen, oasis as O
+    from oracle import oasis as O
     from oracle.svd_bg import OracleSources2DSVD
     from cnmf_e_b200.sources2d import Sources2D
-    d1, d2, T, K, patch, nb = shape
-    D = gen.make_synthetic(d1, d2, T, K, seed=31, nblob=3, bg_amp=60.0)
+    case, patch, nb = shape
+    D = GC.synthetic(case)
+    d1, d2, T = D["Y"].shape
     sn = O.GetSn(D["Y"].reshape(-1, T, order="F").astype(np.float64)).reshape(d1, d2, order="F")
     orc = OracleSources2DSVD(D["Y"], patch, ring_radius=6, nb=nb, options=dict(spatial_algorithm="hals"))
     gpu = Sources2D(d1, d2, T, patch, ring_radius=6, options=dict(background_model="svd", nb=nb, spatial_algorithm="hals"))
@@ -46,11 +49,10 @@ def test_svd_background_chain(built_lib, shape):
 def test_nmf_background_subtraction(built_lib):
     """nmf model: the fit (nnmf, random init) stays in MATLAB; given b, f the BG subtraction Y - b*f of the spatial and
     temporal updates (update_spatial_parallel.m:179-182, update_temporal_parallel.m:165-168) must match the oracle."""
-    from oracle import gen
     from oracle.svd_bg import OracleSources2DSVD
     from cnmf_e_b200.sources2d import Sources2D
     d1, d2, T, K = 40, 36, 400, 4
-    D = gen.make_synthetic(d1, d2, T, K, seed=8, nblob=2, bg_amp=50.0)
+    D = GC.synthetic("nmf_sub")
     Yf = D["Y"].reshape(-1, T, order="F").astype(np.float64)
     u, s, vt = np.linalg.svd(Yf, full_matrices=False)
     b = np.abs(u[:, :1] * s[0]); f = np.abs(vt[:1])                 # a deterministic non-negative rank-1 factorisation

@@ -6,13 +6,16 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
+import gpu_cases as GC
+
 pytestmark = pytest.mark.gpu
 
 
-def _make(d1, d2, T, K, patch, rr, seed, nblob=4):
-    from oracle import gen, cnmfe as OC, oasis as O
+def _make(case, patch, rr):
+    from oracle import cnmfe as OC, oasis as O
     from cnmf_e_b200.sources2d import Sources2D
-    D = gen.make_synthetic(d1, d2, T, K, seed=seed, nblob=nblob)
+    D = GC.synthetic(case)
+    d1, d2, T = D["Y"].shape
     sn = O.GetSn(D["Y"].reshape(-1, T, order="F").astype(np.float64)).reshape(d1, d2, order="F")
     orc = OC.OracleSources2D(D["Y"], patch, ring_radius=rr)
     orc.A, orc.C = D["A0"].copy(), D["C0"].copy()
@@ -61,10 +64,10 @@ def _sync_from_oracle(orc, gpu):
         gpu.b0[i] = np.asarray(orc.b0[mp]).copy()
 
 
-@pytest.mark.parametrize("shape", [(64, 64, 1000, 6, (64, 64)), (96, 80, 600, 10, (48, 40))])
+@pytest.mark.parametrize("shape", [("chain_64", (64, 64)), ("chain_96x80_patches", (48, 40))])
 def test_background_spatial_temporal_chain(built_lib, shape):
-    d1, d2, T, K, patch = shape
-    D, orc, gpu = _make(d1, d2, T, K, patch, 9, seed=7)
+    case, patch = shape
+    D, orc, gpu = _make(case, patch, 9)
     IND = D["IND"]
     # ---- background, first run (uniform W -> every pixel active)
     orc.update_background_parallel()
@@ -102,7 +105,7 @@ def test_background_spatial_temporal_chain(built_lib, shape):
 
 
 def test_hals_and_no_deconv(built_lib):
-    D, orc, gpu = _make(64, 64, 800, 5, (64, 64), 9, seed=11)
+    D, orc, gpu = _make("hals_nodeconv", (64, 64), 9)
     for o in (orc, gpu):
         o.options["spatial_algorithm"] = "hals"
         o.options["deconv_flag"] = False
@@ -117,9 +120,8 @@ def test_hals_and_no_deconv(built_lib):
 def test_bg_identity_property(built_lib):
     """right after a BG update, mean_t(Ysig) = A_prev * mean(C_prev) on patch pixels, and W keeps the
     ring sparsity pattern -- checked through the temporal projection constant at a size the oracle does not need."""
-    from oracle import gen
     from cnmf_e_b200.sources2d import Sources2D
-    D = gen.make_synthetic(128, 128, 1200, 12, seed=3)
+    D = GC.synthetic("bg_identity")
     g = Sources2D(128, 128, 1200, (128, 128), ring_radius=18)
     g.load_video(D["Y"])
     g.A, g.C = D["A0"].copy(), D["C0"].copy()
@@ -135,7 +137,7 @@ def test_bg_identity_property(built_lib):
 def test_update_sn_and_lars(built_lib):
     """update_spatial_parallel(obj, use_parallel, update_sn=true) (:191-194) and spatial_algorithm='lars'
     (utilities/lars_spatial.m incl. its thresh(m) indexing quirk) need the explicit BG-subtracted rows."""
-    D, orc, gpu = _make(64, 48, 700, 5, (64, 48), 9, seed=21)
+    D, orc, gpu = _make("sn_lars", (64, 48), 9)
     orc.update_background_parallel(); gpu.update_background_parallel()
     for o in (orc, gpu):
         o.options["spatial_algorithm"] = "hals_thresh"
@@ -154,7 +156,7 @@ def test_update_sn_and_lars(built_lib):
 
 def test_fast_temporal_use_c_hat_false(built_lib):
     """update_temporal_parallel(obj, use_parallel, use_c_hat=false): fast_temporal (:314-337) instead of the HALS sweeps."""
-    D, orc, gpu = _make(64, 48, 600, 5, (64, 48), 9, seed=33)
+    D, orc, gpu = _make("fast_temporal", (64, 48), 9)
     orc.update_background_parallel(); gpu.update_background_parallel()
     orc.update_temporal_parallel(True, False)
     gpu.update_temporal_parallel(True, False)
@@ -167,7 +169,7 @@ def test_fast_temporal_use_c_hat_false(built_lib):
 def test_background_ring18_parity(built_lib):
     """Ring radius 18 (120 neighbours: the 121 x 121 systems of BASELINE configs[1], all eight 16-column blocks of the
     register-resident LDL' solver) against the oracle: first run (all pixels) and steady state (active pixels only)."""
-    D, orc, gpu = _make(56, 48, 500, 4, (56, 48), 18, seed=5)
+    D, orc, gpu = _make("ring18", (56, 48), 18)
     orc.update_background_parallel()
     gpu.update_background_parallel()
     _check_bg(orc, gpu)
@@ -181,10 +183,10 @@ def test_background_ring18_parity(built_lib):
 def test_no_neurons(built_lib):
     """K = 0: the first BG update still fits the ring weights on the raw video (fit_ring_model.m:25-29, first run = all pixels
     active); a second one skips the patch (update_background_parallel.m:188-199); spatial / temporal are no-ops."""
-    from oracle import gen, cnmfe as OC
+    from oracle import cnmfe as OC
     from cnmf_e_b200.sources2d import Sources2D
     d1, d2, T, rr = 40, 36, 300, 6
-    D = gen.make_synthetic(d1, d2, T, 3, seed=5, nblob=2)
+    D = GC.synthetic("no_neurons")
     orc = OC.OracleSources2D(D["Y"], (d1, d2), ring_radius=rr)
     gpu = Sources2D(d1, d2, T, (d1, d2), ring_radius=rr)
     gpu.load_video(D["Y"])
