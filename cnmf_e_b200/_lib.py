@@ -91,6 +91,7 @@ SYMBOLS = {
     "cnmfe_last_phase_ms": (I, [V, c_float_p]),
     "cnmfe_debug_second_moments": (I, [V, I, I, V]),
     "cnmfe_last_gram_was_tensor": (I, [V]),
+    "cnmfe_last_gram_frames": (I, [V]),
     "cnmfe_debug_video_rows": (I, [V, I, I, V, V]),
     "cnmfe_get_merged_craw": (I, [V, V]),
     "cnmfe_estimate_noise": (I, [V, I, I, V]),

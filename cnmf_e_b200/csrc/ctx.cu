@@ -52,6 +52,7 @@ struct Patch {
     int nr, nc, nrb, ncb, dp, db;
     bool owned = false, uploaded = false, w_uniform = true;
     uint16_t* Yt = nullptr; uint8_t* hi = nullptr; uint8_t* lo = nullptr;
+    uint8_t* hi_k = nullptr; uint8_t* lo_k = nullptr; int planes_kf = 0, Tpad_k = 0;   // byte planes of every kf-th frame (tensor path, kf > 1)
     double* Ysum = nullptr; double* Ymean = nullptr;
     double* W = nullptr; double* b0 = nullptr;
     double* bsvd = nullptr; double* fsvd = nullptr;   // svd background: b [nb][dp] (col-major dp x nb), f [nb][T]
@@ -106,7 +107,7 @@ struct cnmfe_ctx {
     cudaStream_t st = nullptr, st2 = nullptr;   // st2: second-moment kernel, overlapped with the host planning of the BG update
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr, ge0 = nullptr, ge1 = nullptr;
     float phase_ms[7] = {0, 0, 0, 0, 0, 0, 0};
-    int last_gram_tensor = 0;
+    int last_gram_tensor = 0, last_gram_frames = 0;
     int use_c_hat = 1;            // update_temporal_parallel(obj, use_parallel, use_c_hat)
     int trace_major = 0;          // 1: K x T arrays cross the ABI trace-contiguous ([K][T]) instead of MATLAB column-major
     void* ssub_state = nullptr;   // SsubCtx (ctx_ssub.inc): coarse-grid ring model for options.bg_ssub > 1
@@ -439,7 +440,7 @@ extern "C" void cnmfe_destroy(cnmfe_ctx* c) {
     cudaSetDevice(c->device);
     ssub_destroy(c);
     for (Patch& P : c->patches) {
-        for (void* p : {(void*)P.Yt, (void*)P.hi, (void*)P.lo, (void*)P.Ysum, (void*)P.Ymean, (void*)P.W, (void*)P.b0, (void*)P.bsvd, (void*)P.fsvd})
+        for (void* p : {(void*)P.Yt, (void*)P.hi, (void*)P.lo, (void*)P.hi_k, (void*)P.lo_k, (void*)P.Ysum, (void*)P.Ymean, (void*)P.W, (void*)P.b0, (void*)P.bsvd, (void*)P.fsvd})
             if (p) cudaFree(p);
     }
     for (void* p : {(void*)c->C, (void*)c->Cprev, (void*)c->Craw, (void*)c->S, (void*)c->num, (void*)c->den,
@@ -487,6 +488,7 @@ static int upload_common(cnmfe_ctx* c, int ip, const void* Y, int dtype, bool on
         CNMFE_CUDA_OK(cudaMalloc((void**)&P.Ysum, (size_t)P.db * 8));
         CNMFE_CUDA_OK(cudaMalloc((void**)&P.Ymean, (size_t)P.db * 8));
     }
+    P.planes_kf = 0;   // sub-sampled planes belong to the previous video
     CNMFE_CUDA_OK(cudaMemsetAsync(P.Yt, 0, n * 2, c->st));
     CNMFE_CUDA_OK(cudaMemsetAsync(P.hi, 0, n, c->st));
     CNMFE_CUDA_OK(cudaMemsetAsync(P.lo, 0, n, c->st));
@@ -732,8 +734,31 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
             int tc_rc = 1;
             if (c->opt.use_tensor_gram && kf == 1)
                 tc_rc = ring_s2_tensor(P.hi, P.lo, P.nrb, P.ncb, T, c->Tpad, c->rr, d_S2, c->st2);
+            else if (c->opt.use_tensor_gram) {
+                // frame-subsampled fit (fit_ring_model.m:84-90): the tensor kernel runs on compacted byte planes of the kept
+                // frames, rebuilt only when the stride changes (one strided pass over the resident video)
+                const int Tk = (T - 1) / kf + 1, Tpadk = (Tk + 127) / 128 * 128;
+                if (P.planes_kf != kf) {
+                    if (P.hi_k) cudaFree(P.hi_k);
+                    if (P.lo_k) cudaFree(P.lo_k);
+                    P.hi_k = P.lo_k = nullptr; P.planes_kf = 0;
+                    if (cudaMalloc((void**)&P.hi_k, (size_t)P.db * Tpadk) == cudaSuccess &&
+                        cudaMalloc((void**)&P.lo_k, (size_t)P.db * Tpadk) == cudaSuccess) {
+                        dim3 gs(P.db, (Tpadk + 255) / 256);
+                        LAUNCH(subsample_planes_kernel, gs, 256, 0, c->st2, P.Yt, c->Tpad, kf, Tk, Tpadk, P.hi_k, P.lo_k);
+                        P.planes_kf = kf; P.Tpad_k = Tpadk;
+                    } else {
+                        (void)cudaGetLastError();      // no room for the planes: the exact SIMT kernel takes over
+                        if (P.hi_k) cudaFree(P.hi_k);
+                        P.hi_k = nullptr;
+                    }
+                }
+                if (P.planes_kf == kf)
+                    tc_rc = ring_s2_tensor(P.hi_k, P.lo_k, P.nrb, P.ncb, Tk, P.Tpad_k, c->rr, d_S2, c->st2);
+            }
             if (tc_rc < 0) return -1;
             c->last_gram_tensor = (tc_rc == 0);
+            c->last_gram_frames = (T - 1) / kf + 1;
             if (tc_rc != 0) {
                 long long nw = (long long)((P.nrb + 3) / 4) * P.ncb;
                 dim3 gg((unsigned)((nw + 7) / 8), c->ngroups);
@@ -1368,6 +1393,7 @@ extern "C" int cnmfe_debug_second_moments(cnmfe_ctx* c, int ip, int use_tensor, 
     return 0;
 }
 extern "C" int cnmfe_last_gram_was_tensor(cnmfe_ctx* c) { return c ? c->last_gram_tensor : 0; }
+extern "C" int cnmfe_last_gram_frames(cnmfe_ctx* c) { return c ? c->last_gram_frames : 0; }
 
 // sn = estimate_noise(obj, frame_range, 'psd') (@Sources2D/Sources2D.m:328-379) from the RESIDENT video: per-pixel GetSn
 // (OASIS_matlab/functions/GetSn.m) of the raw frames [f0, f1] (1-based inclusive) for every pixel of the owned patches.
@@ -1387,7 +1413,7 @@ extern "C" int cnmfe_estimate_noise(cnmfe_ctx* c, int f0, int f1, double* sn) {
         TAKE_OR_FAIL(d_sn, c->scr.take<double>(CH));
         for (int p0 = 0; p0 < P.dp; p0 += CH) {
             const int m = std::min(CH, P.dp - p0);
-            dim3 gg((n + 255) / 256, m);
+            dim3 gg((n + 255) / 256, m);   // m <= 4096 rows
             LAUNCH(rows_u16_to_f64_kernel, gg, 256, 0, c->st, P.Yt, c->Tpad, P.nrb, P.geom.pr_off, P.geom.pc_off, P.nr, p0,
                    f0 - 1, n, d_rows);
             if (getsn_batch_dev(d_rows, n, m, d_sn, &c->arena, c->st)) return -1;

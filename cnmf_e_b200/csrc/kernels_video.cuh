@@ -28,6 +28,18 @@ __global__ void transpose_chunk_kernel(const TIN* __restrict__ src, int d, int n
     }
 }
 
+// Frame-subsampled byte planes for the tensor-core second moments when fit_ring_model.m:84-90 keeps every kf-th frame:
+// hi_k/lo_k[q][j] = bytes of Yt[q][j * kf], j < Tk; columns Tk .. Tpadk-1 are zero.  grid = (d, ceil(Tpadk/256)).
+__global__ void subsample_planes_kernel(const uint16_t* __restrict__ Yt, int Tpad, int kf, int Tk, int Tpadk,
+                                        uint8_t* __restrict__ hi, uint8_t* __restrict__ lo) {
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;
+    const size_t q = blockIdx.x;
+    if (j >= Tpadk) return;
+    const unsigned v = j < Tk ? Yt[q * Tpad + (size_t)j * kf] : 0u;
+    hi[q * Tpadk + j] = (uint8_t)(v >> 8);
+    lo[q * Tpadk + j] = (uint8_t)(v & 0xffu);
+}
+
 // Ysum[q] = sum_t Yt[q][t]  (exact: integers).  One warp per pixel.
 __global__ void row_sum_kernel(const uint16_t* __restrict__ Yt, int d, int T, int Tpad, double* __restrict__ Ysum) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;

@@ -94,6 +94,44 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
+class _RingWeights(dict):
+    """obj.W: patch -> slot-form ring weights.  After a background update the weights stay on the device (252 MB per 512 x 512
+    patch) and are fetched the first time they are READ here -- the reference keeps obj.W as state nobody but the next update
+    touches (update_background_parallel.m:311-317), so copying them out after every call would only tax the link."""
+
+    def __init__(self, owner):
+        super().__init__()
+        self._owner = owner
+
+    def _sync(self, k=None):
+        o = self._owner
+        if o._ring_w_stale and (k is None or k in o._ring_w_stale):
+            o._pull_ring_weights(sorted(o._ring_w_stale) if k is None else [k])
+
+    def __getitem__(self, k):
+        self._sync(k)
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        self._sync(k)
+        return dict.get(self, k, default)
+
+    def __contains__(self, k):
+        return dict.__contains__(self, k) or k in self._owner._ring_w_stale
+
+    def __setitem__(self, k, v):
+        self._owner._ring_w_stale.discard(k)
+        dict.__setitem__(self, k, v)
+
+    def items(self):
+        self._sync()
+        return dict.items(self)
+
+    def values(self):
+        self._sync()
+        return dict.values(self)
+
+
 class Sources2D:
     def __init__(self, d1, d2, T, patch_dims=None, ring_radius=18, num_neighbors=None, device=0, rank=0,
                  world_size=1, options=None):
@@ -107,8 +145,9 @@ class Sources2D:
                             deconv_flag=True, deconv_options=dict(type="ar1", method="foopsi", smin=-5,
                                                                   optimize_pars=True, optimize_b=True, max_tau=100),
                             replicate_spatial_aprev_quirk=True, use_tensor_gram=True, nb=1,
-                            # multi-GPU: split the final deconvTemporal over ranks; opt-in until validated on >= 2 GPUs
-                            shard_deconv=bool(int(os.environ.get("CNMFE_SHARD_DECONV", "0"))))
+                            # multi-GPU: split the final deconvTemporal over ranks by trace; validated against the
+                            # oracle on 2 and 4 GPUs by tests/test_gpu_multi.py
+                            shard_deconv=bool(int(os.environ.get("CNMFE_SHARD_DECONV", "1"))))
         if options:
             self.options.update(options)
         self.patch_pos, self.block_pos = patch_geometry(self.d1, self.d2, patch_dims, ring_radius)
@@ -141,8 +180,10 @@ class Sources2D:
         self.S = np.zeros((0, self.T))
         self.A_prev = sp.csc_matrix((d, 0))
         self.C_prev = np.zeros((0, self.T))
-        self.W = {}
+        self._ring_w_stale = set()  # patches whose weights on the device are newer than the host copy (fetched on read)
+        self.W = _RingWeights(self)
         self.b0 = {}
+        self._temporal_partial = False   # multi-rank: C_raw / S / per-trace outputs on the device still hold only this rank's rows
         self._ring_synced = {}      # patch -> (W, b0) objects whose contents the device holds
         self._dev = {}              # "A" / "C" / "A_prev" / "C_prev" -> host object whose contents the device holds
         self._pinned = {}           # name -> page-locked reusable host buffer (ring weights)
@@ -195,7 +236,7 @@ class Sources2D:
             # frame-major, pixel index r + c*nrb fastest  == MATLAB memory order of the (nrb, ncb, T) array
             buf = np.ascontiguousarray(np.transpose(blk, (2, 1, 0)))
             L.check(self._lib.cnmfe_upload_block(self._h, i, _ptr(buf), dt))
-        self.P["Ymean"] = Y.mean(axis=2, dtype=np.float64) if self.world_size == 1 else None
+        self.P["Ymean"] = Y.mean(axis=2, dtype=np.float64)     # obj.P.Ymean (cell2mat'ed); load_block_dev callers set it themselves
 
     def load_block_dev(self, i, dev_ptr, dtype):
         """Block of patch i already on the device (frame-major); dtype 0 = uint8, 1 = uint16."""
@@ -279,6 +320,13 @@ class Sources2D:
         self._mark(nameA, A)
         self._mark(nameC, C)
 
+    def set_sn(self, sn=None):
+        """obj.P.sn -> device (d1 x d2 noise map used by hals_thresh / lars and the outlier clamp)."""
+        if sn is not None:
+            self.P["sn"] = np.asarray(sn, dtype=np.float64)
+        L.check(self._lib.cnmfe_set_sn(self._h, _ptr(np.asfortranarray(self.P["sn"], dtype=np.float64))))
+        self.h2d_bytes += self.P["sn"].size * 8
+
     def push_neurons(self):
         self._push_pair(self._lib.cnmfe_set_neurons, "A", self.A, "C", self.C)
 
@@ -310,14 +358,15 @@ class Sources2D:
                 L.check(self._lib.cnmfe_set_bf(self._h, i, _ptr(bf), _ptr(ff), _ptr(b0f)))
             return
         for i in range(self.npatch):
-            W = self.W.get(i)
+            stale = i in self._ring_w_stale          # the device holds newer weights than the host: nothing to send
+            W = None if stale else dict.get(self.W, i)
             b0 = self.b0.get(i)
             if W is None and b0 is None:
                 continue
             # arrays handed out by pull_ring are read-only: an unchanged identity means the device copy is current
             # (the ring weights are ~250 MB at 512x512; re-sending them on every call would dominate the step)
             s = self._ring_synced.get(i)
-            if s is not None and s[0] is W and s[1] is b0:
+            if s is not None and (stale or s[0] is W) and s[1] is b0:
                 continue
             Wf = None if W is None else np.ascontiguousarray(W, dtype=np.float64)   # (d_patch, nnb) C-order == nnb x d_patch col-major
             b0f = None if b0 is None else np.ascontiguousarray(b0, dtype=np.float64)
@@ -325,9 +374,11 @@ class Sources2D:
             self.h2d_bytes += sum(x.nbytes for x in (Wf, b0f) if x is not None)
             # identity is only evidence of "unchanged" for read-only arrays (a writable one may be edited in place)
             ro = all(x is None or not x.flags.writeable for x in (W, b0))
-            self._ring_synced[i] = (W, b0) if ro else None
+            self._ring_synced[i] = (W if not stale else (s[0] if s else None), b0) if ro else None
 
-    def pull_ring(self):
+    def pull_ring(self, weights=True):
+        """obj.b0 (and, with weights=True, obj.W) of the owned patches from the device.  weights=False marks the weights as
+        "newer on the device": they are fetched when obj.W[i] is read."""
         if str(self.options["background_model"]).lower() in ("svd", "nmf"):
             nb = int(self.options.get("nb", 1))
             for i in self.owned_patches():
@@ -335,9 +386,25 @@ class Sources2D:
                 dp = (p[1] - p[0] + 1) * (p[3] - p[2] + 1)
                 b = np.zeros((dp, nb), order="F"); f = np.zeros((nb, self.T), order="F"); b0 = np.zeros(dp)
                 L.check(self._lib.cnmfe_get_bf(self._h, i, _ptr(b), _ptr(f), _ptr(b0)))
+                self.d2h_bytes += b.nbytes + f.nbytes + b0.nbytes
                 self.b[i], self.f[i], self.b0[i] = np.ascontiguousarray(b), np.ascontiguousarray(f), b0
             return
         for i in self.owned_patches():
+            p = self.patch_of(i)
+            dp = (p[1] - p[0] + 1) * (p[3] - p[2] + 1)
+            b0 = np.empty(dp)
+            L.check(self._lib.cnmfe_get_ring(self._h, i, None, _ptr(b0)))
+            self.d2h_bytes += b0.nbytes
+            b0.setflags(write=False)
+            self.b0[i] = b0
+            prev = self._ring_synced.get(i)
+            self._ring_synced[i] = (prev[0] if prev else None, b0)
+            self._ring_w_stale.add(i)
+        if weights:
+            self._pull_ring_weights(self.owned_patches())
+
+    def _pull_ring_weights(self, which):
+        for i in which:
             p = self.patch_of(i)
             dp = (p[1] - p[0] + 1) * (p[3] - p[2] + 1)
             if int(self.options.get("bg_ssub", 1)) > 1:
@@ -346,15 +413,17 @@ class Sources2D:
             else:
                 wshape = (dp, self.nnb)
             # W lands in one of TWO page-locked buffers used in alternation, so the array handed out by the previous
-            # pull_ring (e.g. kept by the caller for a convergence check) stays intact for one more update
+            # pull (e.g. kept by the caller for a convergence check) stays intact for one more update
             self._ring_flip[i] = 1 - self._ring_flip.get(i, 1)
             W = self._pinned_buffer(("W", i, self._ring_flip[i]), wshape).view()
-            b0 = np.empty(dp)
-            L.check(self._lib.cnmfe_get_ring(self._h, i, _ptr(W), _ptr(b0)))
-            self.d2h_bytes += W.nbytes + b0.nbytes
-            W.setflags(write=False); b0.setflags(write=False)
-            self.W[i], self.b0[i] = W, b0
-            self._ring_synced[i] = (W, b0)
+            W.setflags(write=True)
+            L.check(self._lib.cnmfe_get_ring(self._h, i, _ptr(W), None))
+            self.d2h_bytes += W.nbytes
+            W.setflags(write=False)
+            dict.__setitem__(self.W, i, W)
+            self._ring_w_stale.discard(i)
+            prev = self._ring_synced.get(i)
+            self._ring_synced[i] = (W, prev[1] if prev else None)
 
     def ssub_dims(self, i):
         """(d1s, d2s, nnb, r_shift, c_shift) of the coarse ring grid of patch i (bg_ssub > 1)."""
@@ -412,8 +481,10 @@ class Sources2D:
             self.push_neurons()
             self.push_ring()
         L.check(self._lib.cnmfe_update_background(self._h))
+        if not sync_host and self._is_ring():
+            self._ring_w_stale.update(self.owned_patches())
         if sync_host:
-            self.pull_ring()
+            self.pull_ring(weights=False)          # b0 now, W when somebody reads obj.W[i]
             self.b0_new = self.reconstruct_b0()
             if self.world_size > 1:     # patches are disjoint: the sum over ranks assembles the full map (update_background_parallel.m:315)
                 self.b0_new = self._allreduce_sum(self.b0_new.ravel()).reshape(self.d1, self.d2)
@@ -562,7 +633,7 @@ class Sources2D:
             self.push_neurons()
             self.push_prev()
             self.push_ring()
-            L.check(self._lib.cnmfe_set_sn(self._h, _ptr(np.asfortranarray(self.P["sn"], dtype=np.float64))))
+            self.set_sn()
         jc = np.ascontiguousarray(INDc.indptr, dtype=np.int64)
         ir = np.ascontiguousarray(INDc.indices, dtype=np.int64)
         self._ind_jc, self._ind_ir = jc, ir
@@ -602,12 +673,16 @@ class Sources2D:
         if self.world_size > 1:
             self._allreduce_merge_buffers()
         if self.world_size > 1 and self.options.get("shard_deconv"):
+            # the final deconvTemporal is split over the ranks by trace; every rank needs the complete C for the
+            # next update (one exchange now), C_raw / S / kernel_pars only when the host reads them (pull_temporal)
             K = self.A.shape[1]
             k0, k1 = trace_range(K, self.rank, self.world_size)
             L.check(self._lib.cnmfe_update_temporal_finish_part(self._h, k0, k1))
-            self._allreduce_temporal_state(K)
+            self._allreduce_temporal_state(K, (0,))
+            self._temporal_partial = True
         else:
             L.check(self._lib.cnmfe_update_temporal_finish(self._h))
+            self._temporal_partial = False
         if sync_host:
             self.pull_temporal()
 
@@ -630,7 +705,12 @@ class Sources2D:
         L.check(self._lib.cnmfe_set_spatial(self._h, _ptr(vals)))
 
     def pull_temporal(self):
+        """obj.C, obj.C_raw, obj.S, obj.P.kernel_pars, obj.P.neuron_sn from the device.  Multi-rank with shard_deconv: a
+        COLLECTIVE call (the rows of C_raw / S the other ranks deconvolved are exchanged first)."""
         K = self.A.shape[1]
+        if self._temporal_partial:
+            self._allreduce_temporal_state(K, (1, 2, 3))
+            self._temporal_partial = False
         C = np.empty((K, self.T))
         Cr = np.empty((K, self.T))
         S = np.empty((K, self.T))
@@ -701,9 +781,10 @@ class Sources2D:
             td.copy_(b)
             torch.cuda.synchronize(self.device)
 
-    def _allreduce_temporal_state(self, K):
+    def _allreduce_temporal_state(self, K, which=(0, 1, 2, 3)):
         """After cnmfe_update_temporal_finish_part: every rank holds its own rows of C, C_raw, S and of the per-trace
-        outputs and zeros elsewhere; a SUM all-reduce (disjoint supports => a gather, x + 0 exact) completes them."""
+        outputs and zeros elsewhere; a SUM all-reduce (disjoint supports => a gather, x + 0 exact) completes them.
+        which: indices into (C, C_raw, S, per-trace outputs)."""
         import torch
         import torch.distributed as dist
         ptrs = [ctypes.c_void_p() for _ in range(4)]
@@ -714,7 +795,9 @@ class Sources2D:
             def __init__(self, ptr, n):
                 self.__cuda_array_interface__ = dict(shape=(n,), typestr="<f8", data=(ptr, False), version=3)
 
-        for p, n in zip(ptrs, (K * self.T, K * self.T, K * self.T, K * 6)):
+        for j, (p, n) in enumerate(zip(ptrs, (K * self.T, K * self.T, K * self.T, K * 6))):
+            if j not in which:
+                continue
             t = torch.as_tensor(_Dev(p.value, n), device=torch.device("cuda", self.device))
             if dist.get_backend() == "nccl":
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)

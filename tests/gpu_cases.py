@@ -26,7 +26,7 @@ SYNTHETIC = {
     "nmf_fit": dict(d1=48, d2=40, T=500, K=5, seed=17, nblob=3, bg_amp=60.0),
     "hals_uv": dict(d1=48, d2=48, T=1500, K=8, seed=5, nblob=0, bg_amp=0.0),
     "outlier": dict(d1=56, d2=48, T=500, K=4, seed=5, nblob=4),
-    "kf2_long": dict(d1=48, d2=40, T=1500, K=4, seed=9, nblob=3),
+    "kf2_long": dict(d1=48, d2=40, T=4200, K=4, seed=9, nblob=3),
     "multi_gpu": dict(d1=96, d2=80, T=600, K=10, seed=7, nblob=4),
     "post_dev": dict(d1=64, d2=64, T=600, K=6, seed=12, nblob=3),
 }

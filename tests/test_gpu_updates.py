@@ -203,3 +203,25 @@ def test_no_neurons(built_lib):
     gpu.update_spatial_parallel(IND=IND)
     gpu.update_temporal_parallel()
     assert gpu.A.shape == (d1 * d2, 0) and gpu.C.shape == (0, T)
+
+
+@pytest.mark.parametrize("tensor", [True, False])
+def test_background_frame_subsampling(built_lib, tensor):
+    """bg_acceleration (fit_ring_model.m:59-90): once the fitted weights have pmax positive entries per row and T >= 2*100*pmax,
+    only every k-th frame enters the regression.  The tcgen05 kernel then runs on compacted byte planes of the kept frames
+    (round 1 fell back to the SIMT kernel); both must match the oracle."""
+    D, orc, gpu = _make("kf2_long", (48, 40), 3)
+    gpu.options["use_tensor_gram"] = tensor
+    T = D["Y"].shape[2]
+    orc.update_background_parallel(); gpu.update_background_parallel()      # first run: uniform W (pmax = 20 -> every 2nd frame)
+    _check_bg(orc, gpu)
+    assert bool(built_lib.cnmfe_last_gram_was_tensor(gpu._h)) == tensor
+    Wd = sp.csr_matrix(orc.W[(0, 0)])
+    pmax = int((Wd > 0).sum(axis=1).max())
+    assert T // min(T, 100 * pmax) >= 2, "case must trigger frame subsampling (pmax = %d)" % pmax
+    _sync_from_oracle(orc, gpu)
+    orc.C = orc.C * 1.03; gpu.C = orc.C.copy()
+    orc.update_background_parallel(); gpu.update_background_parallel()      # steady state, still subsampled
+    _check_bg(orc, gpu)
+    assert bool(built_lib.cnmfe_last_gram_was_tensor(gpu._h)) == tensor
+    gpu.close()
