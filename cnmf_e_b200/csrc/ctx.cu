@@ -669,6 +669,7 @@ static size_t bg_scratch_bytes(const cnmfe_ctx* c, const Patch& P, int Kb, size_
 }
 
 static int update_background_svd(cnmfe_ctx* c);
+static int update_background_nmf(cnmfe_ctx* c);
 static int ssub_configure(cnmfe_ctx* c, int ssub);
 static int ssub_ensure_patch(cnmfe_ctx* c, int ip, bool need_video);
 static int update_background_ssub(cnmfe_ctx* c);
@@ -684,10 +685,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
     if (!c) { set_error("cnmfe_update_background: null ctx"); return -1; }
     for (Patch& Pq : c->patches) Pq.lp_valid = false;
     if (c->opt.background_model == 1) return update_background_svd(c);
-    if (c->opt.background_model == 2) {
-        set_error("update_background: the nmf model calls the Statistics-toolbox nnmf with a RANDOM initialisation (fit_nmf_model.m:19); fit it in MATLAB and hand b, f over with cnmfe_set_bf -- the nmf BG subtraction of the spatial/temporal updates is built");
-        return -1;
-    }
+    if (c->opt.background_model == 2) return update_background_nmf(c);
     if (c->opt.bg_ssub > 1) return update_background_ssub(c);
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
     for (float& f : c->phase_ms) f = 0;

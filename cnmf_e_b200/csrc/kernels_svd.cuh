@@ -87,6 +87,38 @@ __global__ void svd_init_V_kernel(double* __restrict__ V, int nb, int T) {
                            0.25 * cospi(2.0 * 0.7 * (double)t / (double)T);
 }
 
+// ---- nmf background model (endoscope/fit_nmf_model.m): B = Y - A*C (not centred) factorised by alternating least squares
+// murmur3 finaliser: the deterministic stand-in for nnmf's rand(n, k) start (the reference draws from MATLAB's global stream)
+__host__ __device__ inline double nmf_hash_uniform(unsigned x) {
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    return ((double)(x >> 8) + 0.5) / 16777216.0;
+}
+// rowen[q] = sum_t (Y[q,t] - sum_k A(q,k) C[k][t])^2.  One warp per block pixel.
+__global__ void nmf_row_energy_kernel(const uint16_t* __restrict__ Yt, int db, int T, int Tpad, const int* __restrict__ a_ptr,
+                                      const int* __restrict__ a_col, const double* __restrict__ a_val,
+                                      const double* __restrict__ C, double* __restrict__ rowen) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= db) return;
+    const uint16_t* row = Yt + (size_t)q * Tpad;
+    const int e0 = a_ptr[q], e1 = a_ptr[q + 1];
+    double s = 0.0;
+    for (int t = lane; t < T; t += 32) {
+        double v = (double)row[t];
+        for (int e = e0; e < e1; ++e) v -= a_val[e] * C[(size_t)a_col[e] * T + t];
+        s = fma(v, v, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) rowen[q] = s;
+}
+// b(p, j) = w[q(p)][j] * scale[j]  (patch rows of the block factor, columns re-ordered by `perm`)
+__global__ void nmf_make_b_kernel(const double* __restrict__ Wf, int nb, const double* __restrict__ scale, const int* __restrict__ perm,
+                                  int dp, int nr, int nrb, int pr_off, int pc_off, double* __restrict__ b) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= dp) return;
+    size_t q = (size_t)(p / nr + pc_off) * nrb + (p % nr + pr_off);
+    for (int j = 0; j < nb; ++j) b[(size_t)j * dp + p] = Wf[q * nb + perm[j]] * scale[perm[j]];
+}
+
 // b(p, j) = sum_i u-part: b[p + j*dp] = Z[qp][i] * M[i][j]   (M = R * diag(1/s) * diag(s) = R: b = u*s = Z*R)
 __global__ void svd_make_b_kernel(const double* __restrict__ Z, int nb, const double* __restrict__ M, int dp, int nr,
                                   int nrb, int pr_off, int pc_off, double* __restrict__ b) {

@@ -54,8 +54,9 @@ typedef struct cnmfe_options {
     int use_tensor_gram;     /* 1 = tcgen05 INT8 kernel for the ring second moments, 0 = SIMT reference kernel */
     cnmfe_deconv_opts deconv;
     int background_model;    /* 0 = 'ring' (1p, bg_ssub = 1), 1 = 'svd' (2p default, endoscope/fit_svd_model.m),
-                                2 = 'nmf' (BG subtraction Y - b*f only, update_spatial_parallel.m:179-182; the nnmf fit
-                                itself is randomly initialised in the reference and stays in MATLAB: cnmfe_set_bf) */
+                                2 = 'nmf' (endoscope/fit_nmf_model.m: nnmf alternating least squares on Y - A*C from a fixed
+                                hash start instead of MATLAB's random stream; BG subtraction Y - b*f,
+                                update_spatial_parallel.m:179-182) */
     int nb;                  /* options.nb: number of svd background components (default 1) */
     int bg_ssub;             /* options.bg_ssub (ring model): 1, or > 1 = ring weights on the ceil(block/bg_ssub) grid
                                 (demo_large_data_1p.m:30 uses 2); changing it re-initialises W (update_background_parallel.m:70-118) */
@@ -129,8 +130,9 @@ int cnmfe_ssub_dims(cnmfe_ctx* ctx, int ipatch, int* d1s, int* d2s, int* nnb, in
 int cnmfe_set_bf(cnmfe_ctx* ctx, int ipatch, const double* b, const double* f, const double* b0);
 int cnmfe_get_bf(cnmfe_ctx* ctx, int ipatch, double* b, double* f, double* b0);
 
-/* update_background_parallel(obj, use_parallel) (@Sources2D/update_background_parallel.m:1), ring model, bg_ssub=1.
- * Result stays on the device (W, b0, A_prev<-A, C_prev<-C); fetch with cnmfe_get_ring. */
+/* update_background_parallel(obj, use_parallel) (@Sources2D/update_background_parallel.m:1) for the configured background
+ * model (ring with bg_ssub >= 1, svd, nmf).  Result stays on the device (W, b0 / b, f, b0; A_prev<-A, C_prev<-C); fetch with
+ * cnmfe_get_ring / cnmfe_get_bf. */
 int cnmfe_update_background(cnmfe_ctx* ctx);
 /* update_spatial_parallel(obj, use_parallel, update_sn=false) (@Sources2D/update_spatial_parallel.m:1) up to
  * (not including) post_process_spatial (:341, host/MATLAB).  New A lives on the search pattern. */

@@ -47,7 +47,7 @@ def test_svd_background_chain(built_lib, shape):
 
 
 def test_nmf_background_subtraction(built_lib):
-    """nmf model: the fit (nnmf, random init) stays in MATLAB; given b, f the BG subtraction Y - b*f of the spatial and
+    """nmf model with b, f supplied by the caller (cnmfe_set_bf): the BG subtraction Y - b*f of the spatial and
     temporal updates (update_spatial_parallel.m:179-182, update_temporal_parallel.m:165-168) must match the oracle."""
     from oracle.svd_bg import OracleSources2DSVD
     from cnmf_e_b200.sources2d import Sources2D
@@ -73,6 +73,34 @@ def test_nmf_background_subtraction(built_lib):
     orc.update_temporal_parallel(); gpu.update_temporal_parallel()
     _close(gpu.C_raw, orc.C_raw, 1e-6)
     assert np.array_equal(gpu.S > 0, orc.S > 0)
-    with pytest.raises(Exception):
-        gpu.update_background_parallel()
+    gpu.close()
+
+
+@pytest.mark.parametrize("shape", [("nmf_fit", (48, 40), 1), ("svd_64x60_patches", (32, 30), 2)])
+def test_nmf_background_fit_chain(built_lib, shape):
+    """update_background_parallel with background_model = 'nmf' (fit_nmf_model.m -> nnmf ALS from the shared fixed start) and
+    the spatial / temporal updates on Y - b*f, against oracle/nmf_bg.py.  Tolerance 1e-6: the ALS runs to the same iteration
+    count on both sides and is a contraction, but sums over T and d are ordered differently."""
+    from oracle.nmf_bg import OracleSources2DNMF
+    from cnmf_e_b200.sources2d import Sources2D
+    case, patch, nb = shape
+    D = GC.synthetic(case)
+    d1, d2, T = D["Y"].shape
+    orc = OracleSources2DNMF(D["Y"], patch, ring_radius=6, nb=nb, options=dict(spatial_algorithm="hals"))
+    gpu = Sources2D(d1, d2, T, patch, ring_radius=6, options=dict(background_model="nmf", nb=nb, spatial_algorithm="hals"))
+    gpu.load_video(D["Y"])
+    for o in (orc, gpu):
+        o.A, o.C = D["A0"].copy(), D["C0"].copy()
+    orc.update_background_parallel()
+    gpu.update_background_parallel()
+    for i, mp in enumerate(orc.patches()):
+        assert np.allclose(np.sum(gpu.f[i] ** 2, axis=1), 1.0, rtol=1e-12)          # rows of f have unit length
+        _close(gpu.b[i] @ gpu.f[i], orc.b[mp] @ orc.f[mp], 1e-6)
+        _close(gpu.f[i], orc.f[mp], 1e-6)
+    if len(orc.patches()) == 1:      # the reference's nmf BG subtraction only has consistent shapes for block == patch
+        orc.update_spatial_parallel(IND=D["IND"]); gpu.update_spatial_parallel(IND=D["IND"])
+        _close(gpu.A.toarray(), orc.A.toarray(), 1e-6)
+        orc.update_temporal_parallel(); gpu.update_temporal_parallel()
+        _close(gpu.C_raw, orc.C_raw, 1e-6)
+        assert np.array_equal(gpu.S > 0, orc.S > 0)
     gpu.close()
