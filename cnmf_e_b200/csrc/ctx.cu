@@ -1118,16 +1118,28 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
     if (K == 0) return 0;
     CNMFE_CUDA_OK(cudaMemsetAsync(c->num, 0, (size_t)K * T * 8, c->st));
     CNMFE_CUDA_OK(cudaMemsetAsync(c->den, 0, (size_t)K * 8, c->st));
+    // ---- host planning for every owned patch first: the Gauss-Seidel sweeps of ALL patches then run as ONE launch over the
+    //      concatenated local neurons (block-diagonal V: neurons of different patches never wait for each other), so a rank
+    //      holding several patches pays the dependency-chain latency of HALS_temporal once, not once per patch
+    struct TPlan { int ip, Kt, Kp, koff; LocalSparse LA, LPown; const LocalSparse* LP; };
+    std::vector<TPlan> plans;
+    plans.reserve(c->npatch);
+    int Ktot = 0;
+    size_t per_patch_need = 0, vnnz_bound = 0;
     for (int ip = 0; ip < c->npatch; ++ip) {
         Patch& P = c->patches[ip];
         if (!P.owned) continue;
         if (!P.uploaded) { set_error("update_temporal: block %d not uploaded", ip); return -1; }
-        LocalSparse LA, LPown;
+        plans.emplace_back();
+        TPlan& pl = plans.back();
+        pl.ip = ip;
         HostTick tick;
-        build_local(c, P, c->A, SEL_SUM_BLOCK, ROWS_BLOCK_PATCHONLY, nullptr, &LA);
+        build_local(c, P, c->A, SEL_SUM_BLOCK, ROWS_BLOCK_PATCHONLY, nullptr, &pl.LA);
         tick("tp build_local A");
-        const int Kt = LA.K();
-        if (Kt == 0) continue;   // update_temporal_parallel.m:123-126
+        pl.Kt = pl.LA.K();
+        if (pl.Kt == 0) { plans.pop_back(); continue; }   // update_temporal_parallel.m:123-126
+        LocalSparse& LA = pl.LA;
+        const int Kt = pl.Kt;
         if (!c->use_c_hat) {
             // fast_temporal (update_temporal_parallel.m:314-337): keep only the pixels with A >= 0.5*max(A) per neuron
             std::vector<double> amax(Kt, 0.0);
@@ -1139,16 +1151,45 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
             for (size_t e = 0; e < LA.col.size(); ++e)
                 if (!(LA.val[e] / amax[LA.col[e]] >= 0.5)) LA.val[e] = 0.0;
         }
-        if (!P.lp_valid) build_local(c, P, c->Aprev, SEL_SUM_BLOCK, ROWS_BLOCK, nullptr, &LPown);
-        const LocalSparse& LP = P.lp_valid ? P.lp_cache : LPown;
+        if (!P.lp_valid) build_local(c, P, c->Aprev, SEL_SUM_BLOCK, ROWS_BLOCK, nullptr, &pl.LPown);
+        pl.LP = P.lp_valid ? &P.lp_cache : &pl.LPown;
         tick("tp build_local Aprev");
-        const int Kp = LP.K();
-        size_t need = (c->opt.bg_ssub > 1 ? 4 : 1) * pad256((size_t)P.db * Kt * 8) + 4 * pad256((size_t)Kt * T * 8) + pad256((size_t)std::max(Kp, 1) * T * 8) +
+        pl.Kp = pl.LP->K();
+        pl.koff = Ktot;
+        Ktot += Kt;
+        vnnz_bound += (size_t)Kt * Kt;
+        const int Kp = pl.Kp;
+        size_t need = (c->opt.bg_ssub > 1 ? 4 : 1) * pad256((size_t)P.db * Kt * 8) + pad256((size_t)std::max(Kp, 1) * T * 8) +
                       2 * pad256((size_t)Kt * Kt * 12 + 64) + pad256((size_t)Kt * std::max(Kp, 1) * 8) +
-                      2 * pad256((size_t)(P.db + 1) * 4) + pad256(LA.col.size() * 24 + 64) + pad256(LP.col.size() * 24 + 64) +
+                      2 * pad256((size_t)(P.db + 1) * 4) + pad256(LA.col.size() * 24 + 64) + pad256(pl.LP->col.size() * 24 + 64) +
                       pad256((size_t)(Kt + Kp) * 128 + 64) + (1 << 20);
-        if (c->scr.reserve(need)) return -1;
-        c->scr.reset();
+        per_patch_need = std::max(per_patch_need, need);
+    }
+    if (Ktot == 0) { CNMFE_CUDA_OK(cudaStreamSynchronize(c->st)); return 0; }
+    const size_t persistent = 4 * pad256((size_t)Ktot * T * 8) + 6 * pad256((size_t)(Ktot + 1) * 16) + 2 * pad256(vnnz_bound * 12 + 64) + (1 << 20);
+    if (c->scr.reserve(persistent + per_patch_need)) return -1;
+    c->scr.reset();
+    TAKE_OR_FAIL(d_Uall, c->scr.take<double>((size_t)Ktot * T));
+    TAKE_OR_FAIL(d_Clall, c->scr.take<double>((size_t)Ktot * T));
+    TAKE_OR_FAIL(d_Crawall, c->scr.take<double>((size_t)Ktot * T));
+    TAKE_OR_FAIL(d_Sall, c->scr.take<double>((size_t)Ktot * T));
+    TAKE_OR_FAIL(d_snall, c->scr.take<double>(Ktot));
+    TAKE_OR_FAIL(d_parsall, c->scr.take<double>((size_t)Ktot * 2));
+    TAKE_OR_FAIL(d_aaall, c->scr.take<double>(Ktot));
+    TAKE_OR_FAIL(d_idsall, c->scr.take<int>(Ktot));
+    TAKE_OR_FAIL(d_doneall, c->scr.take<int>(Ktot));
+    TAKE_OR_FAIL(d_orderall, c->scr.take<int>(Ktot + 1));
+    const size_t base_off = c->scr.off;
+    std::vector<int> vptr_all(1, 0), vidx_all;
+    std::vector<double> vval_all, aa_all((size_t)Ktot);
+    vidx_all.reserve(vnnz_bound / 4 + Ktot); vval_all.reserve(vnnz_bound / 4 + Ktot);
+    for (TPlan& pl : plans) {
+        const int ip = pl.ip, Kt = pl.Kt, Kp = pl.Kp;
+        Patch& P = c->patches[ip];
+        const LocalSparse& LA = pl.LA;
+        const LocalSparse& LP = *pl.LP;
+        HostTick tick;
+        c->scr.off = base_off;
         const RingGeom& g = P.geom;
         phase_begin(c);
         TAKE_OR_FAIL(d_aptr, to_dev(c, LA.ptr));
@@ -1157,7 +1198,8 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
         TAKE_OR_FAIL(d_cptr, to_dev(c, LA.cptr));
         TAKE_OR_FAIL(d_crow, to_dev(c, LA.crow));
         TAKE_OR_FAIL(d_cval, to_dev(c, LA.cval));
-        TAKE_OR_FAIL(d_ids, to_dev(c, LA.ids));
+        int* d_ids = d_idsall + pl.koff;
+        CNMFE_CUDA_OK(cudaMemcpyAsync(d_ids, LA.ids.data(), (size_t)Kt * 4, cudaMemcpyHostToDevice, c->st));
         TAKE_OR_FAIL(d_pcptr, to_dev(c, LP.cptr));
         TAKE_OR_FAIL(d_pcrow, to_dev(c, LP.crow));
         TAKE_OR_FAIL(d_pcval, to_dev(c, LP.cval));
@@ -1166,16 +1208,13 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
         std::vector<int> bb = expand_bbox(LA, reach_t, P.nrb, P.ncb);
         TAKE_OR_FAIL(d_bbox, to_dev(c, bb));
         TAKE_OR_FAIL(d_B, c->scr.take<double>((size_t)P.db * Kt));
-        TAKE_OR_FAIL(d_U, c->scr.take<double>((size_t)Kt * T));
-        TAKE_OR_FAIL(d_Cl, c->scr.take<double>((size_t)Kt * T));
-        TAKE_OR_FAIL(d_Crawl, c->scr.take<double>((size_t)Kt * T));
-        TAKE_OR_FAIL(d_Sl, c->scr.take<double>((size_t)Kt * T));
+        double* d_U = d_Uall + (size_t)pl.koff * T;
+        double* d_Cl = d_Clall + (size_t)pl.koff * T;
+        double* d_Crawl = d_Crawall + (size_t)pl.koff * T;
         TAKE_OR_FAIL(d_Ccp, c->scr.take<double>((size_t)std::max(Kp, 1) * T));
         TAKE_OR_FAIL(d_AWA, c->scr.take<double>((size_t)Kt * std::max(Kp, 1)));
         TAKE_OR_FAIL(d_cst, c->scr.take<double>(Kt));
         TAKE_OR_FAIL(d_V, c->scr.take<double>((size_t)Kt * Kt));
-        TAKE_OR_FAIL(d_snl, c->scr.take<double>(Kt));
-        TAKE_OR_FAIL(d_parsl, c->scr.take<double>((size_t)Kt * 2));
         CNMFE_CUDA_OK(cudaMemsetAsync(d_B, 0, (size_t)P.db * Kt * 8, c->st));
         if (c->opt.bg_ssub <= 1) {
             LAUNCH(temporal_build_negWtA_kernel, (P.db + 127) / 128, 128, 0, c->st, g, c->d_off_r, c->d_off_c, P.W, d_aptr,
@@ -1205,43 +1244,51 @@ extern "C" int cnmfe_update_temporal_patches(cnmfe_ctx* c) {
         phase_begin(c);
         launch_proj_bt(c->st, P.Yt, P.Ymean, P.nrb, T, c->Tpad, d_B, Kt, d_bbox, d_U);
         { dim3 gg((T + 255) / 256, Kt); LAUNCH(add_small_matmul_kernel, gg, 256, 0, c->st, d_U, Kt, T, d_cst, d_AWA, Kp, d_Ccp); }
-        phase_end(c, 2);
-        tick("tp projection");
-        // V -> CSR (host), sweeps
-        phase_begin(c);
-        std::vector<double> V((size_t)Kt * Kt);
-        CNMFE_CUDA_OK(cudaMemcpyAsync(V.data(), d_V, V.size() * 8, cudaMemcpyDeviceToHost, c->st));
-        CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
-        std::vector<int> vptr(Kt + 1, 0), vidx;
-        std::vector<double> vval, aa(Kt);
-        for (int k = 0; k < Kt; ++k) {
-            for (int j = 0; j < Kt; ++j) {
-                double v = V[(size_t)k * Kt + j];
-                if (v != 0.0 || j == k) { vidx.push_back(j); vval.push_back(v); }
-            }
-            vptr[k + 1] = (int)vidx.size();
-            aa[k] = V[(size_t)k * Kt + k];
-        }
-        TAKE_OR_FAIL(d_vptr, to_dev(c, vptr));
-        TAKE_OR_FAIL(d_vidx, to_dev(c, vidx));
-        TAKE_OR_FAIL(d_vval, to_dev(c, vval));
-        TAKE_OR_FAIL(d_aa, to_dev(c, aa));
         { dim3 gg((T + 255) / 256, Kt); LAUNCH(gather_rows_kernel, gg, 256, 0, c->st, c->C, d_ids, Kt, T, d_Cl); }
-        CNMFE_CUDA_OK(cudaMemsetAsync(d_Crawl, 0, (size_t)Kt * T * 8, c->st));
-        CNMFE_CUDA_OK(cudaMemsetAsync(d_Sl, 0, (size_t)Kt * T * 8, c->st));
-        CNMFE_CUDA_OK(cudaMemsetAsync(d_parsl, 0, (size_t)Kt * 16, c->st));
         if (!c->use_c_hat) {
             // C_raw = (tmp_A'*Y) ./ aa  (aa = 0 -> row of zeros, weight 0)
             dim3 gg((T + 255) / 256, Kt);
             LAUNCH(rows_div_diag_kernel, gg, 256, 0, c->st, d_U, d_V, Kt, T, d_Crawl);
-        } else if (hals_temporal_dev(d_U, d_vptr, d_vidx, d_vval, d_aa, Kt, T, c->opt.maxIter_temporal, c->opt.deconv_flag,
-                              c->opt.deconv, d_Cl, d_Crawl, d_Sl, d_snl, d_parsl, c->d_done, c->d_ticket, c->d_order,
-                              &c->arena, c->st)) return -1;
-        { dim3 gg((T + 255) / 256, Kt); LAUNCH(temporal_merge_kernel, gg, 256, 0, c->st, d_Crawl, d_V, Kt, T, d_ids, c->num, c->den); }
-        phase_end(c, 4);
-        tick("tp sweeps");
-        CNMFE_CUDA_OK(cudaGetLastError());
+        }
+        phase_end(c, 2);
+        tick("tp projection");
+        // V -> CSR (host), appended to the block-diagonal system of all patches
+        std::vector<double> V((size_t)Kt * Kt);
+        CNMFE_CUDA_OK(cudaMemcpyAsync(V.data(), d_V, V.size() * 8, cudaMemcpyDeviceToHost, c->st));
+        CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+        for (int k = 0; k < Kt; ++k) {
+            for (int j = 0; j < Kt; ++j) {
+                double v = V[(size_t)k * Kt + j];
+                if (v != 0.0 || j == k) { vidx_all.push_back(pl.koff + j); vval_all.push_back(v); }
+            }
+            vptr_all.push_back((int)vidx_all.size());
+            aa_all[(size_t)pl.koff + k] = V[(size_t)k * Kt + k];
+        }
+        tick("tp V csr");
     }
+    // ---- the sweeps of all patches in one launch
+    c->scr.off = base_off;
+    phase_begin(c);
+    TAKE_OR_FAIL(d_vptr, to_dev(c, vptr_all));
+    TAKE_OR_FAIL(d_vidx, to_dev(c, vidx_all));
+    TAKE_OR_FAIL(d_vval, to_dev(c, vval_all));
+    CNMFE_CUDA_OK(cudaMemcpyAsync(d_aaall, aa_all.data(), (size_t)Ktot * 8, cudaMemcpyHostToDevice, c->st));
+    if (c->use_c_hat) {
+        CNMFE_CUDA_OK(cudaMemsetAsync(d_Crawall, 0, (size_t)Ktot * T * 8, c->st));
+        CNMFE_CUDA_OK(cudaMemsetAsync(d_Sall, 0, (size_t)Ktot * T * 8, c->st));
+        CNMFE_CUDA_OK(cudaMemsetAsync(d_parsall, 0, (size_t)Ktot * 16, c->st));
+        if (hals_temporal_dev(d_Uall, d_vptr, d_vidx, d_vval, d_aaall, Ktot, T, c->opt.maxIter_temporal, c->opt.deconv_flag,
+                              c->opt.deconv, d_Clall, d_Crawall, d_Sall, d_snall, d_parsall, d_doneall, c->d_ticket, d_orderall,
+                              &c->arena, c->st)) return -1;
+    }
+    // energy-weighted accumulation, patch after patch (the order the reference adds them, update_temporal_parallel.m:269-280)
+    for (TPlan& pl : plans) {
+        dim3 gg((T + 255) / 256, pl.Kt);
+        LAUNCH(temporal_merge_aa_kernel, gg, 256, 0, c->st, d_Crawall + (size_t)pl.koff * T, d_aaall + pl.koff, T, d_idsall + pl.koff,
+               c->num, c->den);
+    }
+    phase_end(c, 4);
+    CNMFE_CUDA_OK(cudaGetLastError());
     CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
     return 0;
 }

@@ -263,6 +263,15 @@ __global__ void temporal_merge_kernel(const double* __restrict__ Craw, const dou
     if (t == 0) den[ids[k]] += aa;
 }
 
+// same with the energies aa[k] = V[k][k] given as a vector
+__global__ void temporal_merge_aa_kernel(const double* __restrict__ Craw, const double* __restrict__ aa_, int T,
+                                         const int* __restrict__ ids, double* __restrict__ num, double* __restrict__ den) {
+    int k = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    double aa = aa_[k];
+    if (t < T) num[(size_t)ids[k] * T + t] += Craw[(size_t)k * T + t] * aa;
+    if (t == 0) den[ids[k]] += aa;
+}
+
 // dst[k][t] = U[k][t] / V[k][k]  (0 when V[k][k] == 0): fast_temporal, update_temporal_parallel.m:329-335
 __global__ void rows_div_diag_kernel(const double* __restrict__ U, const double* __restrict__ V, int K, int T,
                                      double* __restrict__ dst) {
