@@ -1,7 +1,7 @@
 function update_spatial_parallel(obj, use_parallel, update_sn) %#ok<INUSL>
 %% drop-in for ca_source_extraction/@Sources2D/update_spatial_parallel.m on B200.
 if ~exist('update_sn', 'var') || isempty(update_sn); update_sn = false; end
-h = cnmfe_b200_handle(obj);
+h = cnmfe_b200_push(obj, {'neurons', 'prev', 'sn'});   % options + background state every time: they may have changed since the last call
 search_method = obj.options.search_method;
 if strcmpi(search_method, 'dilate'); obj.options.se = []; end
 % determine_search_location(obj.A, search_method, options) (:66) in the library (host C++, same results)
@@ -18,9 +18,6 @@ if ~isempty(jc)
 else
     IND = sparse(logical(determine_search_location(obj.A, search_method, obj.options)));   % whole field of view
 end
-cnmfe_b200_mex('set_neurons', h, obj.A, obj.C);
-cnmfe_b200_mex('set_prev', h, obj.A_prev, obj.C_prev);
-cnmfe_b200_mex('set_sn', h, obj.P.sn);
 cnmfe_b200_mex('set_search', h, IND);
 if update_sn
     [vals, obj.P.sn] = cnmfe_b200_mex('update_spatial', h, nnz(IND), true, obj.options.d1, obj.options.d2);   % (:191-194, :337-339)
@@ -47,5 +44,7 @@ end
 flog = fopen(obj.P.log_file, 'a');
 fprintf(flog, '[%s]\b', get_minute());
 fprintf(flog, 'Finished updating spatial components.\n');
+spatial = struct('A', obj.A, 'ids', obj.ids);
+cnmfe_b200_save_intermediate(obj, flog, 'spatial', spatial);
 fclose(flog);
 end

@@ -57,11 +57,25 @@ static void deconv_opts_of(const mxArray* s, cnmfe_deconv_opts* o) {
     }
 }
 
+// live contexts: released when MATLAB clears the MEX file or exits (SURVEY.md 8b ownership: ctx pointer handed to MATLAB as a
+// uint64, mexLock'ed, released by 'destroy' / mexAtExit)
+static std::vector<cnmfe_ctx*> g_live;
+static void destroy_all(void) {
+    for (cnmfe_ctx* h : g_live) cnmfe_destroy(h);
+    g_live.clear();
+}
+static int field_int(const mxArray* s, const char* f, int dflt) {
+    const mxArray* v = mxGetField(s, 0, f);
+    return (v && !mxIsEmpty(v)) ? (int)mxGetScalar(v) : dflt;
+}
+
 void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (nrhs < 1 || !mxIsChar(prhs[0])) mexErrMsgIdAndTxt("cnmfe:usage", "cnmfe_b200_mex(command, ...)");
     char cmd[64];
     mxGetString(prhs[0], cmd, sizeof cmd);
     const std::string c(cmd);
+    static bool at_exit_registered = false;
+    if (!at_exit_registered) { mexAtExit(destroy_all); at_exit_registered = true; }
     if (c == "create") {   // h = create(d1,d2,T,patch_pos(4 x np int32),block_pos,ring_radius,num_neighbors,device)
         cnmfe_ctx* h = nullptr;
         int np = (int)mxGetN(prhs[4]);
@@ -70,10 +84,12 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
                            (int)mxGetScalar(prhs[6]), (int)mxGetScalar(prhs[7]), (int)mxGetScalar(prhs[8])), "create");
         plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
         *static_cast<uint64_t*>(mxGetData(plhs[0])) = reinterpret_cast<uint64_t>(h);
+        g_live.push_back(h);
         mexLock();
     } else if (c == "destroy") {
-        cnmfe_destroy(ctx_of(prhs[1]));
-        mexUnlock();
+        cnmfe_ctx* h = ctx_of(prhs[1]);
+        for (size_t i = 0; i < g_live.size(); ++i)
+            if (g_live[i] == h) { g_live.erase(g_live.begin() + i); cnmfe_destroy(h); mexUnlock(); break; }
     } else if (c == "upload_block") {   // upload_block(h, ipatch0, Yblock)  Yblock: nr_b x nc_b x T uint8/uint16
         int dt = mxIsUint8(prhs[3]) ? 0 : (mxIsUint16(prhs[3]) ? 1 : -1);
         if (dt < 0) mexErrMsgIdAndTxt("cnmfe:dtype", "video must be uint8 or uint16");
@@ -92,15 +108,61 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         check(cnmfe_set_search(ctx_of(prhs[1]), (int)mxGetN(prhs[2]), jc.data(), ir.data()), cmd);
     } else if (c == "set_sn") {
         check(cnmfe_set_sn(ctx_of(prhs[1]), mxGetPr(prhs[2])), cmd);
-    } else if (c == "set_options") {   // (h, spatial_alg, maxIter, deconv_flag, bg_acceleration, deconv_options struct)
+    } else if (c == "set_options") {   // (h, struct: spatial_algorithm (code), maxIter, deconv_flag, bg_acceleration, background_model
+                                       //  ('ring'|'svd'|'nmf'), nb, bg_ssub, deconv_options (struct) [, replicate_spatial_aprev_quirk, use_tensor_gram])
+        if (nrhs < 3 || !mxIsStruct(prhs[2])) mexErrMsgIdAndTxt("cnmfe:usage", "set_options(h, options struct)");
+        const mxArray* so = prhs[2];
         cnmfe_options o;
         cnmfe_options_defaults(&o);
-        o.spatial_algorithm = (int)mxGetScalar(prhs[2]);
-        o.maxIter_temporal = (int)mxGetScalar(prhs[3]);
-        o.deconv_flag = (int)mxGetScalar(prhs[4]);
-        o.bg_acceleration = (int)mxGetScalar(prhs[5]);
-        deconv_opts_of(nrhs > 6 ? prhs[6] : nullptr, &o.deconv);
+        o.spatial_algorithm = field_int(so, "spatial_algorithm", o.spatial_algorithm);
+        o.maxIter_temporal = field_int(so, "maxIter", o.maxIter_temporal);
+        o.deconv_flag = field_int(so, "deconv_flag", o.deconv_flag);
+        o.bg_acceleration = field_int(so, "bg_acceleration", o.bg_acceleration);
+        o.nb = field_int(so, "nb", o.nb);
+        o.bg_ssub = field_int(so, "bg_ssub", o.bg_ssub);
+        o.replicate_spatial_aprev_quirk = field_int(so, "replicate_spatial_aprev_quirk", o.replicate_spatial_aprev_quirk);
+        o.use_tensor_gram = field_int(so, "use_tensor_gram", o.use_tensor_gram);
+        const mxArray* bm = mxGetField(so, 0, "background_model");
+        char buf[16];
+        if (bm && !mxGetString(bm, buf, sizeof buf)) {
+            if (!strcmp(buf, "ring")) o.background_model = 0;
+            else if (!strcmp(buf, "svd")) o.background_model = 1;
+            else if (!strcmp(buf, "nmf")) o.background_model = 2;
+            else mexErrMsgIdAndTxt("cnmfe:options", "background_model '%s' unknown (ring, svd, nmf)", buf);
+        }
+        if (o.background_model != 0) o.bg_ssub = 1;
+        deconv_opts_of(mxGetField(so, 0, "deconv_options"), &o.deconv);
         check(cnmfe_set_options(ctx_of(prhs[1]), &o), cmd);
+    } else if (c == "set_use_c_hat") {   // (h, flag): third argument of update_temporal_parallel
+        check(cnmfe_set_use_c_hat(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2])), cmd);
+    } else if (c == "ssub_dims") {   // [d1s, d2s, nnb, r_shift, c_shift] = ssub_dims(h, ipatch0): coarse ring grid for bg_ssub > 1
+        int d1s = 0, d2s = 0, nnb = 0;
+        check(cnmfe_ssub_dims(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), &d1s, &d2s, &nnb, nullptr, nullptr), cmd);
+        plhs[0] = mxCreateDoubleScalar(d1s);
+        if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(d2s);
+        if (nlhs > 2) plhs[2] = mxCreateDoubleScalar(nnb);
+        if (nlhs > 3) {
+            plhs[3] = mxCreateNumericMatrix(1, nnb, mxINT32_CLASS, mxREAL);
+            mxArray* cs = mxCreateNumericMatrix(1, nnb, mxINT32_CLASS, mxREAL);
+            check(cnmfe_ssub_dims(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), &d1s, &d2s, &nnb, (int32_t*)mxGetData(plhs[3]), (int32_t*)mxGetData(cs)), cmd);
+            if (nlhs > 4) plhs[4] = cs;
+        }
+    } else if (c == "set_bf") {   // (h, ipatch0, b (d_patch x nb), f (nb x T), b0 or []): svd / nmf background state
+        const double* b = mxIsEmpty(prhs[3]) ? nullptr : mxGetPr(prhs[3]);
+        const double* f = mxIsEmpty(prhs[4]) ? nullptr : mxGetPr(prhs[4]);
+        const double* b0 = (nrhs > 5 && !mxIsEmpty(prhs[5])) ? mxGetPr(prhs[5]) : nullptr;
+        check(cnmfe_set_bf(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), b, f, b0), cmd);
+    } else if (c == "get_bf") {   // [b, f, b0] = get_bf(h, ipatch0, d_patch, nb, T)
+        mwSize dp = (mwSize)mxGetScalar(prhs[3]), nb = (mwSize)mxGetScalar(prhs[4]), T = (mwSize)mxGetScalar(prhs[5]);
+        plhs[0] = mxCreateDoubleMatrix(dp, nb, mxREAL);
+        mxArray* f = mxCreateDoubleMatrix(nb, T, mxREAL);
+        mxArray* b0 = mxCreateDoubleMatrix(dp, 1, mxREAL);
+        check(cnmfe_get_bf(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), mxGetPr(plhs[0]), mxGetPr(f), mxGetPr(b0)), cmd);
+        if (nlhs > 1) plhs[1] = f;
+        if (nlhs > 2) plhs[2] = b0;
+    } else if (c == "estimate_noise") {   // sn = estimate_noise(h, f0, f1, d1, d2): per-pixel GetSn of the resident video (Sources2D.m:328-379)
+        plhs[0] = mxCreateDoubleMatrix((mwSize)mxGetScalar(prhs[4]), (mwSize)mxGetScalar(prhs[5]), mxREAL);
+        check(cnmfe_estimate_noise(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), (int)mxGetScalar(prhs[3]), mxGetPr(plhs[0])), cmd);
     } else if (c == "ring_offsets") {   // [r_shift, c_shift] = ring_offsets(h)
         int nnb = 0;
         check(cnmfe_ring_offsets(ctx_of(prhs[1]), &nnb, nullptr, nullptr), cmd);
@@ -111,11 +173,12 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         const double* W = mxIsEmpty(prhs[3]) ? nullptr : mxGetPr(prhs[3]);
         const double* b0 = mxIsEmpty(prhs[4]) ? nullptr : mxGetPr(prhs[4]);
         check(cnmfe_set_ring(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), W, b0), cmd);
-    } else if (c == "get_ring") {   // [Wslots, b0] = get_ring(h, ipatch0, nnb, d_patch)
-        mwSize nnb = (mwSize)mxGetScalar(prhs[3]), dp = (mwSize)mxGetScalar(prhs[4]);
-        plhs[0] = mxCreateDoubleMatrix(nnb, dp, mxREAL);
-        plhs[1] = mxCreateDoubleMatrix(dp, 1, mxREAL);
-        check(cnmfe_get_ring(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), mxGetPr(plhs[0]), mxGetPr(plhs[1])), cmd);
+    } else if (c == "get_ring") {   // [Wslots, b0] = get_ring(h, ipatch0, nnb, nW, d_patch): nW = d_patch (bg_ssub = 1) or d1s*d2s (coarse grid)
+        mwSize nnb = (mwSize)mxGetScalar(prhs[3]), nw = (mwSize)mxGetScalar(prhs[4]), dp = (mwSize)mxGetScalar(prhs[5]);
+        plhs[0] = mxCreateDoubleMatrix(nnb, nw, mxREAL);
+        mxArray* b0 = mxCreateDoubleMatrix(dp, 1, mxREAL);
+        check(cnmfe_get_ring(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), mxGetPr(plhs[0]), mxGetPr(b0)), cmd);
+        if (nlhs > 1) plhs[1] = b0;
     } else if (c == "update_background") {
         check(cnmfe_update_background(ctx_of(prhs[1])), cmd);
     } else if (c == "update_spatial") {   // [vals, sn] = update_spatial(h, nnz(IND), update_sn, d1, d2)  -> values on find(IND) order

@@ -1,10 +1,12 @@
-// Minimal stand-in for MATLAB's mex.h (declarations only), so that tests can type-check matlab/cnmfe_b200_mex.cpp against include/cnmfe_b200.h without MATLAB.
+// Stand-in for MATLAB's mex.h so that tests can build matlab/cnmfe_b200_mex.cpp against include/cnmfe_b200.h without MATLAB:
+// type-checks with -fsyntax-only, and -- linked with tests/stubs/mex_impl.cpp, where mxArray is a real malloc-backed array -- runs.
+#pragma once
 #include <cstddef>
 #include <cstdint>
 typedef struct mxArray_tag mxArray;
 typedef size_t mwSize; typedef size_t mwIndex;
 typedef enum { mxREAL, mxCOMPLEX } mxComplexity;
-typedef enum { mxDOUBLE_CLASS, mxINT32_CLASS, mxUINT64_CLASS, mxUINT16_CLASS, mxUINT8_CLASS, mxLOGICAL_CLASS } mxClassID;
+typedef enum { mxDOUBLE_CLASS, mxINT32_CLASS, mxUINT64_CLASS, mxUINT16_CLASS, mxUINT8_CLASS, mxLOGICAL_CLASS, mxCHAR_CLASS, mxSTRUCT_CLASS, mxSINGLE_CLASS } mxClassID;
 extern "C" {
 double* mxGetPr(const mxArray*); void* mxGetData(const mxArray*); mwIndex* mxGetJc(const mxArray*); mwIndex* mxGetIr(const mxArray*);
 mwSize mxGetM(const mxArray*); mwSize mxGetN(const mxArray*); double mxGetScalar(const mxArray*); bool mxIsEmpty(const mxArray*);
