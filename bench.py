@@ -550,7 +550,7 @@ def run_ours(args):
                                                        [float(x) / args.steps for x in phases]))),
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=dict(value=e2e_val, unit="pixel*frames/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                         note="Sources2D.update_* on host numpy state: every call syncs the host mirror (H2D of what changed on the host, D2H of W/b0, A, C/C_raw/S into host arrays); the uint16 video stays resident in HBM (loaded once, like the reference's mat_data)"),
+                         note="Sources2D.update_* on host numpy state: every call syncs the host mirror -- H2D of what changed on the host; D2H of b0, A (values on the search pattern), C, kernel_pars, neuron_sn into host arrays every step; the ring weights W and C_raw / S (state no update reads back from the host) stay on the device until obj.W / obj.C_raw / obj.S are read; the uint16 video stays resident in HBM (loaded once, like the reference's mat_data)"),
                 roofline=roofline, cpu_baseline=cpu)
     print(json.dumps(line))
     if world > 1:

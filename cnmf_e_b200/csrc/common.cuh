@@ -8,6 +8,12 @@
 #ifndef CNMFE_BLOCK
 #define CNMFE_BLOCK 256
 #endif
+// CTA size of the HALS_temporal sweeps: that kernel is a dependency chain on a mostly idle GPU (~100 runnable items on 148 SMs),
+// so a work item gets a bigger CTA than the throughput-bound batch kernels (measured at configs[1]: 256 threads 29.4 ms,
+// 512 threads 21.7 ms, 1024 threads 26.9 ms)
+#ifndef CNMFE_HALS_BLOCK
+#define CNMFE_HALS_BLOCK 512
+#endif
 
 namespace cnmfe {
 

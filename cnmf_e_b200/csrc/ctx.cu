@@ -11,6 +11,7 @@
 #include "internal.h"
 #include "kernels_video.cuh"
 #include "kernels_ring.cuh"
+#include "kernels_ring_mma.cuh"
 #include "kernels_update.cuh"
 #include "kernels_svd.cuh"
 #include "kernels_ssub.cuh"
@@ -847,6 +848,21 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
             CNMFE_CUDA_OK(cudaMemsetAsync(a.prof, 0, 64, c->st));
         }
         const int NMAX = c->nnb + 1;
+        // solver: block LDL' on the fp64 tensor-core path (default) or the register-tile SIMT kernel (CNMFE_RING_SOLVER=simt: checker)
+        const bool solver_simt = getenv("CNMFE_RING_SOLVER") && !strcmp(getenv("CNMFE_RING_SOLVER"), "simt");   // read per call: tests A/B it
+        if (!solver_simt) {
+            const size_t sm = ring_solve_mma_smem_bytes();
+            if (ring_profile) {
+                CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                int occ = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_solve_mma_kernel<true>, RM_THREADS, sm);
+                fprintf(stderr, "[cnmfe ring profile] mma solver: dynamic smem %zu B, occupancy %d CTAs/SM\n", sm, occ);
+                LAUNCH(ring_solve_mma_kernel<true>, (unsigned)alist.size(), RM_THREADS, sm, c->st, a);
+            } else {
+                CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                LAUNCH(ring_solve_mma_kernel<false>, (unsigned)alist.size(), RM_THREADS, sm, c->st, a);
+            }
+        } else {
         size_t smem = ring_solve_smem_bytes(NMAX);
         {
             // shared-memory carve-out: just enough for the two CTAs per SM the register file allows; the rest stays L1, which
@@ -867,6 +883,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         } else {
             CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             LAUNCH(ring_solve_kernel<false>, (unsigned)alist.size(), RING_SOLVE_THREADS, smem, c->st, a);
+        }
         }
         CNMFE_CUDA_OK(cudaGetLastError());
         phase_end(c, 1);

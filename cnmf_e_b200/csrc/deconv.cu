@@ -192,7 +192,7 @@ struct HalsArgs {
 // One work item = (sweep, neuron).  Items are handed out in the reference's sequential order; an item waits until
 // the neurons it overlaps (V(k,j) != 0) have reached the state the sequential loop would have seen
 // (HALS_temporal.m:59-62: neuron k reads rows j<k of THIS sweep and rows j>k of the PREVIOUS sweep).
-__global__ void __launch_bounds__(CNMFE_BLOCK, 512 / CNMFE_BLOCK) hals_temporal_kernel(HalsArgs a) {
+__global__ void __launch_bounds__(CNMFE_HALS_BLOCK, 1) hals_temporal_kernel(HalsArgs a) {
     __shared__ BlockShared sh;
     __shared__ unsigned int s_item;
     TraceWS ws;
@@ -398,7 +398,9 @@ int hals_temporal_dev(const double* U, const int* Vptr, const int* Vidx, const d
         CNMFE_CUDA_OK(cudaMalloc((void**)&a.prof_items, (size_t)maxIter * n_update * 32));
         CNMFE_CUDA_OK(cudaMemsetAsync(a.prof_items, 0, (size_t)maxIter * n_update * 32, st));
     }
-    LAUNCH(hals_temporal_kernel, slots, CNMFE_BLOCK, smem, st, a);
+    int hals_threads = CNMFE_HALS_BLOCK;
+    if (const char* e = getenv("CNMFE_HALS_THREADS")) { const int v = atoi(e); if (v >= 64 && v <= CNMFE_HALS_BLOCK && v % 32 == 0) hals_threads = v; }   // A/B knob
+    LAUNCH(hals_temporal_kernel, slots, hals_threads, smem, st, a);
     CNMFE_CUDA_OK(cudaGetLastError());
     if (profile) {
         unsigned long long h[32];

@@ -41,7 +41,7 @@ struct BlockShared {
     int hist[256];
     int ibc[4];
     double dbc[4];
-    double part[CNMFE_BLOCK];   // block scan partials (cumsum of the update_g kernel table)
+    double part[CNMFE_HALS_BLOCK];   // block scan partials (cumsum of the update_g kernel table); sized for the largest CTA
     double2 stage[32];          // cold scan: (a_m, b_m) of the current window, read back as broadcast 16-byte loads
     double2 snap[32];           // cold scan: running (v, w) before element m
     double2* zfft;              // GetSn FFT buffer in dynamic shared memory (nfft complex), or nullptr -> global scratch

@@ -14,6 +14,7 @@ Out of scope hooks, supplied by the caller exactly where 
 """
 import ctypes
 import os
+import sys
 
 import numpy as np
 import scipy.sparse as sp
@@ -92,6 +93,47 @@ def merge_temporal(num, den):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class _PinnedPool:
+    """Page-locked host buffers for the large device->host copies (ring weights: 252 MB per 512 x 512 patch; C / C_raw / S:
+    K*T*8 each).  A buffer is handed out again only when NOTHING references the array it backed any more -- an array the
+    caller (or this class, e.g. obj.C_prev) still holds is never overwritten; the pool then grows by one buffer instead."""
+
+    def __init__(self, lib):
+        self._lib = lib
+        self._bufs = {}          # (name, shape) -> [base arrays]
+
+    def take(self, name, shape):
+        shape = tuple(int(x) for x in shape)
+        # buffers of this name with another shape (K changed): drop the ones nobody uses any more
+        for key in [k for k in self._bufs if k[0] == name and k[1] != shape]:
+            keep = []
+            for b in self._bufs[key]:
+                if sys.getrefcount(b) > 3:
+                    keep.append(b)
+                else:
+                    self._lib.cnmfe_host_unregister(_ptr(b))
+            if keep:
+                self._bufs[key] = keep
+            else:
+                del self._bufs[key]
+        lst = self._bufs.setdefault((name, shape), [])
+        for b in lst:
+            if sys.getrefcount(b) <= 3:       # the list, the loop variable, getrefcount's argument: no view of it is alive
+                v = b.view()
+                v.setflags(write=True)
+                return v
+        b = np.empty(shape)
+        if b.nbytes >= (1 << 20) and self._lib.cnmfe_host_register(_ptr(b), b.nbytes) == 0:
+            lst.append(b)
+        return b.view()
+
+    def close(self):
+        for lst in self._bufs.values():
+            for b in lst:
+                self._lib.cnmfe_host_unregister(_ptr(b))
+        self._bufs = {}
 
 
 class _RingWeights(dict):
@@ -176,18 +218,18 @@ class Sources2D:
         d = self.d1 * self.d2
         self.A = sp.csc_matrix((d, 0))
         self.C = np.zeros((0, self.T))
-        self.C_raw = np.zeros((0, self.T))
-        self.S = np.zeros((0, self.T))
+        self._C_raw = np.zeros((0, self.T))
+        self._S = np.zeros((0, self.T))
+        self._lazy_temporal = set()      # {"C_raw", "S"}: newer on the device than on the host, fetched when read
         self.A_prev = sp.csc_matrix((d, 0))
         self.C_prev = np.zeros((0, self.T))
         self._ring_w_stale = set()  # patches whose weights on the device are newer than the host copy (fetched on read)
         self.W = _RingWeights(self)
         self.b0 = {}
-        self._temporal_partial = False   # multi-rank: C_raw / S / per-trace outputs on the device still hold only this rank's rows
+        self._temporal_partial = set()   # multi-rank: which of (1: C_raw, 2: S, 3: per-trace outputs) still hold only this rank's rows on the device
         self._ring_synced = {}      # patch -> (W, b0) objects whose contents the device holds
         self._dev = {}              # "A" / "C" / "A_prev" / "C_prev" -> host object whose contents the device holds
-        self._pinned = {}           # name -> page-locked reusable host buffer (ring weights)
-        self._ring_flip = {}        # patch -> which of its two pinned W buffers the last pull_ring filled
+        self._pool = _PinnedPool(self._lib)   # page-locked buffers of the large pulls (never reused while referenced)
         self.h2d_bytes = 0          # bytes this object has sent to / fetched from the device (state, not the video)
         self.d2h_bytes = 0
         self.b = {}
@@ -201,9 +243,7 @@ class Sources2D:
     # ------------------------------------------------------------------ lifetime
     def close(self):
         if getattr(self, "_h", None):
-            for buf in self._pinned.values():
-                self._lib.cnmfe_host_unregister(_ptr(buf))
-            self._pinned = {}
+            self._pool.close()
             self._lib.cnmfe_destroy(self._h)
             self._h = None
 
@@ -333,19 +373,6 @@ class Sources2D:
     def push_prev(self):
         self._push_pair(self._lib.cnmfe_set_prev, "A_prev", self.A_prev, "C_prev", self.C_prev)
 
-    def _pinned_buffer(self, name, shape):
-        """Reusable page-locked float64 host buffer (the ring weights are ~250 MB per 512x512 patch: a fresh pageable
-        array per pull costs more in page faults than the copy itself)."""
-        buf = self._pinned.get(name)
-        if buf is not None and buf.shape == tuple(shape):
-            return buf
-        if buf is not None:
-            self._lib.cnmfe_host_unregister(_ptr(buf))
-        buf = np.zeros(shape)
-        if buf.nbytes >= (1 << 20) and self._lib.cnmfe_host_register(_ptr(buf), buf.nbytes) == 0:
-            self._pinned[name] = buf
-        return buf
-
     def push_ring(self):
         if str(self.options["background_model"]).lower() in ("svd", "nmf"):
             for i in range(self.npatch):
@@ -412,11 +439,9 @@ class Sources2D:
                 wshape = (d1s * d2s, nnb)
             else:
                 wshape = (dp, self.nnb)
-            # W lands in one of TWO page-locked buffers used in alternation, so the array handed out by the previous
-            # pull (e.g. kept by the caller for a convergence check) stays intact for one more update
-            self._ring_flip[i] = 1 - self._ring_flip.get(i, 1)
-            W = self._pinned_buffer(("W", i, self._ring_flip[i]), wshape).view()
-            W.setflags(write=True)
+            # W lands in a page-locked buffer that is reused only once nobody references the array it backed before
+            dict.pop(self.W, i, None)
+            W = self._pool.take(("W", i), wshape)
             L.check(self._lib.cnmfe_get_ring(self._h, i, _ptr(W), None))
             self.d2h_bytes += W.nbytes
             W.setflags(write=False)
@@ -679,10 +704,10 @@ class Sources2D:
             k0, k1 = trace_range(K, self.rank, self.world_size)
             L.check(self._lib.cnmfe_update_temporal_finish_part(self._h, k0, k1))
             self._allreduce_temporal_state(K, (0,))
-            self._temporal_partial = True
+            self._temporal_partial = {1, 2, 3}
         else:
             L.check(self._lib.cnmfe_update_temporal_finish(self._h))
-            self._temporal_partial = False
+            self._temporal_partial = set()
         if sync_host:
             self.pull_temporal()
 
@@ -704,21 +729,63 @@ class Sources2D:
         vals = self._allreduce_sum(vals)
         L.check(self._lib.cnmfe_set_spatial(self._h, _ptr(vals)))
 
-    def pull_temporal(self):
-        """obj.C, obj.C_raw, obj.S, obj.P.kernel_pars, obj.P.neuron_sn from the device.  Multi-rank with shard_deconv: a
-        COLLECTIVE call (the rows of C_raw / S the other ranks deconvolved are exchanged first)."""
+    # obj.C_raw and obj.S: K x T each.  After a temporal update they stay on the device and are copied out when they are
+    # READ (the next update reads neither; the reference's own callers -- merging, deletion, saving -- do).  Reading is a local
+    # device->host copy, never a collective: with several ranks pull_temporal() (collective) completes the device arrays first.
+    @property
+    def C_raw(self):
+        if "C_raw" in self._lazy_temporal:
+            self._fetch_lazy_temporal()
+        return self._C_raw
+
+    @C_raw.setter
+    def C_raw(self, v):
+        self._lazy_temporal.discard("C_raw")
+        self._C_raw = v
+
+    @property
+    def S(self):
+        if "S" in self._lazy_temporal:
+            self._fetch_lazy_temporal()
+        return self._S
+
+    @S.setter
+    def S(self, v):
+        self._lazy_temporal.discard("S")
+        self._S = v
+
+    def _fetch_lazy_temporal(self):
+        K = self.A.shape[1]
+        if self._temporal_partial & {1, 2}:
+            # reading an attribute must never start a collective (one rank reading would dead-lock the others)
+            raise L.CnmfeError("obj.C_raw / obj.S: the rows deconvolved by the other ranks have not been exchanged yet -- "
+                               "call pull_temporal() on ALL ranks after update_temporal_parallel(sync_host=False)")
+        self._C_raw = self._S = None          # release the buffers of the previous iteration before taking new ones
+        Cr = self._pool.take("C_raw", (K, self.T))
+        S = self._pool.take("S", (K, self.T))
+        L.check(self._lib.cnmfe_get_temporal(self._h, None, _ptr(Cr), _ptr(S), None, None))
+        self.d2h_bytes += Cr.nbytes + S.nbytes
+        self._C_raw, self._S = self._freeze(Cr), self._freeze(S)
+        self._lazy_temporal.clear()
+
+    def pull_temporal(self, lazy=True):
+        """obj.C, obj.P.kernel_pars, obj.P.neuron_sn from the device now; obj.C_raw and obj.S when they are read (lazy=False:
+        now).  Multi-rank with shard_deconv: a COLLECTIVE call (exchanges, on the devices, the rows of C_raw / S / kernel_pars
+        that the other ranks deconvolved)."""
         K = self.A.shape[1]
         if self._temporal_partial:
-            self._allreduce_temporal_state(K, (1, 2, 3))
-            self._temporal_partial = False
-        C = np.empty((K, self.T))
-        Cr = np.empty((K, self.T))
-        S = np.empty((K, self.T))
+            # device-side exchange (NVLink) of the rows the other ranks deconvolved; the copies to the host stay lazy
+            self._allreduce_temporal_state(K, tuple(sorted(self._temporal_partial)))
+            self._temporal_partial = set()
+        C = self._pool.take("C", (K, self.T))
         kp = np.zeros((K, 2))
         nsn = np.zeros(K)
-        L.check(self._lib.cnmfe_get_temporal(self._h, _ptr(C), _ptr(Cr), _ptr(S), _ptr(kp), _ptr(nsn)))
-        self.d2h_bytes += C.nbytes + Cr.nbytes + S.nbytes + kp.nbytes + nsn.nbytes
-        self.C, self.C_raw, self.S = self._freeze(C), self._freeze(Cr), self._freeze(S)
+        L.check(self._lib.cnmfe_get_temporal(self._h, _ptr(C), None, None, _ptr(kp), _ptr(nsn)))
+        self.d2h_bytes += C.nbytes + kp.nbytes + nsn.nbytes
+        self.C = self._freeze(C)
+        self._lazy_temporal = {"C_raw", "S"}
+        if not lazy:
+            self._fetch_lazy_temporal()
         self._mark("C", self.C)
         self.P["kernel_pars"], self.P["neuron_sn"] = kp, nsn
         if self.P.get("Ymean") is not None and self._is_ring():          # update_temporal_parallel.m:291-295

@@ -225,3 +225,20 @@ def test_background_frame_subsampling(built_lib, tensor):
     _check_bg(orc, gpu)
     assert bool(built_lib.cnmfe_last_gram_was_tensor(gpu._h)) == tensor
     gpu.close()
+
+
+def test_ring_solvers_agree(built_lib, monkeypatch):
+    """The block-LDL' solver on the fp64 tensor-core path (default) and the register-tile SIMT solver (CNMFE_RING_SOLVER=simt,
+    kept as the checker) give the same weights to rounding; both were compared with the oracle above."""
+    res = {}
+    for solver in ("mma", "simt"):
+        monkeypatch.setenv("CNMFE_RING_SOLVER", solver)
+        D, orc, gpu = _make("ring18", (56, 48), 18)
+        gpu.update_background_parallel()
+        res[solver] = np.array(gpu.W[0], copy=True)
+        if solver == "mma":
+            orc.update_background_parallel()
+            _check_bg(orc, gpu)
+        gpu.close()
+    scale = np.abs(res["simt"]).max()
+    assert np.abs(res["mma"] - res["simt"]).max() <= 1e-9 * scale
