@@ -45,6 +45,7 @@ SYMBOLS = {
     "cnmfe_options_defaults": (None, [ctypes.POINTER(Options)]),
     "cnmfe_launch_count": (ctypes.c_ulonglong, []),
     "cnmfe_deconvolve": (I, [V, I, I, ctypes.POINTER(DeconvOpts), V, V, V, V, V, V, V, V, V, I]),
+    "cnmfe_deconvolve_dev": (I, [V, I, I, ctypes.POINTER(DeconvOpts), V, V, V, V, V, I]),
     "cnmfe_get_sn": (I, [V, I, I, V, I]),
     "cnmfe_hals_temporal_uv": (I, [V, V, I, I, V, I, ctypes.POINTER(DeconvOpts), V, V, V, V, I]),
     "cnmfe_update_temporal_finish_part": (I, [V, I, I]),

@@ -857,10 +857,10 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
                 int occ = 0;
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ring_solve_mma_kernel<true>, RM_THREADS, sm);
                 fprintf(stderr, "[cnmfe ring profile] mma solver: dynamic smem %zu B, occupancy %d CTAs/SM\n", sm, occ);
-                LAUNCH(ring_solve_mma_kernel<true>, (unsigned)alist.size(), RM_THREADS, sm, c->st, a);
+                LAUNCH(ring_solve_mma_kernel<true>, (unsigned)((alist.size() + RM_PIX - 1) / RM_PIX), RM_THREADS, sm, c->st, a);
             } else {
                 CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_solve_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-                LAUNCH(ring_solve_mma_kernel<false>, (unsigned)alist.size(), RM_THREADS, sm, c->st, a);
+                LAUNCH(ring_solve_mma_kernel<false>, (unsigned)((alist.size() + RM_PIX - 1) / RM_PIX), RM_THREADS, sm, c->st, a);
             }
         } else {
         size_t smem = ring_solve_smem_bytes(NMAX);

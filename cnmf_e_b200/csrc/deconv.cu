@@ -543,6 +543,21 @@ extern "C" int cnmfe_deconvolve(const double* Y, int T, int N, const cnmfe_decon
     return rc;
 }
 
+// deconvolveCa on traces that already live on the device (BASELINE configs[4]: 5000 x 100000 AR2 is 4 GB in, 8 GB out -- the
+// host entry point above would spend its time on the PCIe copies).  All pointers are device pointers on `device`; Y, c, s are
+// [N][T] trace-contiguous; sn_in / pars_in ([N][2]) / outs ([N][6] = b, g1, g2, smin, lam, sn) may be NULL.  Asynchronous on the
+// legacy default stream; the per-device workspace is cached, so the call is not re-entrant per device.
+extern "C" int cnmfe_deconvolve_dev(const double* Y_dev, int T, int N, const cnmfe_deconv_opts* opts, const double* sn_dev,
+                                    const double* pars_dev, double* c_dev, double* s_dev, double* outs_dev, int device) {
+    if (!Y_dev || !opts || T <= 0 || N < 0 || device < 0 || device >= 64) { set_error("cnmfe_deconvolve_dev: bad arguments"); return -1; }
+    if (N == 0) return 0;
+    if (use_device(device)) return -1;
+    static TraceArena arenas[64];
+    if (deconv_batch_dev(Y_dev, T, N, *opts, sn_dev, pars_dev, 0, c_dev, s_dev, nullptr, outs_dev, &arenas[device], 0)) return -1;
+    CNMFE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int cnmfe_get_sn(const double* Y, int T, int N, double* sn, int device) {
     if (!Y || !sn || T <= 0 || N < 0) { set_error("cnmfe_get_sn: bad arguments"); return -1; }
     if (N == 0) return 0;

@@ -22,8 +22,19 @@
 
 namespace cnmfe {
 
-#define RM_THREADS 256
+// RM_PIX pixels per CTA (8 warps each).  2 = two pixels factorise in lock step behind CTA-wide barriers (see rm_factor_step);
+// 1 = one pixel per CTA, two independent CTAs per SM.  RM_PIVOT2 = 2 x 2 block pivots in the 8 x 8 inversion.
+#ifndef RM_PIX
+#define RM_PIX 1
+#endif
+#ifndef RM_PIVOT2
+#define RM_PIVOT2 0
+#endif
+#define RM_GROUP 256
+#define RM_THREADS (RM_GROUP * RM_PIX)
 #define RM_KSET 8
+// barrier of one pixel group (named barrier 1 + group, 256 threads); __syncthreads() = both groups
+#define RM_GSYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(RM_GROUP) : "memory")
 
 __device__ __forceinline__ void rm_dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -35,7 +46,7 @@ __device__ __forceinline__ void rm_store_fo(double* blk, int r, int q, double v0
     blk[rm_fo(r, 2 * q + 1)] = v1;
 }
 
-struct RmSmem {
+struct alignas(16) RmSmem {
     double X[2][16 * 64];      // panel blocks G_IK, fragment order, double-buffered by step parity
     double NP[2][16 * 64];     // -P_I
     double Mi[2][64];          // D^-1
@@ -49,10 +60,14 @@ struct RmSmem {
     int wcnt[8];
     int n, nk;
 };
-__host__ __device__ inline size_t ring_solve_mma_smem_bytes() { return sizeof(RmSmem); }
+__host__ __device__ inline size_t ring_solve_mma_smem_bytes() { return RM_PIX * sizeof(RmSmem); }
 
-// in-warp inverse of an 8 x 8 SPD block held as a C fragment (Gauss-Jordan, no pivoting)
-__device__ __forceinline__ void rm_invert8(double& m0, double& m1, int r, int q) {
+// in-warp inverse of an 8 x 8 SPD block held as a C fragment: block Gauss-Jordan with 2 x 2 pivots (principal 2 x 2 blocks of an
+// SPD matrix are SPD, so no pivoting).  One reciprocal (of the 2 x 2 determinant) per TWO eliminated columns: the dependent
+// chain -- what the whole factorisation waits for -- is 4 x (shuffle, det, rcp, 3 fma levels) instead of 8 x (shuffle, rcp, 2).
+// Pivot columns 2m, 2m+1 are exactly the two elements of the lanes with q == m.
+#if !RM_PIVOT2
+__device__ __forceinline__ void rm_invert8(double& m0, double& m1, int r, int q) {      // scalar pivots
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const double mk = (k & 1) ? m1 : m0;
@@ -70,36 +85,71 @@ __device__ __forceinline__ void rm_invert8(double& m0, double& m1, int r, int q)
         }
     }
 }
+#else
+__device__ __forceinline__ void rm_invert8(double& m0, double& m1, int r, int q) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int k = 2 * m;
+        // pivot block [[a, b], [b, c]]
+        const double a = __shfl_sync(0xffffffffu, m0, 4 * k + m), b = __shfl_sync(0xffffffffu, m1, 4 * k + m);
+        const double c = __shfl_sync(0xffffffffu, m1, 4 * (k + 1) + m);
+        // my row's entries in the pivot columns, the pivot rows' entries in my columns
+        const double f0 = __shfl_sync(0xffffffffu, m0, 4 * r + m), f1 = __shfl_sync(0xffffffffu, m1, 4 * r + m);
+        double g00 = __shfl_sync(0xffffffffu, m0, 4 * k + q), g01 = __shfl_sync(0xffffffffu, m1, 4 * k + q);
+        double g10 = __shfl_sync(0xffffffffu, m0, 4 * (k + 1) + q), g11 = __shfl_sync(0xffffffffu, m1, 4 * (k + 1) + q);
+        if (q == m) { g00 = 1.0; g01 = 0.0; g10 = 0.0; g11 = 1.0; }      // the pivot columns receive Pinv / -f * Pinv
+        const double rd = __drcp_rn(fma(a, c, -(b * b)));
+        const double i00 = c * rd, i01 = -(b * rd), i11 = a * rd;
+        const double s00 = fma(i01, g10, i00 * g00), s01 = fma(i01, g11, i00 * g01);     // Pinv * (pivot rows)
+        const double s10 = fma(i11, g10, i01 * g00), s11 = fma(i11, g11, i01 * g01);
+        if (r == k) { m0 = s00; m1 = s01; }
+        else if (r == k + 1) { m0 = s10; m1 = s11; }
+        else {
+            const double t0 = (q == m) ? 0.0 : m0, t1 = (q == m) ? 0.0 : m1;
+            m0 = fma(-f1, s10, fma(-f0, s00, t0));
+            m1 = fma(-f1, s11, fma(-f0, s01, t1));
+        }
+    }
+}
+#endif
 
+// pivot block of step K held in (m0, m1) by its owner warp: invert and publish (K < 15), or -- block 15, whose last row/column is
+// the right-hand side -- pivot on [[A', 0], [0, 1]] and solve the row against it
+template <int K>
+__device__ __forceinline__ void rm_pivot(double m0, double m1, const int r, const int q, RmSmem& S) {
+    if (K == 15) {
+        const double z0 = m0, z1 = m1;                       // row 7 = rhs entries (lanes r == 7)
+        if (r == 7) { m0 = 0.0; m1 = (q == 3) ? 1.0 : 0.0; }
+        else if (q == 3) m1 = 0.0;
+        rm_invert8(m0, m1, r, q);
+        const double zv0 = __shfl_sync(0xffffffffu, z0, 28 + (r >> 1)), zv1 = __shfl_sync(0xffffffffu, z1, 28 + (r >> 1));
+        const double zr = (r & 1) ? zv1 : zv0;               // z[r]
+        double t0 = zr * m0, t1 = zr * m1;
+        if (r == 7) { t0 = 0.0; t1 = 0.0; }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); }
+        if (r == 0) { S.xs[120 + 2 * q] = t0; S.xs[120 + 2 * q + 1] = (q == 3) ? 0.0 : t1; }
+    } else {
+        rm_invert8(m0, m1, r, q);
+        rm_store_fo(S.Mi[K & 1], r, q, m0, m1);
+    }
+}
+
+// Step K of the factorisation.  TWO pixels share a CTA (warps 0-7 and 8-15) and run the factorisation in lock step behind
+// CTA-wide barriers: the pivot inversion is a chain of dependent fp64 operations, and DMMAs issued by other warps of the same
+// SM sub-partition occupy the fp64 pipe 16 cycles at a time -- with two independent CTAs per SM (or a look-ahead that overlaps
+// the pivot with the trailing update) every link of the chain queued behind them (measured: 3.2 k cycles per step).  In lock
+// step both pixels pivot while no DMMA is in flight on the SM, then both run their trailing updates at the pipe's full rate.
 template <int K>
 __device__ __forceinline__ void rm_factor_step(double (&acc)[17][2], const int w, const int lane, RmSmem& S) {
     const int r = lane >> 2, q = lane & 3;
     double* Xb = S.X[K & 1];
     double* NPb = S.NP[K & 1];
-    double* Mi = S.Mi[K & 1];
+    const double* Mi = S.Mi[K & 1];
     constexpr int SB = K, SA = 16 - K;     // slots of the column-K blocks (row-B / row-A reading of the slot)
     // (1) pivot block: owner inverts and publishes
     const bool ownA = (K <= 7) && (w == K), ownB = (K >= 8) && (15 - w == K);
-    if (ownA || ownB) {
-        double m0 = ownA ? acc[SA][0] : acc[SB][0], m1 = ownA ? acc[SA][1] : acc[SB][1];
-        if (K == 15) {
-            // block 15 holds the right-hand side in its last row/column: pivot on [[A', 0], [0, 1]] and solve the row against it
-            const double z0 = m0, z1 = m1;                       // row 7 = rhs entries (lanes r == 7)
-            if (r == 7) { m0 = 0.0; m1 = (q == 3) ? 1.0 : 0.0; }
-            else if (q == 3) m1 = 0.0;
-            rm_invert8(m0, m1, r, q);
-            const double zv0 = __shfl_sync(0xffffffffu, z0, 28 + (r >> 1)), zv1 = __shfl_sync(0xffffffffu, z1, 28 + (r >> 1));
-            const double zr = (r & 1) ? zv1 : zv0;                                          // z[r]
-            double t0 = zr * m0, t1 = zr * m1;
-            if (r == 7) { t0 = 0.0; t1 = 0.0; }
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); }
-            if (r == 0) { S.xs[120 + 2 * q] = t0; S.xs[120 + 2 * q + 1] = (q == 3) ? 0.0 : t1; }
-        } else {
-            rm_invert8(m0, m1, r, q);
-            rm_store_fo(Mi, r, q, m0, m1);
-        }
-    }
+    if (ownA || ownB) rm_pivot<K>(ownA ? acc[SA][0] : acc[SB][0], ownA ? acc[SA][1] : acc[SB][1], r, q, S);
     if (K == 15) return;
     __syncthreads();
     // (2) panel: P_I = X_I * Minv for my blocks of column K
@@ -135,24 +185,32 @@ __device__ __forceinline__ void rm_factor_step(double (&acc)[17][2], const int w
     double2 npB = make_double2(0.0, 0.0), npA = make_double2(0.0, 0.0);
     if (panB) npB = *reinterpret_cast<const double2*>(NPb + (15 - w) * 64 + lane * 2);
     if (K <= 7) { if (panA) npA = *reinterpret_cast<const double2*>(NPb + w * 64 + lane * 2); }
+    // Slots K < s < 16-K hold a block with J > K in EVERY warp (row B reading: J = s > K; row A reading: J = 16-s > K), so that
+    // part of the loop is branch-free: the compiler hoists the operand loads and interleaves the DMMAs of different slots
 #pragma unroll
     for (int s = 0; s < 17; ++s) {
-        const bool canB = (s > K) && (s <= 15), canA = (s < 16 - K) && (s >= 9);   // row A lives in slots >= 16-w >= 9
-        if (!canB && !canA) continue;
+        if (!(s > K && s < 16 - K)) continue;
         const bool isB = (s <= 15 - w);
-        const bool active = isB ? canB : canA;
-        if (active) {
-            const int J = isB ? s : 16 - s;
-            const double2 xb = *reinterpret_cast<const double2*>(Xb + J * 64 + lane * 2);
-            const double2 np = isB ? npB : npA;
-            rm_dmma(acc[s][0], acc[s][1], np.x, xb.x);
-            rm_dmma(acc[s][0], acc[s][1], np.y, xb.y);
+        const int J = isB ? s : 16 - s;
+        const double2 xb = *reinterpret_cast<const double2*>(Xb + J * 64 + lane * 2);
+        const double2 np = isB ? npB : npA;
+        rm_dmma(acc[s][0], acc[s][1], np.x, xb.x);
+        rm_dmma(acc[s][0], acc[s][1], np.y, xb.y);
+    }
+    // the remaining slots (s >= 16-K, and s > K) belong to row B in the warps with s <= 15-w and are finished blocks elsewhere
+#pragma unroll
+    for (int s = 0; s < 17; ++s) {
+        if (!(s > K && s >= 16 - K && s <= 15)) continue;
+        if (s <= 15 - w) {
+            const double2 xb = *reinterpret_cast<const double2*>(Xb + s * 64 + lane * 2);
+            rm_dmma(acc[s][0], acc[s][1], npB.x, xb.x);
+            rm_dmma(acc[s][0], acc[s][1], npB.y, xb.y);
         }
     }
 }
 
 template <int K>
-__device__ __forceinline__ void rm_back_step(const double (&acc)[17][2], const int w, const int lane, RmSmem& S) {
+__device__ __forceinline__ void rm_back_step(const double (&acc)[17][2], const int w, const int lane, const int grp, RmSmem& S) {
     // x_K = w_K - sum_{I > K} P_IK' x_I   (column K of the factor: slot K of the warps with 15-w > K, slot 16-K of those with w > K)
     const int r = lane >> 2, q = lane & 3;
     double t0 = 0.0, t1 = 0.0;
@@ -163,29 +221,36 @@ __device__ __forceinline__ void rm_back_step(const double (&acc)[17][2], const i
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); }
     if (r == 0) { S.part[w][2 * q] = t0; S.part[w][2 * q + 1] = t1; }
-    __syncthreads();
-    if (threadIdx.x < 8) {
-        double s = S.zs[8 * K + threadIdx.x];
+    RM_GSYNC();
+    if (w == 0 && lane < 8) {
+        double s = S.zs[8 * K + lane];
 #pragma unroll
-        for (int ww = 0; ww < 8; ++ww) s -= S.part[ww][threadIdx.x];
-        S.xs[8 * K + threadIdx.x] = s;
+        for (int ww = 0; ww < 8; ++ww) s -= S.part[ww][lane];
+        S.xs[8 * K + lane] = s;
     }
-    __syncthreads();
+    RM_GSYNC();
 }
 
 template <bool PROF>
-__global__ void __launch_bounds__(RM_THREADS, 2) ring_solve_mma_kernel(RingSolveArgs a) {
+__global__ void __launch_bounds__(RM_THREADS, 3 - RM_PIX) ring_solve_mma_kernel(RingSolveArgs a) {
     extern __shared__ __align__(16) unsigned char rm_smem_raw[];
-    RmSmem& S = *reinterpret_cast<RmSmem*>(rm_smem_raw);
     const RingGeom& g = a.g;
-    if ((int)blockIdx.x >= (a.n_active_dev ? *a.n_active_dev : a.n_active)) return;
-    const int p = a.active_list[blockIdx.x];
-    const int tid = threadIdx.x, lane = tid & 31, w = warp_id_uniform();
+    const int n_act = a.n_active_dev ? *a.n_active_dev : a.n_active;
+    if (RM_PIX * (int)blockIdx.x >= n_act) return;
+    const int wall = warp_id_uniform();
+    const int grp = wall >> 3, w = wall & 7;                      // pixel group of this warp, warp index inside the group
+    RmSmem& S = reinterpret_cast<RmSmem*>(rm_smem_raw)[grp];
+    // an odd pixel count leaves the last CTA's second group without a pixel: it recomputes the first one's (the lock-step
+    // barriers need both groups) and does not store
+    const int pidx = RM_PIX * (int)blockIdx.x + grp;
+    const bool store = pidx < n_act;
+    const int p = a.active_list[store ? pidx : pidx - 1];
+    const int tid = threadIdx.x & (RM_GROUP - 1), lane = tid & 31;
     const int r = lane >> 2, q = lane & 3;
     const int pr = p % g.nr + g.pr_off, pc = p / g.nr + g.pc_off;
     const size_t qm = (size_t)pc * g.nrb + pr;
     long long pt0 = PROF ? clock64() : 0;
-#define RM_PROF(i) do { if (PROF && tid == 0) { long long _t = clock64(); atomicAdd(a.prof + (i), (unsigned long long)(_t - pt0)); pt0 = _t; } } while (0)
+#define RM_PROF(i) do { if (PROF && threadIdx.x == 0) { long long _t = clock64(); atomicAdd(a.prof + (i), (unsigned long long)(_t - pt0)); pt0 = _t; } } while (0)
     // ---- valid ring neighbours (inside the FOV), compacted in slot order
     {
         int dr = 0, dc = 0;
@@ -198,7 +263,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) ring_solve_mma_kernel(RingSolve
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (lane == 0) S.wcnt[w] = __popc(m);
         if (tid < 128) { S.qi[tid] = (int)qm; S.elin[tid] = 0; S.xs[tid] = 0.0; S.zs[tid] = 0.0; S.bits[tid] = 0u; }
-        __syncthreads();
+        RM_GSYNC();
         int base = 0;
         for (int ww = 0; ww < w; ++ww) base += S.wcnt[ww];
         if (ok) {
@@ -211,7 +276,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) ring_solve_mma_kernel(RingSolve
             S.n = nn;
         }
     }
-    __syncthreads();
+    RM_GSYNC();
     const int n = S.n;
     if (tid < 128) {
         const int i = tid;
@@ -229,27 +294,38 @@ __global__ void __launch_bounds__(RM_THREADS, 2) ring_solve_mma_kernel(RingSolve
         S.ym[i] = y; S.S1[i] = s1; S.s1c[i] = s1c;
         S.ap0[i] = p0; S.ap1[i] = p1; S.qoff[i] = qo;
     }
-    __syncthreads();
+    RM_GSYNC();
     RM_PROF(0);
     // ---- assemble: Cov(i,j) = raw(i,j) - Ybar_j*S1_i - Ybar_i*S1c_j  (see kernels_ring.cuh); diagonal blocks are assembled in
     //      full (the pivot inversion reads both triangles)
     double acc[17][2];
     const int iA = 8 * w + r, iB = 8 * (15 - w) + r;
-#pragma unroll
-    for (int s = 0; s < 17; ++s) {
-        const bool isB = (s <= 15 - w);
-        const int i = isB ? iB : iA, J = isB ? s : 16 - s;
-        const bool vi = (i < n) || (i == 127);
-        const int ei = S.elin[i];
-        const long long qoi = S.qoff[i];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int j = 8 * J + 2 * q + e;
-            const int lin = ei - S.elin[j];
-            const long long off = (lin >= 0 ? S.qoff[j] : qoi) + (long long)abs(lin);
-            const double* ptr = (vi && j < n) ? a.S2 + off : &ring_zero_moment;
-            acc[s][e] = __ldg(ptr);
+    {
+        const bool viA = (iA < n) || (iA == 127), viB = (iB < n) || (iB == 127);
+        const int eiA = S.elin[iA], eiB = S.elin[iB];
+        const long long qoA = S.qoff[iA], qoB = S.qoff[iB];
+        // addresses of a batch of slots first, then all its loads: the gathers are L2 latency bound, so as many as the register
+        // budget allows are kept in flight
+#define RM_ASM_BATCH(S0, S1)                                                                                       \
+        {                                                                                                          \
+            const double* ptr[(S1) - (S0)][2];                                                                     \
+            _Pragma("unroll") for (int s = (S0); s < (S1); ++s) {                                                  \
+                const bool isB = (s <= 15 - w);                                                                    \
+                const int J = isB ? s : 16 - s, j0 = 8 * J + 2 * q;                                                \
+                const bool vi = isB ? viB : viA;                                                                   \
+                const int ei = isB ? eiB : eiA;                                                                    \
+                const long long qoi = isB ? qoB : qoA;                                                             \
+                const int2 ej = *reinterpret_cast<const int2*>(S.elin + j0);                                       \
+                const longlong2 qj = *reinterpret_cast<const longlong2*>(S.qoff + j0);                            \
+                const int l0 = ei - ej.x, l1 = ei - ej.y;                                                          \
+                ptr[s - (S0)][0] = (vi && j0 < n) ? a.S2 + ((l0 >= 0 ? qj.x : qoi) + (long long)abs(l0)) : &ring_zero_moment;     \
+                ptr[s - (S0)][1] = (vi && j0 + 1 < n) ? a.S2 + ((l1 >= 0 ? qj.y : qoi) + (long long)abs(l1)) : &ring_zero_moment; \
+            }                                                                                                      \
+            _Pragma("unroll") for (int s = (S0); s < (S1); ++s) { acc[s][0] = __ldg(ptr[s - (S0)][0]); acc[s][1] = __ldg(ptr[s - (S0)][1]); } \
         }
+        RM_ASM_BATCH(0, 9)
+        RM_ASM_BATCH(9, 17)
+#undef RM_ASM_BATCH
     }
     {
         const double ymA = S.ym[iA], s1A = S.S1[iA], ymB = S.ym[iB], s1B = S.S1[iB];
@@ -268,7 +344,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) ring_solve_mma_kernel(RingSolve
     // ---- neuron corrections: Cov_Bf = Cov_Y - N_x.A_y - A_x.N_y ; sum_sel Bf(x) = S1c_x - A_x.Csum
     if (tid < 128)
         for (int e = S.ap0[tid]; e < S.ap1[tid]; ++e) { const int k = a.a_col[e]; atomicOr(&S.bits[(k >> 5) & 127], 1u << (k & 31)); }
-    __syncthreads();
+    RM_GSYNC();
     if (w == 0) {
         int base = 0;
         for (int w0 = 0; w0 < 128; w0 += 32) {
@@ -284,20 +360,20 @@ __global__ void __launch_bounds__(RM_THREADS, 2) ring_solve_mma_kernel(RingSolve
         }
         if (lane == 0) S.nk = min(base, RING_KALL);
     }
-    __syncthreads();
+    RM_GSYNC();
     const int nall = S.nk;
     RM_PROF(2);
-    if (PROF && tid == 0) atomicAdd(a.prof + 7, (unsigned long long)nall);
+    if (PROF && threadIdx.x == 0) atomicAdd(a.prof + 7, (unsigned long long)nall);
     {
         double* XA = &S.X[0][0];      // RM_KSET x 128 A rows of the indices; the panel buffers are idle until the factorisation
         double* XN = &S.NP[0][0];     // RM_KSET x 128 N rows
         for (int kbase = 0; kbase < nall; kbase += RM_KSET) {
             const int* kset = S.kall + kbase;
             const int nk = min(RM_KSET, nall - kbase);
-            __syncthreads();
-            for (int x = tid; x < RM_KSET * 128; x += RM_THREADS) { XA[x] = 0.0; XN[x] = 0.0; }
-            __syncthreads();
-            for (int x = tid; x < 128 * nk; x += RM_THREADS) {
+            RM_GSYNC();
+            for (int x = tid; x < RM_KSET * 128; x += RM_GROUP) { XA[x] = 0.0; XN[x] = 0.0; }
+            RM_GSYNC();
+            for (int x = tid; x < 128 * nk; x += RM_GROUP) {
                 const int y = x & 127, z = x >> 7;
                 if (y < n || y == 127) XN[z * 128 + y] = a.N[(size_t)S.qi[y] * a.K + kset[z]];
                 else if (y == n) XN[z * 128 + y] = a.Csum[kset[z]];
@@ -307,7 +383,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) ring_solve_mma_kernel(RingSolve
                     const int k = a.a_col[e];
                     for (int z = 0; z < nk; ++z) if (kset[z] == k) XA[z * 128 + tid] = a.a_val[e];
                 }
-            __syncthreads();
+            RM_GSYNC();
             for (int z = 0; z < nk; ++z) {
                 const double* xa = XA + z * 128;
                 const double* xn = XN + z * 128;
@@ -324,7 +400,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) ring_solve_mma_kernel(RingSolve
                 }
             }
         }
-        __syncthreads();
+        RM_GSYNC();
     }
     RM_PROF(3);
     // ---- ridge 1e-5 * trace over the indices 0..n (ring + ones row); padding gets a unit diagonal
@@ -337,7 +413,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) ring_solve_mma_kernel(RingSolve
             if (2 * q + 1 == r) S.dg[8 * I + r] = acc[s][1];
         }
     }
-    __syncthreads();
+    RM_GSYNC();
     double lam;
     {
         // fixed-order sum: 16 groups of 8 consecutive indices, then a shuffle tree
@@ -362,6 +438,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) ring_solve_mma_kernel(RingSolve
     }
     RM_PROF(4);
     // ---- block LDL' of the augmented matrix
+    __syncthreads();                                               // both pixels enter the factorisation together
     rm_factor_step<0>(acc, w, lane, S);
     rm_factor_step<1>(acc, w, lane, S);
     rm_factor_step<2>(acc, w, lane, S);
@@ -381,22 +458,23 @@ __global__ void __launch_bounds__(RM_THREADS, 2) ring_solve_mma_kernel(RingSolve
     __syncthreads();
     RM_PROF(5);
     // ---- x = L^-T w, block columns 14 .. 0 (block 15 was solved with its pivot)
-    rm_back_step<14>(acc, w, lane, S);
-    rm_back_step<13>(acc, w, lane, S);
-    rm_back_step<12>(acc, w, lane, S);
-    rm_back_step<11>(acc, w, lane, S);
-    rm_back_step<10>(acc, w, lane, S);
-    rm_back_step<9>(acc, w, lane, S);
-    rm_back_step<8>(acc, w, lane, S);
-    rm_back_step<7>(acc, w, lane, S);
-    rm_back_step<6>(acc, w, lane, S);
-    rm_back_step<5>(acc, w, lane, S);
-    rm_back_step<4>(acc, w, lane, S);
-    rm_back_step<3>(acc, w, lane, S);
-    rm_back_step<2>(acc, w, lane, S);
-    rm_back_step<1>(acc, w, lane, S);
-    rm_back_step<0>(acc, w, lane, S);
-    for (int i = tid; i < n; i += RM_THREADS) a.W[(size_t)p * g.nnb + S.slot[i]] = S.xs[i] + 1e-100;
+    rm_back_step<14>(acc, w, lane, grp, S);
+    rm_back_step<13>(acc, w, lane, grp, S);
+    rm_back_step<12>(acc, w, lane, grp, S);
+    rm_back_step<11>(acc, w, lane, grp, S);
+    rm_back_step<10>(acc, w, lane, grp, S);
+    rm_back_step<9>(acc, w, lane, grp, S);
+    rm_back_step<8>(acc, w, lane, grp, S);
+    rm_back_step<7>(acc, w, lane, grp, S);
+    rm_back_step<6>(acc, w, lane, grp, S);
+    rm_back_step<5>(acc, w, lane, grp, S);
+    rm_back_step<4>(acc, w, lane, grp, S);
+    rm_back_step<3>(acc, w, lane, grp, S);
+    rm_back_step<2>(acc, w, lane, grp, S);
+    rm_back_step<1>(acc, w, lane, grp, S);
+    rm_back_step<0>(acc, w, lane, grp, S);
+    if (store)
+        for (int i = tid; i < n; i += RM_GROUP) a.W[(size_t)p * g.nnb + S.slot[i]] = S.xs[i] + 1e-100;
     RM_PROF(6);
 #undef RM_PROF
 }

@@ -77,6 +77,11 @@ int cnmfe_deconvolve(const double* Y, int T, int N, const cnmfe_deconv_opts* opt
                      const double* pars_in, double* c, double* s, double* b, double* pars, double* sn,
                      double* smin, double* lam, int device);
 
+/* same on DEVICE arrays (all pointers on `device`; Y, c, s are N traces of T contiguous doubles; sn_in, pars_in (2 per trace),
+ * outs (6 per trace: b, g1, g2, smin, lambda, sn) may be NULL).  Asynchronous on the legacy default stream. */
+int cnmfe_deconvolve_dev(const double* Y_dev, int T, int N, const cnmfe_deconv_opts* opts, const double* sn_dev,
+                         const double* pars_dev, double* c_dev, double* s_dev, double* outs_dev, int device);
+
 /* sn = GetSn(Y)  (OASIS_matlab/functions/GetSn.m:1; logmexp over [0.25,0.5]).  Y is T x N, sn has N entries. */
 int cnmfe_get_sn(const double* Y, int T, int N, double* sn, int device);
 

@@ -72,6 +72,14 @@ def test_thresholded_ar2(built_lib):
     _compare(Y, dict(type="ar2", method="thresholded", pars=[1.7, -0.712]), built_lib)
 
 
+def test_ar2_at_c5_length(built_lib):
+    """BASELINE configs[4] trace length (T = 100000, AR2, gen_data(g=[1.7,-0.712], noise 1, seed 3) restated): parity with the
+    oracle, not only invariants -- deconvolveCa(y, 'ar2', 'foopsi', pars, 'smin', -3) and the 'thresholded' variant."""
+    Y, _, _ = _traces("ar2_c5")
+    _compare(Y, dict(type="ar2", method="foopsi", pars=[1.7, -0.712], smin=-3), built_lib)
+    _compare(Y[:3], dict(type="ar2", method="thresholded", pars=[1.7, -0.712]), built_lib)
+
+
 def test_pav_invariants_large(built_lib):
     """Size-independent properties at a BASELINE-scale T: s>=smin or 0, c_t = g c_{t-1} off spikes."""
     from cnmf_e_b200 import oasis as G
