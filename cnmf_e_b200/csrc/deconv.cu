@@ -335,10 +335,6 @@ int deconv_batch_dev(const double* Y, int T, int N, const cnmfe_deconv_opts& o, 
         set_error("deconvolve: thresholded_oasisAR2 with optimize_b / optimize_pars is not built");
         return -1;
     }
-    if (o.method == 2 && o.optimize_b) {
-        set_error("deconvolve: thresholded with optimize_b is not built (needs estimate_baseline_noise)");
-        return -1;
-    }
     int dev = 0;
     cudaGetDevice(&dev);
     int slots, smode; size_t smem;

@@ -576,35 +576,69 @@ __device__ int block_oasis_ar1(const double* y, int T, double g, double lam, dou
     return n;
 }
 
-// exclusive->inclusive cumsum of squares of h[0..m] into hh (block scan, chunked).
-__device__ void block_cumsum_sq(const double* h, double* hh, int m1, BlockShared* sh, double* part /*blockDim*/) {
-    int per = (m1 + blockDim.x - 1) / blockDim.x;
-    int b = threadIdx.x * per, e = min(m1, b + per);
+// inclusive cumsum of squares of h[0..m1) into hh: thread-chunked, warp shuffle scan of the chunk sums, one more shuffle scan
+// over the warp totals (two barriers; the old version serialised blockDim/32 partials per lane of warp 0)
+__device__ void block_cumsum_sq(const double* h, double* hh, int m1, BlockShared* sh, double* part /*>= 32 doubles*/) {
+    const int per = (m1 + blockDim.x - 1) / blockDim.x;
+    const int b = threadIdx.x * per, e = min(m1, b + per);
+    const int lane = threadIdx.x & 31, wid = warp_id_uniform(), nw = (blockDim.x + 31) >> 5;
     double a = 0.0;
     for (int j = b; j < e; ++j) a += h[j] * h[j];
-    part[threadIdx.x] = a;
-    __syncthreads();
-    if (warp_id_uniform() == 0) {
-        // exclusive scan of the blockDim partials: lane = blockDim/32 consecutive partials, then a warp scan
-        const int lane = threadIdx.x, per2 = (int)blockDim.x >> 5, b0 = lane * per2;
-        double sl = 0.0;
-        for (int i = 0; i < per2; ++i) sl += part[b0 + i];
-        double incl = sl;
+    double incl = a;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        double run = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) run = 0.0;
-        for (int i = 0; i < per2; ++i) { double x = part[b0 + i]; part[b0 + i] = run; run += x; }
-    }
+    for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) part[wid] = incl;
     __syncthreads();
-    a = part[threadIdx.x];
+    double wt = (lane < nw) ? part[lane] : 0.0;         // every warp scans the (<= 32) warp totals itself
+    double winc = wt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+    const double wbase = __shfl_sync(0xffffffffu, winc - wt, wid);
+    a = wbase + (incl - a);
     for (int j = b; j < e; ++j) { a += h[j] * h[j]; hh[j] = a; }
     __syncthreads();
+    (void)sh;
 }
 
 #define RSS_SHORT_POOL 256
 #define RSS_LONG_POOL 768
+// Per-pool energy Q_p = sum_{t in pool} y_t^2 -> ws.sv (free during update_g).  Pools are fixed while fminbnd runs, so this
+// is computed once per update_g; rss_g then needs ONE pass over the trace per evaluation.
+__device__ void block_pool_energy(const double* y, int n, TraceWS& ws, BlockShared* sh) {
+    if (sh->ysm) y = sh->ysm;
+    const bool ps = (n <= sh->pcap);
+    const int* const ptab = ps ? sh->ptsm : ws.pt;
+    const int* const ltab = ps ? sh->plsm : ws.pl;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int grp = lane >> 3, gl = lane & 7;
+    for (int p0 = warp * 4; p0 < n; p0 += nw * 4) {
+        const int p = p0 + grp;
+        int l = 0, t0 = 0;
+        if (p < n) { l = ltab[p]; t0 = ptab[p]; }
+        const int le = (l <= RSS_SHORT_POOL) ? l : 0;
+        double q = 0.0;
+        for (int j = gl; j < le; j += 8) { const double v = y[t0 + j]; q = fma(v, v, q); }
+        __syncwarp();
+        q += __shfl_xor_sync(0xffffffffu, q, 4);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        if (le > 0 && gl == 0) ws.sv[p] = q;
+    }
+    for (int p = warp; p < n; p += nw) {
+        const int t0 = ptab[p], l = ltab[p];
+        if (l <= RSS_SHORT_POOL) continue;
+        double q = 0.0;
+        for (int j = lane; j < l; j += 32) { const double v = y[t0 + j]; q = fma(v, v, q); }
+        q = warp_sum(q);
+        if (lane == 0) ws.sv[p] = q;
+    }
+    __syncthreads();
+}
+
 // rss_g of update_g (foopsi_oasisAR1.m:165-178).  Leaves ws.h / ws.hh holding this g's tables.
+// One pass per evaluation: with h = g^(0..l-1), dy = sum y h, sh = sum h over a pool,
+//   dot = yp' h = dy - pen sh,  tv = max(dot / hh(l), 0),  sum (y - tv h)^2 = Q - tv (2 dy - tv hh(l))
+// (the reference forms c = tv h and then res = y - c: the same number, summed in another order; Q from block_pool_energy).
 __device__ double block_rss_g(const double* y, int n, double g, double lam, int maxl, TraceWS& ws,
                               BlockShared* sh) {
     const double lg = log(g), pen = lam * (1.0 - g);
@@ -616,17 +650,16 @@ __device__ double block_rss_g(const double* y, int n, double g, double lam, int 
     double* const hhtab = hs ? sh->hhsm : ws.hh;
     const int* const ptab = ps ? sh->ptsm : ws.pt;
     const int* const ltab = ps ? sh->plsm : ws.pl;
+    const double* const Q = ws.sv;
     if (sh->prof) { if (threadIdx.x == 0) { sh->pc[20] += 1ull; sh->pc[21] += (unsigned long long)maxl; sh->pc[22] += (unsigned long long)n; } __syncwarp(); }
     for (int j = threadIdx.x; j <= maxl; j += blockDim.x) htab[j] = exp(lg * (double)j);
     __syncthreads();
     CNMFE_PROF(sh, 16);
     block_cumsum_sq(htab, hhtab, maxl + 1, sh, sh->part);
     CNMFE_PROF(sh, 17);
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     double rss = 0.0;
-    // Pools are short on average (T / n ~ 25-50 samples) and there are hundreds of them, so a warp per pool spends its
-    // time in per-pool latencies (metadata load -> data load -> shuffle tree -> division -> second pass).  Short pools are
-    // therefore handled FOUR per warp (8 lanes each: 64-byte coalesced reads, 3-step reduction); long ones take a warp.
+    // short pools four per warp (8 lanes each), the others a warp each
     {
         const int grp = lane >> 3, gl = lane & 7;
         for (int p0 = warp * 4; p0 < n; p0 += nw * 4) {
@@ -634,83 +667,49 @@ __device__ double block_rss_g(const double* y, int n, double g, double lam, int 
             int l = 0, t0 = 0;
             if (p < n) { l = ltab[p]; t0 = ptab[p]; }
             const int le = (l <= RSS_SHORT_POOL) ? l : 0;
-            // loads of four steps are issued together, the sums keep the one-at-a-time order
-            double dot = 0.0;
+            double dy = 0.0, shs = 0.0;
             {
                 int j = gl;
                 for (; j + 24 < le; j += 32) {
                     const double y0 = y[t0 + j], y1 = y[t0 + j + 8], y2 = y[t0 + j + 16], y3 = y[t0 + j + 24];
                     const double h0 = htab[j], h1 = htab[j + 8], h2 = htab[j + 16], h3 = htab[j + 24];
-                    dot += (y0 - pen) * h0; dot += (y1 - pen) * h1; dot += (y2 - pen) * h2; dot += (y3 - pen) * h3;
+                    dy = fma(y0, h0, dy); dy = fma(y1, h1, dy); dy = fma(y2, h2, dy); dy = fma(y3, h3, dy);
+                    shs += (h0 + h1) + (h2 + h3);
                 }
-                for (; j < le; j += 8) dot += (y[t0 + j] - pen) * htab[j];
+                for (; j < le; j += 8) { const double hv = htab[j]; dy = fma(y[t0 + j], hv, dy); shs += hv; }
             }
             __syncwarp();
-            dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-            if (le > 0) {
-                const double tv = fmax(dot / hhtab[l - 1], 0.0);
-                int j = gl;
-                for (; j + 24 < le; j += 32) {
-                    const double y0 = y[t0 + j], y1 = y[t0 + j + 8], y2 = y[t0 + j + 16], y3 = y[t0 + j + 24];
-                    const double h0 = htab[j], h1 = htab[j + 8], h2 = htab[j + 16], h3 = htab[j + 24];
-                    const double r0 = y0 - tv * h0, r1 = y1 - tv * h1, r2 = y2 - tv * h2, r3 = y3 - tv * h3;
-                    rss += r0 * r0; rss += r1 * r1; rss += r2 * r2; rss += r3 * r3;
-                }
-                for (; j < le; j += 8) {
-                    const double r = y[t0 + j] - tv * htab[j];
-                    rss += r * r;
-                }
+            dy += __shfl_xor_sync(0xffffffffu, dy, 4); shs += __shfl_xor_sync(0xffffffffu, shs, 4);
+            dy += __shfl_xor_sync(0xffffffffu, dy, 2); shs += __shfl_xor_sync(0xffffffffu, shs, 2);
+            dy += __shfl_xor_sync(0xffffffffu, dy, 1); shs += __shfl_xor_sync(0xffffffffu, shs, 1);
+            if (le > 0 && gl == 0) {
+                const double hhl = hhtab[l - 1];
+                const double tv = fmax((dy - pen * shs) / hhl, 0.0);
+                rss += Q[p] - tv * (2.0 * dy - tv * hhl);
             }
         }
         __syncwarp();
     }
     CNMFE_PROF(sh, 24);
-    // very long pools (quiet stretches: thousands of samples) by the whole CTA, one after the other: a single warp would
-    // chain l/128 load batches of the kernel table from L2
-    for (int k = 0; k < sh->nlong; ++k) {
-        const int p = sh->longp[k];
-        const int t0 = ptab[p], l = ltab[p];
-        double d = 0.0;
-        for (int j = threadIdx.x; j < l; j += blockDim.x) d += (y[t0 + j] - pen) * htab[j];
-        d = block_sum(d, sh->red);
-        const double tv = fmax(d / hhtab[l - 1], 0.0);
-        for (int j = threadIdx.x; j < l; j += blockDim.x) {
-            const double r = y[t0 + j] - tv * htab[j];
-            rss += r * r;
-        }
-    }
-    CNMFE_PROF(sh, 25);
-    if (sh->prof) { if (threadIdx.x == 0) sh->pc[26] += (unsigned long long)sh->nlong; __syncwarp(); }
-    const int long_thr = sh->long_thr;
     for (int p = warp; p < n; p += nw) {
-        int t0 = ptab[p], l = ltab[p];
-        if (l <= RSS_SHORT_POOL || l > long_thr) continue;
-        double dot = 0.0;
+        const int t0 = ptab[p], l = ltab[p];
+        if (l <= RSS_SHORT_POOL) continue;
+        double dy = 0.0, shs = 0.0;
         {
             int j = lane;
             for (; j + 96 < l; j += 128) {
                 const double y0 = y[t0 + j], y1 = y[t0 + j + 32], y2 = y[t0 + j + 64], y3 = y[t0 + j + 96];
                 const double h0 = htab[j], h1 = htab[j + 32], h2 = htab[j + 64], h3 = htab[j + 96];
-                dot += (y0 - pen) * h0; dot += (y1 - pen) * h1; dot += (y2 - pen) * h2; dot += (y3 - pen) * h3;
+                dy = fma(y0, h0, dy); dy = fma(y1, h1, dy); dy = fma(y2, h2, dy); dy = fma(y3, h3, dy);
+                shs += (h0 + h1) + (h2 + h3);
             }
-            for (; j < l; j += 32) dot += (y[t0 + j] - pen) * htab[j];
+            for (; j < l; j += 32) { const double hv = htab[j]; dy = fma(y[t0 + j], hv, dy); shs += hv; }
         }
-        dot = warp_sum(dot);
-        double tv = fmax(dot / hhtab[l - 1], 0.0);
-        {
-            int j = lane;
-            for (; j + 96 < l; j += 128) {
-                const double y0 = y[t0 + j], y1 = y[t0 + j + 32], y2 = y[t0 + j + 64], y3 = y[t0 + j + 96];
-                const double h0 = htab[j], h1 = htab[j + 32], h2 = htab[j + 64], h3 = htab[j + 96];
-                const double r0 = y0 - tv * h0, r1 = y1 - tv * h1, r2 = y2 - tv * h2, r3 = y3 - tv * h3;
-                rss += r0 * r0; rss += r1 * r1; rss += r2 * r2; rss += r3 * r3;
-            }
-            for (; j < l; j += 32) {
-                double r = y[t0 + j] - tv * htab[j];
-                rss += r * r;
-            }
+        dy = warp_sum(dy); shs = warp_sum(shs);
+        if (lane == 0) {
+            const double hhl = hhtab[l - 1];
+            const double tv = fmax((dy - pen * shs) / hhl, 0.0);
+            rss += Q[p] - tv * (2.0 * dy - tv * hhl);
         }
     }
     __syncthreads();
@@ -798,25 +797,8 @@ __device__ double block_update_g(const double* y, int T, int* n_io, double lam, 
             for (int p = threadIdx.x; p < n; p += blockDim.x) { sh->ptsm[p] = ws.pt[p]; sh->plsm[p] = ws.pl[p]; }
         __syncthreads();
     }
-    // pools longer than RSS_LONG_POOL, sorted (the order fixes the order of the additions -> deterministic)
-    if (threadIdx.x == 0) sh->nlong = 0;
-    __syncthreads();
-    for (int p = threadIdx.x; p < n; p += blockDim.x)
-        if (ws.pl[p] > RSS_LONG_POOL) { const int k = atomicAdd(&sh->nlong, 1); if (k < 128) sh->longp[k] = p; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int nl = sh->nlong;
-        if (nl > 128) { nl = 0; sh->long_thr = 0x7fffffff; }     // cannot list them all: the warp path takes every length
-        else sh->long_thr = RSS_LONG_POOL;
-        for (int i = 1; i < nl; ++i) {
-            const int v = sh->longp[i];
-            int j = i - 1;
-            while (j >= 0 && sh->longp[j] > v) { sh->longp[j + 1] = sh->longp[j]; --j; }
-            sh->longp[j + 1] = v;
-        }
-        sh->nlong = nl;
-    }
-    __syncthreads();
+    if (!sh->ysm) __syncthreads();
+    block_pool_energy(y, n, ws, sh);       // Q_p of the (fixed) pools: rss_g is then one pass per evaluation
     const double* const hh_last = (maxl < sh->hcap) ? sh->hhsm : ws.hh;   // where the last rss_g evaluation left cumsum(h.^2)
     CNMFE_PROF(sh, 10);
     double g = block_fminbnd_rss(y, n, lam, maxl, g_lo, g_hi, ws, sh);

@@ -146,14 +146,110 @@ __device__ double choose_smin_ar2(double g1, double g2, double sn, double prob) 
     return sn / sqrt(nrm) * normcdfinv(prob);
 }
 
-// thresholded_oasisAR1, optimize_b = false branch (thresholded_oasisAR1.m:104-140,186-213)
-__device__ void block_thresholded_ar1(const double* __restrict__ y, int T, double g, double sn, bool optimize_g,
+// [b, sn] = estimate_baseline_noise(y) (OASIS_matlab/functions/estimate_baseline_noise.m:1-40): histogram of y on a grid derived
+// from the deciles (hist.m semantics: bin centres, edges half-way, (edge_k, edge_k+1] bins, ends extended to min / max), then
+// fit_gauss1(bins, nums, 0.3, 3) (functions/fit_gauss1.m: Guo's iteratively re-weighted log-parabola fit, 3 x 3 systems solved
+// by Gaussian elimination with partial pivoting like mldivide).  Counts in ws.st (ints); the fit is serial work for one thread.
+__device__ void block_estimate_baseline_noise(const double* __restrict__ y, int T, TraceWS& ws, BlockShared* sh, double* b_out,
+                                              double* sn_out) {
+    double temp[11];
+    for (int i = 0; i <= 10; ++i) temp[i] = block_quantile(y, T, (double)i / 10.0, sh);
+    double mind = INFINITY;
+    for (int i = 0; i < 10; ++i) mind = fmin(mind, temp[i + 1] - temp[i]);
+    const double dbin = fmax(mind / 3.0, (temp[10] - temp[0]) / 1000.0);
+    const int nb = dbin > 0.0 ? (int)floor((temp[10] - temp[0]) / dbin + 1e-10) + 1 : 0;
+    if (nb <= 0) {     // isempty(bins): b = mean(y), sn = 0
+        double a = 0.0;
+        for (int i = threadIdx.x; i < T; i += blockDim.x) a += y[i];
+        *b_out = block_sum(a, sh->red) / (double)T; *sn_out = 0.0;
+        return;
+    }
+    int* cnt = reinterpret_cast<int*>(ws.scr);          // nb <= 1001 ints; the scratch holds >= 3 * nfft (>= 768) doubles
+    const double c0 = temp[0], ymin = temp[0], ymax = temp[10];
+    __syncthreads();
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) cnt[k] = 0;
+    __syncthreads();
+    // shifted edge j (0..nb): first = min(c0 - dbin/2, min y), last = max(c_{nb-1}, max y), else c_{j-1} + (c_j - c_{j-1})/2
+    auto edge = [&](int j) -> double {
+        double e;
+        if (j == 0) { const double w0 = (nb > 1) ? ((c0 + dbin * 1.0) - c0) : 0.0; e = fmin(c0 - w0 / 2.0, ymin); }
+        else if (j == nb) e = fmax(c0 + dbin * (double)(nb - 1), ymax);
+        else { const double ca = c0 + dbin * (double)(j - 1), cb = c0 + dbin * (double)j; e = ca + (cb - ca) / 2.0; }
+        const double ae = fabs(e);                                   // xx + eps(xx): spacing to the next double above |xx|
+        return e + (__longlong_as_double(__double_as_longlong(ae) + 1) - ae);
+    };
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        const double v = y[i];
+        int k = (int)floor((v - c0) / dbin + 0.5);                  // nearest centre, then exact edge tests
+        k = min(max(k, 0), nb - 1);
+        while (k > 0 && v < edge(k)) --k;
+        while (k < nb - 1 && v >= edge(k + 1)) ++k;
+        atomicAdd(&cnt[k], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int mx = 0;
+        for (int k = 0; k < nb; ++k) mx = max(mx, cnt[k]);
+        const double thr = 0.3 * (double)mx;
+        double p[3] = {0.0, 0.0, 0.0};
+        for (int it = 0; it < 3; ++it) {
+            double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, rhs[3] = {0, 0, 0};
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+            for (int k = 0; k < nb; ++k) {
+                const double n0 = (double)cnt[k];
+                if (!(n0 > thr)) continue;
+                const double x = c0 + dbin * (double)k, x2 = x * x;
+                const double ly = (it == 0) ? log(n0) : (p[0] + p[1] * x + p[2] * x2);
+                const double yv = (it == 0) ? n0 : exp(ly), y2 = yv * yv, y2l = y2 * ly;
+                s0 += y2; s1 += x * y2; s2 += x2 * y2; s3 += x2 * x * y2; s4 += x2 * x2 * y2;
+                rhs[0] += y2l; rhs[1] += x * y2l; rhs[2] += x2 * y2l;
+            }
+            M[0][0] = s0; M[0][1] = s1; M[0][2] = s2; M[1][0] = s1; M[1][1] = s2; M[1][2] = s3; M[2][0] = s2; M[2][1] = s3; M[2][2] = s4;
+            for (int c = 0; c < 3; ++c) {                 // elimination with partial pivoting
+                int piv = c;
+                for (int r = c + 1; r < 3; ++r) if (fabs(M[r][c]) > fabs(M[piv][c])) piv = r;
+                if (piv != c) {
+                    for (int k = 0; k < 3; ++k) { const double t = M[c][k]; M[c][k] = M[piv][k]; M[piv][k] = t; }
+                    const double t = rhs[c]; rhs[c] = rhs[piv]; rhs[piv] = t;
+                }
+                for (int r = c + 1; r < 3; ++r) {
+                    const double f = M[r][c] / M[c][c];
+                    for (int k = c; k < 3; ++k) M[r][k] = M[r][k] - f * M[c][k];
+                    rhs[r] = rhs[r] - f * rhs[c];
+                }
+            }
+            for (int r = 2; r >= 0; --r) {
+                double acc = rhs[r];
+                for (int k = r + 1; k < 3; ++k) acc -= M[r][k] * p[k];
+                p[r] = acc / M[r][r];
+            }
+        }
+        sh->dbc[0] = -p[1] / 2.0 / p[2];
+        sh->dbc[1] = sqrt(fabs(-0.5 / p[2]));
+    }
+    __syncthreads();
+    *b_out = sh->dbc[0]; *sn_out = sh->dbc[1];
+    __syncthreads();
+}
+
+// thresholded_oasisAR1 (thresholded_oasisAR1.m:104-184,186-213), both branches: optimize_b fits y - b with b from
+// estimate_baseline_noise (:142) and b = mean(y - solution) after every update_smin (:180)
+__device__ void block_thresholded_ar1(const double* __restrict__ yraw, int T, double g, double sn, bool optimize_b, bool optimize_g,
                                       int maxIter, double thresh_factor, double p_noise, double g_lo, double g_hi,
                                       bool has_tau_range, TraceWS& ws, BlockShared* sh, DeconvOut* out) {
     double smin = choose_smin_ar1(g, sn, p_noise);
     const double thresh = thresh_factor * sn * sn * (double)T, tol = 1e-4;
     if (has_tau_range) g = fmin(fmax(g, g_lo), g_hi);
     bool g_conv = false;
+    double b = 0.0;
+    const double* y = yraw;                 // the trace the pools are fitted to: y - b (ws.yb) when the baseline is optimised
+    if (optimize_b) {
+        double sn_unused;
+        block_estimate_baseline_noise(yraw, T, ws, sh, &b, &sn_unused);
+        for (int i = threadIdx.x; i < T; i += blockDim.x) ws.yb[i] = yraw[i] - b;
+        __syncthreads();
+        y = ws.yb;
+    }
     int n = block_oasis_ar1(y, T, g, 0.0, smin, ws, sh);
     double RSS0 = block_rss(y, ws.c, 0.0, T, sh);
     for (int it = 0; it < maxIter; ++it) {
@@ -161,7 +257,10 @@ __device__ void block_thresholded_ar1(const double* __restrict__ y, int T, doubl
         if (optimize_g && !g_conv) {
             double g0 = g;
             g = block_update_g(y, T, &n, 0.0, smin, g_lo, g_hi, ws, sh);
-            if (fabs(g - g0) / g0 < 1e-4) g_conv = true;
+            if (fabs(g - g0) / g0 < 1e-4) {
+                g_conv = true;
+                if (optimize_b) n = block_oasis_ar1(y, T, g, 0.0, smin, ws, sh);     // :156: cold re-run, optimize_b branch only
+            }
         }
         double RSS = block_rss(y, ws.c, 0.0, T, sh);
         if (fabs(RSS - RSS0) < tol) break;
@@ -201,8 +300,15 @@ __device__ void block_thresholded_ar1(const double* __restrict__ y, int T, doubl
                 if (sq > thr) ind_end = ind; else break;
             }
         }
+        if (optimize_b) {       // b = mean(y - solution) (:180); the next iteration fits y - b
+            double a = 0.0;
+            for (int i = threadIdx.x; i < T; i += blockDim.x) a += yraw[i] - ws.c[i];
+            b = block_sum(a, sh->red) / (double)T;
+            for (int i = threadIdx.x; i < T; i += blockDim.x) ws.yb[i] = yraw[i] - b;
+            __syncthreads();
+        }
     }
-    out->b = 0.0; out->g1 = g; out->g2 = 0.0; out->smin = smin;
+    out->b = b; out->g1 = g; out->g2 = 0.0; out->smin = smin;
 }
 
 // deconvolveCa (deconvolveCa.m:60-206).  y: T samples (read-only).  Results: ws.c, ws.s, *out.
@@ -256,7 +362,7 @@ __device__ void block_deconvolveCa(const double* __restrict__ y, int T, const cn
         block_constrained_ar1(y, T, g1, sn, o.optimize_b != 0, o.optimize_pars != 0, maxIter, g_lo, g_hi,
                               o.has_tau_range != 0, ws, sh, out);
     } else if (o.type == 1) {
-        block_thresholded_ar1(y, T, g1, sn, o.optimize_pars != 0, maxIter, o.thresh_factor, o.p_noise, g_lo, g_hi,
+        block_thresholded_ar1(y, T, g1, sn, o.optimize_b != 0, o.optimize_pars != 0, maxIter, o.thresh_factor, o.p_noise, g_lo, g_hi,
                               o.has_tau_range != 0, ws, sh, out);
     } else {
         // thresholded_oasisAR2 with optimize_b = optimize_g = false: its loop (:96-126) exits at the first

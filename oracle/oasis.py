@@ -571,12 +571,93 @@ def constrained_oasisAR1(y, g=None, sn=None, optimize_b=False, optimize_g=False,
     return st["solution"], st["spks"], st["b"], g, st["lam"], st["aset"]
 
 
+def hist_centers(y, centers):
+    """nums = hist(y, centers) (MATLAB hist.m with a vector of bin CENTRES): edges half-way between the centres, the first and
+    the last bin extended to min(y) / max(y), bins of the form (edge_k, edge_k+1] (hist.m shifts the edges by eps for that)."""
+    y = np.asarray(y, dtype=np.float64).ravel()
+    xx = np.asarray(centers, dtype=np.float64).ravel()
+    binwidth = np.concatenate([np.diff(xx), [0.0]])
+    edges = np.concatenate([[xx[0] - binwidth[0] / 2], xx + binwidth / 2])
+    edges[0] = min(edges[0], y.min())
+    edges[-1] = max(edges[-1], y.max())
+    bins = edges + np.spacing(edges)
+    k = np.searchsorted(bins, y, side="right")          # number of shifted edges <= y
+    k = np.clip(k, 1, xx.size) - 1                       # first / last histc bins are merged into their neighbours
+    return np.bincount(k, minlength=xx.size).astype(np.float64)
+
+
+def _solve_small(M, b):
+    """M \\ b for a small square system: Gaussian elimination with partial pivoting (what mldivide does for a general square
+    matrix), written out so that the CUDA path performs the same operations in the same order."""
+    M = np.array(M, dtype=np.float64)
+    b = np.array(b, dtype=np.float64)
+    n = b.size
+    for c in range(n):
+        piv = c + int(np.argmax(np.abs(M[c:, c])))
+        if piv != c:
+            M[[c, piv]] = M[[piv, c]]
+            b[[c, piv]] = b[[piv, c]]
+        for r in range(c + 1, n):
+            f = M[r, c] / M[c, c]
+            M[r, c:] = M[r, c:] - f * M[c, c:]
+            b[r] = b[r] - f * b[c]
+    x = np.zeros(n)
+    for r in range(n - 1, -1, -1):
+        x[r] = (b[r] - M[r, r + 1:] @ x[r + 1:]) / M[r, r]
+    return x
+
+
+def fit_gauss1(x, y, thr=0.1, maxIter=5, mu_fix=False):
+    """functions/fit_gauss1.m:1-92 (Guo 2011, iteratively re-weighted log-parabola fit)."""
+    x = np.asarray(x, dtype=np.float64).ravel()
+    y = np.asarray(y, dtype=np.float64).ravel()
+    ind = y > y.max() * thr
+    x, y = x[ind], y[ind]
+    x2, x3, x4 = x ** 2, x ** 3, x ** 4
+    y2 = y ** 2
+    logy = np.log(y)
+    y2logy = y2 * logy
+    p = None
+    for _ in range(int(maxIter)):
+        if mu_fix:
+            M = [[y2.sum(), x2 @ y2], [x2 @ y2, x4 @ y2]]
+            p = _solve_small(M, [y2logy.sum(), x2 @ y2logy])
+            logy = p[0] + p[1] * x2
+        else:
+            M = [[y2.sum(), x @ y2, x2 @ y2], [x @ y2, x2 @ y2, x3 @ y2], [x2 @ y2, x3 @ y2, x4 @ y2]]
+            p = _solve_small(M, [y2logy.sum(), x @ y2logy, x2 @ y2logy])
+            logy = p[0] + p[1] * x + p[2] * x2
+        y = np.exp(logy)
+        y2 = y ** 2
+        y2logy = y2 * logy
+    if mu_fix:
+        return 0.0, float(np.sqrt(-0.5 / p[1])), float(np.exp(p[0]))
+    return float(-p[1] / 2 / p[2]), float(abs(np.sqrt(-0.5 / p[2] + 0j))), float(np.exp(p[0] - 0.25 * p[1] ** 2 / p[2]))
+
+
+def estimate_baseline_noise(y, bmin=-np.inf):
+    """functions/estimate_baseline_noise.m:1-40: histogram on a grid from the deciles, Gaussian fit of its peak.  The grid
+    `temp(1):dbin:temp(end)` is restated as temp(1) + k*dbin (MATLAB's colon operator fills long ranges from both ends; the
+    two agree to rounding)."""
+    y = np.asarray(y, dtype=np.float64).ravel()
+    temp = np.array([quantile(y, q) for q in np.arange(0, 11) / 10.0])
+    dbin = max(np.min(np.diff(temp)) / 3, (temp.max() - temp.min()) / 1000)
+    nb = int(np.floor((temp[-1] - temp[0]) / dbin + 1e-10)) + 1 if dbin > 0 else 0
+    if nb <= 0:
+        return float(np.mean(y)), 0.0
+    bins = temp[0] + dbin * np.arange(nb)
+    nums = hist_centers(y, bins)
+    b, sn, _ = fit_gauss1(bins, nums, 0.3, 3)
+    if b < bmin:
+        b = bmin
+        _, sn, _ = fit_gauss1(bins - bmin, nums, 0.3, 3, False)
+    return b, sn
+
+
 def thresholded_oasisAR1(y, g=None, sn=None, optimize_b=False, optimize_g=False, decimate=None, maxIter=10,
                          thresh_factor=1.0, p_noise=0.9999, tau_range=None):
-    """thresholded_oasisAR1.m:40-184 (optimize_b=False branch; the optimize_b branch needs
-    estimate_baseline_noise/hist and is not restated)."""
-    if optimize_b:
-        raise NotImplementedError("thresholded_oasisAR1 oracle: optimize_b branch not restated")
+    """thresholded_oasisAR1.m:40-184, both branches (optimize_b: baseline from estimate_baseline_noise, then
+    b = mean(y - solution) after every update_smin, :141-181)."""
     y = np.asarray(y, dtype=np.float64).ravel()
     T = y.size
     g = float(np.atleast_1d(g)[0])
@@ -589,9 +670,9 @@ def thresholded_oasisAR1(y, g=None, sn=None, optimize_b=False, optimize_g=False,
         g = min(max(g, g_range[0]), g_range[1])
     g_converged = False
     tol = 1e-4
-    b = 0.0
-    solution, spks, aset = oasisAR1(y, g, None, smin)
-    res = y - solution
+    b = estimate_baseline_noise(y)[0] if optimize_b else 0.0
+    solution, spks, aset = oasisAR1(y - b, g, None, smin)
+    res = y - solution - b
     RSS0 = float(res @ res)
 
     def update_smin(yy, smin, solution, spks, aset, thr):
@@ -619,17 +700,21 @@ def thresholded_oasisAR1(y, g=None, sn=None, optimize_b=False, optimize_g=False,
             break
         if optimize_g and not g_converged:
             g0 = g
-            solution, aset, g, spks = _update_g_ar1(y, aset, 0.0, smin, g_range)
+            solution, aset, g, spks = _update_g_ar1(y - b, aset, 0.0, smin, g_range)
             if abs(g - g0) / g0 < 1e-4:
                 g_converged = True
-        res = y - solution
+                if optimize_b:                       # :156 -- only the optimize_b branch re-runs a cold oasisAR1
+                    solution, spks, aset = oasisAR1(y - b, g, None, smin)
+        res = y - solution - b
         RSS = float(res @ res)
         if abs(RSS - RSS0) < tol:
             break
         if abs(RSS - thresh) < tol or np.sum(solution) < 1e-9:
             break
         RSS0 = RSS
-        smin, solution, spks, aset = update_smin(y, smin, solution, spks, aset, np.sqrt(thresh))
+        smin, solution, spks, aset = update_smin(y - b, smin, solution, spks, aset, np.sqrt(thresh))
+        if optimize_b:
+            b = float(np.mean(y - solution))         # :180
     return solution, spks, b, g, smin, aset
 
 

@@ -36,6 +36,7 @@ NOISE_CASE = (40, 36, 400, 3, 6)      # d1, d2, T, K, ring radius of "noise"
 TRACES = {
     "ar1_n01": (0.95, 0.1, 3000, 30, 0.5, 0, 6, 13),
     "ar1_n03": (0.95, 0.3, 3000, 30, 0.5, 0, 6, 13),
+    "ar1_baseline": (0.95, 0.3, 3000, 30, 0.5, 0.7, 5, 17),
     "ar1_getsn_1000": (0.95, 0.3, 1000, 30, 0.5, 0, 3, 13),
     "ar1_getsn_3000": (0.95, 0.3, 3000, 30, 0.5, 0, 3, 13),
     "ar1_getsn_10000": (0.95, 0.3, 10000, 30, 0.5, 0, 3, 13),

@@ -61,6 +61,14 @@ def test_thresholded_ar1(built_lib):
     _compare(Y, dict(method="thresholded", optimize_pars=True), built_lib, rtol=1e-6)
 
 
+def test_thresholded_ar1_optimize_b(built_lib):
+    """thresholded_oasisAR1 with optimize_b (estimate_baseline_noise + fit_gauss1, thresholded_oasisAR1.m:141-181), with and
+    without optimize_pars, on traces with a non-zero baseline."""
+    Y, _, _ = _traces("ar1_baseline")
+    _compare(Y, dict(method="thresholded", optimize_b=True), built_lib, rtol=1e-6)
+    _compare(Y, dict(method="thresholded", optimize_b=True, optimize_pars=True), built_lib, rtol=1e-6)
+
+
 def test_foopsi_ar2(built_lib):
     Y, _, _ = _traces("ar2_4")
     _compare(Y, dict(type="ar2", method="foopsi", pars=[1.7, -0.712], smin=-3), built_lib)
@@ -73,7 +81,7 @@ def test_thresholded_ar2(built_lib):
 
 
 def test_ar2_at_c5_length(built_lib):
-    """BASELINE configs[4] trace length (T = 100000, AR2, gen_data(g=[1.7,-0.712], noise 1, seed 3) restated): parity with the
+    """BASELINE configs[4] trace length (T = 100000, AR2 traces of functions/gen_data.m with g = [1.7, -0.712], noise 1, seed 3, restated): parity with the
     oracle, not only invariants -- deconvolveCa(y, 'ar2', 'foopsi', pars, 'smin', -3) and the 'thresholded' variant."""
     Y, _, _ = _traces("ar2_c5")
     _compare(Y, dict(type="ar2", method="foopsi", pars=[1.7, -0.712], smin=-3), built_lib)

@@ -96,3 +96,23 @@ def test_gen_data_spikes_follow_matlab_rand_stream():
     """MT19937 + column-major fill: first uniform of RandomState(13) is MATLAB's rand after rng(13)."""
     rs = np.random.RandomState(13)
     assert abs(rs.rand() - 0.7777024105738202) < 1e-15
+
+
+def test_fit_gauss1_and_baseline_noise_known_answers():
+    """fit_gauss1 recovers an exact Gaussian; hist_centers equals an explicit-edge histogram; estimate_baseline_noise recovers
+    the baseline / noise of a Gaussian sample with sparse positive transients (functions/estimate_baseline_noise.m)."""
+    from oracle import oasis as O
+    x = np.linspace(-3, 5, 161)
+    mu, sig, A = O.fit_gauss1(x, 7.0 * np.exp(-(x - 1.2) ** 2 / 2 / 0.8 ** 2), 0.3, 3)
+    assert abs(mu - 1.2) < 1e-9 and abs(sig - 0.8) < 1e-9 and abs(A - 7.0) < 1e-8
+    rs = np.random.RandomState(1)
+    y = rs.randn(4000)
+    c = np.linspace(-2, 2, 9)
+    edges = np.concatenate([[min(c[0] - 0.25, y.min())], (c[:-1] + c[1:]) / 2, [max(c[-1], y.max())]])
+    ref = np.histogram(y, edges)[0]
+    assert np.array_equal(O.hist_centers(y, c), ref)
+    y = 2.5 + 0.3 * rs.randn(20000)
+    y[::40] += 4.0
+    b, sn = O.estimate_baseline_noise(y)
+    assert abs(b - 2.5) < 0.02 and abs(sn - 0.3) < 0.02
+    assert np.allclose(O._solve_small([[2.0, 1, 0], [1, 3, 1], [0, 1, 4]], [1.0, 2, 3]), np.linalg.solve([[2.0, 1, 0], [1, 3, 1], [0, 1, 4]], [1.0, 2, 3]))
