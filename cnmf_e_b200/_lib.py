@@ -86,6 +86,8 @@ SYMBOLS = {
     "cnmfe_host_register": (I, [V, ctypes.c_size_t]),
     "cnmfe_host_unregister": (I, [V]),
     "cnmfe_get_temporal": (I, [V, V, V, V, V, V]),
+    "cnmfe_compute_rss": (I, [V, I, I, V, V, V]),
+    "cnmfe_reconstruct_background": (I, [V, I, I, I, V, V, V]),
     "cnmfe_sync": (I, [V]),
     "cnmfe_timer_begin": (I, [V]),
     "cnmfe_timer_end": (I, [V, c_float_p]),

@@ -1491,6 +1491,116 @@ extern "C" int cnmfe_estimate_noise(cnmfe_ctx* c, int f0, int f1, double* sn) {
     return 0;
 }
 
+// ---- compute_RSS / reconstruct_background (Sources2D.m:1247-1510), ring model with bg_ssub = 1.
+// Both walk the patch in chunks of explicit BG-subtracted rows (ysig_rows_kernel, the kernel behind update_sn) -- see the algebra
+// at bg_cst_kernel.  mode 0: rss_out[0] = RSS of patch ip over frames [f0, f1] (1-based inclusive).  mode 1: ybg_out =
+// background of the patch for those frames, d_patch x nframes in the boundary layout.
+static int bg_rows_pass(cnmfe_ctx* c, int ip, int f0, int f1, const double* b0_map, const double* b0_new_map, int mode,
+                        double* rss_out, double* ybg_out) {
+    if (c->opt.background_model != 0 || c->opt.bg_ssub != 1) { set_error("compute_RSS / reconstruct_background are built for the ring model with bg_ssub = 1"); return -1; }
+    if (!b0_map || !b0_new_map) { set_error("compute_RSS / reconstruct_background: b0 (reconstruct_b0) and b0_new maps are required"); return -1; }
+    if (f0 < 1 || f1 > c->T || f1 < f0) { set_error("frame range [%d, %d] outside [1, %d]", f0, f1, c->T); return -1; }
+    CNMFE_CUDA_OK(cudaSetDevice(c->device));
+    Patch& P = c->patches[ip];
+    if (!P.owned || !P.uploaded) { set_error("block %d not resident", ip); return -1; }
+    const int T = c->T, nf = f1 - f0 + 1, CH = 1024;
+    LocalSparse LA, LP;
+    build_local(c, P, c->A, SEL_SUM_BLOCK, ROWS_BLOCK, nullptr, &LA);          // A(logical(mask), ind): every neuron of the block
+    build_local(c, P, c->Aprev, SEL_SUM_BLOCK, ROWS_BLOCK, nullptr, &LP);
+    const int Ka = LA.K(), Kp = LP.K();
+    if (Kp > YSIG_MAXK) { set_error("%d previous neurons touch block %d (explicit rows handle <= %d)", Kp, ip, YSIG_MAXK); return -1; }
+    size_t need = pad256((size_t)CH * T * 8) + pad256((size_t)std::max(Kp, 1) * T * 8) + 2 * pad256((size_t)(P.db + 1) * 4) +
+                  pad256(LA.col.size() * 12 + 64) + pad256(LP.col.size() * 12 + 64) + 4 * pad256((size_t)P.db * 8) +
+                  3 * pad256((size_t)P.dp * 8) + pad256((size_t)CH * nf * 8) * (mode ? 2 : 0) + pad256((size_t)(Ka + Kp + CH) * 16) + (1 << 20);
+    if (c->scr.reserve(need)) return -1;
+    c->scr.reset();
+    const RingGeom& g = P.geom;
+    TAKE_OR_FAIL(d_aptr, to_dev(c, LA.ptr));
+    TAKE_OR_FAIL(d_acol, to_dev(c, LA.col));
+    TAKE_OR_FAIL(d_aval, to_dev(c, LA.val));
+    TAKE_OR_FAIL(d_aids, to_dev(c, LA.ids));
+    TAKE_OR_FAIL(d_pptr, to_dev(c, LP.ptr));
+    TAKE_OR_FAIL(d_pcol, to_dev(c, LP.col));
+    TAKE_OR_FAIL(d_pval, to_dev(c, LP.val));
+    TAKE_OR_FAIL(d_pids, to_dev(c, LP.ids));
+    TAKE_OR_FAIL(d_Ccp, c->scr.take<double>((size_t)std::max(Kp, 1) * T));
+    TAKE_OR_FAIL(d_Cpmean, c->scr.take<double>(std::max(Kp, 1)));
+    if (Kp > 0) LAUNCH(gather_center_rows_kernel, Kp, 256, 0, c->st, c->Cprev, d_pids, Kp, T, d_Ccp, d_Cpmean);
+    // block / patch vectors of the two b0 maps
+    std::vector<double> b0blk(P.db), b0new(P.dp), b0p(P.dp);
+    for (int q = 0; q < P.db; ++q) b0blk[q] = b0_map[(size_t)(q / P.nrb + P.block.c0) * c->d1 + (q % P.nrb + P.block.r0)];
+    for (int p = 0; p < P.dp; ++p) {
+        const size_t f = (size_t)(p / P.nr + P.patch.c0) * c->d1 + (p % P.nr + P.patch.r0);
+        b0new[p] = b0_new_map[f]; b0p[p] = b0_map[f];
+    }
+    TAKE_OR_FAIL(d_b0blk, to_dev(c, b0blk));
+    TAKE_OR_FAIL(d_b0new, to_dev(c, b0new));
+    TAKE_OR_FAIL(d_b0p, to_dev(c, b0p));
+    TAKE_OR_FAIL(d_meanR, c->scr.take<double>(P.db));
+    TAKE_OR_FAIL(d_cst, c->scr.take<double>(P.dp));
+    TAKE_OR_FAIL(d_rowsY, c->scr.take<double>((size_t)CH * T));
+    TAKE_OR_FAIL(d_rows, c->scr.take<int>(CH));
+    TAKE_OR_FAIL(d_part, c->scr.take<double>(CH));
+    LAUNCH(bg_meanR_kernel, (P.db + 255) / 256, 256, 0, c->st, P.db, P.Ymean, d_pptr, d_pcol, d_pval, d_Cpmean, d_meanR);
+    // the explicit rows use the b0 the caller's map holds for the patch (obj.b0{m}), like the reference (b0_ = reconstruct_b0())
+    LAUNCH(bg_cst_kernel, (P.dp + 255) / 256, 256, 0, c->st, g, c->d_off_r, c->d_off_c, P.W, d_b0p, d_b0new, d_b0blk, d_meanR, d_cst);
+    double* d_out = nullptr; double* d_tr = nullptr;
+    if (mode == 1) {
+        d_out = c->scr.take<double>((size_t)CH * nf); d_tr = c->scr.take<double>((size_t)CH * nf);
+        if (!d_out || !d_tr) { set_error("scratch exhausted"); return -1; }
+    }
+    std::vector<int> rows(CH);
+    std::vector<double> part(CH), chunk;
+    double total = 0.0;
+    for (int b = 0; b < P.dp; b += CH) {
+        const int nr = std::min(CH, P.dp - b);
+        for (int i = 0; i < nr; ++i) rows[i] = b + i;
+        CNMFE_CUDA_OK(cudaMemcpyAsync(d_rows, rows.data(), (size_t)nr * 4, cudaMemcpyHostToDevice, c->st));
+        dim3 gg(nr, (T + YSIG_TCHUNK - 1) / YSIG_TCHUNK);
+        LAUNCH(ysig_rows_kernel, gg, 256, 0, c->st, g, c->d_off_r, c->d_off_c, P.W, d_b0p, P.Yt, P.Ymean, T, c->Tpad, d_pptr, d_pcol,
+               d_pval, Kp, d_Ccp, d_rows, d_rowsY);
+        if (mode == 0) {
+            LAUNCH(rss_rows_kernel, nr, 256, 0, c->st, g, d_rowsY, d_rows, T, f0 - 1, f1, d_aptr, d_acol, d_aval, d_aids, c->C, d_cst, d_part);
+            CNMFE_CUDA_OK(cudaMemcpyAsync(part.data(), d_part, (size_t)nr * 8, cudaMemcpyDeviceToHost, c->st));
+            CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+            for (int i = 0; i < nr; ++i) total += part[i];
+        } else {
+            dim3 g2((nf + 255) / 256, nr);
+            LAUNCH(ybg_rows_kernel, g2, 256, 0, c->st, g, d_rowsY, d_rows, P.Yt, T, c->Tpad, f0 - 1, f1, d_cst, d_out);
+            if (c->trace_major) {        // [p][t]: rows b .. b+nr of the output
+                CNMFE_CUDA_OK(cudaMemcpyAsync(ybg_out + (size_t)b * nf, d_out, (size_t)nr * nf * 8, cudaMemcpyDeviceToHost, c->st));
+                CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+            } else {                     // MATLAB d_patch x nframes column-major: element (p, t) at p + t * d_patch
+                chunk.resize((size_t)nr * nf);
+                CNMFE_CUDA_OK(cudaMemcpyAsync(chunk.data(), d_out, (size_t)nr * nf * 8, cudaMemcpyDeviceToHost, c->st));
+                CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+                for (int i = 0; i < nr; ++i)
+                    for (int t = 0; t < nf; ++t) ybg_out[(size_t)(b + i) + (size_t)t * P.dp] = chunk[(size_t)i * nf + t];
+            }
+        }
+    }
+    CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+    CNMFE_CUDA_OK(cudaGetLastError());
+    if (mode == 0) *rss_out = total;
+    return 0;
+}
+
+// [RSS_total, RSS] = compute_RSS(obj, frame_range) (Sources2D.m:1358-1510): rss[ip] for the owned patches (others untouched)
+extern "C" int cnmfe_compute_rss(cnmfe_ctx* c, int f0, int f1, const double* b0_map, const double* b0_new_map, double* rss) {
+    if (!c || !rss) { set_error("cnmfe_compute_rss: null"); return -1; }
+    for (int ip = 0; ip < c->npatch; ++ip) {
+        if (!c->patches[ip].owned) continue;
+        if (bg_rows_pass(c, ip, f0, f1, b0_map, b0_new_map, 0, rss + ip, nullptr)) return -1;
+    }
+    return 0;
+}
+// Ybg = reconstruct_background(obj, frame_range) (Sources2D.m:1247-1356), one patch at a time: d_patch x (f1-f0+1)
+extern "C" int cnmfe_reconstruct_background(cnmfe_ctx* c, int ip, int f0, int f1, const double* b0_map, const double* b0_new_map,
+                                            double* Ybg) {
+    if (!c || ip < 0 || ip >= c->npatch || !Ybg) { set_error("cnmfe_reconstruct_background: bad arguments"); return -1; }
+    return bg_rows_pass(c, ip, f0, f1, b0_map, b0_new_map, 1, nullptr, Ybg);
+}
+
 // merged C_raw = sum_p aa_p C_raw,p / sum_p aa_p (update_temporal_parallel.m:269-280) as it ENTERED the final deconvTemporal,
 // i.e. before deconvTemporal.m:84 subtracts the baseline; valid after cnmfe_update_temporal_finish[_part] (rows this rank
 // finished).  K x T in the boundary layout (cnmfe_set_trace_major).  Lets a checker re-run deconvolveCa on the same input.

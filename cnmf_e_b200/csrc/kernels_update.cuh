@@ -384,6 +384,68 @@ ysig_rows_kernel(RingGeom g, const int* __restrict__ off_r, const int* __restric
     }
 }
 
+// ---- compute_RSS / reconstruct_background (Sources2D.m:1247-1510, ring model, bg_ssub = 1) from explicit rows of Ysig:
+//   Bf(p,t)   = sum_i W(p,i) [Y(q_i,t) - b0_(q_i) - (Aprev Cprev)(q_i,t)]           (:1322-1325, :1475-1476)
+//             = Y(p,t) - b0(p) - Ysig(p,t) + sum_i W(p,i) (meanR - b0_)(q_i),   meanR = Ybar - Aprev mean(Cprev)
+//   Ybg(p,t)  = Bf(p,t) + b0_new(p) = Y(p,t) - Ysig(p,t) - cst(p)
+//   resid     = (Y - A C)(p,t) - Ybg(p,t) = Ysig(p,t) - (A C)(p,t) + cst(p)
+//   cst(p)    = b0(p) - b0_new(p) + sum_i W(p,i) (b0_ - meanR)(q_i)
+// cst for every patch pixel.  b0blk / meanR: block vectors.  One thread per patch pixel.
+__global__ void bg_cst_kernel(RingGeom g, const int* __restrict__ off_r, const int* __restrict__ off_c,
+                              const double* __restrict__ W, const double* __restrict__ b0, const double* __restrict__ b0new,
+                              const double* __restrict__ b0blk, const double* __restrict__ meanR, double* __restrict__ cst) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.nr * g.nc) return;
+    const int r = p % g.nr + g.pr_off, c = p / g.nr + g.pc_off;
+    double acc = 0.0;
+    for (int i = 0; i < g.nnb; ++i) {
+        const int r2 = r + off_r[i], c2 = c + off_c[i];
+        const int fr = r2 + g.br0, fc = c2 + g.bc0;
+        if (fr < 0 || fr >= g.d1 || fc < 0 || fc >= g.d2) continue;
+        const size_t q = (size_t)c2 * g.nrb + r2;
+        acc += W[(size_t)p * g.nnb + i] * (b0blk[q] - meanR[q]);
+    }
+    cst[p] = b0[p] - b0new[p] + acc;
+}
+// meanR[q] = Ybar[q] - sum_k Aprev(q,k) * mean(Cprev_k)   (block pixels)
+__global__ void bg_meanR_kernel(int db, const double* __restrict__ Ymean, const int* __restrict__ ap_ptr, const int* __restrict__ ap_col,
+                                const double* __restrict__ ap_val, const double* __restrict__ Cpmean, double* __restrict__ meanR) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= db) return;
+    double s = Ymean[q];
+    for (int e = ap_ptr[q]; e < ap_ptr[q + 1]; ++e) s -= ap_val[e] * Cpmean[ap_col[e]];
+    meanR[q] = s;
+}
+// rss[i] = sum_{t in [f0, f1)} (Ysig_i(t) - sum_k A(p_i,k) C(gid_k,t) + cst(p_i))^2, one CTA per row.  a_ptr indexed by BLOCK pixel.
+__global__ void __launch_bounds__(256)
+rss_rows_kernel(RingGeom g, const double* __restrict__ rowsY, const int* __restrict__ rows, int T, int f0, int f1,
+                const int* __restrict__ a_ptr, const int* __restrict__ a_col, const double* __restrict__ a_val,
+                const int* __restrict__ gid, const double* __restrict__ C, const double* __restrict__ cst, double* __restrict__ out) {
+    __shared__ double red[32];
+    const int p = rows[blockIdx.x];
+    const size_t q = (size_t)(p / g.nr + g.pc_off) * g.nrb + (p % g.nr + g.pr_off);
+    const int e0 = a_ptr[q], e1 = a_ptr[q + 1];
+    const double cp = cst[p];
+    const double* y = rowsY + (size_t)blockIdx.x * T;
+    double acc = 0.0;
+    for (int t = f0 + threadIdx.x; t < f1; t += blockDim.x) {
+        double v = y[t] + cp;
+        for (int e = e0; e < e1; ++e) v -= a_val[e] * C[(size_t)gid[a_col[e]] * T + t];
+        acc = fma(v, v, acc);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = acc;
+}
+// Ybg rows: out[i][t - f0] = Y(p_i,t) - Ysig_i(t) - cst(p_i)
+__global__ void ybg_rows_kernel(RingGeom g, const double* __restrict__ rowsY, const int* __restrict__ rows, const uint16_t* __restrict__ Yt,
+                                int T, int Tpad, int f0, int f1, const double* __restrict__ cst, double* __restrict__ out) {
+    const int i = blockIdx.y, t = f0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= f1) return;
+    const int p = rows[i];
+    const size_t q = (size_t)(p / g.nr + g.pc_off) * g.nrb + (p % g.nr + g.pr_off);
+    out[(size_t)i * (f1 - f0) + (t - f0)] = (double)Yt[q * Tpad + t] - rowsY[(size_t)i * T + t] - cst[p];
+}
+
 // energy[i] = sum_t (X[i][t] - mean_t X[i])^2   (lars_spatial.m:42,50: Y centred, sum(Y.^2,2))
 __global__ void rows_centered_energy_kernel(const double* __restrict__ X, int T, double* __restrict__ energy) {
     __shared__ double red[32];

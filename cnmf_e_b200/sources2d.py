@@ -561,6 +561,44 @@ class Sources2D:
             sn = np.ascontiguousarray(sn[np.ix_(rmap, cmap)])
         return sn
 
+    # ---- diagnostics on the fused BG subtraction (SURVEY.md 8f row 2) ---------------------------------------------------
+    def _b0_maps(self):
+        b0 = self.reconstruct_b0()
+        if self.world_size > 1:
+            b0 = self._allreduce_sum(b0.ravel()).reshape(self.d1, self.d2)
+        return np.asfortranarray(b0), np.asfortranarray(np.asarray(self.b0_new, dtype=np.float64))
+
+    def compute_RSS(self, frame_range=None):
+        """[RSS_total, RSS] = compute_RSS(obj, frame_range) (@Sources2D/Sources2D.m:1358-1510; ring model, bg_ssub = 1).  Uses the
+        state on the host (A, C, A_prev, C_prev, W, b0, b0_new), sent to the device if it changed.  Multi-rank: a collective
+        call; RSS of the patches this rank owns are summed over the ranks."""
+        f0, f1 = (1, self.T) if frame_range is None else (int(frame_range[0]), int(frame_range[1]))
+        self._push_options(); self.push_neurons(); self.push_prev(); self.push_ring()
+        b0, b0n = self._b0_maps()
+        rss = np.zeros(self.npatch)
+        L.check(self._lib.cnmfe_compute_rss(self._h, f0, f1, _ptr(b0), _ptr(b0n), _ptr(rss)))
+        if self.world_size > 1:
+            rss = self._allreduce_sum(rss)
+        self.P["RSS"] = float(rss.sum())
+        return self.P["RSS"], rss
+
+    def reconstruct_background(self, frame_range=None):
+        """Ybg = reconstruct_background(obj, frame_range) (@Sources2D/Sources2D.m:1247-1356; ring model, bg_ssub = 1): (d1, d2,
+        nframes) array, filled on the patches this rank owns."""
+        f0, f1 = (1, self.T) if frame_range is None else (int(frame_range[0]), int(frame_range[1]))
+        self._push_options(); self.push_prev(); self.push_ring()
+        b0, b0n = self._b0_maps()
+        nf = f1 - f0 + 1
+        out = np.zeros((self.d1, self.d2, nf))
+        for i in self.owned_patches():
+            p = self.patch_of(i)
+            nr, nc = p[1] - p[0] + 1, p[3] - p[2] + 1
+            buf = np.empty((nr * nc, nf))              # [pixel][frame] (trace-major boundary layout)
+            L.check(self._lib.cnmfe_reconstruct_background(self._h, i, f0, f1, _ptr(b0), _ptr(b0n), _ptr(buf)))
+            self.d2h_bytes += buf.nbytes
+            out[p[0] - 1:p[1], p[2] - 1:p[3], :] = buf.reshape(nr, nc, nf, order="F")
+        return out
+
     # ---- host-side brackets of the spatial update (library C++: csrc/host_spatial.cu) ----------------------------------
     def determine_search_location(self, A=None, min_size=3.0, max_size=8.0, dist=3.0, method="ellipse", nrgthr=0.9999,
                                   nb=1, bSiz=3):

@@ -212,6 +212,14 @@ int cnmfe_debug_local_view(int d1, int d2, const int* patch_pos, const int* bloc
                            const int64_t* ir, const double* pr, int sel, int rows, const int64_t* vjc, const int64_t* vir,
                            const double* vpr, int* n_local, int* n_kept, int* ids, int* ptr, int* col, double* val,
                            int64_t* entry_src, int* cptr, int* crow, double* cval, int* bbox);
+/* [RSS_total, RSS] = compute_RSS(obj, frame_range) (@Sources2D/Sources2D.m:1358-1510) and Ybg = reconstruct_background(obj,
+ * frame_range) (:1247-1356) for the ring model with bg_ssub = 1, from the resident video and the state the context holds (A, C,
+ * A_prev, C_prev, W).  f0, f1: 1-based inclusive frames.  b0_map = obj.reconstruct_b0() and b0_new_map = obj.b0_new, both d1 x d2
+ * column-major (the halo of a block reads b0 of neighbouring patches, which another rank may own).  rss: npatch entries, written for
+ * the owned patches.  Ybg: d_patch x (f1-f0+1) in the boundary layout (column-major, or [pixel][frame] with cnmfe_set_trace_major). */
+int cnmfe_compute_rss(cnmfe_ctx* ctx, int f0, int f1, const double* b0_map, const double* b0_new_map, double* rss);
+int cnmfe_reconstruct_background(cnmfe_ctx* ctx, int ipatch, int f0, int f1, const double* b0_map, const double* b0_new_map,
+                                 double* Ybg);
 /* block the host until all queued device work of ctx is done */
 int cnmfe_sync(cnmfe_ctx* ctx);
 /* CUDA-event timing of the kernels on the ctx stream: begin/end bracket a region, returns milliseconds */

@@ -160,6 +160,15 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         check(cnmfe_get_bf(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), mxGetPr(plhs[0]), mxGetPr(f), mxGetPr(b0)), cmd);
         if (nlhs > 1) plhs[1] = f;
         if (nlhs > 2) plhs[2] = b0;
+    } else if (c == "compute_rss") {   // rss = compute_rss(h, f0, f1, b0_map (d1 x d2), b0_new (d1 x d2), npatch): Sources2D.compute_RSS, per patch
+        plhs[0] = mxCreateDoubleMatrix((mwSize)mxGetScalar(prhs[6]), 1, mxREAL);
+        check(cnmfe_compute_rss(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), (int)mxGetScalar(prhs[3]), mxGetPr(prhs[4]), mxGetPr(prhs[5]),
+                                mxGetPr(plhs[0])), cmd);
+    } else if (c == "reconstruct_background") {   // Ybg = reconstruct_background(h, ipatch0, f0, f1, b0_map, b0_new, d_patch): d_patch x nframes
+        const int f0 = (int)mxGetScalar(prhs[3]), f1 = (int)mxGetScalar(prhs[4]);
+        plhs[0] = mxCreateDoubleMatrix((mwSize)mxGetScalar(prhs[7]), (mwSize)(f1 - f0 + 1), mxREAL);
+        check(cnmfe_reconstruct_background(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), f0, f1, mxGetPr(prhs[5]), mxGetPr(prhs[6]),
+                                           mxGetPr(plhs[0])), cmd);
     } else if (c == "estimate_noise") {   // sn = estimate_noise(h, f0, f1, d1, d2): per-pixel GetSn of the resident video (Sources2D.m:328-379)
         plhs[0] = mxCreateDoubleMatrix((mwSize)mxGetScalar(prhs[4]), (mwSize)mxGetScalar(prhs[5]), mxREAL);
         check(cnmfe_estimate_noise(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), (int)mxGetScalar(prhs[3]), mxGetPr(plhs[0])), cmd);

@@ -601,6 +601,43 @@ class OracleSources2D:
             self.C = self.C_raw.copy()
         self.b0_new = self.P["Ymean"] - (self.A @ self.C.mean(axis=1)).reshape(self.d1, self.d2, order="F")
 
+    def reconstruct_background(self, frame_range=None):
+        """Ybg = reconstruct_background(obj, frame_range) (Sources2D.m:1247-1356), ring model, bg_ssub = 1:
+        Ybg(patch) = W * (Y - b0_ - A_prev*C_prev) + b0_new(patch), b0_ = reconstruct_b0() on the block."""
+        f0, f1 = (1, self.T) if frame_range is None else (int(frame_range[0]), int(frame_range[1]))
+        Tf = f1 - f0 + 1
+        b0_ = self.reconstruct_b0().ravel(order="F")
+        b0n = np.asarray(self.b0_new).ravel(order="F")
+        Apcsr = sp.csr_matrix(self.A_prev)
+        Ybg = np.zeros((self.d1 * self.d2, Tf))
+        for mp in self.patches():
+            tb, tp = self.block_pos[mp], self.patch_pos[mp]
+            bm, pm = self._block_mask(tb), self._block_mask(tp)
+            ind = np.asarray(Apcsr[bm, :].sum(axis=0)).ravel() > 0
+            A_patch = Apcsr[bm, :][:, ind]
+            C_patch = self.C_prev[ind, f0 - 1:f1]
+            Yp = self._get_block(tb)[:, f0 - 1:f1].astype(np.float64) - b0_[bm][:, None]
+            Bf = sp.csr_matrix(self.W[mp]) @ (Yp - A_patch @ C_patch)
+            Ybg[pm, :] = Bf + b0n[pm][:, None]
+        return Ybg.reshape(self.d1, self.d2, Tf, order="F")
+
+    def compute_RSS(self, frame_range=None):
+        """[RSS_total, RSS] = compute_RSS(obj, frame_range) (Sources2D.m:1358-1510), ring model, bg_ssub = 1:
+        per patch sum((Y(patch) - A*C) - (W*(Y - b0_ - A_prev*C_prev) + b0_new(patch))).^2."""
+        f0, f1 = (1, self.T) if frame_range is None else (int(frame_range[0]), int(frame_range[1]))
+        Ybg = self.reconstruct_background((f0, f1)).reshape(self.d1 * self.d2, -1, order="F")
+        Acsr = sp.csr_matrix(self.A)
+        RSS = {}
+        for mp in self.patches():
+            tb, tp = self.block_pos[mp], self.patch_pos[mp]
+            bm, pm = self._block_mask(tb), self._block_mask(tp)
+            ind = np.asarray(Acsr[bm, :].sum(axis=0)).ravel() > 0
+            YmAC = self._get_block(tp)[:, f0 - 1:f1].astype(np.float64) - Acsr[pm, :][:, ind] @ self.C[ind, f0 - 1:f1]
+            RSS[mp] = float(np.sum((YmAC - Ybg[pm, :]) ** 2))
+        total = float(sum(RSS.values()))
+        self.P["RSS"] = total
+        return total, RSS
+
     def deconvTemporal(self):
         """deconvTemporal.m:62-105 (serial branch)."""
         K, T = self.C_raw.shape

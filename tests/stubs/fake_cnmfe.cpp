@@ -76,6 +76,16 @@ int cnmfe_set_bf(cnmfe_ctx*, int ip, const double* b, const double* f, const dou
 }
 int cnmfe_get_bf(cnmfe_ctx*, int ip, double* b, double* f, double* b0) { printf("get_bf ip=%d\n", ip); b[0] = 1; f[0] = 2; b0[0] = 3; return 0; }
 int cnmfe_estimate_noise(cnmfe_ctx*, int f0, int f1, double* sn) { printf("estimate_noise %d %d\n", f0, f1); sn[0] = 9; return 0; }
+int cnmfe_compute_rss(cnmfe_ctx* c, int f0, int f1, const double* b0, const double* b0n, double* rss) {
+    printf("compute_rss %d %d b0=%g b0new=%g\n", f0, f1, b0[0], b0n[0]);
+    for (int i = 0; i < c->np; ++i) rss[i] = 10.0 + i;
+    return 0;
+}
+int cnmfe_reconstruct_background(cnmfe_ctx*, int ip, int f0, int f1, const double* b0, const double* b0n, double* Y) {
+    printf("reconstruct_background ip=%d %d %d b0=%g b0new=%g\n", ip, f0, f1, b0[0], b0n[0]);
+    Y[0] = 5.5;
+    return 0;
+}
 int cnmfe_update_background(cnmfe_ctx*) { printf("update_background\n"); return 0; }
 int cnmfe_update_spatial_ex(cnmfe_ctx*, int usn) { printf("update_spatial update_sn=%d\n", usn); return 0; }
 int cnmfe_get_spatial(cnmfe_ctx*, double* v) { v[0] = 0.25; v[1] = 0.5; return 0; }

@@ -74,6 +74,11 @@ int main(int argc, char** argv) {
         printf("get_bf -> b %zux%zu f %zux%zu b0 %zux%zu\n", mxGetM(gb[0]), mxGetN(gb[0]), mxGetM(gb[1]), mxGetN(gb[1]), mxGetM(gb[2]), mxGetN(gb[2]));
         auto en = call(1, {t_string("estimate_noise"), h, t_scalar(1), t_scalar(T), t_scalar(d1), t_scalar(d2)});
         printf("estimate_noise -> %zux%zu sn0=%g\n", mxGetM(en[0]), mxGetN(en[0]), mxGetPr(en[0])[0]);
+        std::vector<double> bmap(d1 * d2, 3.25), bnew(d1 * d2, 4.5);
+        auto rs = call(1, {t_string("compute_rss"), h, t_scalar(1), t_scalar(T), t_double(d1, d2, bmap.data()), t_double(d1, d2, bnew.data()), t_scalar(2)});
+        printf("compute_rss -> %zux%zu rss1=%g\n", mxGetM(rs[0]), mxGetN(rs[0]), mxGetPr(rs[0])[1]);
+        auto yb = call(1, {t_string("reconstruct_background"), h, t_scalar(1), t_scalar(3), t_scalar(12), t_double(d1, d2, bmap.data()), t_double(d1, d2, bnew.data()), t_scalar(12)});
+        printf("reconstruct_background -> %zux%zu y0=%g\n", mxGetM(yb[0]), mxGetN(yb[0]), mxGetPr(yb[0])[0]);
         std::vector<double> y(T * 3, 0.125);
         auto dc = call(7, {t_string("deconvolve"), t_double(T, 3, y.data()), dopt, t_double(0, 0, nullptr), t_double(0, 0, nullptr)});
         printf("deconvolve -> c %zux%zu pars %zux%zu lam0=%g\n", mxGetM(dc[0]), mxGetN(dc[0]), mxGetM(dc[3]), mxGetN(dc[3]), mxGetPr(dc[6])[0]);

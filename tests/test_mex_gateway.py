@@ -50,6 +50,10 @@ def test_gateway_marshalling_against_recording_library(tmp_path):
         "set_bf ip=0 b0=0.5 f1=0.25 b0vec=null",
         "get_bf -> b 12x1 f 1x40 b0 12x1",
         "estimate_noise -> 6x4 sn0=9",
+        "compute_rss 1 40 b0=3.25 b0new=4.5",
+        "compute_rss -> 2x1 rss1=11",
+        "reconstruct_background ip=1 3 12 b0=3.25 b0new=4.5",
+        "reconstruct_background -> 12x10 y0=5.5",
         "deconvolve T=40 N=3 type=1 method=0 sn=null pars=null y0=0.125 dev=0",
         "deconvolve -> c 40x3 pars 2x3 lam0=7",
         "rejected: cnmfe:options: background_model 'pca' unknown (ring, svd, nmf)",
