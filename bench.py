@@ -480,7 +480,7 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (ring second moments), live CUDA-event time on the launching stream
+    # ---- roofline of the two big kernels of the background update (live CUDA-event times on the launching streams)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -497,27 +497,30 @@ def run_ours(args):
     int8_ops = 2.0 * 4.0 * ND * db * T_fit       # u16 x u16 = 4 u8 x u8 products, 2 ops per MAC
     gram_s = max(gram_ms / 1e3 / args.steps, 1e-9)
     achieved = int8_ops / gram_s / 1e12
-    roofline = dict(bound="tensor", kernel="ring second moments S2 (%s)" % ("tcgen05 INT8" if lib.cnmfe_last_gram_was_tensor(obj._h) else "SIMT u64"),
-                    achieved=achieved, peak=2.0 * bf16, unit="TOP/s (int8 dense)", frac=achieved / (2.0 * bf16),
-                    traffic=(89.47e9 * (T_fit / 10000.0) * (db / 262144.0) if (lib.cnmfe_last_gram_was_tensor(obj._h) and ss == 1) else None),
-                    traffic_source="dram__bytes_read.sum (84.24 GB) + dram__bytes_write.sum (5.23 GB) of one ncu --set full capture (profiles/r1_ncu_full_gram.csv), scaled by frames/10000 and pixels/262144",
-                    peak_source=peak_src, ms_per_launch=1e3 * gram_s,
-                    algorithmic_ops_per_launch=int8_ops,
-                    hbm_iteration=dict(algorithmic_bytes=3.0 * d1 * d2 * T * 2 / world, gbs=3.0 * d1 * d2 * T * 2 / world / (t_max / args.steps) / 1e9,
-                                       peak_gbs=peaks.get("hbm_gbs", 6650.0)))
+    gram_roof = dict(bound="tensor", kernel="ring_s2_tc_kernel: banded second moments S2 (%s)" % ("tcgen05 INT8" if lib.cnmfe_last_gram_was_tensor(obj._h) else "SIMT u64"),
+                     achieved=achieved, peak=2.0 * bf16, unit="TOP/s (int8 dense)", frac=achieved / (2.0 * bf16),
+                     traffic=(89.47e9 * (T_fit / 10000.0) * (db / 262144.0) if (lib.cnmfe_last_gram_was_tensor(obj._h) and ss == 1) else None),
+                     traffic_source="dram__bytes_read.sum (84.24 GB) + dram__bytes_write.sum (5.23 GB) of one ncu --set full capture (profiles/r1_ncu_full_gram.csv), scaled by frames/10000 and pixels/262144",
+                     peak_source=peak_src, ms_per_launch=1e3 * gram_s, algorithmic_ops_per_launch=int8_ops)
     # ---- the other kernels of the step, each against the bound that applies to it (live per-phase CUDA-event times)
     ph = [float(x) / args.steps / 1e3 for x in phases]          # seconds per step
     nnb1 = 121 if ss == 1 else None
     others = {}
+    solve_roof = None
     if nnb1 and ph[1] > 0:
-        dpx = float(sum(int(b[1] - b[0] + 1) * int(b[3] - b[2] + 1) for b in nblk))
-        sol_bytes = dpx * (nnb1 * (nnb1 + 1) / 2 + nnb1) * 8.0      # moment gather + weights out, all pixels active
-        sol_flop = dpx * (2.0 * nnb1 ** 3 / 6.0 + 2.0 * nnb1 ** 2)  # LDL' + two triangular solves (fp64)
-        others["ring_solve_kernel"] = dict(ms=1e3 * ph[1], bound="shared-memory operand bandwidth / latency (fp64, not tensor)",
-                                           algorithmic_bytes=sol_bytes, hbm_gbs=sol_bytes / ph[1] / 1e9,
-                                           hbm_frac=sol_bytes / ph[1] / 1e9 / peaks.get("hbm_gbs", 6650.0),
-                                           fp64_tflops=sol_flop / ph[1] / 1e12, fp64_frac_of_36_tf=sol_flop / ph[1] / 36.0e12,
-                                           evidence="profiles/r1_ncu_full_solve.csv: LDS wavefronts 50 % of peak, fp64 pipe 27 %, barrier stalls 39 %")
+        n_act = float(lib.cnmfe_last_active_pixels(obj._h)) or float(sum(int(b[1] - b[0] + 1) * int(b[3] - b[2] + 1) for b in nblk))
+        n1 = nnb1 + 1                                              # ring pixels + ones row + right-hand side row of the augmented system
+        sol_bytes = n_act * (nnb1 * (nnb1 + 1) / 2 + nnb1) * 8.0   # moment gather + weights out
+        sol_flop = n_act * (2.0 * n1 ** 3 / 6.0 + 2.0 * n1 ** 2)   # LDL' of the augmented matrix + back substitution (fp64; mul and add counted)
+        fp64_peak = 36.5                                           # TFLOP/s: DMMA m8n8k4 == DFMA rate measured on this pool by scripts/micro/dmma.cu
+        solve_roof = dict(bound="tensor", kernel="ring_solve_mma_kernel: per-pixel 122 x 122 block LDL' (fp64 tensor path, DMMA.8x8x4)",
+                          achieved=sol_flop / ph[1] / 1e12, peak=fp64_peak, unit="TFLOP/s (fp64)", frac=sol_flop / ph[1] / 1e12 / fp64_peak,
+                          traffic=11.07e9 * (n_act / 235617.0),
+                          traffic_source="dram__bytes_read.sum (10.80 GB) + dram__bytes_write.sum (0.27 GB) of one ncu --set full capture (profiles/r2_ncu_full_solve_mma.csv), scaled by active pixels/235617",
+                          peak_source="fp64 tensor-path rate measured by scripts/micro/dmma.cu on this pool's B200 (36.5 TFLOP/s for DMMA and for DFMA); MEASURED_PEAKS.json carries no fp64 figure",
+                          ms_per_launch=1e3 * ph[1], algorithmic_ops_per_launch=sol_flop, algorithmic_bytes_per_launch=sol_bytes,
+                          active_pixels=n_act,
+                          note="latency bound, not pipe bound: the 16 block pivots (8 x 8 inversions, a chain of dependent reciprocals) serialise each pixel; ncu: DMMA sub-pipe 20.9 % active, barrier stalls 37 % (profiles/r2_ncu_source_solve_mma_top.txt)")
     if ph[2] > 0:
         pb = 3.0 * d1 * d2 * T * 2 / world
         others["projections (proj_mc_tile x2, proj_bt_list)"] = dict(ms=1e3 * ph[2], bound="hbm", algorithmic_bytes=pb, gbs=pb / ph[2] / 1e9,
@@ -525,7 +528,17 @@ def run_ours(args):
                                                                     note="three streaming passes over the resident uint16 video (SURVEY 8d: 3*d*T*2 B)")
     if ph[4] > 0:
         others["hals_temporal_kernel"] = dict(ms=1e3 * ph[4], bound="dependency chain (5 sweeps x overlapping-neuron chain of exact sequential OASIS fits)",
-                                              note="CNMFE_HALS_PROFILE=1 prints the critical chain; see profiles/README_r1.md")
+                                              note="CNMFE_HALS_PROFILE=1 prints the critical chain; see profiles/README_r2.md")
+    # `roofline` = the kernel with the largest share of the step; the other one goes under other_kernels
+    if solve_roof is not None and ph[1] >= gram_s:
+        roofline = solve_roof
+        others["ring_s2_tc_kernel"] = gram_roof
+    else:
+        roofline = gram_roof
+        if solve_roof is not None:
+            others["ring_solve_mma_kernel"] = solve_roof
+    roofline["hbm_iteration"] = dict(algorithmic_bytes=3.0 * d1 * d2 * T * 2 / world, gbs=3.0 * d1 * d2 * T * 2 / world / (t_max / args.steps) / 1e9,
+                                     peak_gbs=peaks.get("hbm_gbs", 6650.0))
     roofline["other_kernels"] = others
     # ---- CPU baseline, bounded sample, rank 0
     cores = os.cpu_count()

@@ -109,6 +109,7 @@ struct cnmfe_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr, ge0 = nullptr, ge1 = nullptr;
     float phase_ms[7] = {0, 0, 0, 0, 0, 0, 0};
     int last_gram_tensor = 0, last_gram_frames = 0;
+    long long last_active_pixels = 0;   // pixels whose ring weights the last background update refitted
     int use_c_hat = 1;            // update_temporal_parallel(obj, use_parallel, use_c_hat)
     int trace_major = 0;          // 1: K x T arrays cross the ABI trace-contiguous ([K][T]) instead of MATLAB column-major
     void* ssub_state = nullptr;   // SsubCtx (ctx_ssub.inc): coarse-grid ring model for options.bg_ssub > 1
@@ -692,6 +693,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
     for (float& f : c->phase_ms) f = 0;
     const int T = c->T;
     const bool flag_first = c->first_bg;
+    c->last_active_pixels = 0;
     for (int ip = 0; ip < c->npatch; ++ip) {
         Patch& P = c->patches[ip];
         if (!P.owned) continue;
@@ -809,6 +811,7 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
                         if (act[p]) alist.push_back(p);
                     }
         if (alist.empty()) { CNMFE_CUDA_OK(cudaStreamSynchronize(c->st2)); continue; }
+        c->last_active_pixels += (long long)alist.size();
         TAKE_OR_FAIL(d_alist, to_dev(c, alist));
         phase_end(c, 6);
         tick("bg active list");
@@ -1456,6 +1459,7 @@ extern "C" int cnmfe_debug_second_moments(cnmfe_ctx* c, int ip, int use_tensor, 
 }
 extern "C" int cnmfe_last_gram_was_tensor(cnmfe_ctx* c) { return c ? c->last_gram_tensor : 0; }
 extern "C" int cnmfe_last_gram_frames(cnmfe_ctx* c) { return c ? c->last_gram_frames : 0; }
+extern "C" long long cnmfe_last_active_pixels(cnmfe_ctx* c) { return c ? c->last_active_pixels : 0; }
 
 // sn = estimate_noise(obj, frame_range, 'psd') (@Sources2D/Sources2D.m:328-379) from the RESIDENT video: per-pixel GetSn
 // (OASIS_matlab/functions/GetSn.m) of the raw frames [f0, f1] (1-based inclusive) for every pixel of the owned patches.

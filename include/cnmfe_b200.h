@@ -237,6 +237,8 @@ int cnmfe_debug_second_moments(cnmfe_ctx* ctx, int ipatch, int use_tensor, doubl
 int cnmfe_last_gram_was_tensor(cnmfe_ctx* ctx);
 /* number of frames the last ring fit used (T, or ceil(T/k) with the frame stride k of fit_ring_model.m:84-90) */
 int cnmfe_last_gram_frames(cnmfe_ctx* ctx);
+/* number of pixels whose ring weights the last cnmfe_update_background refitted (ind_active of fit_ring_model.m:25-29) */
+long long cnmfe_last_active_pixels(cnmfe_ctx* ctx);
 /* rows of the resident video: out[i][0..T) = Y(block pixel idx[i], :) of block ipatch, idx = r + c*nr_block (0-based) */
 int cnmfe_debug_video_rows(cnmfe_ctx* ctx, int ipatch, int n, const int32_t* idx, uint16_t* out);
 /* the merged C_raw (update_temporal_parallel.m:269-280) as it entered the final deconvTemporal (before deconvTemporal.m:84
