@@ -75,8 +75,9 @@ def _disk_mask(d1, d2, centres, radius):
                          shape=(d1 * d2, len(centres)))
 
 
-def make_problem(d1, d2, T, K, seed):
-    """Global (all-rank) description: neurons, traces, background parameters.  SURVEY.md §8d recipe."""
+def make_problem(d1, d2, T, K, seed, kind="1p"):
+    """Global (all-rank) description: neurons, traces, background parameters.  SURVEY.md §8d recipe.
+    kind "2p" (configs[3]): rank-1 background b (x) f, b = 100 (1 + 0.5 blur_30(N(0,1)) / max|.|), f = 1 + 0.1 lowpass, noise 1."""
     from scipy.ndimage import gaussian_filter
     rng = np.random.default_rng(seed)
     centres = _place_centres(rng, d1, d2, K)
@@ -99,7 +100,14 @@ def make_problem(d1, d2, T, K, seed):
     A0.data = np.maximum(A0.data * (1 + 0.2 * rng.standard_normal(A0.data.size)), 0.0)
     C0 = C + rng.normal(0, 0.2, C.shape)
     IND = _disk_mask(d1, d2, centres, 8.5)
-    return dict(A=A, C=C, S=S, b0=b0, blob_centres=bc, f=f, A0=A0, C0=C0, IND=IND, centres=centres)
+    out = dict(A=A, C=C, S=S, b0=b0, blob_centres=bc, f=f, A0=A0, C0=C0, IND=IND, centres=centres, sn=10.0)
+    if kind == "2p":
+        fld = gaussian_filter(rng.standard_normal((d1, d2)), 30.0)
+        out["bgb"] = 100.0 * (1.0 + 0.5 * fld / np.abs(fld).max())
+        lp = gaussian_filter(rng.standard_normal(T + 900), 150.0)[450:450 + T]
+        out["bgf"] = 1.0 + 0.1 * lp / np.abs(lp).max()
+        out["b0"] = np.zeros((d1, d2)); out["blob_centres"] = bc[:0]; out["f"] = f[:0]; out["sn"] = 1.0
+    return out
 
 
 def build_block_on_gpu(prob, block, d1, T, seed, device, sn=10.0, chunk=500):
@@ -125,11 +133,20 @@ def build_block_on_gpu(prob, block, d1, T, seed, device, sn=10.0, chunk=500):
     for (br, bcc) in prob["blob_centres"]:
         g = torch.exp(-((rows[None, :] - br) ** 2 + (cols[:, None] - bcc) ** 2) / (2 * 60.0 ** 2))
         blobs.append(g.reshape(-1))
-    blobs = torch.stack(blobs, 1)          # (ncb*nrb, nblob)
+    blobs = torch.stack(blobs, 1) if blobs else None          # (ncb*nrb, nblob)
+    bgb = bgf = None
+    if "bgb" in prob:
+        bgb = torch.from_numpy(prob["bgb"][r0 - 1:r1, c0 - 1:c1].T.astype(np.float32).copy()).to(dev).reshape(-1, 1)
+        bgf = torch.from_numpy(prob["bgf"].astype(np.float32)).to(dev)
+    sn = float(prob.get("sn", sn))
     gen = torch.Generator(device=dev)
     for t0 in range(0, T, chunk):
         t1 = min(T, t0 + chunk)
-        X = torch.sparse.mm(A_t, C_t[:, t0:t1]) + blobs @ f_t[:, t0:t1] + b0_t.reshape(-1, 1)
+        X = torch.sparse.mm(A_t, C_t[:, t0:t1]) + b0_t.reshape(-1, 1)
+        if blobs is not None:
+            X = X + blobs @ f_t[:, t0:t1]
+        if bgb is not None:
+            X = X + bgb * bgf[None, t0:t1]
         X = X.reshape(ncb, nrb, t1 - t0)
         for j in range(ncb):
             gen.manual_seed(seed * 1000003 + (c0 - 1 + j) * 4099 + t0)
@@ -351,10 +368,18 @@ def run_ours(args):
         d1, d2, T, K, patch_dims, seed, scaling = 1024, 1024, args.frames or 20000, 1000, (256, 256), 20260925 + 3, "strong"
         if 16 % world:
             raise SystemExit("--workload c3 shards 16 patches: --gpus must divide 16")
+    elif args.workload == "c4":
+        # BASELINE.json configs[3]: synthetic 2p 512 x 512 x 50000, 200 neurons, rank-1 nmf background (demo_large_data_2p path), one patch
+        d1, d2, T, K, patch_dims, seed, scaling = 512, 512, args.frames or 50000, 200, (512, 512), 20260925 + 4, "weak"
+        if world != 1:
+            raise SystemExit("--workload c4 is a single-patch, single-GPU configuration")
     else:
         d1, d2, T, K, patch_dims, seed, scaling = D1, D2_PER_GPU * world, args.frames or T_FULL, K_PER_GPU * world, (D1, D2_PER_GPU), SEED, "weak"
-    prob = make_problem(d1, d2, T, K, seed)
+    c4 = args.workload == "c4"
+    prob = make_problem(d1, d2, T, K, seed, kind="2p" if c4 else "1p")
     opts = dict(spatial_algorithm="nnls", use_tensor_gram=bool(args.tensor), bg_ssub=args.bg_ssub)
+    if c4:
+        opts.update(background_model="nmf", nb=1, bg_ssub=1)
     obj = Sources2D(d1, d2, T, patch_dims, ring_radius=RING, device=local, rank=rank, world_size=world,
                     options=opts)
     for i in obj.owned_patches():
@@ -364,7 +389,7 @@ def run_ours(args):
         del blk
         torch.cuda.empty_cache()
     obj.A, obj.C = prob["A0"].copy(), prob["C0"].copy()
-    obj.P["sn"] = np.full((d1, d2), 10.0)
+    obj.P["sn"] = np.full((d1, d2), float(prob["sn"]))
     IND = prob["IND"]
 
     def barrier():
@@ -470,7 +495,7 @@ def run_ours(args):
     checks = None
     if rank == 0:
         checks = full_size_invariants(obj.A, IND, obj.C, obj.S, obj.P.get("kernel_pars"), obj.P.get("neuron_sn"))
-        if world == 1 and not args.no_oracle_checks:
+        if world == 1 and not args.no_oracle_checks and not c4:
             checks["oracle"] = full_size_oracle_checks(obj, IND)
             checks["ok"] = bool(checks.get("ok", False) and checks["oracle"].get("ok", False))
     # bytes the Sources2D mirror actually moved (it re-sends only host state that changed since the last sync)
@@ -529,6 +554,14 @@ def run_ours(args):
     if ph[4] > 0:
         others["hals_temporal_kernel"] = dict(ms=1e3 * ph[4], bound="dependency chain (5 sweeps x overlapping-neuron chain of exact sequential OASIS fits)",
                                               note="CNMFE_HALS_PROFILE=1 prints the critical chain; see profiles/README_r2.md")
+    if c4:
+        iters = int(lib.cnmfe_last_nmf_iterations(obj._h))
+        nb_bytes = (2.0 * iters + 1.0) * d1 * d2 * T * 2.0         # two streaming passes per ALS iteration + the ||B||^2 pass, u16 video
+        gram_roof = dict(bound="hbm", kernel="nmf background fit: matrix-free ALS on the resident video (proj_mc_tile + svd_colsum_partial per iteration)",
+                         achieved=nb_bytes / gram_s / 1e9, peak=peaks.get("hbm_gbs", 6650.0), unit="GB/s", frac=nb_bytes / gram_s / 1e9 / peaks.get("hbm_gbs", 6650.0),
+                         traffic=None, peak_source="hbm_gbs of MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s", ms_per_launch=1e3 * gram_s,
+                         algorithmic_bytes_per_launch=nb_bytes, als_iterations=iters)
+        solve_roof = None
     # `roofline` = the kernel with the largest share of the step; the other one goes under other_kernels
     if solve_roof is not None and ph[1] >= gram_s:
         roofline = solve_roof
@@ -552,7 +585,7 @@ def run_ours(args):
                 n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * t_max / args.steps,
                 higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="f64 (exact int64 second moments from the u16 video)",
                 data="synthetic",
-                config=dict(workload=("configs[2]" if args.workload == "c3" else "configs[1]") + ": synthetic 1p %dx%dx%d uint16, %d neurons, ring-BG r=18 (120 nbrs, bg_ssub=BGSSUB), %dx%d patches (%d per GPU, 19-px halo blocks), nnls spatial, foopsi/ar1 OASIS (smin=-5, optimize_pars, optimize_b)".replace("BGSSUB", str(args.bg_ssub)) % (d1, d2, T, K, patch_dims[0], patch_dims[1], len(obj.owned_patches())),
+                config=dict(workload=({"c3": "configs[2]", "c4": "configs[3] (2p, rank-1 nmf background instead of the ring)"}.get(args.workload, "configs[1]")) + ": synthetic %dx%dx%d uint16, %d neurons, ring-BG r=18 (120 nbrs, bg_ssub=BGSSUB), %dx%d patches (%d per GPU, 19-px halo blocks), nnls spatial, foopsi/ar1 OASIS (smin=-5, optimize_pars, optimize_b)".replace("BGSSUB", str(args.bg_ssub)) % (d1, d2, T, K, patch_dims[0], patch_dims[1], len(obj.owned_patches())),
                             patches=dict(grid=[int(obj.nr_patch), int(obj.nc_patch)], owned_by_rank0=[int(x) for x in obj.owned_patches()],
                                          gram_tensor=bool(lib.cnmfe_last_gram_was_tensor(obj._h))),
                             l2="inputs (%.1f GB resident video per GPU) larger than L2; no flush needed" % (float(sum(int(b[1] - b[0] + 1) * int(b[3] - b[2] + 1) for b in nblk)) * T * 2 / 1e9),
@@ -673,7 +706,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-oracle-checks", action="store_true", help="skip the post-timing oracle spot checks of the full-size results")
     ap.add_argument("--bg-ssub", type=int, default=1, help="options.bg_ssub of the ring model (configs[1] is quoted at 1)")
-    ap.add_argument("--workload", default="iteration", choices=["iteration", "c3", "oasis"])
+    ap.add_argument("--workload", default="iteration", choices=["iteration", "c3", "c4", "oasis"])
     ap.add_argument("--oasis-traces", type=int, default=5000)
     ap.add_argument("--oasis-frames", type=int, default=100000)
     args = ap.parse_args()

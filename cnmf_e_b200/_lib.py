@@ -96,6 +96,7 @@ SYMBOLS = {
     "cnmfe_last_gram_was_tensor": (I, [V]),
     "cnmfe_last_gram_frames": (I, [V]),
     "cnmfe_last_active_pixels": (ctypes.c_longlong, [V]),
+    "cnmfe_last_nmf_iterations": (I, [V]),
     "cnmfe_debug_video_rows": (I, [V, I, I, V, V]),
     "cnmfe_get_merged_craw": (I, [V, V]),
     "cnmfe_estimate_noise": (I, [V, I, I, V]),

@@ -110,6 +110,7 @@ struct cnmfe_ctx {
     float phase_ms[7] = {0, 0, 0, 0, 0, 0, 0};
     int last_gram_tensor = 0, last_gram_frames = 0;
     long long last_active_pixels = 0;   // pixels whose ring weights the last background update refitted
+    int last_nmf_iters = 0;             // ALS iterations of the last nmf background fit (summed over the owned patches)
     int use_c_hat = 1;            // update_temporal_parallel(obj, use_parallel, use_c_hat)
     int trace_major = 0;          // 1: K x T arrays cross the ABI trace-contiguous ([K][T]) instead of MATLAB column-major
     void* ssub_state = nullptr;   // SsubCtx (ctx_ssub.inc): coarse-grid ring model for options.bg_ssub > 1
@@ -1460,6 +1461,7 @@ extern "C" int cnmfe_debug_second_moments(cnmfe_ctx* c, int ip, int use_tensor, 
 extern "C" int cnmfe_last_gram_was_tensor(cnmfe_ctx* c) { return c ? c->last_gram_tensor : 0; }
 extern "C" int cnmfe_last_gram_frames(cnmfe_ctx* c) { return c ? c->last_gram_frames : 0; }
 extern "C" long long cnmfe_last_active_pixels(cnmfe_ctx* c) { return c ? c->last_active_pixels : 0; }
+extern "C" int cnmfe_last_nmf_iterations(cnmfe_ctx* c) { return c ? c->last_nmf_iters : 0; }
 
 // sn = estimate_noise(obj, frame_range, 'psd') (@Sources2D/Sources2D.m:328-379) from the RESIDENT video: per-pixel GetSn
 // (OASIS_matlab/functions/GetSn.m) of the raw frames [f0, f1] (1-based inclusive) for every pixel of the owned patches.

@@ -239,6 +239,8 @@ int cnmfe_last_gram_was_tensor(cnmfe_ctx* ctx);
 int cnmfe_last_gram_frames(cnmfe_ctx* ctx);
 /* number of pixels whose ring weights the last cnmfe_update_background refitted (ind_active of fit_ring_model.m:25-29) */
 long long cnmfe_last_active_pixels(cnmfe_ctx* ctx);
+/* alternating-least-squares iterations the last nmf background fit took (nnmf stops on its TolX / TolFun tests), summed over patches */
+int cnmfe_last_nmf_iterations(cnmfe_ctx* ctx);
 /* rows of the resident video: out[i][0..T) = Y(block pixel idx[i], :) of block ipatch, idx = r + c*nr_block (0-based) */
 int cnmfe_debug_video_rows(cnmfe_ctx* ctx, int ipatch, int n, const int32_t* idx, uint16_t* out);
 /* the merged C_raw (update_temporal_parallel.m:269-280) as it entered the final deconvTemporal (before deconvTemporal.m:84
