@@ -64,6 +64,11 @@ struct Patch {
     // local view of A_prev on the block (SEL_SUM_BLOCK, ROWS_BLOCK): built by the ring BG update (A_prev = A there) and reused
     // by the spatial and temporal updates of the same iteration
     LocalSparse lp_cache; bool lp_valid = false;
+    // centred projections M = (Y - Ybar) * Cc' computed by the ring BG update (all frames), kept for the spatial update of the same
+    // iteration: C does not change in between (demo_large_data_1p.m:199-201), so the spatial update would stream the video again for
+    // the very same numbers.  [db][mc_K] doubles; valid while c->C_version == mc_Cver.
+    double* Mcache = nullptr; size_t Mcache_cap = 0; bool mc_valid = false; unsigned long long mc_Cver = 0;
+    int mc_K = 0; std::vector<int> mc_ids, mc_bbox;
 };
 
 // Local (per patch) sparse view of a d x K matrix.
@@ -110,6 +115,7 @@ struct cnmfe_ctx {
     float phase_ms[7] = {0, 0, 0, 0, 0, 0, 0};
     int last_gram_tensor = 0, last_gram_frames = 0;
     long long last_active_pixels = 0;   // pixels whose ring weights the last background update refitted
+    unsigned long long C_version = 1;   // bumped whenever the device copy of obj.C changes (guards Patch::Mcache)
     int last_nmf_iters = 0;             // ALS iterations of the last nmf background fit (summed over the owned patches)
     int use_c_hat = 1;            // update_temporal_parallel(obj, use_parallel, use_c_hat)
     int trace_major = 0;          // 1: K x T arrays cross the ABI trace-contiguous ([K][T]) instead of MATLAB column-major
@@ -162,6 +168,7 @@ int ensure_K(cnmfe_ctx* c, int K) {
     for (double** p : {&c->den, &c->kpars, &c->nsn, &c->outs}) { if (*p) cudaFree(*p); *p = nullptr; }
     if (c->d_done) cudaFree(c->d_done);
     if (c->d_order) cudaFree(c->d_order);
+    ++c->C_version;
     CNMFE_CUDA_OK(cudaMalloc((void**)&c->C, n * 8));
     CNMFE_CUDA_OK(cudaMalloc((void**)&c->Craw, n * 8));
     CNMFE_CUDA_OK(cudaMalloc((void**)&c->S, n * 8));
@@ -443,7 +450,7 @@ extern "C" void cnmfe_destroy(cnmfe_ctx* c) {
     cudaSetDevice(c->device);
     ssub_destroy(c);
     for (Patch& P : c->patches) {
-        for (void* p : {(void*)P.Yt, (void*)P.hi, (void*)P.lo, (void*)P.hi_k, (void*)P.lo_k, (void*)P.Ysum, (void*)P.Ymean, (void*)P.W, (void*)P.b0, (void*)P.bsvd, (void*)P.fsvd})
+        for (void* p : {(void*)P.Yt, (void*)P.hi, (void*)P.lo, (void*)P.hi_k, (void*)P.lo_k, (void*)P.Ysum, (void*)P.Ymean, (void*)P.W, (void*)P.b0, (void*)P.bsvd, (void*)P.fsvd, (void*)P.Mcache})
             if (p) cudaFree(p);
     }
     for (void* p : {(void*)c->C, (void*)c->Cprev, (void*)c->Craw, (void*)c->S, (void*)c->num, (void*)c->den,
@@ -540,6 +547,7 @@ extern "C" int cnmfe_set_neurons(cnmfe_ctx* c, int K, const int64_t* jc, const i
     if (K != c->K) { c->have_spatial = false; }
     c->K = K;
     if (ensure_K(c, K)) return -1;
+    if (!keepC) ++c->C_version;
     return keepC ? 0 : upload_KT(c, C, K, c->C);
 }
 
@@ -828,6 +836,20 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
             CNMFE_CUDA_OK(cudaMemsetAsync(d_N, 0, (size_t)P.db * Kb * 8, c->st));
             launch_proj_mc(c->st, P.Yt, P.Ymean, P.nrb, P.ncb, T, c->Tpad,
                    kf, d_Cc, Kb, d_bbox, d_N);
+            P.mc_valid = false;
+            const size_t mc_n = (size_t)P.db * Kb;
+            if (kf == 1 && mc_n * 8 <= ((size_t)6 << 30) && !getenv("CNMFE_NO_PROJ_CACHE")) {
+                if (mc_n > P.Mcache_cap) {
+                    if (P.Mcache) cudaFree(P.Mcache);
+                    P.Mcache = nullptr; P.Mcache_cap = 0;
+                    if (cudaMalloc((void**)&P.Mcache, (mc_n + mc_n / 16) * 8) == cudaSuccess) P.Mcache_cap = mc_n + mc_n / 16;
+                    else (void)cudaGetLastError();
+                }
+                if (P.Mcache) {
+                    CNMFE_CUDA_OK(cudaMemcpyAsync(P.Mcache, d_N, mc_n * 8, cudaMemcpyDeviceToDevice, c->st));
+                    P.mc_valid = true; P.mc_Cver = c->C_version; P.mc_K = Kb; P.mc_ids = L.ids; P.mc_bbox = bb;
+                }
+            }
             LAUNCH(ring_make_N_kernel, P.db, 64, 0, c->st, d_N, Kb, d_ptr, d_col, d_val, d_Vsel, (size_t)P.db);
         }
         phase_end(c, 2);
@@ -1063,8 +1085,25 @@ extern "C" int cnmfe_update_spatial_ex(cnmfe_ctx* c, int update_sn) {
         phase_begin(c);
         CNMFE_CUDA_OK(cudaMemsetAsync(d_D, 0, (size_t)P.db * Ks * 8, c->st));
         {
-            launch_proj_mc(c->st, P.Yt, P.Ymean, P.nrb, P.ncb, T, c->Tpad, 1,
-                   d_Cc, Ks, d_bbox, d_D);
+            // the BG update of this iteration projected the same centred traces on a larger box around every neuron: reuse it
+            bool cached = P.mc_valid && P.mc_Cver == c->C_version && !ssub;
+            std::vector<int> kmap(Ks, -1);
+            for (int k = 0; cached && k < Ks; ++k) {
+                const auto it = std::lower_bound(P.mc_ids.begin(), P.mc_ids.end(), LS.ids[k]);
+                if (it == P.mc_ids.end() || *it != LS.ids[k]) { cached = false; break; }
+                const int kb = (int)(it - P.mc_ids.begin());
+                const int* sb = &bb[4 * k]; const int* cb = &P.mc_bbox[4 * kb];
+                if (sb[1] >= sb[0] && (sb[0] < cb[0] || sb[1] > cb[1] || sb[2] < cb[2] || sb[3] > cb[3])) { cached = false; break; }
+                kmap[k] = kb;
+            }
+            if (cached) {
+                TAKE_OR_FAIL(d_kmap, to_dev(c, kmap));
+                dim3 gg((unsigned)P.db, (Ks + 127) / 128);
+                LAUNCH(proj_from_cache_kernel, gg, 128, 0, c->st, P.Mcache, P.mc_K, d_kmap, d_bbox, P.nrb, Ks, d_D);
+            } else {
+                launch_proj_mc(c->st, P.Yt, P.Ymean, P.nrb, P.ncb, T, c->Tpad, 1,
+                       d_Cc, Ks, d_bbox, d_D);
+            }
         }
         if (Kp > 0) LAUNCH(spatial_make_D_kernel, P.db, 64, 0, c->st, d_D, Ks, d_pptr, d_pcol, d_pval, d_P2);
         if (!ssub) {
@@ -1325,6 +1364,7 @@ extern "C" int cnmfe_update_temporal_finish(cnmfe_ctx* c) {
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
     const int T = c->T, K = c->K;
     if (K == 0) return 0;
+    ++c->C_version;
     phase_begin(c);
     { dim3 gg((T + 255) / 256, K); LAUNCH(temporal_divide_kernel, gg, 256, 0, c->st, c->num, c->den, K, T); }
     if (c->opt.deconv_flag) {
@@ -1353,6 +1393,7 @@ extern "C" int cnmfe_update_temporal_finish_part(cnmfe_ctx* c, int k0, int k1) {
     const int T = c->T, K = c->K;
     if (K == 0) return 0;
     if (k0 < 0 || k1 > K || k0 > k1) { set_error("cnmfe_update_temporal_finish_part: range [%d, %d) outside [0, %d)", k0, k1, K); return -1; }
+    ++c->C_version;
     phase_begin(c);
     const int n = k1 - k0;
     for (double* buf : {c->C, c->Craw, c->S}) {
@@ -1380,6 +1421,7 @@ extern "C" int cnmfe_update_temporal_finish_part(cnmfe_ctx* c, int k0, int k1) {
 // device buffers of obj.C, obj.C_raw, obj.S (K x T each, trace contiguous) and of the 6 per-trace outputs (K x 6)
 extern "C" int cnmfe_temporal_state_buffers(cnmfe_ctx* c, double** C_dev, double** Craw_dev, double** S_dev, double** outs_dev) {
     if (!c || !C_dev || !Craw_dev || !S_dev || !outs_dev) { set_error("cnmfe_temporal_state_buffers: null"); return -1; }
+    ++c->C_version;      // the caller is about to write into C (cross-rank exchange)
     *C_dev = c->C; *Craw_dev = c->Craw; *S_dev = c->S; *outs_dev = c->outs;
     return 0;
 }

@@ -461,6 +461,19 @@ proj_bt_list_kernel(const uint16_t* __restrict__ Yt, const double* __restrict__ 
     }
 }
 
+// D[q][k] = Mc[q][kmap[k]] inside neuron k's box (block coordinates r0 r1 c0 c1), untouched (zero) elsewhere: the centred
+// projections of the spatial update taken from the ones the background update of the same iteration computed
+__global__ void proj_from_cache_kernel(const double* __restrict__ Mc, int Kb, const int* __restrict__ kmap, const int* __restrict__ bbox,
+                                       int nrb, int Ks, double* __restrict__ D) {
+    const size_t q = blockIdx.x;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    if (k >= Ks) return;
+    const int r = (int)(q % nrb), c = (int)(q / nrb);
+    const int* b = bbox + 4 * k;
+    if (r < b[0] || r > b[1] || c < b[2] || c > b[3]) return;
+    D[q * Ks + k] = Mc[q * Kb + kmap[k]];
+}
+
 // host-side dispatch: the tiled kernels cover the all-frames case; frame-subsampled fits (kf > 1) and odd T use the
 // warp-per-pixel-group kernels above
 inline void launch_proj_mc(cudaStream_t st, const uint16_t* Yt, const double* Ymean, int nrb, int ncb, int T, int Tpad,
