@@ -483,8 +483,8 @@ extern "C" int cnmfe_set_options(cnmfe_ctx* c, const cnmfe_options* o) {
 
 static int upload_common(cnmfe_ctx* c, int ip, const void* Y, int dtype, bool on_device) {
     if (!c || ip < 0 || ip >= c->npatch || !Y) { set_error("cnmfe_upload_block: bad arguments"); return -1; }
-    if (dtype != 0 && dtype != 1) {
-        set_error("cnmfe_upload_block: dtype %d unsupported (0 = uint8, 1 = uint16); the exact-integer path needs an integer video", dtype);
+    if (dtype < 0 || dtype > 3) {
+        set_error("cnmfe_upload_block: dtype %d unsupported (0 = uint8, 1 = uint16, 2 = single, 3 = double holding integer counts)", dtype);
         return -1;
     }
     CNMFE_CUDA_OK(cudaSetDevice(c->device));
@@ -502,10 +502,14 @@ static int upload_common(cnmfe_ctx* c, int ip, const void* Y, int dtype, bool on
     CNMFE_CUDA_OK(cudaMemsetAsync(P.Yt, 0, n * 2, c->st));
     CNMFE_CUDA_OK(cudaMemsetAsync(P.hi, 0, n, c->st));
     CNMFE_CUDA_OK(cudaMemsetAsync(P.lo, 0, n, c->st));
-    const size_t esz = dtype == 0 ? 1 : 2;
+    const size_t esz = dtype == 0 ? 1 : (dtype == 1 ? 2 : (dtype == 2 ? 4 : 8));
     const int chunk = 256;
-    void* stage = nullptr;
+    void* stage = nullptr; uint16_t* conv = nullptr;
     if (!on_device) CNMFE_CUDA_OK(cudaMalloc(&stage, (size_t)chunk * P.db * esz));
+    if (dtype >= 2) {      // integer counts stored as floating point: exact conversion, anything else is refused below
+        CNMFE_CUDA_OK(cudaMalloc((void**)&conv, (size_t)chunk * P.db * 2));
+        CNMFE_CUDA_OK(cudaMemsetAsync(c->d_err, 0, 4, c->st));
+    }
     for (int t0 = 0; t0 < c->T; t0 += chunk) {
         int nf = std::min(chunk, c->T - t0);
         const char* src = (const char*)Y + (size_t)t0 * P.db * esz;
@@ -515,9 +519,27 @@ static int upload_common(cnmfe_ctx* c, int ip, const void* Y, int dtype, bool on
             dsrc = stage;
         }
         dim3 g((P.db + 31) / 32, (nf + 31) / 32), b(32, 8);
+        if (dtype >= 2) {
+            const size_t n1 = (size_t)nf * P.db;
+            if (dtype == 2) LAUNCH(float_to_u16_kernel<float>, (unsigned)((n1 + 255) / 256), 256, 0, c->st, (const float*)dsrc, n1, conv, c->d_err);
+            else LAUNCH(float_to_u16_kernel<double>, (unsigned)((n1 + 255) / 256), 256, 0, c->st, (const double*)dsrc, n1, conv, c->d_err);
+            dsrc = conv;
+        }
         if (dtype == 0) LAUNCH(transpose_chunk_kernel<uint8_t>, g, b, 0, c->st, (const uint8_t*)dsrc, P.db, nf, t0, c->Tpad, P.Yt, P.hi, P.lo);
         else LAUNCH(transpose_chunk_kernel<uint16_t>, g, b, 0, c->st, (const uint16_t*)dsrc, P.db, nf, t0, c->Tpad, P.Yt, P.hi, P.lo);
         if (!on_device) CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+    }
+    if (dtype >= 2) {
+        int bad = 0;
+        CNMFE_CUDA_OK(cudaMemcpyAsync(&bad, c->d_err, 4, cudaMemcpyDeviceToHost, c->st));
+        CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+        cudaFree(conv);
+        if (bad) {
+            if (stage) cudaFree(stage);
+            set_error("cnmfe_upload_block: the floating-point video holds values that are not integers in [0, 65535]; the exact path "
+                      "works on integer counts (convert or rescale the movie to uint16 first)");
+            return -1;
+        }
     }
     LAUNCH(row_sum_kernel, (P.db * 32 + 255) / 256, 256, 0, c->st, P.Yt, P.db, c->T, c->Tpad, P.Ysum);
     CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));

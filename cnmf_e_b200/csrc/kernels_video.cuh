@@ -28,6 +28,17 @@ __global__ void transpose_chunk_kernel(const TIN* __restrict__ src, int d, int n
     }
 }
 
+// float / double frames holding integer counts (distribute_data.m:144-147 keeps the source class, which may be 'single'):
+// exact conversion to uint16, with a flag raised for any value that is not an integer in [0, 65535] (or NaN)
+template <typename TIN>
+__global__ void float_to_u16_kernel(const TIN* __restrict__ src, size_t n, uint16_t* __restrict__ dst, int* __restrict__ bad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = (double)src[i];
+    if (!(v >= 0.0 && v <= 65535.0) || v != floor(v)) { atomicExch(bad, 1); dst[i] = 0; return; }
+    dst[i] = (uint16_t)v;
+}
+
 // Frame-subsampled byte planes for the tensor-core second moments when fit_ring_model.m:84-90 keeps every kf-th frame:
 // hi_k/lo_k[q][j] = bytes of Yt[q][j * kf], j < Tk; columns Tk .. Tpadk-1 are zero.  grid = (d, ceil(Tpadk/256)).
 __global__ void subsample_planes_kernel(const uint16_t* __restrict__ Yt, int Tpad, int kf, int Tk, int Tpadk,

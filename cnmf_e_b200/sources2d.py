@@ -267,9 +267,10 @@ class Sources2D:
         """Y: (d1,d2,T) uint8/uint16 array (numpy).  Uploads the blocks of the owned patches (get_patch_data.m with
         with_overlap=true) and keeps them resident."""
         Y = np.asarray(Y)
-        if Y.dtype not in (np.uint8, np.uint16):
-            raise L.CnmfeError("video dtype %s unsupported: the exact-integer path takes uint8/uint16" % Y.dtype)
-        dt = 0 if Y.dtype == np.uint8 else 1
+        codes = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2, np.dtype(np.float64): 3}
+        if Y.dtype not in codes:
+            raise L.CnmfeError("video dtype %s unsupported: uint8 / uint16, or single / double holding integer counts" % Y.dtype)
+        dt = codes[Y.dtype]
         for i in self.owned_patches():
             b = self.block_of(i)
             blk = Y[b[0] - 1:b[1], b[2] - 1:b[3], :]

@@ -105,7 +105,8 @@ int cnmfe_set_options(cnmfe_ctx* ctx, const cnmfe_options* opts);
 
 /* get_patch_data(mat_data, patch_pos, frame_range, true) (endoscope/get_patch_data.m:1): hand the block of patch
  * `ipatch` (nr_block x nc_block x T, column-major, native dtype) to the device once; it stays resident.
- * dtype: 0 = uint8, 1 = uint16 (the dtypes distribute_data.m:144-147 writes for the demos). */
+ * dtype: 0 = uint8, 1 = uint16 (the dtypes distribute_data.m:144-147 writes for the demos), 2 = single, 3 = double -- accepted when
+ * every value is an integer count in [0, 65535] (converted exactly; the source class of a TIFF may be 'single'), refused otherwise. */
 int cnmfe_upload_block(cnmfe_ctx* ctx, int ipatch, const void* Y, int dtype);
 /* same, Y already in device memory (frame-major nr_block*nc_block per frame, as MATLAB lays it out) */
 int cnmfe_upload_block_dev(cnmfe_ctx* ctx, int ipatch, const void* Y_dev, int dtype);

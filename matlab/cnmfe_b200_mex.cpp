@@ -91,8 +91,8 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         for (size_t i = 0; i < g_live.size(); ++i)
             if (g_live[i] == h) { g_live.erase(g_live.begin() + i); cnmfe_destroy(h); mexUnlock(); break; }
     } else if (c == "upload_block") {   // upload_block(h, ipatch0, Yblock)  Yblock: nr_b x nc_b x T uint8/uint16
-        int dt = mxIsUint8(prhs[3]) ? 0 : (mxIsUint16(prhs[3]) ? 1 : -1);
-        if (dt < 0) mexErrMsgIdAndTxt("cnmfe:dtype", "video must be uint8 or uint16");
+        int dt = mxIsUint8(prhs[3]) ? 0 : (mxIsUint16(prhs[3]) ? 1 : (mxIsSingle(prhs[3]) ? 2 : (mxIsDouble(prhs[3]) ? 3 : -1)));
+        if (dt < 0) mexErrMsgIdAndTxt("cnmfe:dtype", "video must be uint8, uint16, or single/double holding integer counts");
         check(cnmfe_upload_block(ctx_of(prhs[1]), (int)mxGetScalar(prhs[2]), mxGetData(prhs[3]), dt), "upload_block");
     } else if (c == "set_neurons" || c == "set_prev") {   // (h, A sparse d x K, C K x T)
         std::vector<int64_t> jc, ir;

@@ -242,3 +242,25 @@ def test_ring_solvers_agree(built_lib, monkeypatch):
         gpu.close()
     scale = np.abs(res["simt"]).max()
     assert np.abs(res["mma"] - res["simt"]).max() <= 1e-9 * scale
+
+
+def test_float_video_with_integer_counts(built_lib):
+    """distribute_data.m:144-147 keeps the source class of the movie, which may be 'single': a floating-point video holding
+    integer counts is converted exactly (same results as the uint16 movie); anything else is refused, never rounded."""
+    from cnmf_e_b200.sources2d import Sources2D
+    from cnmf_e_b200 import _lib as LL
+    D = GC.synthetic("no_neurons")
+    d1, d2, T = D["Y"].shape
+    res = []
+    for Y in (D["Y"], D["Y"].astype(np.float32), D["Y"].astype(np.float64)):
+        g = Sources2D(d1, d2, T, (d1, d2), ring_radius=6)
+        g.load_video(Y)
+        g.A, g.C = D["A0"].copy(), D["C0"].copy()
+        g.update_background_parallel()
+        res.append(np.array(g.W[0], copy=True))
+        g.close()
+    assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
+    g = Sources2D(d1, d2, T, (d1, d2), ring_radius=6)
+    with pytest.raises(LL.CnmfeError):
+        g.load_video(D["Y"].astype(np.float32) + 0.25)
+    g.close()
