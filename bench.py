@@ -492,6 +492,14 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
     e2e_val = float(d1) * d2 * T / float(te_t.item())
+    # per-rank wall / phase times (multi-GPU: where the step waits -- the merge collective runs at the pace of the slowest rank)
+    per_rank = None
+    if world > 1:
+        mine = dict(rank=rank, call_wall_ms=[float(x) / args.steps for x in call_ms], phase_ms=[float(x) / args.steps for x in phases],
+                    device_ms=1e3 * t_dev / args.steps, wall_ms=1e3 * wall / args.steps)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = gathered
     checks = None
     if rank == 0:
         checks = full_size_invariants(obj.A, IND, obj.C, obj.S, obj.P.get("kernel_pars"), obj.P.get("neuron_sn"))
@@ -589,7 +597,7 @@ def run_ours(args):
                             patches=dict(grid=[int(obj.nr_patch), int(obj.nc_patch)], owned_by_rank0=[int(x) for x in obj.owned_patches()],
                                          gram_tensor=bool(lib.cnmfe_last_gram_was_tensor(obj._h))),
                             l2="inputs (%.1f GB resident video per GPU) larger than L2; no flush needed" % (float(sum(int(b[1] - b[0] + 1) * int(b[3] - b[2] + 1) for b in nblk)) * T * 2 / 1e9),
-                            full_size_checks=checks,
+                            full_size_checks=checks, per_rank=per_rank,
                             seed=SEED, device_ms_per_step=1e3 * t_dev / args.steps, wall_ms_per_step=1e3 * wall / args.steps,
                             call_wall_ms_per_step=dict(zip(["update_background", "update_spatial", "update_temporal"], [float(x) / args.steps for x in call_ms])),
                             phase_ms_per_step=dict(zip(["gram", "ring_solve", "projections", "spatial_solve", "temporal_sweeps", "deconvTemporal", "other"],
