@@ -27,7 +27,8 @@ class Options(ctypes.Structure):
     _fields_ = [("spatial_algorithm", ctypes.c_int), ("maxIter_temporal", ctypes.c_int),
                 ("deconv_flag", ctypes.c_int), ("bg_acceleration", ctypes.c_int),
                 ("replicate_spatial_aprev_quirk", ctypes.c_int), ("use_tensor_gram", ctypes.c_int),
-                ("deconv", DeconvOpts), ("background_model", ctypes.c_int), ("nb", ctypes.c_int), ("bg_ssub", ctypes.c_int)]
+                ("deconv", DeconvOpts), ("background_model", ctypes.c_int), ("nb", ctypes.c_int), ("bg_ssub", ctypes.c_int),
+                ("thresh_outlier", ctypes.c_double)]
 
 
 class CnmfeError(RuntimeError):

@@ -476,6 +476,9 @@ extern "C" int cnmfe_set_options(cnmfe_ctx* c, const cnmfe_options* o) {
     if (o->background_model < 0 || o->background_model > 2) { set_error("background_model must be 0 (ring), 1 (svd) or 2 (nmf)"); return -1; }
     if (o->background_model >= 1 && (o->nb < 1 || o->nb > SVD_MAXNB)) { set_error("svd background: nb must be in 1..%d", SVD_MAXNB); return -1; }
     if (o->bg_ssub < 1 || o->bg_ssub > 8) { set_error("bg_ssub must be in 1..8"); return -1; }
+    if (!std::isnan(o->thresh_outlier) && (o->background_model != 0 || o->bg_ssub != 1)) {
+        set_error("thresh_outlier is built for the ring model with bg_ssub = 1 (leave it NaN, the CNMFSetParms default, otherwise)"); return -1;
+    }
     if (o->background_model == 0) { CNMFE_CUDA_OK(cudaSetDevice(c->device)); if (ssub_configure(c, o->bg_ssub)) return -1; }
     c->opt = *o;
     return 0;
@@ -690,6 +693,9 @@ extern "C" int cnmfe_last_phase_ms(cnmfe_ctx* c, float* ms7) {
 static size_t bg_scratch_bytes(const cnmfe_ctx* c, const Patch& P, int Kb, size_t nnzA) {
     size_t ND = (size_t)ring_num_disp(c->rr);
     size_t b = 0;
+    if (!std::isnan(c->opt.thresh_outlier))      // explicit path: Bf [db][T], a chunk of explicit rows, masks, zero vectors
+        b += pad256((size_t)P.db * c->T * 8) + pad256((size_t)1024 * c->T * 8) + 4 * pad256((size_t)(P.db + 1) * 8) + 2 * pad256((size_t)c->T * 4) +
+             pad256((size_t)P.dp * 8) + (1 << 20);
     b += pad256(ND * P.db * 8);                 // S2
     b += pad256((size_t)P.db * std::max(Kb, 1) * 8);   // Mc / N
     b += pad256((size_t)std::max(Kb, 1) * c->T * 8);   // Cc
@@ -761,7 +767,12 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         const size_t ND = (size_t)ring_num_disp(c->rr);
         double* d_S2 = c->scr.take<double>(ND * P.db);
         if (!d_S2) { set_error("scratch exhausted"); return -1; }
-        {
+        const bool outlier = !std::isnan(c->opt.thresh_outlier);    // explicit fp64 path (fit_ring_model.m:48-70), moments computed below
+        if (outlier) {
+            CNMFE_CUDA_OK(cudaEventRecord(c->ge0, c->st2));
+            CNMFE_CUDA_OK(cudaEventRecord(c->ge1, c->st2));
+            c->last_gram_tensor = 0;
+        } else {
             CNMFE_CUDA_OK(cudaEventRecord(c->ge0, c->st2));
             int tc_rc = 1;
             if (c->opt.use_tensor_gram && kf == 1)
@@ -847,11 +858,87 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         phase_end(c, 6);
         tick("bg active list");
         CNMFE_CUDA_OK(cudaStreamWaitEvent(c->st, c->ge1, 0));   // what follows needs the SMs (and then the moments)
+        // ---- options.thresh_outlier: explicit Bf, clamp against the previous fit, frame selection, fp64 moments
+        const double* S2_use = d_S2; const double* S1_use = nullptr; const double* Ym_use = P.Ymean;
+        const int* aptr_use = d_ptr; int K_use = Kb; double nsel_use = 0.0;
+        if (outlier) {
+            phase_begin(c);
+            if (Kb > YSIG_MAXK) { set_error("update_background: %d neurons touch block %d (the thresh_outlier path handles <= %d)", Kb, ip, YSIG_MAXK); return -1; }
+            const int CH = 1024;
+            TAKE_OR_FAIL(d_Bf, c->scr.take<double>((size_t)P.db * T));
+            TAKE_OR_FAIL(d_rowsY, c->scr.take<double>((size_t)CH * T));
+            TAKE_OR_FAIL(d_rows, c->scr.take<int>(CH));
+            TAKE_OR_FAIL(d_zero, c->scr.take<double>(P.db + 1));
+            TAKE_OR_FAIL(d_zptr, c->scr.take<int>(P.db + 1));
+            TAKE_OR_FAIL(d_S1x, c->scr.take<double>(P.db));
+            TAKE_OR_FAIL(d_cnt, c->scr.take<int>(T));
+            TAKE_OR_FAIL(d_mask, c->scr.take<unsigned char>(T));
+            std::vector<double> snp(P.dp);
+            for (int p = 0; p < P.dp; ++p) snp[p] = c->sn[(size_t)(p / P.nr + P.patch.c0) * c->d1 + (p % P.nr + P.patch.r0)];
+            TAKE_OR_FAIL(d_snp, to_dev(c, snp));
+            CNMFE_CUDA_OK(cudaMemsetAsync(d_zero, 0, (size_t)(P.db + 1) * 8, c->st));
+            CNMFE_CUDA_OK(cudaMemsetAsync(d_zptr, 0, (size_t)(P.db + 1) * 4, c->st));
+            CNMFE_CUDA_OK(cudaMemsetAsync(d_cnt, 0, (size_t)T * 4, c->st));
+            CNMFE_CUDA_OK(cudaMemsetAsync(d_S2, 0, ND * P.db * 8, c->st));
+            for (int q0 = 0; q0 < P.db; q0 += 32768) {
+                dim3 gg((T + 255) / 256, std::min(32768, P.db - q0));
+                LAUNCH(bf_rows_kernel, gg, 256, 0, c->st, P.Yt, P.Ymean, T, c->Tpad, d_ptr, d_col, d_val, d_Cc, q0, d_Bf);
+            }
+            std::vector<int> rows(CH);
+            for (int b = 0; b < P.dp; b += CH) {
+                const int nr = std::min(CH, P.dp - b);
+                for (int i = 0; i < nr; ++i) rows[i] = b + i;
+                CNMFE_CUDA_OK(cudaMemcpyAsync(d_rows, rows.data(), (size_t)nr * 4, cudaMemcpyHostToDevice, c->st));
+                dim3 gg(nr, (T + YSIG_TCHUNK - 1) / YSIG_TCHUNK);
+                // Y - W_old * Bf for the rows of this chunk (b0 = 0; "previous" neurons = the current A, C of fit_ring_model's Bf)
+                LAUNCH(ysig_rows_kernel, gg, 256, 0, c->st, g, c->d_off_r, c->d_off_c, P.W, d_zero, P.Yt, P.Ymean, T, c->Tpad, d_ptr, d_col,
+                       d_val, Kb, d_Cc, d_rows, d_rowsY);
+                dim3 g2((T + 255) / 256, nr);
+                LAUNCH(bf_clamp_kernel, g2, 256, 0, c->st, g, d_rowsY, d_rows, P.Yt, T, c->Tpad, d_snp, c->opt.thresh_outlier, d_Bf, d_cnt);
+                CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));      // `rows` is reused by the next chunk
+            }
+            // frames (fit_ring_model.m:59-70): with nmax = 100 pmax < T keep the frames whose outlier count is <= quantile(counts, nmax/T)
+            std::vector<int> cnt(T);
+            CNMFE_CUDA_OK(cudaMemcpy(cnt.data(), d_cnt, (size_t)T * 4, cudaMemcpyDeviceToHost));
+            std::vector<unsigned char> mask(T, 1);
+            long long nmax = 100LL * pmax;
+            int Tsel = T;
+            if (nmax < T) {
+                std::vector<double> srt(cnt.begin(), cnt.end());
+                std::sort(srt.begin(), srt.end());
+                const double pos = ((double)nmax / (double)T) * (double)T + 0.5;     // MATLAB quantile: sorted x(i) at (i - 0.5)/n
+                double qv;
+                if (pos < 1.0) qv = srt[0];
+                else if (pos >= (double)T) qv = srt[T - 1];
+                else { const int lo = (int)std::floor(pos); const double fr = pos - lo; qv = srt[lo - 1] + fr * (srt[lo] - srt[lo - 1]); }
+                Tsel = 0;
+                for (int t = 0; t < T; ++t) { mask[t] = ((double)cnt[t] <= qv) ? 1 : 0; Tsel += mask[t]; }
+                nmax = Tsel;
+            }
+            if (c->opt.bg_acceleration) {            // :84-90 on the selected frames
+                const long long nk = std::max<long long>(1, std::min<long long>(Tsel, nmax));
+                const int k2 = (int)(Tsel / nk);
+                if (k2 > 1) { int j = 0; for (int t = 0; t < T; ++t) if (mask[t]) { if (j % k2) mask[t] = 0; ++j; } }
+            }
+            int nsel_i = 0;
+            for (int t = 0; t < T; ++t) nsel_i += mask[t];
+            CNMFE_CUDA_OK(cudaMemcpyAsync(d_mask, mask.data(), (size_t)T, cudaMemcpyHostToDevice, c->st));
+            {
+                long long nw = (long long)((P.nrb + 3) / 4) * P.ncb;
+                dim3 gg((unsigned)((nw + 7) / 8), c->ngroups);
+                LAUNCH(ring_s2_f64_kernel, gg, 256, 0, c->st, d_Bf, P.nrb, P.ncb, T, d_mask, c->rr, c->d_groups, c->ngroups, d_S2, ND);
+                LAUNCH(bf_row_sum_kernel, (unsigned)(((size_t)P.db * 32 + 255) / 256), 256, 0, c->st, d_Bf, P.db, T, d_mask, d_S1x);
+            }
+            CNMFE_CUDA_OK(cudaStreamSynchronize(c->st));
+            c->last_gram_frames = nsel_i;
+            S2_use = d_S2; S1_use = d_S1x; Ym_use = d_zero; aptr_use = d_zptr; K_use = 0; nsel_use = (double)nsel_i;
+            phase_end(c, 0);
+        }
         // projections needed by the neuron corrections
         phase_begin(c);
         double* d_N = c->scr.take<double>((size_t)P.db * std::max(Kb, 1));
         if (!d_N) { set_error("scratch exhausted"); return -1; }
-        if (Kb > 0) {
+        if (Kb > 0 && !outlier) {
             // (only the light kernels above share the SMs with the second-moment kernel; this Gram of the traces waits for it)
             dim3 gg(Kb, Kb);
             LAUNCH(small_gram_kernel, gg, 128, 0, c->st, d_Cc, Kb, d_Cc, Kb, T, kf, d_Vsel, d_Csum);
@@ -886,8 +973,8 @@ extern "C" int cnmfe_update_background(cnmfe_ctx* c) {
         // assemble + solve
         phase_begin(c);
         RingSolveArgs a;
-        a.g = g; a.off_r = c->d_off_r; a.off_c = c->d_off_c; a.S2 = d_S2; a.S1 = d_S1; a.Ymean = P.Ymean;
-        a.nsel = nsel; a.a_ptr = d_ptr; a.a_col = d_col; a.a_val = d_val; a.N = d_N; a.K = Kb; a.Csum = d_Csum;
+        a.g = g; a.off_r = c->d_off_r; a.off_c = c->d_off_c; a.S2 = S2_use; a.S1 = outlier ? S1_use : d_S1; a.Ymean = Ym_use;
+        a.nsel = outlier ? nsel_use : nsel; a.a_ptr = aptr_use; a.a_col = d_col; a.a_val = d_val; a.N = d_N; a.K = K_use; a.Csum = d_Csum;
         a.active = d_active; a.active_list = d_alist; a.n_active = (int)alist.size(); a.n_active_dev = nullptr; a.W = P.W; a.db = (size_t)P.db; a.ND = ND;
         a.prof = nullptr;
         static const bool ring_profile = getenv("CNMFE_RING_PROFILE") != nullptr;

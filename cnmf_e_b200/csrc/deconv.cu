@@ -474,7 +474,7 @@ extern "C" void cnmfe_options_defaults(cnmfe_options* o) {
     memset(o, 0, sizeof(*o));
     o->spatial_algorithm = 0; o->maxIter_temporal = 5; o->deconv_flag = 1; o->bg_acceleration = 1;
     o->replicate_spatial_aprev_quirk = 1; o->use_tensor_gram = 1;
-    o->background_model = 0; o->nb = 1; o->bg_ssub = 1;
+    o->background_model = 0; o->nb = 1; o->bg_ssub = 1; o->thresh_outlier = NAN;
     cnmfe_deconv_defaults(&o->deconv);
 }
 

@@ -103,6 +103,87 @@ ring_s2_simt_kernel(const uint16_t* __restrict__ Yt, int nrb, int ncb, int T, in
         }
 }
 
+// ---- explicit path for options.thresh_outlier (fit_ring_model.m:48-70): the outlier clamp is a per-element non-linearity of Bf, so
+// the moments cannot come from the integer video; Bf is materialised in fp64 ([db][T]) and its banded second moments over the
+// selected frames are accumulated in fp64.  Same displacement layout as the integer kernel, so the solver is shared.
+// Bf[q][t] = (Y[q,t] - Ybar_q) - sum_k A(q,k) Cc[k][t]   (block pixels; grid = (ceil(T/256), rows))
+__global__ void bf_rows_kernel(const uint16_t* __restrict__ Yt, const double* __restrict__ Ymean, int T, int Tpad,
+                               const int* __restrict__ a_ptr, const int* __restrict__ a_col, const double* __restrict__ a_val,
+                               const double* __restrict__ Cc, int q0, double* __restrict__ Bf) {
+    const size_t q = (size_t)q0 + blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double v = (double)Yt[q * Tpad + t] - Ymean[q];
+    for (int e = a_ptr[q]; e < a_ptr[q + 1]; ++e) v -= a_val[e] * Cc[(size_t)a_col[e] * T + t];
+    Bf[q * T + t] = v;
+}
+// clamp of the patch rows: rowsY[i][t] = Y(p_i,t) - Bf_old(p_i,t) (ysig_rows_kernel with b0 = 0 and the CURRENT A, C), so
+// Bf_old = Y - rowsY;  where Bf > Bf_old + thr * sn(p): Bf <- Bf_old and the frame's outlier count goes up (:50-54, :63)
+__global__ void bf_clamp_kernel(RingGeom g, const double* __restrict__ rowsY, const int* __restrict__ rows, const uint16_t* __restrict__ Yt,
+                                int T, int Tpad, const double* __restrict__ sn, double thr, double* __restrict__ Bf, int* __restrict__ counts) {
+    const int i = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int p = rows[i];
+    const size_t q = (size_t)(p / g.nr + g.pc_off) * g.nrb + (p % g.nr + g.pr_off);
+    const double bold = (double)Yt[q * Tpad + t] - rowsY[(size_t)i * T + t];
+    if (Bf[q * T + t] > bold + thr * sn[p]) { Bf[q * T + t] = bold; atomicAdd(&counts[t], 1); }
+}
+// S2[q][id(D)] = sum_{t: mask[t]} Bf[q][t] * Bf[q+D][t];  same warp tiling as ring_s2_simt_kernel (4 pixels x 4 dr at one dc)
+__global__ void __launch_bounds__(256)
+ring_s2_f64_kernel(const double* __restrict__ Bf, int nrb, int ncb, int T, const unsigned char* __restrict__ mask, int rr,
+                   const int* __restrict__ groups, int ngroups, double* __restrict__ S2, size_t ND) {
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gpc = (nrb + 3) / 4;
+    const long long wid = (long long)blockIdx.x * 8 + wib;
+    if (wid >= (long long)gpc * ncb) return;
+    const int c = (int)(wid / gpc), r0 = (int)(wid % gpc) * 4;
+    const int dc = groups[2 * blockIdx.y], dr0 = groups[2 * blockIdx.y + 1];
+    const int c2 = c + dc;
+    if (c2 >= ncb) return;
+    const double* yr[4];
+    const double* zr[7];
+    bool yv[4], zv[7];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { const int r = r0 + p; yv[p] = r < nrb; yr[p] = Bf + ((size_t)c * nrb + (yv[p] ? r : 0)) * T; }
+#pragma unroll
+    for (int j = 0; j < 7; ++j) { const int r = r0 + dr0 + j; zv[j] = (r >= 0 && r < nrb); zr[j] = Bf + ((size_t)c2 * nrb + (zv[j] ? r : 0)) * T; }
+    double acc[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) acc[p][dd] = 0.0;
+    for (int t = lane; t < T; t += 32) {
+        if (!mask[t]) continue;
+        double y[4], z[7];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) y[p] = yv[p] ? yr[p][t] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) z[j] = zv[j] ? zr[j][t] : 0.0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) acc[p][dd] = fma(y[p], z[p + dd], acc[p][dd]);
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) {
+            const double v = warp_sum(acc[p][dd]);
+            const int dr = dr0 + dd;
+            if (lane == 0 && yv[p] && zv[p + dd] && dr <= 2 * rr && dr >= -2 * rr && (dc > 0 || dr >= 0))
+                S2[((size_t)c * nrb + r0 + p) * ND + ring_disp_id(dr, dc, rr)] = v;
+        }
+}
+// S1[q] = sum_{t: mask[t]} Bf[q][t]   (one warp per block pixel)
+__global__ void bf_row_sum_kernel(const double* __restrict__ Bf, int db, int T, const unsigned char* __restrict__ mask, double* __restrict__ S1) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= db) return;
+    double s = 0.0;
+    for (int t = lane; t < T; t += 32) if (mask[t]) s += Bf[(size_t)q * T + t];
+    s = warp_sum(s);
+    if (lane == 0) S1[q] = s;
+}
+
 // ind_active (fit_ring_model.m:25-29) and b0 (:44).  One thread per patch pixel.
 __global__ void ring_active_b0_kernel(RingGeom g, const int* __restrict__ off_r, const int* __restrict__ off_c,
                                       const double* __restrict__ W, const double* __restrict__ sumA,

@@ -291,8 +291,7 @@ class Sources2D:
         model = str(opt["background_model"]).lower()
         if model not in ("ring", "svd", "nmf"):
             raise L.CnmfeError("background_model must be 'ring', 'svd' or 'nmf'")
-        if not (opt["thresh_outlier"] is None or np.isnan(opt["thresh_outlier"])):
-            raise L.CnmfeError("thresh_outlier (fit_ring_model.m:50-70 outlier clamp) is not built; leave it NaN")
+        o.thresh_outlier = float("nan") if opt["thresh_outlier"] is None else float(opt["thresh_outlier"])
         o.spatial_algorithm = _SPATIAL[str(opt["spatial_algorithm"]).lower()] if \
             str(opt["spatial_algorithm"]).lower() in _SPATIAL else 2
         o.maxIter_temporal = int(opt["maxIter"])
@@ -506,6 +505,9 @@ class Sources2D:
         if sync_host:
             self.push_neurons()
             self.push_ring()
+            to = self.options["thresh_outlier"]
+            if to is not None and not np.isnan(to):
+                self.set_sn()                      # the outlier clamp compares with thresh_outlier * obj.P.sn (fit_ring_model.m:51)
         L.check(self._lib.cnmfe_update_background(self._h))
         if not sync_host and self._is_ring():
             self._ring_w_stale.update(self.owned_patches())

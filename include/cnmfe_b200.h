@@ -60,6 +60,8 @@ typedef struct cnmfe_options {
     int nb;                  /* options.nb: number of svd background components (default 1) */
     int bg_ssub;             /* options.bg_ssub (ring model): 1, or > 1 = ring weights on the ceil(block/bg_ssub) grid
                                 (demo_large_data_1p.m:30 uses 2); changing it re-initialises W (update_background_parallel.m:70-118) */
+    double thresh_outlier;   /* options.thresh_outlier (CNMFSetParms default NaN = off): outlier clamp + frame selection of
+                                fit_ring_model.m:48-70.  Non-NaN selects the explicit fp64 path (Bf materialised; ring model, bg_ssub = 1) */
 } cnmfe_options;
 
 const char* cnmfe_last_error(void);

@@ -3,7 +3,9 @@ function update_background_parallel(obj, use_parallel) %#ok<INUSD>
 % Same signature and side effects (obj.W, obj.b0, obj.b, obj.f, obj.b0_new, obj.A_prev, obj.C_prev, log line, intermediate
 % snapshot); the arithmetic runs in libcnmfe_b200.so through cnmfe_b200_mex.  use_parallel is accepted and ignored: the library
 % does its own intra-call concurrency (a parfor pool would create one CUDA context and one video copy per worker).
-h = cnmfe_b200_push(obj, {'neurons'});            % context + blocks on first use; options, W/b0 (or b/f), A, C
+what = {'neurons'};
+if ~isnan(obj.options.thresh_outlier); what{end+1} = 'sn'; end   % the outlier clamp compares with thresh_outlier * obj.P.sn
+h = cnmfe_b200_push(obj, what);                   % context + blocks on first use; options, W/b0 (or b/f), A, C
 cnmfe_b200_mex('update_background', h);
 md = obj.P.mat_data;
 patch_pos = md.patch_pos;  block_pos = md.block_pos;  dims = md.dims;

@@ -122,6 +122,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         o.bg_ssub = field_int(so, "bg_ssub", o.bg_ssub);
         o.replicate_spatial_aprev_quirk = field_int(so, "replicate_spatial_aprev_quirk", o.replicate_spatial_aprev_quirk);
         o.use_tensor_gram = field_int(so, "use_tensor_gram", o.use_tensor_gram);
+        o.thresh_outlier = getfield_d(so, "thresh_outlier", o.thresh_outlier);     // NaN (CNMFSetParms default) = no outlier clamp
         const mxArray* bm = mxGetField(so, 0, "background_model");
         char buf[16];
         if (bm && !mxGetString(bm, buf, sizeof buf)) {

@@ -4,10 +4,7 @@ function h = cnmfe_b200_push(obj, what)
 % the parts named in `what`: 'neurons' (obj.A, obj.C), 'prev' (obj.A_prev, obj.C_prev), 'sn' (obj.P.sn).
 h = cnmfe_b200_handle(obj);
 o = obj.options;
-if ~isnan(o.thresh_outlier)
-    error('cnmfe:b200', 'thresh_outlier (fit_ring_model.m:50-70) is not available in the B200 path; leave it NaN (the CNMFSetParms default)');
-end
-s = struct('spatial_algorithm', cnmfe_b200_alg(o.spatial_algorithm), 'maxIter', o.maxIter, 'deconv_flag', logical(o.deconv_flag), ...
+s = struct('thresh_outlier', o.thresh_outlier, 'spatial_algorithm', cnmfe_b200_alg(o.spatial_algorithm), 'maxIter', o.maxIter, 'deconv_flag', logical(o.deconv_flag), ...
     'bg_acceleration', logical(o.bg_acceleration), 'background_model', lower(o.background_model), 'nb', o.nb, 'bg_ssub', o.bg_ssub, ...
     'deconv_options', cnmfe_b200_deconv(o.deconv_options));
 cnmfe_b200_mex('set_options', h, s);

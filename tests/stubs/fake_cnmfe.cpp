@@ -17,7 +17,7 @@ void cnmfe_deconv_defaults(cnmfe_deconv_opts* o) {
 void cnmfe_options_defaults(cnmfe_options* o) {
     memset(o, 0, sizeof *o);
     o->maxIter_temporal = 5; o->deconv_flag = 1; o->bg_acceleration = 1; o->replicate_spatial_aprev_quirk = 1; o->use_tensor_gram = 1;
-    o->nb = 1; o->bg_ssub = 1;
+    o->nb = 1; o->bg_ssub = 1; o->thresh_outlier = 0.0 / 0.0;
     cnmfe_deconv_defaults(&o->deconv);
 }
 int cnmfe_create(cnmfe_ctx** ctx, int d1, int d2, int T, int npatch, const int32_t* pp, const int32_t* bp, const uint8_t* owned,
@@ -35,9 +35,9 @@ int cnmfe_upload_block(cnmfe_ctx*, int ip, const void* Y, int dtype) {
     return 0;
 }
 int cnmfe_set_options(cnmfe_ctx*, const cnmfe_options* o) {
-    printf("set_options alg=%d maxIter=%d deconv_flag=%d accel=%d quirk=%d tensor=%d model=%d nb=%d ssub=%d | type=%d method=%d optb=%d optp=%d maxIter=%d "
+    printf("set_options alg=%d maxIter=%d deconv_flag=%d accel=%d quirk=%d tensor=%d model=%d nb=%d ssub=%d outlier=%g | type=%d method=%d optb=%d optp=%d maxIter=%d "
            "smin=%g lambda=%g max_tau=%g tau_range=%d\n", o->spatial_algorithm, o->maxIter_temporal, o->deconv_flag, o->bg_acceleration,
-           o->replicate_spatial_aprev_quirk, o->use_tensor_gram, o->background_model, o->nb, o->bg_ssub, o->deconv.type, o->deconv.method,
+           o->replicate_spatial_aprev_quirk, o->use_tensor_gram, o->background_model, o->nb, o->bg_ssub, o->thresh_outlier, o->deconv.type, o->deconv.method,
            o->deconv.optimize_b, o->deconv.optimize_pars, o->deconv.maxIter, o->deconv.smin, o->deconv.lambda, o->deconv.max_tau, o->deconv.has_tau_range);
     return 0;
 }

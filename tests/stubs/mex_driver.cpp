@@ -31,7 +31,7 @@ int main(int argc, char** argv) {
         mxArray* o = t_struct();
         t_setfield(o, "spatial_algorithm", t_scalar(2)); t_setfield(o, "maxIter", t_scalar(5)); t_setfield(o, "deconv_flag", t_logical(true));
         t_setfield(o, "bg_acceleration", t_logical(true)); t_setfield(o, "background_model", t_string("ring")); t_setfield(o, "nb", t_scalar(1));
-        t_setfield(o, "bg_ssub", t_scalar(2)); t_setfield(o, "deconv_options", dopt);
+        t_setfield(o, "bg_ssub", t_scalar(2)); t_setfield(o, "deconv_options", dopt); t_setfield(o, "thresh_outlier", t_scalar(2.5));
         call(0, {t_string("set_options"), h, o});
         auto sd = call(5, {t_string("ssub_dims"), h, t_scalar(1)});
         printf("ssub_dims -> d1s=%g d2s=%g nnb=%g r_shift[3]=%d c_shift[3]=%d\n", mxGetScalar(sd[0]), mxGetScalar(sd[1]), mxGetScalar(sd[2]),

@@ -264,3 +264,23 @@ def test_float_video_with_integer_counts(built_lib):
     with pytest.raises(LL.CnmfeError):
         g.load_video(D["Y"].astype(np.float32) + 0.25)
     g.close()
+
+
+@pytest.mark.parametrize("shape", [("outlier", (56, 48), 9), ("kf2_long", (48, 40), 3)])
+def test_background_thresh_outlier(built_lib, shape):
+    """options.thresh_outlier (fit_ring_model.m:48-70): residuals above W_old*Bf + thr*sn are clamped to the previous fit and,
+    when T > 100*pmax, only the frames with few outliers enter the regression (second case).  Explicit fp64 path on the GPU."""
+    case, patch, rr = shape
+    D, orc, gpu = _make(case, patch, rr)
+    for o in (orc, gpu):
+        o.options["thresh_outlier"] = 3.0
+    orc.update_background_parallel(); gpu.update_background_parallel()      # first run: W_old uniform
+    _check_bg(orc, gpu)
+    _sync_from_oracle(orc, gpu)
+    orc.C = orc.C * 1.03; gpu.C = orc.C.copy()
+    orc.update_background_parallel(); gpu.update_background_parallel()      # steady state: clamp against the fitted weights
+    _check_bg(orc, gpu)
+    T = D["Y"].shape[2]
+    used = built_lib.cnmfe_last_gram_frames(gpu._h)
+    assert (used < T) == (case == "kf2_long"), "frame selection expected only when T > 100 * pmax (used %d of %d)" % (used, T)
+    gpu.close()

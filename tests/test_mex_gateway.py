@@ -33,7 +33,7 @@ def test_gateway_marshalling_against_recording_library(tmp_path):
         "create d1=6 d2=4 T=40 np=2 pp0=[1 3 1 4] bp1=[2 6 1 4] owned=null rr=2 nn=0 dev=0",
         "upload_block ip=0 dtype=1 first=1234",
         # demo_large_data_1p.m: nnls, bg_ssub = 2, deconv_options = struct('type','ar1','method','foopsi','smin',-5,'optimize_pars',true,'optimize_b',true,'max_tau',100)
-        "set_options alg=2 maxIter=5 deconv_flag=1 accel=1 quirk=1 tensor=1 model=0 nb=1 ssub=2 | type=1 method=0 optb=1 optp=1 maxIter=10 smin=-5 lambda=0 max_tau=100 tau_range=0",
+        "set_options alg=2 maxIter=5 deconv_flag=1 accel=1 quirk=1 tensor=1 model=0 nb=1 ssub=2 outlier=2.5 | type=1 method=0 optb=1 optp=1 maxIter=10 smin=-5 lambda=0 max_tau=100 tau_range=0",
         "ssub_dims -> d1s=3 d2s=2 nnb=4 r_shift[3]=3 c_shift[3]=-3",
         "ring_offsets -> n=4 r_shift[0]=-2 c_shift[0]=2",
         "set_ring ip=1 W=set b0=set W1=1.5 b00=2.5",
