@@ -158,42 +158,99 @@ def build_block_on_gpu(prob, block, d1, T, seed, device, sn=10.0, chunk=500):
 
 # ----------------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  NVML in-process (a sample every 20 ms: the default timed region
+    is about a second, shorter than an `nvidia-smi` start-up); `nvidia-smi -lms` is the fallback, started ahead of the region
+    (`prepare`) with only the lines that arrive inside it kept."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.h, self.nv = index, [], None, None, None
+        self.on = False
+        self.alive = True
+        self.source = None
 
-    def start(self):
+    def prepare(self):
+        """Before the warm-up: open NVML (or launch nvidia-smi) so that sampling costs nothing when the region starts."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.nv, self.h, self.source = nv, h, "nvml"
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        bits = (("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = float("nan")
+        while self.alive:
+            if self.on:
+                try:
+                    sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self.samples.append((sm, mx, [n for n, b in bits if r & b]))
+                except Exception:
+                    pass
+            time.sleep(0.02)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
-
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for s in self.samples:
-            p = [x.strip() for x in s.split(",")]
+            if not self.on:
+                continue
+            p = [x.strip() for x in line.strip().split(",")]
             if len(p) < 7:
                 continue
             try:
-                sm.append(float(p[0])); mx.append(float(p[1]))
+                sm, mx = float(p[0]), float(p[1])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.samples.append((sm, mx, [n for n, v in zip(names, p[3:7]) if v.lower().startswith("active")]))
+
+    def start(self):
+        if self.source is None:
+            self.prepare()
+        self.on = True
+
+    def stop(self):
+        self.on = False
+        self.alive = False
+        if self.proc:
+            self.proc.terminate()
+        sm = [s[0] for s in self.samples]
+        mx = [s[1] for s in self.samples if s[1] == s[1]]
+        reasons = set()
+        for s in self.samples:
+            reasons.update(s[2])
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), source=self.source)
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm
@@ -415,10 +472,12 @@ def run_ours(args):
     import ctypes
     lib.cnmfe_set_sn(obj._h, np.asfortranarray(obj.P["sn"]).ctypes.data_as(ctypes.c_void_p))
     phases = np.zeros(7)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.prepare()
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = lib.cnmfe_launch_count()
@@ -641,6 +700,7 @@ def run_oasis_stress(args):
         _lib.check(lib.cnmfe_deconvolve_dev(V(y.data_ptr()), T, N, ctypes.byref(d), None, V(pars_d.data_ptr()), V(c.data_ptr()),
                                             V(s_.data_ptr()), V(outs.data_ptr()), 0))
     sampler = ClockSampler(0)
+    sampler.prepare()
     launches0 = lib.cnmfe_launch_count()
     for _ in range(max(3, args.warmup)):
         step()

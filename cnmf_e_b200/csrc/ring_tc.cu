@@ -387,6 +387,7 @@ int ring_s2_tensor(const uint8_t* hi, const uint8_t* lo, int nrb, int ncb, int T
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (const char* e = getenv("CNMFE_TC_SMS")) { int v = atoi(e); if (v >= CL && v < sms) sms = v; }   // A/B knob: SMs the kernel occupies
     void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams) =
         CL == 4 ? ring_s2_tc_kernel<4> : (CL == 2 ? ring_s2_tc_kernel<2> : ring_s2_tc_kernel<1>);
     CNMFE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
