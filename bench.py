@@ -547,6 +547,10 @@ def run_ours(args):
         step_e2e()
     barrier()
     e2e_t = (time.perf_counter() - te) / nE
+    # bytes the Sources2D mirror moved inside the e2e region (it re-sends only host state that changed since the last sync);
+    # taken here, before the post-timing checks read the lazily mirrored W / C_raw / S
+    h2d = (obj.h2d_bytes - h2d0) // nE + d1 * d2 * 8
+    d2h = (obj.d2h_bytes - d2h0) // nE
     te_t = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
@@ -565,9 +569,6 @@ def run_ours(args):
         if world == 1 and not args.no_oracle_checks and not c4:
             checks["oracle"] = full_size_oracle_checks(obj, IND)
             checks["ok"] = bool(checks.get("ok", False) and checks["oracle"].get("ok", False))
-    # bytes the Sources2D mirror actually moved (it re-sends only host state that changed since the last sync)
-    h2d = (obj.h2d_bytes - h2d0) // nE + d1 * d2 * 8
-    d2h = (obj.d2h_bytes - d2h0) // nE
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -331,8 +331,8 @@ int deconv_batch_dev(const double* Y, int T, int N, const cnmfe_deconv_opts& o, 
         set_error("deconvolve: ar2 + 'constrained' is the legacy constrained_foopsi (CVX/LARS) path: not built");
         return -1;
     }
-    if (o.type == 2 && o.method == 2 && (o.optimize_b || o.optimize_pars)) {
-        set_error("deconvolve: thresholded_oasisAR2 with optimize_b / optimize_pars is not built");
+    if (o.type == 2 && o.method == 2 && o.optimize_pars) {
+        set_error("deconvolve: thresholded_oasisAR2 with optimize_pars (update_g of the AR(2) kernel: a dense spike-amplitude solve per fminbnd evaluation) is not built");
         return -1;
     }
     int dev = 0;

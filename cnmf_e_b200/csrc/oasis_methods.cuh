@@ -365,11 +365,21 @@ __device__ void block_deconvolveCa(const double* __restrict__ y, int T, const cn
         block_thresholded_ar1(y, T, g1, sn, o.optimize_b != 0, o.optimize_pars != 0, maxIter, o.thresh_factor, o.p_noise, g_lo, g_hi,
                               o.has_tau_range != 0, ws, sh, out);
     } else {
-        // thresholded_oasisAR2 with optimize_b = optimize_g = false: its loop (:96-126) exits at the first
-        // abs(RSS-RSS0)<tol test, so the result is one oasisAR2 pass with smin = choose_smin(g, sn, 0.99999999) (:72)
+        // thresholded_oasisAR2 with optimize_g = false: both loops (:96-126, :133-163) exit at their first
+        // abs(RSS-RSS0)<tol test (RSS is recomputed from the unchanged solution), so the result is one oasisAR2 pass with
+        // smin = choose_smin(g, sn, 0.99999999) (:72) -- on y - b with b = estimate_baseline_noise(y) when optimize_b (:129-130)
         const double smin = choose_smin_ar2(g1, g2, sn, 0.99999999);
-        block_oasis_ar2(y, T, g1, g2, 0.0, smin, ws, sh);
-        out->b = 0.0; out->smin = smin;
+        double b = 0.0;
+        const double* yfit = y;
+        if (o.optimize_b) {
+            double sn_unused;
+            block_estimate_baseline_noise(y, T, ws, sh, &b, &sn_unused);
+            for (int i = threadIdx.x; i < T; i += blockDim.x) ws.yb[i] = y[i] - b;
+            __syncthreads();
+            yfit = ws.yb;
+        }
+        block_oasis_ar2(yfit, T, g1, g2, 0.0, smin, ws, sh);
+        out->b = b; out->smin = smin;
     }
     // avoid nan output (deconvolveCa.m:206)
     for (int i = threadIdx.x; i < T; i += blockDim.x) {

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "internal.h"
 
@@ -331,6 +332,222 @@ ring_s2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     }
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair variant
+// cta_group::2: the two CTAs of a cluster (two SMs) work on two column-adjacent pixel tiles (32 x 8 pixels) against the SAME
+// neighbour column, as ONE M = 256 MMA: each CTA stages its own A tiles (hi, lo) and only HALF of the B operand -- the leader
+// the hi plane of the neighbour column, its peer the lo plane ([B_hi; B_lo] is the N = 224 operand, split by halves across
+// the pair) -- and the tensor cores exchange the halves.  Why: the single-CTA kernel is bound by shared-memory bandwidth
+// (per 32-byte K step the MMAs read 22 KB of operands and TMA writes 15 KB against 224 MMA cycles = 165 B/clk of a 128 B/clk
+// port; measured 0.71 of the MMA rate, and the time scales with 1/SMs, so it is not the chip-level L2).  The pair reads
+// 15 KB and writes 11.5 KB per K step and CTA (118 B/clk), and a stage is 46 KB instead of 60 KB, so four stages fit.
+// Price: the pair covers 8 pixel columns, so 44 instead of 40 neighbour columns per tile (37 of them useful per pixel).
+namespace tc2 {
+constexpr int MR = tc::MR, MC = tc::MC, NB = tc::NB, BSHIFT = tc::BSHIFT, KSTAGE = tc::KSTAGE;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = tc::A_BYTES;                      // one byte plane of this CTA's pixel tile
+constexpr int B_BYTES = tc::B_BYTES;                      // ONE byte plane of the neighbour column (this CTA's half of B)
+constexpr int STAGE_BYTES = 2 * A_BYTES + B_BYTES;        // 47104
+constexpr int PAIR_TX = 2 * STAGE_BYTES;                  // bytes that land per stage in the two CTAs together
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + tc::EPI_BYTES;
+constexpr int COL_HH = 0, COL_HL = NB, COL_LH = 2 * NB, COL_LL = 3 * NB;   // A_hi x [B_hi;B_lo] | A_lo x [B_hi;B_lo]
+constexpr int PAIR_COLS = 2 * MC;
+}  // namespace tc2
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// box -> this CTA's shared memory, transaction bytes -> the mbarrier `bar` (a shared::cluster address: the leader's barrier)
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :
+        : "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void mma_i8_pair(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        :
+        : "r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// cluster work item g -> (r0, first column of the pair's 8, neighbour column)
+__device__ __forceinline__ void tc2_decode(const TcParams& P, long long g, int* r0, int* c0, int* cB) {
+    const int j = (int)(g % P.nbc);
+    const long long tile = g / P.nbc;
+    const int tr = (int)(tile % P.ntr), tcx = (int)(tile / P.ntr);
+    *r0 = tr * tc2::MR; *c0 = tcx * tc2::PAIR_COLS; *cB = *c0 + j;
+}
+
+__global__ void __launch_bounds__(tc::THREADS, 1)
+ring_s2_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                       const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                       const TcParams P) {
+    using namespace tc2;
+    constexpr int EPI_WARPS = tc::EPI_WARPS, EPI_STRIDE = tc::EPI_STRIDE;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = bars;                 // [STAGES]  used in the leader only (both CTAs' TMA bytes land on it)
+    uint64_t* empty_bar = bars + STAGES;       // [STAGES]  one per CTA (multicast commit)
+    uint64_t* tmem_full = bars + 2 * STAGES;   // [1]       one per CTA (multicast commit)
+    uint64_t* tmem_empty = tmem_full + 1;      // [1]       used in the leader only (both CTAs' epilogue warps arrive on it)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+    double* epi_buf = reinterpret_cast<double*>(tiles + STAGES * STAGE_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = (int)cluster_ctarank();   // 0 = leader (issues the MMAs), 1 = peer
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
+        mbar_init(smem_u32(tmem_full), 1);
+        mbar_init(smem_u32(tmem_empty), 2 * EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)tc::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int nkb = P.kb1 - P.kb0;
+    const long long g0 = blockIdx.x / 2, gstep = gridDim.x / 2;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const CUtensorMap* mapB = crank == 0 ? &tmB_hi : &tmB_lo;
+            for (long long g = g0; g < P.ngroups; g += gstep) {
+                int r0, c0, cB;
+                tc2_decode(P, g, &r0, &c0, &cB);
+                c0 += crank * MC;
+                const int rB0 = max(0, r0 - BSHIFT);
+                for (int kb = P.kb0; kb < P.kb1; ++kb) {
+                    mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+                    const uint32_t fb_local = smem_u32(full_bar + stage);
+                    const uint32_t fb = mapa_u32(fb_local, 0);            // the leader's barrier
+                    uint8_t* st = tiles + stage * STAGE_BYTES;
+                    if (crank == 0) mbar_expect_tx(fb_local, PAIR_TX);
+                    tma_load_3d_pair(smem_u32(st), &tmA_hi, fb, kb * KSTAGE, r0, c0);
+                    tma_load_3d_pair(smem_u32(st + A_BYTES), &tmA_lo, fb, kb * KSTAGE, r0, c0);
+                    tma_load_3d_pair(smem_u32(st + 2 * A_BYTES), mapB, fb, kb * KSTAGE, rB0, cB);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (one lane of the leader)
+        if (lane == 0 && crank == 0) {
+            // M = 256 (128 rows per CTA), N = 2 * NB = [B_hi; B_lo] (first half in the leader, second in the peer)
+            const uint32_t idesc = (2u << 4) | ((uint32_t)((2 * NB) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (long long g = g0; g < P.ngroups; g += gstep) {
+                mbar_wait(smem_u32(tmem_empty), acc_phase ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(smem_u32(full_bar + stage), phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < KSTAGE / 32; ++ks) {
+                        const uint64_t dAh = make_desc_sw128(sa + ks * 32);
+                        const uint64_t dAl = make_desc_sw128(sa + A_BYTES + ks * 32);
+                        const uint64_t dB = make_desc_sw128(sa + 2 * A_BYTES + ks * 32);
+                        const uint32_t acc = (kb | ks) != 0 ? 1u : 0u;
+                        mma_i8_pair(tmem_base + COL_HH, dAh, dB, idesc, acc);      // [hh | hl]
+                        mma_i8_pair(tmem_base + COL_LH, dAl, dB, idesc, acc);      // [lh | ll]
+                    }
+                    umma_commit_pair_mc(smem_u32(empty_bar + stage), (uint16_t)3);   // frees the stage in both CTAs
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair_mc(smem_u32(tmem_full), (uint16_t)3);               // accumulators complete, both CTAs
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (both CTAs, own pixel tile)
+        const int quad = warp & 3;
+        const int cc_begin = ((warp - 2) >> 2) ? 64 : 0, cc_end = ((warp - 2) >> 2) ? NB : 64;
+        const uint32_t empty_leader = mapa_u32(smem_u32(tmem_empty), 0);
+        uint32_t acc_phase = 0;
+        for (long long g = g0; g < P.ngroups; g += gstep) {
+            int r0, c0, cB;
+            tc2_decode(P, g, &r0, &c0, &cB);
+            c0 += crank * MC;
+            const int rB0 = max(0, r0 - BSHIFT);
+            const int cp = c0 + quad;
+            const int dc = cB - cp;
+            const bool warp_ok = (cp < P.ncb) && (cB < P.ncb) && (dc >= 0) && (dc <= 2 * P.rr);   // warp-uniform
+            mbar_wait(smem_u32(tmem_full), acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+            double* stg = epi_buf + (warp - 2) * (32 * EPI_STRIDE);
+            const int hx = lane & 15, hp = lane >> 4;
+            const int id0 = (dc == 0) ? 0 : (2 * P.rr + 1) + (dc - 1) * (4 * P.rr + 1) + 2 * P.rr;
+            if (warp_ok)
+#pragma unroll 1
+            for (int cc = cc_begin; cc < cc_end; cc += 16) {
+                uint32_t hh[16], hl[16], lh[16], ll[16];
+                tmem_ld16(taddr + COL_HH + cc, hh);
+                tmem_ld16(taddr + COL_HL + cc, hl);
+                tmem_ld16(taddr + COL_LH + cc, lh);
+                tmem_ld16(taddr + COL_LL + cc, ll);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int x = 0; x < 16; ++x) {
+                    const long long v = ((long long)(int)hh[x] << 16) + (((long long)(int)hl[x] + (long long)(int)lh[x]) << 8) +
+                                        (long long)(int)ll[x];
+                    stg[lane * EPI_STRIDE + x] = (double)v;
+                }
+                __syncwarp();
+                const int rn = rB0 + cc + hx;
+#pragma unroll 4
+                for (int it = 0; it < 16; ++it) {
+                    const int px = 2 * it + hp, rp = r0 + px;
+                    const int dr = rn - rp;
+                    if (rp < P.nrb && rn < P.nrb && dr >= -2 * P.rr && dr <= 2 * P.rr && (dc > 0 || dr >= 0)) {
+                        double* o = P.S2 + ((size_t)cp * P.nrb + rp) * (size_t)P.ND + (id0 + dr);
+                        const double val = stg[px * EPI_STRIDE + hx];
+                        if (P.accumulate) *o += val; else *o = val;
+                    }
+                }
+                __syncwarp();
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(empty_leader);
+            acc_phase ^= 1;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                        // no CTA leaves while its peer may still signal its barriers or read its B half
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tc::TMEM_COLS)
+                     : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -376,6 +593,44 @@ int ring_s2_tensor(const uint8_t* hi, const uint8_t* lo, int nrb, int ncb, int T
     P.ntr = (nrb + MR - 1) / MR; P.ntc = (ncb + MC - 1) / MC; P.nbc = MC + 2 * rr;
     P.nitems = (long long)P.ntr * P.ntc * P.nbc;
     P.S2 = S2;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (const char* e = getenv("CNMFE_TC_SMS")) { int v = atoi(e); if (v >= 2 && v < sms) sms = v; }   // A/B knob: SMs the kernel occupies
+    const int nkb_total = Tpad / KSTAGE, per_pass = MAX_K_BYTES / KSTAGE;
+    // CNMFE_TC_MODE=pair selects the CTA-pair kernel (cta_group::2); default: the one-CTA kernel with the multicast A tile
+    const char* mode = getenv("CNMFE_TC_MODE");
+    if (mode && !strcmp(mode, "pair")) {
+        P.nbc = tc2::PAIR_COLS + 2 * rr;
+        P.ntc = (ncb + tc2::PAIR_COLS - 1) / tc2::PAIR_COLS;
+        P.nitems = (long long)P.ntr * P.ntc * P.nbc;
+        P.ngroups = P.nitems;
+        CUtensorMap mAh, mAl, mBh, mBl;
+        if (make_map(&mAh, hi, Tpad, nrb, ncb, MR, MC) || make_map(&mAl, lo, Tpad, nrb, ncb, MR, MC) ||
+            make_map(&mBh, hi, Tpad, nrb, ncb, NB, 1) || make_map(&mBl, lo, Tpad, nrb, ncb, NB, 1))
+            return -1;
+        CNMFE_CUDA_OK(cudaFuncSetAttribute(ring_s2_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = tc2::SMEM_BYTES; cfg.stream = st;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int nclusters = sms / 2;
+        cfg.gridDim = dim3((unsigned)(nclusters * 2));
+        int maxc = 0;
+        if (cudaOccupancyMaxActiveClusters(&maxc, ring_s2_tc_pair_kernel, &cfg) == cudaSuccess && maxc > 0 && maxc < nclusters) nclusters = maxc;
+        if (P.ngroups < nclusters) nclusters = (int)P.ngroups;
+        cfg.gridDim = dim3((unsigned)(nclusters * 2));
+        for (int kb0 = 0, pass = 0; kb0 < nkb_total; kb0 += per_pass, ++pass) {
+            P.kb0 = kb0; P.kb1 = kb0 + per_pass < nkb_total ? kb0 + per_pass : nkb_total;
+            P.accumulate = pass > 0;
+            CNMFE_CUDA_OK(cudaLaunchKernelEx(&cfg, ring_s2_tc_pair_kernel, mAh, mAl, mBh, mBl, P));
+            ++g_launch_count;
+            CNMFE_CUDA_OK(cudaGetLastError());
+        }
+        return 0;
+    }
     // cluster size: 2 when the neighbour-column count allows it (measured: 1 -> 29.2 ms, 2 -> 28.6 ms, 4 -> 32.9 ms: fewer
     // co-resident clusters).  CNMFE_TC_CLUSTER=1|2|4 overrides for A/B measurements.
     int CL = (P.nbc % 2 == 0) ? 2 : 1;
@@ -384,10 +639,6 @@ int ring_s2_tensor(const uint8_t* hi, const uint8_t* lo, int nrb, int ncb, int T
     if (make_map(&mAh, hi, Tpad, nrb, ncb, MR, MC / CL) || make_map(&mAl, lo, Tpad, nrb, ncb, MR, MC / CL) ||
         make_map(&mBh, hi, Tpad, nrb, ncb, NB, 1) || make_map(&mBl, lo, Tpad, nrb, ncb, NB, 1))
         return -1;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (const char* e = getenv("CNMFE_TC_SMS")) { int v = atoi(e); if (v >= CL && v < sms) sms = v; }   // A/B knob: SMs the kernel occupies
     void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, TcParams) =
         CL == 4 ? ring_s2_tc_kernel<4> : (CL == 2 ? ring_s2_tc_kernel<2> : ring_s2_tc_kernel<1>);
     CNMFE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -407,7 +658,6 @@ int ring_s2_tensor(const uint8_t* hi, const uint8_t* lo, int nrb, int ncb, int T
     P.ngroups = P.nitems / CL;
     if (P.ngroups < nclusters) nclusters = (int)P.ngroups;
     cfg.gridDim = dim3((unsigned)(nclusters * CL));
-    const int nkb_total = Tpad / KSTAGE, per_pass = MAX_K_BYTES / KSTAGE;
     for (int kb0 = 0, pass = 0; kb0 < nkb_total; kb0 += per_pass, ++pass) {
         P.kb0 = kb0; P.kb1 = kb0 + per_pass < nkb_total ? kb0 + per_pass : nkb_total;
         P.accumulate = pass > 0;

@@ -720,29 +720,33 @@ def thresholded_oasisAR1(y, g=None, sn=None, optimize_b=False, optimize_g=False,
 
 def thresholded_oasisAR2(y, g, sn, smin=None, optimize_b=False, optimize_g=False, decimate=None, maxIter=10,
                          thresh_factor=1.0):
-    """thresholded_oasisAR2.m:38-126 with optimize_b = optimize_g = false.  NB: in that configuration the loop at
-    :96-126 exits at its first `abs(RSS-RSS0)<tol` test (RSS is recomputed from the unchanged solution), so the result
-    is ONE oasisAR2 pass with smin = choose_smin(g, sn, 0.99999999) (:72); update_smin (:175-201, warm-started AR2) is
-    unreachable and not restated."""
-    if optimize_b or optimize_g:
-        raise NotImplementedError("thresholded_oasisAR2 oracle: optimize_b / optimize_g branches not restated")
+    """thresholded_oasisAR2.m:38-166 with optimize_g = false.  NB: in that configuration both loops (:96-126 and
+    :133-163) exit at their first `abs(RSS-RSS0)<tol` test (RSS is recomputed from the unchanged solution), so the result
+    is ONE oasisAR2 pass with smin = choose_smin(g, sn, 0.99999999) (:72) -- fitted to y - b with
+    b = estimate_baseline_noise(y) (:129-130) when optimize_b; update_smin (:175-201, warm-started AR2) is unreachable and
+    not restated.  optimize_g (update_g of the AR(2) kernel, :236-321) is not restated."""
+    if optimize_g:
+        raise NotImplementedError("thresholded_oasisAR2 oracle: optimize_g branch not restated")
     y = np.asarray(y, dtype=np.float64).ravel()
     T = y.size
     smin = choose_smin(g, sn, 0.99999999)
     thresh = thresh_factor * sn * sn * T
     tol = 1e-4
     b = 0.0
-    solution, spks, aset = oasisAR2(y, g, None, smin)
-    res = y - solution
+    if optimize_b:
+        b, _ = estimate_baseline_noise(y)
+    solution, spks, aset = oasisAR2(y - b, g, None, smin)
+    res = y - solution - b
     RSS0 = float(res @ res)
     for _ in range(int(maxIter)):
         if len(aset) == 0:
             break
-        res = y - solution
+        res = y - solution - b
         RSS = float(res @ res)
         if abs(RSS - RSS0) < tol:
             break
         raise NotImplementedError("thresholded_oasisAR2 oracle: update_smin reached")   # pragma: no cover
+    _ = thresh
     return solution, spks, b, np.asarray(g, dtype=np.float64)[:2], smin, aset
 
 

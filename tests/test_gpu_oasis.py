@@ -78,6 +78,8 @@ def test_foopsi_ar2(built_lib):
 def test_thresholded_ar2(built_lib):
     Y, _, _ = _traces("ar2_3")
     _compare(Y, dict(type="ar2", method="thresholded", pars=[1.7, -0.712]), built_lib)
+    # optimize_b (thresholded_oasisAR2.m:127-163): baseline from estimate_baseline_noise, one pass on y - b
+    _compare(Y + 7.5, dict(type="ar2", method="thresholded", pars=[1.7, -0.712], optimize_b=True), built_lib)
 
 
 def test_ar2_at_c5_length(built_lib):
