@@ -408,7 +408,7 @@ int hals_temporal_dev(const double* U, const int* Vptr, const int* Vidx, const d
         fprintf(stderr, "[cnmfe hals profile] K=%d T=%d slots=%d:", K, T, slots);
         for (int i = 0; i < 12; ++i) fprintf(stderr, " %s=%.0fk", nm[i], h[14] ? (double)h[i] / (double)h[14] / 1e3 : 0.0);
         fprintf(stderr, " cycles/item; items=%llu iters/item=%.2f block0 clock64=%llu globaltimer_ns=%llu\n", h[14], h[14] ? (double)h[15] / (double)h[14] : 0.0, h[12], h[13]);
-        if (h[20]) fprintf(stderr, "[cnmfe hals profile] rss_g: %.1f evals/item, per eval: h table %.0f, cumsum %.0f, pools: 8-lane %.0f + cta-long %.0f + warp %.0f, sum %.0f cycles; mean maxl %.0f, mean pools %.0f, mean long pools %.2f\n",
+        if (h[20]) fprintf(stderr, "[cnmfe hals profile] rss_g: %.1f evals/item, per eval: h+hh tables %.0f, partial dots along the trace %.0f, per-pool terms %.0f (+%.0f +%.0f), sum %.0f cycles; mean maxl %.0f, mean pools %.0f, mean long pools %.2f\n",
                            (double)h[20] / h[14], (double)h[16] / h[20], (double)h[17] / h[20], (double)h[24] / h[20], (double)h[25] / h[20], (double)h[18] / h[20], (double)h[19] / h[20],
                            (double)h[21] / h[20], (double)h[22] / h[20], (double)h[26] / h[20]);
         // critical path: walk back from the item that finished last through the dependency that released it

@@ -364,9 +364,42 @@ __device__ int block_time_constant(const double* __restrict__ y, int T, int p, d
 }
 
 // ------------------------------------------------------------------------------------------------ AR(1) PAV
-// gp[m] = g^m for m in [0, 2T+1]; pow() in the loop is replaced by this table (same values: gp[m] = pow(g,m)).
+// gp[m] = g^m for m in [0, 2T+1]; pow() in the loop is replaced by this table.  Two levels: g^m = g^(64 a) * g^b with both
+// factors from pow() (one call per thread instead of ~40: pow is ~1000 cycles of the per-item latency chain), i.e. within
+// 2.5 ulp of the correctly rounded power instead of 1 ulp.  The coarse powers are parked in the tail of the table itself
+// (entries the fine pass overwrites last), the fine ones in gp[0..63].
 __device__ void block_pow_table(double g, int T, double* gp) {
-    for (int m = threadIdx.x; m <= 2 * T + 1; m += blockDim.x) gp[m] = pow(g, (double)m);
+    const int M = 2 * T + 2;                       // entries
+    const int na = (M + 63) >> 6;                  // coarse powers g^(64 a), a < na
+    __syncthreads();
+    if (M < 64 * 8 || na + 64 > M) {
+        for (int m = threadIdx.x; m < M; m += blockDim.x) gp[m] = pow(g, (double)m);
+        __syncthreads();
+        return;
+    }
+    // stage: fine powers -> gp[0..63] (their final place), coarse powers -> gp[M - na + a] (top of the table)
+    double* const ca = gp + (M - na);
+    for (int i = threadIdx.x; i < 64 + na; i += blockDim.x) {
+        if (i < 64) gp[i] = pow(g, (double)i);
+        else ca[i - 64] = pow(g, (double)(64 * (i - 64)));
+    }
+    __syncthreads();
+    // every thread keeps the coarse powers it needs in registers before anything in the tail is overwritten
+    const int per = (M - 64 + (int)blockDim.x - 1) / (int)blockDim.x;       // entries 64 .. M-1, contiguous chunk per thread
+    const int b0 = 64 + (int)threadIdx.x * per, b1 = min(M, b0 + per);
+    double c_lo = 0.0, c_hi = 0.0, c_hi2 = 0.0;
+    int a0 = 0;
+    if (b0 < b1) { a0 = b0 >> 6; c_lo = ca[a0]; c_hi = ca[min(a0 + 1, na - 1)]; c_hi2 = ca[min(a0 + 2, na - 1)]; }
+    __syncthreads();
+    if (per <= 128) {
+        for (int m = b0; m < b1; ++m) {
+            const int ia = (m >> 6) - a0;
+            gp[m] = (ia == 0 ? c_lo : (ia == 1 ? c_hi : c_hi2)) * gp[m & 63];
+        }
+    } else {
+        // very long traces (chunk spans more than three coarse steps): fall back to pow for this thread's entries
+        for (int m = b0; m < b1; ++m) gp[m] = pow(g, (double)m);
+    }
     __syncthreads();
 }
 
@@ -635,11 +668,33 @@ __device__ void block_pool_energy(const double* y, int n, TraceWS& ws, BlockShar
     __syncthreads();
 }
 
+// Work split of rss_g: thread i owns the samples [ns i, ns (i+1)) of the trace (ns odd: the lanes of a warp then read
+// shared memory 8 ns bytes apart without bank conflicts).  The pools are fixed while fminbnd runs, so the pool that
+// contains a thread's first sample is found once per update_g.
+struct RssPlan { int ns, p_start; };
+__device__ RssPlan block_rss_plan(int T, int n, const int* ptab) {
+    RssPlan pl;
+    int ns = (T + (int)blockDim.x - 1) / (int)blockDim.x;
+    if (!(ns & 1)) ++ns;
+    pl.ns = ns;
+    const int tA = ns * (int)threadIdx.x;
+    int lo = 0, hi = n - 1;                    // largest p with ptab[p] <= tA
+    if (tA < T) {
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (ptab[mid] <= tA) lo = mid; else hi = mid - 1; }
+    }
+    pl.p_start = lo;
+    return pl;
+}
+
 // rss_g of update_g (foopsi_oasisAR1.m:165-178).  Leaves ws.h / ws.hh holding this g's tables.
-// One pass per evaluation: with h = g^(0..l-1), dy = sum y h, sh = sum h over a pool,
+// With h = g^(0..l-1), dy = sum y h over a pool and sh = sum h = (1 - g^l) / (1 - g):
 //   dot = yp' h = dy - pen sh,  tv = max(dot / hh(l), 0),  sum (y - tv h)^2 = Q - tv (2 dy - tv hh(l))
 // (the reference forms c = tv h and then res = y - c: the same number, summed in another order; Q from block_pool_energy).
-__device__ double block_rss_g(const double* y, int n, double g, double lam, int maxl, TraceWS& ws,
+// Two passes, no per-pool loops on the critical path: (1) every thread walks its ns consecutive samples and writes one partial
+// dot product per (thread chunk, pool) pair into slot chunk + pool -- both indices only grow along the trace, so the slot is
+// unique and a pool's partials are consecutive; (2) one thread per pool adds its partials in ascending order (deterministic)
+// and forms the pool's term.  Per evaluation: ~ns + maxl/ns sequential steps instead of the longest pool's length.
+__device__ double block_rss_g(const double* y, int T, int n, double g, double lam, int maxl, const RssPlan& plan, TraceWS& ws,
                               BlockShared* sh) {
     const double lg = log(g), pen = lam * (1.0 - g);
     __syncthreads();
@@ -651,68 +706,58 @@ __device__ double block_rss_g(const double* y, int n, double g, double lam, int 
     const int* const ptab = ps ? sh->ptsm : ws.pt;
     const int* const ltab = ps ? sh->plsm : ws.pl;
     const double* const Q = ws.sv;
+    double* const slots = ws.scr;                               // <= blockDim + n partial sums
     if (sh->prof) { if (threadIdx.x == 0) { sh->pc[20] += 1ull; sh->pc[21] += (unsigned long long)maxl; sh->pc[22] += (unsigned long long)n; } __syncwarp(); }
-    for (int j = threadIdx.x; j <= maxl; j += blockDim.x) htab[j] = exp(lg * (double)j);
+    // h = g^(0..maxl) and hh = cumsum(h.^2) in closed form, hh(j) = (1 - g^(2 (j+1))) / (1 - g^2): the geometric sum the
+    // reference accumulates numerically (within ~1e-14 relative of the sequential cumsum for g <= 0.999; no scan, no barrier)
+    {
+        const double g2 = g * g, inv = 1.0 / (1.0 - g2);
+        for (int j = threadIdx.x; j <= maxl; j += blockDim.x) {
+            const double hv = exp(lg * (double)j);
+            htab[j] = hv;
+            hhtab[j] = fma(-g2 * hv, hv, 1.0) * inv;
+        }
+    }
     __syncthreads();
     CNMFE_PROF(sh, 16);
-    block_cumsum_sq(htab, hhtab, maxl + 1, sh, sh->part);
-    CNMFE_PROF(sh, 17);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    double rss = 0.0;
-    // short pools four per warp (8 lanes each), the others a warp each
+    // (1) partial dot products along the trace
     {
-        const int grp = lane >> 3, gl = lane & 7;
-        for (int p0 = warp * 4; p0 < n; p0 += nw * 4) {
-            const int p = p0 + grp;
-            int l = 0, t0 = 0;
-            if (p < n) { l = ltab[p]; t0 = ptab[p]; }
-            const int le = (l <= RSS_SHORT_POOL) ? l : 0;
-            double dy = 0.0, shs = 0.0;
-            {
-                int j = gl;
-                for (; j + 24 < le; j += 32) {
-                    const double y0 = y[t0 + j], y1 = y[t0 + j + 8], y2 = y[t0 + j + 16], y3 = y[t0 + j + 24];
-                    const double h0 = htab[j], h1 = htab[j + 8], h2 = htab[j + 16], h3 = htab[j + 24];
-                    dy = fma(y0, h0, dy); dy = fma(y1, h1, dy); dy = fma(y2, h2, dy); dy = fma(y3, h3, dy);
-                    shs += (h0 + h1) + (h2 + h3);
+        const int ns = plan.ns, c = (int)threadIdx.x;
+        int t = ns * c;
+        if (t < T) {
+            const int te = min(T, t + ns);
+            int p = plan.p_start;
+            int t0 = ptab[p], tend = t0 + ltab[p];
+            double acc = 0.0;
+            for (; t < te; ++t) {
+                if (t == tend) {
+                    slots[c + p] = acc; acc = 0.0;
+                    ++p; t0 = tend; tend = t0 + ltab[p];
                 }
-                for (; j < le; j += 8) { const double hv = htab[j]; dy = fma(y[t0 + j], hv, dy); shs += hv; }
+                acc = fma(y[t], htab[t - t0], acc);
             }
-            __syncwarp();
-            dy += __shfl_xor_sync(0xffffffffu, dy, 4); shs += __shfl_xor_sync(0xffffffffu, shs, 4);
-            dy += __shfl_xor_sync(0xffffffffu, dy, 2); shs += __shfl_xor_sync(0xffffffffu, shs, 2);
-            dy += __shfl_xor_sync(0xffffffffu, dy, 1); shs += __shfl_xor_sync(0xffffffffu, shs, 1);
-            if (le > 0 && gl == 0) {
-                const double hhl = hhtab[l - 1];
-                const double tv = fmax((dy - pen * shs) / hhl, 0.0);
-                rss += Q[p] - tv * (2.0 * dy - tv * hhl);
-            }
+            slots[c + p] = acc;
         }
-        __syncwarp();
     }
-    CNMFE_PROF(sh, 24);
-    for (int p = warp; p < n; p += nw) {
-        const int t0 = ptab[p], l = ltab[p];
-        if (l <= RSS_SHORT_POOL) continue;
-        double dy = 0.0, shs = 0.0;
-        {
-            int j = lane;
-            for (; j + 96 < l; j += 128) {
-                const double y0 = y[t0 + j], y1 = y[t0 + j + 32], y2 = y[t0 + j + 64], y3 = y[t0 + j + 96];
-                const double h0 = htab[j], h1 = htab[j + 32], h2 = htab[j + 64], h3 = htab[j + 96];
-                dy = fma(y0, h0, dy); dy = fma(y1, h1, dy); dy = fma(y2, h2, dy); dy = fma(y3, h3, dy);
-                shs += (h0 + h1) + (h2 + h3);
-            }
-            for (; j < l; j += 32) { const double hv = htab[j]; dy = fma(y[t0 + j], hv, dy); shs += hv; }
-        }
-        dy = warp_sum(dy); shs = warp_sum(shs);
-        if (lane == 0) {
+    __syncthreads();
+    CNMFE_PROF(sh, 17);
+    // (2) one thread per pool
+    double rss = 0.0;
+    {
+        const int ns = plan.ns;
+        const double inv1g = 1.0 / (1.0 - g);
+        for (int p = threadIdx.x; p < n; p += blockDim.x) {
+            const int t0 = ptab[p], l = ltab[p];
+            const int c0 = t0 / ns, c1 = (t0 + l - 1) / ns;
+            double dy = 0.0;
+            for (int c = c0; c <= c1; ++c) dy += slots[c + p];
+            const double shs = (1.0 - g * htab[l - 1]) * inv1g;
             const double hhl = hhtab[l - 1];
             const double tv = fmax((dy - pen * shs) / hhl, 0.0);
             rss += Q[p] - tv * (2.0 * dy - tv * hhl);
         }
     }
-    __syncthreads();
+    CNMFE_PROF(sh, 24);
     CNMFE_PROF(sh, 18);
     rss = block_sum(rss, sh->red);
     CNMFE_PROF(sh, 19);
@@ -720,12 +765,12 @@ __device__ double block_rss_g(const double* y, int n, double g, double lam, int 
 }
 
 // MATLAB fminbnd on rss_g over [ax,bx]; returns xf (all threads run the scalar logic redundantly).
-__device__ double block_fminbnd_rss(const double* y, int n, double lam, int maxl, double ax, double bx,
-                                    TraceWS& ws, BlockShared* sh) {
+__device__ double block_fminbnd_rss(const double* y, int T, int n, double lam, int maxl, double ax, double bx,
+                                    const RssPlan& plan, TraceWS& ws, BlockShared* sh) {
     const double tol = 1e-4, seps = 1.4901161193847656e-08, cgold = 0.3819660112501051;
     double a = ax, b = bx;
     double v = a + cgold * (b - a), w = v, xf = v, d = 0.0, e = 0.0, x = xf;
-    double fx = block_rss_g(y, n, x, lam, maxl, ws, sh);
+    double fx = block_rss_g(y, T, n, x, lam, maxl, plan, ws, sh);
     int funccount = 1, iter = 0;
     double fv = fx, fw = fx;
     double xm = 0.5 * (a + b);
@@ -760,7 +805,7 @@ __device__ double block_fminbnd_rss(const double* y, int n, double lam, int maxl
         }
         double si = (d > 0.0 ? 1.0 : (d < 0.0 ? -1.0 : 0.0)) + (d == 0.0 ? 1.0 : 0.0);
         x = xf + si * fmax(fabs(d), tol1);
-        double fu = block_rss_g(y, n, x, lam, maxl, ws, sh);
+        double fu = block_rss_g(y, T, n, x, lam, maxl, plan, ws, sh);
         ++funccount; ++iter;
         if (fu <= fx) {
             if (x >= xf) a = xf; else b = xf;
@@ -801,7 +846,8 @@ __device__ double block_update_g(const double* y, int T, int* n_io, double lam, 
     block_pool_energy(y, n, ws, sh);       // Q_p of the (fixed) pools: rss_g is then one pass per evaluation
     const double* const hh_last = (maxl < sh->hcap) ? sh->hhsm : ws.hh;   // where the last rss_g evaluation left cumsum(h.^2)
     CNMFE_PROF(sh, 10);
-    double g = block_fminbnd_rss(y, n, lam, maxl, g_lo, g_hi, ws, sh);
+    const RssPlan plan = block_rss_plan(T, n, (n <= sh->pcap && sh->ysm) ? sh->ptsm : ws.pt);
+    double g = block_fminbnd_rss(y, T, n, lam, maxl, g_lo, g_hi, plan, ws, sh);
     CNMFE_PROF(sh, 7);
     // rebuild pools: v from the returned g, w from the LAST evaluated kernel (ws.hh), foopsi_oasisAR1.m:153-162
     const double lg = log(g), pen = lam * (1.0 - g);
