@@ -51,6 +51,7 @@ struct BlockShared {
     int* ptsm;                  // update_g: pool starts / lengths when n <= pcap, else ws.pt / ws.pl
     int* plsm;
     int hcap, pcap;
+    int dyn_bytes;              // dynamic shared memory actually allocated for this launch (trace_smem_bind)
     int nlong, long_thr;        // update_g: pools longer than long_thr, in ascending pool order (handled by the whole CTA)
     int longp[128];
     unsigned long long* prof;   // optional per-phase cycle counters (CNMFE_HALS_PROFILE diagnostics), else nullptr
@@ -114,6 +115,11 @@ __device__ inline void trace_smem_bind(BlockShared* sh, unsigned char* dyn, int 
     sh->plsm = (mode & 2) ? sh->ptsm + TRACE_PCAP : nullptr;
     sh->hcap = (mode & 2) ? TRACE_HCAP : 0;
     sh->pcap = (mode & 2) ? TRACE_PCAP : 0;
+    {
+        const size_t fb = (mode & 1) ? (size_t)welch_nfft(T) * 16 : 0;
+        const size_t sb = (mode & 2) ? L.y_bytes + 2 * (size_t)TRACE_HCAP * 8 + 2 * (size_t)TRACE_PCAP * 4 : 0;
+        sh->dyn_bytes = (int)(fb > sb ? fb : sb);
+    }
 }
 
 __host__ __device__ inline size_t trace_scratch_doubles(int T) {
@@ -227,15 +233,27 @@ __device__ void block_fft(double2* z, const double2* tw, int n, int logn) {
     }
     __syncthreads();
     for (int s = 1; s <= logn; ++s) {
-        int m = 1 << s, half = m >> 1, tstride = n >> s;
-        for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
-            int grp = b / half, j = b - grp * half;
-            int i0 = grp * m + j, i1 = i0 + half;
-            double2 w = tw[j * tstride];
-            double2 u = z[i0], v = z[i1];
-            double tr = v.x * w.x - v.y * w.y, ti = v.x * w.y + v.y * w.x;
-            z[i0] = make_double2(u.x + tr, u.y + ti);
-            z[i1] = make_double2(u.x - tr, u.y - ti);
+        const int half = 1 << (s - 1), tshift = logn - s;
+        // two butterflies per thread in flight: their operand loads are issued together (the stages are latency bound; four
+        // in flight spill registers under the kernel's 128-register cap and were slower)
+        for (int b0 = threadIdx.x; b0 < (n >> 1); b0 += 2 * blockDim.x) {
+            const int bA = b0, bB = b0 + (int)blockDim.x;
+            const bool hasB = bB < (n >> 1);
+            const int iA = ((bA >> (s - 1)) << s) + (bA & (half - 1));
+            const int iB = hasB ? ((bB >> (s - 1)) << s) + (bB & (half - 1)) : iA;
+            const double2 wA = tw[(bA & (half - 1)) << tshift], wB = tw[(bB & (half - 1)) << tshift];
+            const double2 uA = z[iA], vA = z[iA + half];
+            const double2 uB = z[iB], vB = z[iB + half];
+            {
+                const double tr = vA.x * wA.x - vA.y * wA.y, ti = vA.x * wA.y + vA.y * wA.x;
+                z[iA] = make_double2(uA.x + tr, uA.y + ti);
+                z[iA + half] = make_double2(uA.x - tr, uA.y - ti);
+            }
+            if (hasB) {
+                const double tr = vB.x * wB.x - vB.y * wB.y, ti = vB.x * wB.y + vB.y * wB.x;
+                z[iB] = make_double2(uB.x + tr, uB.y + ti);
+                z[iB + half] = make_double2(uB.x - tr, uB.y - ti);
+            }
         }
         __syncthreads();
     }
@@ -251,6 +269,8 @@ __device__ double block_getsn(const double* __restrict__ x, int N, double* scr, 
     int logn = 0;
     while ((1 << logn) < nfft) ++logn;
     double2* z = sh->zfft ? sh->zfft : reinterpret_cast<double2*>(scr);
+    // twiddles in the global scratch (L1): the early stages read them with strides of 2^k entries, which in shared memory
+    // would be 32-way bank conflicts (measured: GetSn 195 k -> 345 k cycles with a shared-memory table)
     double2* tw = reinterpret_cast<double2*>(scr + 2 * (size_t)nfft);
     double* acc = scr + 3 * (size_t)nfft;
     const int f0 = nfft / 4, nf = nfft / 4 + 1;
@@ -366,40 +386,24 @@ __device__ int block_time_constant(const double* __restrict__ y, int T, int p, d
 // ------------------------------------------------------------------------------------------------ AR(1) PAV
 // gp[m] = g^m for m in [0, 2T+1]; pow() in the loop is replaced by this table.  Two levels: g^m = g^(64 a) * g^b with both
 // factors from pow() (one call per thread instead of ~40: pow is ~1000 cycles of the per-item latency chain), i.e. within
-// 2.5 ulp of the correctly rounded power instead of 1 ulp.  The coarse powers are parked in the tail of the table itself
-// (entries the fine pass overwrites last), the fine ones in gp[0..63].
+// 2.5 ulp of the correctly rounded power instead of 1 ulp.  Both small tables live in shared memory.
 __device__ void block_pow_table(double g, int T, double* gp) {
     const int M = 2 * T + 2;                       // entries
     const int na = (M + 63) >> 6;                  // coarse powers g^(64 a), a < na
+    __shared__ double pw_fine[64];
+    __shared__ double pw_coarse[512];
     __syncthreads();
-    if (M < 64 * 8 || na + 64 > M) {
+    if (na > 512) {                                // very long traces: one pow per entry
         for (int m = threadIdx.x; m < M; m += blockDim.x) gp[m] = pow(g, (double)m);
         __syncthreads();
         return;
     }
-    // stage: fine powers -> gp[0..63] (their final place), coarse powers -> gp[M - na + a] (top of the table)
-    double* const ca = gp + (M - na);
     for (int i = threadIdx.x; i < 64 + na; i += blockDim.x) {
-        if (i < 64) gp[i] = pow(g, (double)i);
-        else ca[i - 64] = pow(g, (double)(64 * (i - 64)));
+        if (i < 64) pw_fine[i] = pow(g, (double)i);
+        else pw_coarse[i - 64] = pow(g, (double)(64 * (i - 64)));
     }
     __syncthreads();
-    // every thread keeps the coarse powers it needs in registers before anything in the tail is overwritten
-    const int per = (M - 64 + (int)blockDim.x - 1) / (int)blockDim.x;       // entries 64 .. M-1, contiguous chunk per thread
-    const int b0 = 64 + (int)threadIdx.x * per, b1 = min(M, b0 + per);
-    double c_lo = 0.0, c_hi = 0.0, c_hi2 = 0.0;
-    int a0 = 0;
-    if (b0 < b1) { a0 = b0 >> 6; c_lo = ca[a0]; c_hi = ca[min(a0 + 1, na - 1)]; c_hi2 = ca[min(a0 + 2, na - 1)]; }
-    __syncthreads();
-    if (per <= 128) {
-        for (int m = b0; m < b1; ++m) {
-            const int ia = (m >> 6) - a0;
-            gp[m] = (ia == 0 ? c_lo : (ia == 1 ? c_hi : c_hi2)) * gp[m & 63];
-        }
-    } else {
-        // very long traces (chunk spans more than three coarse steps): fall back to pow for this thread's entries
-        for (int m = b0; m < b1; ++m) gp[m] = pow(g, (double)m);
-    }
+    for (int m = threadIdx.x; m < M; m += blockDim.x) gp[m] = pw_coarse[m >> 6] * pw_fine[m & 63];
     __syncthreads();
 }
 
@@ -483,11 +487,13 @@ __device__ void block_oasis_ar1_solution(const TraceWS& ws, int n, double g, int
 // to the first event (a new pool is accepted, or a back-track merge is needed) is committed.  Decisions and values are
 // identical to the element-by-element loop; only the divisions/table look-ups are parallelised.
 __device__ int warp_oasis_ar1_cold(const double* __restrict__ y, int T, double g, double lam, double smin,
-                                   TraceWS& ws, double2* stage, double2* snap) {
+                                   TraceWS& ws, double2* stage, double2* snap, const double* gsm, int gsm_n) {
     __syncwarp();   // enter converged (see common.cuh: divergent warps take the slow shuffle path)
     const int lane = threadIdx.x & 31;
     const double pen = lam * (1.0 - g);
-    const double* gp = ws.gp;
+    const double* gpg = ws.gp;
+    // powers of g: the head of the table from shared memory (gsm, gsm_n entries; pools are rarely longer), the rest from global
+    auto gpw = [&](int idx) { return idx < gsm_n ? gsm[idx] : gpg[idx]; };
     double* pv = ws.pv; double* pw = ws.pw; int* pt = ws.pt; int* pl = ws.pl;
     auto val = [&](int idx) { return (idx == T - 1) ? (y[idx] - lam) : (y[idx] - pen); };
     int top = 0, i = 1, lt = 1;
@@ -509,15 +515,15 @@ __device__ int warp_oasis_ar1_cold(const double* __restrict__ y, int T, double g
         if (pf_i == i && pf_lt == lt) { yj = pf_y; e1 = pf_e1; e2 = pf_e2; }
         else {
             yj = in ? val(idx) : 0.0;
-            e1 = in ? gp[lt + lane] : 0.0;
-            e2 = in ? gp[2 * (lt + lane)] : 0.0;
+            e1 = in ? gpw(lt + lane) : 0.0;
+            e2 = in ? gpw(2 * (lt + lane)) : 0.0;
         }
         {
             const int ni = i + m, nlt = lt + m, nidx = ni + lane;
             const bool nin = nidx < T;
             pf_y = nin ? val(nidx) : 0.0;
-            pf_e1 = nin ? gp[nlt + lane] : 0.0;
-            pf_e2 = nin ? gp[2 * (nlt + lane)] : 0.0;
+            pf_e1 = nin ? gpw(nlt + lane) : 0.0;
+            pf_e2 = nin ? gpw(2 * (nlt + lane)) : 0.0;
             pf_i = ni; pf_lt = nlt;
         }
         const double aj = yj * e1;
@@ -539,8 +545,26 @@ __device__ int warp_oasis_ar1_cold(const double* __restrict__ y, int T, double g
         const double2 own = snap[lane];
         const double vj = own.x, wj = own.y;
         const double vj1 = vj + aj, wj1 = wj + e2;   // the same additions the chain performed for this element
-        const bool fwd = in && (yj >= vj / wj * e1 + smin);
-        const bool back = in && !fwd && (top > 0) && (vj1 / wj1 < rp);
+        // The reference's tests are  yj >= vj / wj * e1 + smin  and  vj1 / wj1 < rp  (two divisions, ~110 cycles each, on the
+        // chain).  Multiplied through by w > 0 they are  wj (yj - smin) - vj e1 >= 0  and  vj1 - rp wj1 < 0; evaluated that way
+        // the sign is certain whenever the margin exceeds the rounding of both forms (a few ulp of the terms), and then it IS
+        // the reference's decision.  Only when some lane's margin is inside that band (practically never) does the window
+        // fall back to the divisions, so decisions stay identical to the element-by-element loop.
+        bool fwd, back;
+        {
+            const double t1 = wj * (yj - smin), t2 = vj * e1;
+            const double mF = t1 - t2, bF = 64.0 * 2.220446049250313e-16 * (fabs(t1) + fabs(t2) + fabs(wj * smin));
+            const double t3 = rp * wj1;
+            const double mB = vj1 - t3, bB = 64.0 * 2.220446049250313e-16 * (fabs(vj1) + fabs(t3));
+            const bool unsureF = in && !(fabs(mF) > bF);
+            fwd = in && (mF >= 0.0);
+            const bool unsureB = in && !fwd && (top > 0) && !(fabs(mB) > bB);
+            back = in && !fwd && (top > 0) && (mB < 0.0);
+            if (__any_sync(0xffffffffu, unsureF || unsureB)) {
+                fwd = in && (yj >= vj / wj * e1 + smin);
+                back = in && !fwd && (top > 0) && (vj1 / wj1 < rp);
+            }
+        }
         const unsigned mf = __ballot_sync(0xffffffffu, fwd), mb = __ballot_sync(0xffffffffu, back);
         const unsigned ev = mf | mb;
         if (ev == 0u) {
@@ -576,7 +600,7 @@ __device__ int warp_oasis_ar1_cold(const double* __restrict__ y, int T, double g
                     --top;
                     if (top > 0) {
                         bv = pv[top - 1]; bw = pw[top - 1]; bl = pl[top - 1];
-                        bg1 = gp[bl]; bg2 = gp[2 * bl];
+                        bg1 = gpw(bl); bg2 = gpw(2 * bl);
                         rp = fmax(0.0, bv / bw * bg1) + smin;
                     }
                 } else break;
@@ -596,8 +620,20 @@ __device__ int block_oasis_ar1(const double* y, int T, double g, double lam, dou
     block_pow_table(g, T, ws.gp);
     __syncthreads();
     CNMFE_PROF(sh, 11);
+    // the scan is one warp's dependency chain: its operands come from shared memory when the launch staged it (the trace
+    // into the update_g buffer, the head of the power table into the h / hh tables -- both idle during the scan)
+    const double* ysc = y;
+    const double* gsm = nullptr;
+    int gsm_n = 0;
+    if (sh->ysm) {
+        for (int i = threadIdx.x; i < T; i += blockDim.x) sh->ysm[i] = y[i];
+        gsm_n = min(2 * TRACE_HCAP, 2 * T + 2);
+        for (int i = threadIdx.x; i < gsm_n; i += blockDim.x) sh->hsm[i] = ws.gp[i];
+        ysc = sh->ysm; gsm = sh->hsm;
+        __syncthreads();
+    }
     if (warp_id_uniform() == 0) {
-        int n = warp_oasis_ar1_cold(y, T, g, lam, smin, ws, sh->stage, sh->snap);
+        int n = warp_oasis_ar1_cold(ysc, T, g, lam, smin, ws, sh->stage, sh->snap, gsm, gsm_n);
         if (threadIdx.x == 0) sh->ibc[2] = n;
     }
     __syncthreads();
