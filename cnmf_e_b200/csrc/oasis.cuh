@@ -433,7 +433,17 @@ __device__ int block_oasis_ar1_run(TraceWS& ws, int n, double smin, BlockShared*
             const double vi = nv, wi = nwt;
             const int li = nl, ti = ntt;
             if (i + 1 < n) { nv = v[i + 1]; nwt = w[i + 1]; nl = l[i + 1]; ntt = t[i + 1]; }
-            if (vi / wi >= vt / wt * gp[lt] + smin) {
+            // forward test  vi / wi >= vt / wt * g^lt + smin  (oasisAR1.m:63-64) multiplied through by wi wt > 0; the divisions
+            // are only evaluated when the margin is within the rounding of either form (see warp_oasis_ar1_cold)
+            bool fwd;
+            {
+                const double glt = gp[lt];
+                const double a1 = vi * wt, a2 = vt * glt * wi, a3 = smin * wi * wt;
+                const double mF = a1 - a2 - a3;
+                if (fabs(mF) > 64.0 * 2.220446049250313e-16 * (fabs(a1) + fabs(a2) + fabs(a3))) fwd = mF >= 0.0;
+                else fwd = vi / wi >= vt / wt * glt + smin;
+            }
+            if (fwd) {
                 v[top] = vt; w[top] = wt; l[top] = lt;
                 ++top;
                 t[top] = ti;
@@ -446,7 +456,17 @@ __device__ int block_oasis_ar1_run(TraceWS& ws, int n, double smin, BlockShared*
             while (top > 0) {
                 double vp = v[top - 1], wp = w[top - 1];
                 int lp = l[top - 1];
-                if (vt / wt < fmax(0.0, vp / wp * gp[lp]) + smin) {
+                // back-track test  vt / wt < max(0, vp / wp * g^lp) + smin, same filter
+                bool merge;
+                {
+                    const double glp = gp[lp];
+                    const double pq = vp * glp;                     // sign of vp / wp * g^lp (wp > 0)
+                    const double b1 = vt * wp, b2 = (pq > 0.0 ? pq : 0.0) * wt, b3 = smin * wp * wt;
+                    const double mB = b1 - b2 - b3;
+                    if (fabs(mB) > 64.0 * 2.220446049250313e-16 * (fabs(b1) + fabs(b2) + fabs(b3))) merge = mB < 0.0;
+                    else merge = vt / wt < fmax(0.0, vp / wp * glp) + smin;
+                }
+                if (merge) {
                     vt = vp + vt * gp[lp];
                     wt = wp + wt * gp[2 * lp];
                     lt = lp + lt;
@@ -756,7 +776,8 @@ __device__ double block_rss_g(const double* y, int T, int n, double g, double la
     }
     __syncthreads();
     CNMFE_PROF(sh, 16);
-    // (1) partial dot products along the trace
+    // (1) partial dot products along the trace: the thread's samples split at the pool borders into segments, each a
+    //     branch-free dot product
     {
         const int ns = plan.ns, c = (int)threadIdx.x;
         int t = ns * c;
@@ -764,33 +785,52 @@ __device__ double block_rss_g(const double* y, int T, int n, double g, double la
             const int te = min(T, t + ns);
             int p = plan.p_start;
             int t0 = ptab[p], tend = t0 + ltab[p];
-            double acc = 0.0;
-            for (; t < te; ++t) {
-                if (t == tend) {
-                    slots[c + p] = acc; acc = 0.0;
-                    ++p; t0 = tend; tend = t0 + ltab[p];
+            while (true) {
+                const int se = min(te, tend);
+                const double* yy = y + t;
+                const double* hh_ = htab + (t - t0);
+                const int len = se - t;
+                double acc = 0.0;
+                int k = 0;
+                for (; k + 4 <= len; k += 4) {
+                    const double y0 = yy[k], y1 = yy[k + 1], y2 = yy[k + 2], y3 = yy[k + 3];
+                    const double h0 = hh_[k], h1 = hh_[k + 1], h2 = hh_[k + 2], h3 = hh_[k + 3];
+                    acc = fma(y0, h0, acc); acc = fma(y1, h1, acc); acc = fma(y2, h2, acc); acc = fma(y3, h3, acc);
                 }
-                acc = fma(y[t], htab[t - t0], acc);
+                for (; k < len; ++k) acc = fma(yy[k], hh_[k], acc);
+                slots[c + p] = acc;
+                t = se;
+                if (t >= te) break;
+                ++p; t0 = tend; tend = t0 + ltab[p];
             }
-            slots[c + p] = acc;
         }
     }
     __syncthreads();
     CNMFE_PROF(sh, 17);
-    // (2) one thread per pool
+    // (2) four lanes per pool: each adds every fourth partial in ascending order, then a fixed two-level shuffle tree
     double rss = 0.0;
     {
         const int ns = plan.ns;
         const double inv1g = 1.0 / (1.0 - g);
-        for (int p = threadIdx.x; p < n; p += blockDim.x) {
-            const int t0 = ptab[p], l = ltab[p];
-            const int c0 = t0 / ns, c1 = (t0 + l - 1) / ns;
+        const int q = (int)threadIdx.x & 3;
+        for (int pb = 0; pb < n; pb += (int)blockDim.x >> 2) {
+            const int p = pb + ((int)threadIdx.x >> 2);
             double dy = 0.0;
-            for (int c = c0; c <= c1; ++c) dy += slots[c + p];
-            const double shs = (1.0 - g * htab[l - 1]) * inv1g;
-            const double hhl = hhtab[l - 1];
-            const double tv = fmax((dy - pen * shs) / hhl, 0.0);
-            rss += Q[p] - tv * (2.0 * dy - tv * hhl);
+            int l = 1;
+            if (p < n) {
+                const int t0 = ptab[p];
+                l = ltab[p];
+                const int c0 = t0 / ns, c1 = (t0 + l - 1) / ns;
+                for (int c = c0 + q; c <= c1; c += 4) dy += slots[c + p];
+            }
+            dy += __shfl_xor_sync(0xffffffffu, dy, 1);
+            dy += __shfl_xor_sync(0xffffffffu, dy, 2);
+            if (p < n && q == 0) {
+                const double shs = (1.0 - g * htab[l - 1]) * inv1g;
+                const double hhl = hhtab[l - 1];
+                const double tv = fmax((dy - pen * shs) / hhl, 0.0);
+                rss += Q[p] - tv * (2.0 * dy - tv * hhl);
+            }
         }
     }
     CNMFE_PROF(sh, 24);
