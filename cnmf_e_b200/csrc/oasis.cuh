@@ -36,12 +36,14 @@ struct TraceWS {
     int* sl;       // T
 };
 
+#define TRACE_PART 1280
 struct BlockShared {
     double red[32];
     int hist[256];
     int ibc[4];
     double dbc[4];
-    double part[CNMFE_HALS_BLOCK];   // block scan partials (cumsum of the update_g kernel table); sized for the largest CTA
+    double part[TRACE_PART];    // block-wide scratch: scan partials, the two factor tables of block_pow_table (64 + 512), the
+                                // partial sums of rss_g (one per (thread chunk, pool) pair while they fit, else global scratch)
     double2 stage[32];          // cold scan: (a_m, b_m) of the current window, read back as broadcast 16-byte loads
     double2 snap[32];           // cold scan: running (v, w) before element m
     double2* zfft;              // GetSn FFT buffer in dynamic shared memory (nfft complex), or nullptr -> global scratch
@@ -386,12 +388,12 @@ __device__ int block_time_constant(const double* __restrict__ y, int T, int p, d
 // ------------------------------------------------------------------------------------------------ AR(1) PAV
 // gp[m] = g^m for m in [0, 2T+1]; pow() in the loop is replaced by this table.  Two levels: g^m = g^(64 a) * g^b with both
 // factors from pow() (one call per thread instead of ~40: pow is ~1000 cycles of the per-item latency chain), i.e. within
-// 2.5 ulp of the correctly rounded power instead of 1 ulp.  Both small tables live in shared memory.
-__device__ void block_pow_table(double g, int T, double* gp) {
+// 2.5 ulp of the correctly rounded power instead of 1 ulp.  Both small tables live in shared memory (sh->part).
+__device__ void block_pow_table(double g, int T, double* gp, BlockShared* sh) {
     const int M = 2 * T + 2;                       // entries
     const int na = (M + 63) >> 6;                  // coarse powers g^(64 a), a < na
-    __shared__ double pw_fine[64];
-    __shared__ double pw_coarse[512];
+    double* const pw_fine = sh->part;              // 64
+    double* const pw_coarse = sh->part + 64;       // <= 512
     __syncthreads();
     if (na > 512) {                                // very long traces: one pow per entry
         for (int m = threadIdx.x; m < M; m += blockDim.x) gp[m] = pow(g, (double)m);
@@ -637,7 +639,7 @@ __device__ int warp_oasis_ar1_cold(const double* __restrict__ y, int T, double g
 __device__ int block_oasis_ar1(const double* y, int T, double g, double lam, double smin, TraceWS& ws,
                                BlockShared* sh) {
     CNMFE_PROF(sh, 10);
-    block_pow_table(g, T, ws.gp);
+    block_pow_table(g, T, ws.gp, sh);
     __syncthreads();
     CNMFE_PROF(sh, 11);
     // the scan is one warp's dependency chain: its operands come from shared memory when the launch staged it (the trace
@@ -762,7 +764,12 @@ __device__ double block_rss_g(const double* y, int T, int n, double g, double la
     const int* const ptab = ps ? sh->ptsm : ws.pt;
     const int* const ltab = ps ? sh->plsm : ws.pl;
     const double* const Q = ws.sv;
-    double* const slots = ws.scr;                               // <= blockDim + n partial sums
+    // <= chunks + n partial sums: in shared memory while they fit -- through the global scratch every evaluation paid a
+    // store -> barrier -> load round trip to L2 (~2 k cycles)
+    const int nchunks = (T + plan.ns - 1) / plan.ns;
+    const bool slots_sm = nchunks + n <= TRACE_PART;
+    double* const slots = ws.scr;
+    double* const slots_s = sh->part;
     if (sh->prof) { if (threadIdx.x == 0) { sh->pc[20] += 1ull; sh->pc[21] += (unsigned long long)maxl; sh->pc[22] += (unsigned long long)n; } __syncwarp(); }
     // h = g^(0..maxl) and hh = cumsum(h.^2) in closed form, hh(j) = (1 - g^(2 (j+1))) / (1 - g^2): the geometric sum the
     // reference accumulates numerically (within ~1e-14 relative of the sequential cumsum for g <= 0.999; no scan, no barrier)
@@ -798,7 +805,7 @@ __device__ double block_rss_g(const double* y, int T, int n, double g, double la
                     acc = fma(y0, h0, acc); acc = fma(y1, h1, acc); acc = fma(y2, h2, acc); acc = fma(y3, h3, acc);
                 }
                 for (; k < len; ++k) acc = fma(yy[k], hh_[k], acc);
-                slots[c + p] = acc;
+                if (slots_sm) slots_s[c + p] = acc; else slots[c + p] = acc;
                 t = se;
                 if (t >= te) break;
                 ++p; t0 = tend; tend = t0 + ltab[p];
@@ -821,7 +828,8 @@ __device__ double block_rss_g(const double* y, int T, int n, double g, double la
                 const int t0 = ptab[p];
                 l = ltab[p];
                 const int c0 = t0 / ns, c1 = (t0 + l - 1) / ns;
-                for (int c = c0 + q; c <= c1; c += 4) dy += slots[c + p];
+                if (slots_sm) { for (int c = c0 + q; c <= c1; c += 4) dy += slots_s[c + p]; }
+                else { for (int c = c0 + q; c <= c1; c += 4) dy += slots[c + p]; }
             }
             dy += __shfl_xor_sync(0xffffffffu, dy, 1);
             dy += __shfl_xor_sync(0xffffffffu, dy, 2);
@@ -937,7 +945,7 @@ __device__ double block_update_g(const double* y, int T, int* n_io, double lam, 
     }
     __syncthreads();
     CNMFE_PROF(sh, 8);
-    block_pow_table(g, T, ws.gp);
+    block_pow_table(g, T, ws.gp, sh);
     CNMFE_PROF(sh, 11);
     n = block_oasis_ar1_run(ws, n, smin, sh);
     CNMFE_PROF(sh, 9);

@@ -276,7 +276,7 @@ __device__ void block_thresholded_ar1(const double* __restrict__ yraw, int T, do
         const int nsv = n < 9 ? n : 9;
         int ind_start = 1, ind_end = nsv;
         const double thr = sqrt(thresh);
-        block_pow_table(g, T, ws.gp);
+        block_pow_table(g, T, ws.gp, sh);
         while (ind_end - ind_start > 1) {
             int ind = (ind_start + ind_end) / 2;
             double tmp_smin = smin + (double)(ind - 1) * ((s_max - smin) / (double)(nsv - 1));
