@@ -4,7 +4,7 @@ timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -8 | tee gpurun_out/r2
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3 | tee gpurun_out/r2_smoke.log
 timeout 900 python bench.py 2>gpurun_out/r2_bench.err | tail -1 > gpurun_out/r2_bench_n1.json
 timeout 600 python bench.py --impl reference 2>gpurun_out/r2_ref.err | tail -1 > gpurun_out/r2_bench_reference.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2_launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:cnmfe -c 400 --csv --log-file gpurun_out/r2_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu --no-oracle-checks > gpurun_out/r2_ncu_bench.log 2>&1
 python - <<'PY'
 import json
@@ -16,12 +16,3 @@ print(json.dumps(d['cpu_baseline']))
 print(open('gpurun_out/r2_bench_reference.json').read()[:600])
 PY
 tail -3 gpurun_out/r2_bench.err
-# A/B: SMs occupied by the second-moment kernel (is it bound per SM or by the chip-level L2 throughput?)
-for n in 132 116 100; do
-  CNMFE_TC_SMS=$n timeout 300 python bench.py --steps 3 --warmup 1 --no-cpu --no-oracle-checks 2>/dev/null | tail -1 > gpurun_out/r2p_tcsms_$n.json
-  python - <<PY
-import json
-d = json.load(open('gpurun_out/r2p_tcsms_$n.json'))
-print('TC_SMS', $n, d['ms_per_step'], json.dumps(d['config']['phase_ms_per_step']))
-PY
-done
