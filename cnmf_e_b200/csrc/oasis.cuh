@@ -227,35 +227,37 @@ __device__ double block_mean_below(const double* x, int n, double thr, BlockShar
 }
 
 // ------------------------------------------------------------------------------------------------ GetSn
-// In-place radix-2 DIT FFT of z[0..n) (interleaved re,im), twiddles tw[j] = (cos, -sin)(2 pi j / n), j < n/2.
+__device__ __forceinline__ double2 cmul2(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// In-place radix-4 decimation-in-frequency FFT of z[0..n) (interleaved re,im), twiddles tw[j] = (cos, -sin)(2 pi j / n), j < n/2.
+// The input is in natural order and the output is left in BIT-REVERSED order (X[k] at z[brev(k)]): the caller indexes it
+// through fft_brev, so there is no permutation pass (in shared memory a bit reversal is a 32-way bank conflict), and two
+// radix-2 stages per barrier halve the latency-bound stage count.  One radix-4 butterfly = stage s on (x0,x2), (x1,x3) and
+// stage s-1 on the results; w_m^(j+m/4) = -i w_m^j, w_(m/2)^j = w_m^(2j).
+__device__ __forceinline__ int fft_brev(int i, int logn) { return (int)(__brev((unsigned)i) >> (32 - logn)); }
 __device__ void block_fft(double2* z, const double2* tw, int n, int logn) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int j = (int)(__brev((unsigned)i) >> (32 - logn));
-        if (j > i) { double2 a = z[i]; z[i] = z[j]; z[j] = a; }
+    int s = logn;
+    for (; s >= 2; s -= 2) {
+        const int quarter = 1 << (s - 2), tshift = logn - s;
+        for (int b = threadIdx.x; b < (n >> 2); b += blockDim.x) {
+            const int g = b >> (s - 2), j = b & (quarter - 1);
+            const int i0 = (g << s) + j;
+            const double2 w1 = tw[j << tshift], w2 = tw[(2 * j) << tshift];
+            const double2 x0 = z[i0], x1 = z[i0 + quarter], x2 = z[i0 + 2 * quarter], x3 = z[i0 + 3 * quarter];
+            const double2 a0 = make_double2(x0.x + x2.x, x0.y + x2.y), d0 = make_double2(x0.x - x2.x, x0.y - x2.y);
+            const double2 a1 = make_double2(x1.x + x3.x, x1.y + x3.y), d1 = make_double2(x1.y - x3.y, x3.x - x1.x);   // -i (x1 - x3)
+            const double2 a2 = cmul2(d0, w1), a3 = cmul2(d1, w1);
+            z[i0] = make_double2(a0.x + a1.x, a0.y + a1.y);
+            z[i0 + quarter] = cmul2(make_double2(a0.x - a1.x, a0.y - a1.y), w2);
+            z[i0 + 2 * quarter] = make_double2(a2.x + a3.x, a2.y + a3.y);
+            z[i0 + 3 * quarter] = cmul2(make_double2(a2.x - a3.x, a2.y - a3.y), w2);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int s = 1; s <= logn; ++s) {
-        const int half = 1 << (s - 1), tshift = logn - s;
-        // two butterflies per thread in flight: their operand loads are issued together (the stages are latency bound; four
-        // in flight spill registers under the kernel's 128-register cap and were slower)
-        for (int b0 = threadIdx.x; b0 < (n >> 1); b0 += 2 * blockDim.x) {
-            const int bA = b0, bB = b0 + (int)blockDim.x;
-            const bool hasB = bB < (n >> 1);
-            const int iA = ((bA >> (s - 1)) << s) + (bA & (half - 1));
-            const int iB = hasB ? ((bB >> (s - 1)) << s) + (bB & (half - 1)) : iA;
-            const double2 wA = tw[(bA & (half - 1)) << tshift], wB = tw[(bB & (half - 1)) << tshift];
-            const double2 uA = z[iA], vA = z[iA + half];
-            const double2 uB = z[iB], vB = z[iB + half];
-            {
-                const double tr = vA.x * wA.x - vA.y * wA.y, ti = vA.x * wA.y + vA.y * wA.x;
-                z[iA] = make_double2(uA.x + tr, uA.y + ti);
-                z[iA + half] = make_double2(uA.x - tr, uA.y - ti);
-            }
-            if (hasB) {
-                const double tr = vB.x * wB.x - vB.y * wB.y, ti = vB.x * wB.y + vB.y * wB.x;
-                z[iB] = make_double2(uB.x + tr, uB.y + ti);
-                z[iB + half] = make_double2(uB.x - tr, uB.y - ti);
-            }
+    if (s == 1) {
+        for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
+            const double2 u = z[2 * b], v = z[2 * b + 1];
+            z[2 * b] = make_double2(u.x + v.x, u.y + v.y);
+            z[2 * b + 1] = make_double2(u.x - v.x, u.y - v.y);
         }
         __syncthreads();
     }
@@ -307,7 +309,7 @@ __device__ double block_getsn(const double* __restrict__ x, int N, double* scr, 
         block_fft(z, tw, nfft, logn);
         for (int j = threadIdx.x; j < nf; j += blockDim.x) {
             int f = f0 + j;
-            double2 a = z[f], b = z[(nfft - f) & (nfft - 1)];
+            double2 a = z[fft_brev(f, logn)], b = z[fft_brev((nfft - f) & (nfft - 1), logn)];
             double xr = 0.5 * (a.x + b.x), xi = 0.5 * (a.y - b.y);
             double p = xr * xr + xi * xi;
             if (two) {
