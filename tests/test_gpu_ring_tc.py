@@ -50,3 +50,20 @@ def test_tensor_long_video_two_passes(built_lib):
     """T > 16384 frames: the kernel runs two K passes and accumulates (int32 accumulators must not overflow)."""
     Y, out, ND = _moments(40, 8, 17000, 2, seed=9)
     assert np.array_equal(out[0], out[1])
+
+
+@pytest.mark.parametrize("shape", [(64, 48, 700, 9), (100, 37, 1300, 18)])
+def test_cta_pair_kernel_equals_simt(built_lib, shape, monkeypatch):
+    """The cta_group::2 variant (two SMs share one M = 256 MMA, each staging half of the neighbour operand; opt-in with
+    CNMFE_TC_MODE=pair, read per call) is bit-exact too -- incl. an odd number of columns, where the pair's second tile is
+    partly outside the block."""
+    monkeypatch.setenv("CNMFE_TC_MODE", "pair")
+    d1, d2, T, rr = shape
+    _, out, _ = _moments(d1, d2, T, rr, seed=6)
+    assert np.array_equal(out[0], out[1]), "CTA-pair moments differ from the SIMT kernel: max |diff| = %g" % np.abs(out[0] - out[1]).max()
+
+
+def test_cta_pair_kernel_two_passes(built_lib, monkeypatch):
+    monkeypatch.setenv("CNMFE_TC_MODE", "pair")
+    _, out, _ = _moments(40, 8, 17000, 2, seed=10)
+    assert np.array_equal(out[0], out[1])
