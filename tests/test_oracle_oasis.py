@@ -92,6 +92,24 @@ def test_ar2_recursion_and_threshold():
     assert np.corrcoef(c, truth[0])[0, 1] > 0.9
 
 
+def test_ar2_thresholded_optimize_b_is_one_pass_on_the_baseline_corrected_trace():
+    """thresholded_oasisAR2.m:127-163 with optimize_g = false: b = estimate_baseline_noise(y), then ONE oasisAR2 pass on y - b
+    (the loop exits at its first RSS test).  A constant added to the trace moves b by (nearly) that constant -- the histogram
+    bins of estimate_baseline_noise are not exactly shift invariant in floating point."""
+    Y, _, _ = O.gen_data([1.7, -0.712], 0.5, 3000, 30, 0.5, 0, 1, 7)
+    y = Y[0]
+    opts = dict(type="ar2", pars=[1.7, -0.712], method="thresholded", optimize_b=True)
+    c0, s0, o0 = O.deconvolveCa(y, opts)
+    c1, s1, o1 = O.deconvolveCa(y + 12.5, opts)
+    assert abs((o1["b"] - o0["b"]) - 12.5) < 0.05
+    assert np.mean((s0 > 0) != (s1 > 0)) < 0.01
+    b_ref, _ = O.estimate_baseline_noise(y)
+    assert abs(o0["b"] - b_ref) < 1e-12
+    smin = O.choose_smin([1.7, -0.712], o0["sn"], 0.99999999)
+    c_ref, s_ref, _ = O.oasisAR2(y - b_ref, [1.7, -0.712], None, smin)
+    assert np.array_equal(c0, c_ref) and np.array_equal(s0, s_ref)
+
+
 def test_gen_data_spikes_follow_matlab_rand_stream():
     """MT19937 + column-major fill: first uniform of RandomState(13) is MATLAB's rand after rng(13)."""
     rs = np.random.RandomState(13)
