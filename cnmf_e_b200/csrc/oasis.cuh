@@ -669,32 +669,7 @@ __device__ int block_oasis_ar1(const double* y, int T, double g, double lam, dou
     return n;
 }
 
-// inclusive cumsum of squares of h[0..m1) into hh: thread-chunked, warp shuffle scan of the chunk sums, one more shuffle scan
-// over the warp totals (two barriers; the old version serialised blockDim/32 partials per lane of warp 0)
-__device__ void block_cumsum_sq(const double* h, double* hh, int m1, BlockShared* sh, double* part /*>= 32 doubles*/) {
-    const int per = (m1 + blockDim.x - 1) / blockDim.x;
-    const int b = threadIdx.x * per, e = min(m1, b + per);
-    const int lane = threadIdx.x & 31, wid = warp_id_uniform(), nw = (blockDim.x + 31) >> 5;
-    double a = 0.0;
-    for (int j = b; j < e; ++j) a += h[j] * h[j];
-    double incl = a;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) part[wid] = incl;
-    __syncthreads();
-    double wt = (lane < nw) ? part[lane] : 0.0;         // every warp scans the (<= 32) warp totals itself
-    double winc = wt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
-    const double wbase = __shfl_sync(0xffffffffu, winc - wt, wid);
-    a = wbase + (incl - a);
-    for (int j = b; j < e; ++j) { a += h[j] * h[j]; hh[j] = a; }
-    __syncthreads();
-    (void)sh;
-}
-
 #define RSS_SHORT_POOL 256
-#define RSS_LONG_POOL 768
 // Per-pool energy Q_p = sum_{t in pool} y_t^2 -> ws.sv (free during update_g).  Pools are fixed while fminbnd runs, so this
 // is computed once per update_g; rss_g then needs ONE pass over the trace per evaluation.
 __device__ void block_pool_energy(const double* y, int n, TraceWS& ws, BlockShared* sh) {
