@@ -89,9 +89,10 @@ __host__ __device__ inline int welch_nfft(int T) {
 // Dynamic shared memory of the per-trace kernels.  Two users that never overlap in time share it:
 //   GetSn      the Welch FFT buffer (nfft complex doubles) when it fits 64 KB;
 //   update_g   a copy of the trace (T doubles), the kernel table h and its cumsum (TRACE_HCAP doubles each) and the pool
-//              starts/lengths (TRACE_PCAP ints each): fminbnd evaluates rss_g ~9 times per FOOPSI iteration; every
-//              evaluation reads the trace twice and chases pool -> length -> cumsum look-ups, and from L2 those
-//              dependent latencies were 85 % of rss_g.
+//              starts/lengths (TRACE_PCAP ints each): fminbnd evaluates rss_g ~24 times per item and from L2 the dependent
+//              look-ups were 85 % of rss_g;
+//   cold scan  the same trace buffer + the head of the power table in the h / hh region (the scan is one warp's chain);
+//   quantiles  (none: the radix select reads the trace through L1 -- keep the carve-out small).
 #define TRACE_HCAP 1024
 #define TRACE_PCAP 1024
 struct TraceSmem { size_t total, y_bytes; int fft, stage; };

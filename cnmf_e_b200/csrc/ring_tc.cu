@@ -9,10 +9,14 @@
 //
 // Work item = (pixel tile of MR x MC = 32 x 4 = 128 pixels = MMA M, one neighbour column of NB = 112 rows = MMA N).
 // Per item the K loop streams all frames: TMA (3-D boxes {128 B of t, rows, cols}, SWIZZLE_128B) -> 3-stage smem ring
-// -> 16 MMAs per stage (4 K-steps of 32 B x 4 byte-plane products) into three accumulators (hh, hl+lh, ll), then the
-// epilogue warps read TMEM (tcgen05.ld 32x32b), combine in int64 and write the (pixel, displacement) run.
+// -> 8 MMAs per stage (4 K-steps of 32 B x {A_hi, A_lo} x [B_hi; B_lo] as one N = 224 operand) into three accumulators
+// (hh, hl+lh, ll), then the epilogue warps read TMEM (tcgen05.ld 32x32b), combine in int64 and write the (pixel,
+// displacement) run.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..9 = epilogue (TMEM lane quadrant warp % 4,
 // two warps per quadrant splitting the columns: the accumulators are single-buffered, so the epilogue is a pipeline bubble).
+// Two kernels: ring_s2_tc_kernel (one CTA per item, cluster-of-2 multicast of the pixel tile; default) and
+// ring_s2_tc_pair_kernel (cta_group::2: two SMs per M = 256 MMA, each staging half of the neighbour operand; opt-in) --
+// what bounds each is measured in DESIGN.md section 5.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -151,7 +155,8 @@ __device__ __forceinline__ bool tc_decode(const TcParams& P, long long g, int ra
 
 // CL = CTAs per cluster.  The CL CTAs of a cluster work on the SAME pixel tile with CL consecutive neighbour columns, so
 // the A tile (the larger operand) is fetched from L2 once per cluster: every CTA loads 1/CL of it and multicasts the slice
-// to all of them.  The kernel is bound by the L2 -> SM fill rate (60 KB per 896 MMA cycles at CL = 1), not by the MMAs.
+// to all of them.  The kernel is bound per SM by shared-memory port traffic (operand reads of the MMAs + TMA writes = 37 KB per
+// 224 MMA cycles; its time scales with 1 / SMs), not by the MMAs or the chip-level L2.
 template <int CL>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 ring_s2_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
